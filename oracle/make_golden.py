@@ -1,0 +1,197 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference numpy half.
+
+Runs only in the build container (needs /root/reference, which is read-only and absent on the GPU
+box).  The reference modules are imported from where they lie, with the stub packages in
+oracle/stubs standing in for gym / pyprind / rand_param_envs (absent, no network).  Nothing from
+the reference is copied: only its numeric outputs are stored.
+
+    python oracle/make_golden.py          # rewrites tests/golden/
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree %s not present: golden vectors can only be regenerated in the build container" % REF)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'stubs'))
+    sys.path.insert(0, REF)
+    sys.path.insert(0, ROOT)
+
+
+def gen_point_corner_steps():
+    """normalize(MetaPointEnvCorner).step over scripted actions for the three reward types."""
+    from meta_policy_search.envs.point_envs.point_env_2d_corner import MetaPointEnvCorner
+    from meta_policy_search.envs.normalized_env import normalize
+    out = {}
+    T, n_env = 60, 24
+    rng = np.random.RandomState(7)
+    # policy-space actions in [-10,10]-ish, biased toward a random corner so that the sparse
+    # reward's three branches (inside radius / goal is nearest corner / other corner) all occur
+    drift = rng.choice([-1.0, 1.0], size=(n_env, 2)) * 4.0
+    actions = drift[None] + 6.0 * rng.randn(T, n_env, 2)
+    actions[::7] *= 3.0          # exercise the clip at the action bounds
+    out['actions'] = actions
+    for rtype in ('sparse', 'dense', 'dense_squared'):
+        env = normalize(MetaPointEnvCorner(reward_type=rtype))
+        np.random.seed(11)
+        tasks = env.sample_tasks(n_env)
+        obs0 = np.zeros((n_env, 2))
+        obs = np.zeros((T, n_env, 2))
+        rew = np.zeros((T, n_env))
+        import copy
+        envs = [copy.deepcopy(env) for _ in range(n_env)]
+        for i, e in enumerate(envs):
+            e.set_task(tasks[i])
+            obs0[i] = e.reset()
+        for t in range(T):
+            for i, e in enumerate(envs):
+                o, r, d, info = e.step(actions[t, i])
+                assert d is False and info == {}
+                obs[t, i], rew[t, i] = o, r
+        out['goals'] = np.asarray(tasks, dtype=np.float64)
+        out['obs0'] = obs0
+        out['next_obs_' + rtype] = obs
+        out['rewards_' + rtype] = rew
+    np.savez_compressed(os.path.join(OUT, 'point_corner_steps.npz'), **out)
+
+
+def gen_point_env_steps():
+    """MetaPointEnv (tests' PointEnv: origin goal, early done) under normalize."""
+    from meta_policy_search.envs.point_envs.point_env_2d import MetaPointEnv
+    from meta_policy_search.envs.normalized_env import normalize
+    T, n_env = 80, 8
+    np.random.seed(3)
+    envs = [normalize(MetaPointEnv()) for _ in range(n_env)]
+    obs0 = np.asarray([e.reset() for e in envs])
+    obs = np.zeros((T, n_env, 2)); rew = np.zeros((T, n_env)); done = np.zeros((T, n_env), dtype=bool)
+    acts = np.zeros((T, n_env, 2))
+    cur = obs0.copy()
+    for t in range(T):
+        for i, e in enumerate(envs):
+            a = -cur[i] * 100.0 / 2.0          # head to the origin (policy-space: a_env = a/100 -> clip 0.1)
+            acts[t, i] = a
+            o, r, d, _ = e.step(a)
+            obs[t, i], rew[t, i], done[t, i] = o, r, d
+            cur[i] = o
+    np.savez_compressed(os.path.join(OUT, 'point_env_steps.npz'), obs0=obs0, actions=acts, next_obs=obs,
+                        rewards=rew, dones=done)
+
+
+def gen_process_samples():
+    """MetaSampleProcessor + LinearFeatureBaseline on synthetic paths (several settings)."""
+    from meta_policy_search.samplers.meta_sample_processor import MetaSampleProcessor
+    from meta_policy_search.baselines.linear_baseline import LinearFeatureBaseline
+    from collections import OrderedDict
+    out = {}
+    cases = dict(
+        a=dict(M=3, E=4, H=20, Do=2, Da=2, discount=0.99, gae_lambda=1.0, normalize_adv=True, positive_adv=False),
+        b=dict(M=2, E=5, H=33, Do=2, Da=2, discount=0.95, gae_lambda=0.9, normalize_adv=False, positive_adv=False),
+        c=dict(M=2, E=6, H=25, Do=17, Da=6, discount=0.99, gae_lambda=0.97, normalize_adv=True, positive_adv=True),
+        d=dict(M=4, E=20, H=100, Do=2, Da=2, discount=0.99, gae_lambda=1.0, normalize_adv=True, positive_adv=False),
+        e=dict(M=2, E=20, H=200, Do=17, Da=6, discount=0.99, gae_lambda=1.0, normalize_adv=True, positive_adv=False),
+    )
+    for name, c in cases.items():
+        rng = np.random.RandomState(ord(name) + 5)
+        M, E, H, Do, Da = c['M'], c['E'], c['H'], c['Do'], c['Da']
+        # float32-representable inputs (the CUDA path holds trajectories in float32)
+        obs = np.cumsum(0.3 * rng.randn(M, E, H, Do), axis=2)
+        if name == 'c':
+            obs[0, 0, :5] *= 40.0        # exercise the +-10 feature clip
+        obs = obs.astype(np.float32).astype(np.float64)
+        act = rng.randn(M, E, H, Da).astype(np.float32).astype(np.float64)
+        rew = (rng.randn(M, E, H) * (rng.rand(M, E, H) < 0.6)).astype(np.float32).astype(np.float64)
+        mean = rng.randn(M, E, H, Da).astype(np.float32).astype(np.float64)
+        log_std = np.tile(rng.randn(M, 1, 1, Da) * 0.1, (1, E, H, 1)).astype(np.float32).astype(np.float64)
+        paths = OrderedDict()
+        for m in range(M):
+            paths[m] = [dict(observations=obs[m, e], actions=act[m, e], rewards=rew[m, e], env_infos={},
+                             agent_infos=dict(mean=mean[m, e], log_std=log_std[m, e])) for e in range(E)]
+        proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=c['discount'], gae_lambda=c['gae_lambda'],
+                                   normalize_adv=c['normalize_adv'], positive_adv=c['positive_adv'])
+        # capture the per-task coefficients: the shared baseline is re-fitted inside the task loop
+        coeffs = []
+        orig_fit = proc.baseline.fit
+
+        def fit_and_record(paths_, target_key='returns'):
+            orig_fit(paths_, target_key=target_key)
+            coeffs.append(np.array(proc.baseline._coeffs))
+        proc.baseline.fit = fit_and_record
+        data = proc.process_samples(paths, log=False)
+        pre = 'case_%s_' % name
+        for k, v in c.items():
+            out[pre + 'cfg_' + k] = np.asarray(v)
+        out[pre + 'obs'], out[pre + 'act'], out[pre + 'rew'] = obs.astype(np.float32), act.astype(np.float32), rew.astype(np.float32)
+        out[pre + 'returns'] = np.stack([d['returns'] for d in data])
+        out[pre + 'advantages'] = np.stack([d['advantages'] for d in data])
+        out[pre + 'adj_avg_rewards'] = np.stack([d['adj_avg_rewards'] for d in data])
+        if name == 'a':
+            out[pre + 'observations_stacked'] = np.stack([d['observations'] for d in data]).astype(np.float32)
+        out[pre + 'coeffs'] = np.stack(coeffs)
+        assert len(data[0].keys()) == 8
+    np.savez_compressed(os.path.join(OUT, 'process_samples.npz'), **out)
+
+
+def gen_sampler_rollout():
+    """Reference MetaSampler(parallel=False) + normalize(MetaPointEnvCorner) driven by the oracle's
+    numpy policy with injected action noise: pins RNG consumption order, index mapping, rollouts."""
+    from meta_policy_search.samplers.meta_sampler import MetaSampler
+    from meta_policy_search.envs.point_envs.point_env_2d_corner import MetaPointEnvCorner
+    from meta_policy_search.envs.normalized_env import normalize
+    from oracle.tf_half import OraclePolicy, init_params
+    M, E, H = 5, 4, 100          # BASELINE.json configs[0]
+    rng = np.random.RandomState(123)
+    theta = init_params(2, 2, (64, 64), rng=rng)
+    noise = rng.randn(2, H, M, E, 2).astype(np.float32)
+    np.random.seed(1)
+    env = normalize(MetaPointEnvCorner())
+    out = dict(theta=theta, noise=noise)
+    phase = [0]
+    policy = OraclePolicy(M, 2, 2, theta=theta, noise=lambda t, shape: noise[phase[0], t])
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M,
+                          max_path_length=H, parallel=False)
+    for it in range(2):
+        sampler.update_tasks()
+        goals = np.asarray([e.get_task() for e in sampler.vec_env.envs[::E]], dtype=np.float64)
+        policy.switch_to_pre_update()
+        phase[0] = it
+        paths = sampler.obtain_samples()
+        pre = 'it%d_' % it
+        out[pre + 'goals'] = goals
+        out[pre + 'obs'] = np.stack([np.stack([p['observations'] for p in paths[m]]) for m in range(M)])
+        out[pre + 'act'] = np.stack([np.stack([p['actions'] for p in paths[m]]) for m in range(M)])
+        out[pre + 'rew'] = np.stack([np.stack([p['rewards'] for p in paths[m]]) for m in range(M)])
+        out[pre + 'mean'] = np.stack([np.stack([p['agent_infos']['mean'] for p in paths[m]]) for m in range(M)])
+    out['rng_probe_after'] = np.random.uniform(size=4)     # pins how many draws were consumed
+    np.savez_compressed(os.path.join(OUT, 'sampler_rollout.npz'), **out)
+
+
+def gen_baseline_known():
+    """discount_cumsum / feature matrix known answers straight from the reference utils."""
+    from meta_policy_search.utils import utils
+    from meta_policy_search.baselines.linear_baseline import LinearFeatureBaseline
+    rng = np.random.RandomState(0)
+    x = rng.randn(37)
+    obs = rng.randn(9, 3) * 8
+    b = LinearFeatureBaseline()
+    np.savez_compressed(os.path.join(OUT, 'utils_known.npz'), x=x, dc_099=utils.discount_cumsum(x, 0.99),
+                        dc_05=utils.discount_cumsum(x, 0.5), obs=obs, feats=b._features(dict(observations=obs)),
+                        norm_adv=utils.normalize_advantages(x), pos_adv=utils.shift_advantages_to_positive(x))
+
+
+if __name__ == '__main__':
+    _import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    gen_point_corner_steps()
+    gen_point_env_steps()
+    gen_process_samples()
+    gen_sampler_rollout()
+    gen_baseline_known()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
