@@ -1,0 +1,210 @@
+/*
+ * promp_b200 - C ABI of the B200-native ProMP hot path.
+ *
+ * The reference (jonasrothfuss/ProMP @ 93ae339) is pure Python and has no FFI of its own: its
+ * "operator interface" for this path is the set of Python methods that meta_trainer.py calls
+ * (SURVEY.md section 8b).  Each entry point below replaces the body of one of those methods and
+ * cites it (paths relative to /root/reference/meta_policy_search/).  promp_b200/_lib.py holds the
+ * ctypes binding; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in _host.  The library never allocates,
+ *    frees or retains memory: inputs, outputs and workspaces are owned by the caller.
+ *  - All entry points are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per
+ *    stream, and return 0 on success or a negative promp_status; promp_last_error() gives the text.
+ *  - Tensors are dense, row-major, float32 unless stated.  M = meta_batch_size (tasks), E = envs
+ *    (rollouts) per task, H = max_path_length, N = E*H samples per task with the reference's index
+ *    contract n = e*H + t (samplers/meta_sampler.py:117, samplers/base.py:165-173).
+ *  - A policy parameter set is a flat vector of P floats in the reference's variable creation
+ *    order (policies/gaussian_mlp_policy.py:55-80): W0[Do,Hd] b0[Hd] W1[Hd,Hd] b1[Hd] W2[Hd,Da]
+ *    b2[Da] log_std[Da], kernels [in,out] row-major (policies/networks/mlp.py:100).
+ *    `params` + `param_stride`: task m reads params + m*param_stride; stride 0 = one shared theta
+ *    (pre-update policy), stride P = per-task theta_i' (post-update policy).
+ */
+#ifndef PROMP_B200_H
+#define PROMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PROMP_OK = 0,
+    PROMP_ERR_INVALID_ARG = -1,     /* bad dimension / unsupported combination / null pointer */
+    PROMP_ERR_CUDA = -2,            /* a CUDA runtime call or kernel launch failed            */
+    PROMP_ERR_WORKSPACE = -3        /* workspace too small                                     */
+} promp_status;
+
+/* env kinds (envs/point_envs/point_env_2d_corner.py, envs/point_envs/point_env_2d.py,
+ * envs/mujoco_envs/half_cheetah_rand_direc.py [analytic surrogate]) */
+enum { PROMP_ENV_POINT_CORNER = 0, PROMP_ENV_POINT = 1, PROMP_ENV_CHEETAH_DIR = 2 };
+/* MetaPointEnvCorner.reward_type (point_env_2d_corner.py:13-16) */
+enum { PROMP_REWARD_SPARSE = 0, PROMP_REWARD_DENSE = 1, PROMP_REWARD_DENSE_SQUARED = 2 };
+/* objective kinds of promp_policy_grad */
+enum {
+    PROMP_OBJ_RATIO = 0,   /* -mean(ratio*adv)                       meta_algos/pro_mp.py:59-65          */
+    PROMP_OBJ_LOGLIK = 1,  /* -mean(logp*adv)                        meta_algos/trpo_maml.py:58-62       */
+    PROMP_OBJ_CLIP = 2,    /* -mean(min(r*adv, clip(r,1-e,1+e)*adv)) meta_algos/pro_mp.py:135-141        */
+    PROMP_OBJ_NONE = 3     /* only the kl_coeff * mean KL(old||new) term                                 */
+};
+/* baseline kinds of promp_process_samples */
+enum { PROMP_BASELINE_ZERO = 0, PROMP_BASELINE_LINEAR_FEATURE = 1 };
+
+const char* promp_last_error(void);
+int promp_version(void);
+
+/* Number of policy parameters P for (obs_dim, act_dim, hidden,hidden). */
+int promp_num_params(int obs_dim, int act_dim, int hidden);
+/* State floats per env for init_state / final_state: 2 (point envs), 18 (cheetah: qpos[9] qvel[9]). */
+int promp_env_state_dim(int env_kind);
+/* Floats per task in task_params: 2 (point corner goal), 0 -> pass 1 dummy (point), 1 (cheetah dir). */
+int promp_env_task_dim(int env_kind);
+
+/*
+ * Fused vectorised rollout: MetaSampler.obtain_samples (samplers/meta_sampler.py:59-137) with
+ * MetaIterativeEnvExecutor.reset/step (samplers/vectorized_env_executor.py:25-75),
+ * MetaGaussianMLPPolicy.get_actions (policies/meta_gaussian_mlp_policy.py:99-157),
+ * NormalizedEnv.step (envs/normalized_env.py:109-123) and the env's step/reward, for all H steps of
+ * all M*E envs in one launch.  One warp per env; weights live in registers; trajectory records are
+ * staged in shared memory and flushed as coalesced float32 rows.
+ *
+ *   task_params [M, task_dim]   goal (x,y) / direction
+ *   init_state  [M, E, state_dim] or NULL  -> NULL draws the reset state in-kernel (Philox4x32-10)
+ *   noise       [M, E, H, Da]    or NULL  -> NULL draws N(0,1) action noise in-kernel
+ *   seed, stream_id             Philox key / sub-stream (use a fresh stream_id per sampling phase)
+ *   clip_reported_log_std       1 = pre-update mode: reported log_std = max(log_std, min_log_std)
+ *                               (policies/gaussian_mlp_policy.py:71); sampling always uses the raw one
+ * outputs (all written):
+ *   obs [M,E,H,Do]  act [M,E,H,Da]  mean [M,E,H,Da]  rew [M,E,H]  done [M,E,H] (uint8)
+ *   info [2,M,E,H]  (cheetah: reward_run, reward_ctrl; others: untouched, may be NULL)
+ *   log_std_out [M,Da]  the per-task reported log_std (constant over the phase)
+ *   final_state [M,E,state_dim] or NULL
+ */
+int promp_rollout(int env_kind, int reward_type, float sparse_radius,
+                  int M, int E, int H, int hidden,
+                  const float* params, int64_t param_stride,
+                  const float* task_params, const float* init_state, const float* noise,
+                  uint64_t seed, uint64_t stream_id,
+                  int clip_reported_log_std, float min_log_std,
+                  float* obs, float* act, float* mean, float* rew, uint8_t* done, float* info,
+                  float* log_std_out, float* final_state, void* stream);
+
+/*
+ * One vectorised env step (MetaIterativeEnvExecutor.step, samplers/vectorized_env_executor.py:25-52)
+ * for policies that are not device-resident: state [n_env, state_dim] is updated in place.
+ *   actions [n_env, Da] policy-space actions (NormalizedEnv rescale+clip applied inside)
+ *   task_params [n_env, task_dim] (already expanded per env)
+ *   ts [n_env] int32 step counters, incremented; when ts reaches H (or the env is done) the env is
+ *   reset from reset_state [n_env, state_dim] (caller-provided fresh reset states) and ts = 0.
+ *   next_obs [n_env, Do], rew [n_env], done [n_env] uint8, info [2, n_env] or NULL
+ */
+int promp_env_step(int env_kind, int reward_type, float sparse_radius, int n_env, int H,
+                   float* state, int32_t* ts, const float* actions, const float* task_params,
+                   const float* reset_state, float* next_obs, float* rew, uint8_t* done, float* info,
+                   void* stream);
+
+/* obs [n_env, Do] from state [n_env, state_dim] (env.reset observation). */
+int promp_env_observe(int env_kind, int n_env, const float* state, float* obs, void* stream);
+
+/*
+ * MetaSampleProcessor.process_samples (samplers/meta_sample_processor.py:8-49 ->
+ * samplers/base.py:99-133): per task discounted returns (utils/utils.py:74-81), LinearFeatureBaseline
+ * fit (baselines/linear_baseline.py:55-77, features :101-106) + predict (:17-33), GAE
+ * (samplers/base.py:151-162), per-task advantage normalisation / positive shift
+ * (utils/utils.py:59-71), path statistics (samplers/base.py:135-149).  One CTA per task; the Gram
+ * matrix, solve, scans and moments run in float64 like the reference's numpy.
+ *
+ *   obs [M,E,H,Do]  rew [M,E,H]
+ * outputs:
+ *   returns [M,E,H]  adv [M,E,H]
+ *   coeffs  [M,F] float64, F = 2*Do+4 (may be NULL)
+ *   stats   [M,8] float64: sum R_0, sum G, sum G^2, max G, min G (G = undiscounted return per path),
+ *           sum r, sum r^2, reg_coeff finally used            (may be NULL)
+ *   workspace: float64 scratch, >= promp_process_workspace_bytes(M,E,H,Do) bytes
+ */
+int64_t promp_process_workspace_bytes(int M, int E, int H, int obs_dim);
+int promp_process_samples(int M, int E, int H, int obs_dim, const float* obs, const float* rew,
+                          double discount, double gae_lambda, double reg_coeff, int baseline_kind,
+                          int normalize_adv, int positive_adv,
+                          float* returns, float* adv, double* coeffs, double* stats,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* adj_avg_rewards = (r - mean_all)/(std_all + 1e-8) (samplers/meta_sample_processor.py:40-44);
+ * mean/std are passed by the caller (reduced over all tasks / ranks from `stats`). */
+int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, double std, float* out, void* stream);
+
+/*
+ * Per-task objective value, KL and gradient w.r.t. the task's parameter set, optionally fused with
+ * the inner SGD step.  Covers
+ *   - MAMLAlgo._adapt        (meta_algos/base.py:217-242, graph :158-215): obj RATIO|LOGLIK,
+ *                            out_params = params - inner_lr * grad
+ *   - the step-s surrogate / clipped outer objective and KL terms of ProMP.build_graph
+ *                            (meta_algos/pro_mp.py:88-163) and TRPOMAML.build_graph
+ *                            (meta_algos/trpo_maml.py:100-159)
+ *   - DiagonalGaussian.log_likelihood_sym / likelihood_ratio_sym / kl_sym
+ *                            (policies/distributions/diagonal_gaussian.py:16-109)
+ *   - forward_mlp            (policies/networks/mlp.py:65-119)
+ * Objective_m = obj_scale * surr_kind(m) + kl_coeff * mean_n KL(old || new)(m).
+ *
+ *   obs [M,N,Do] act [M,N,Da] adv [M,N] old_mean [M,N,Da]
+ *   old_log_std: [M,Da] if ls_per_sample == 0 else [M,N,Da]
+ *   clip_log_std: 1 = evaluate with max(log_std, min_log_std) and mask its gradient (the
+ *                 distribution_info_sym(params=None) path, policies/gaussian_mlp_policy.py:71,161)
+ * outputs:
+ *   grad       [M,P] or NULL (NULL = values only)
+ *   out_params [M,P] or NULL: params_m - sgd_lr * grad_m      (needs grad != NULL)
+ *   stats      [M,4]: surrogate value (unscaled), mean KL(old||new), mean ratio, unused
+ *   workspace  >= promp_policy_workspace_bytes(M,N,Do,Da,hidden) bytes
+ */
+int64_t promp_policy_workspace_bytes(int M, int N, int obs_dim, int act_dim, int hidden);
+int promp_policy_grad(int obs_dim, int act_dim, int hidden, int M, int N,
+                      const float* params, int64_t param_stride,
+                      const float* obs, const float* act, const float* adv,
+                      const float* old_mean, const float* old_log_std, int ls_per_sample,
+                      int obj_kind, float obj_scale, float clip_eps, float kl_coeff,
+                      int clip_log_std, float min_log_std,
+                      float* grad, float* out_params, float sgd_lr, float* stats,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Second-order term of the MAML meta-gradient for one inner step
+ * (tf.gradients through _adapt_sym, meta_algos/base.py:192-215 with pro_mp.py:103,117):
+ *   out_m = vec_m - inner_lr * H_m(params_m) vec_m + kl_coeff * grad_theta mean KL(old||new)(m)
+ * where H_m is the Hessian of the inner surrogate (obj RATIO or LOGLIK) of task m on (obs, act, adv,
+ * old dist) evaluated at params_m, computed exactly (forward-over-reverse through the tanh MLP and
+ * the Gaussian log-likelihood), not by finite differences.
+ *   vec [M,P], out [M,P] (may alias vec); stats [M,4] as in promp_policy_grad (surr, KL) or NULL
+ */
+int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int N,
+                     const float* params, int64_t param_stride,
+                     const float* obs, const float* act, const float* adv,
+                     const float* old_mean, const float* old_log_std, int ls_per_sample,
+                     int obj_kind, float inner_lr, float kl_coeff,
+                     int clip_log_std, float min_log_std,
+                     const float* vec, float* out, float* stats,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* out[P] = scale * sum_m in[m,P]   (mean over tasks of the meta objective, pro_mp.py:151-155). */
+int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, void* stream);
+
+/*
+ * tf.train.AdamOptimizer step as used by MAMLFirstOrderOptimizer.optimize
+ * (optimizers/maml_first_order_optimizer.py:48-64, 102-107):
+ *   t += 1; lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g^2;
+ *   theta -= lr_t*m/(sqrt(v)+eps).      step is a device int32 counter (persistent slot state).
+ */
+int promp_adam_tf1(int P, float* theta, const float* grad, float* m, float* v, int32_t* step,
+                   float lr, float beta1, float beta2, float eps, void* stream);
+
+/* Policy forward only (MetaGaussianMLPPolicy.get_actions without sampling / distribution_info_sym):
+ * mean [M,N,Da] for obs [M,N,Do]. */
+int promp_policy_forward(int obs_dim, int act_dim, int hidden, int M, int N,
+                         const float* params, int64_t param_stride, const float* obs, float* mean,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROMP_B200_H */

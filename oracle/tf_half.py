@@ -131,6 +131,8 @@ def meta_objective(theta, all_data, dims, inner_lr, algo='promp', clip_eps=0.3, 
     theta [P] (requires_grad).  all_data: list (len S = num_inner_grad_steps+1) of phase dicts.
     Returns (objective, inner_kls [S-1], outer_kl)."""
     M = all_data[0]['obs'].shape[0]
+    if not theta.requires_grad:
+        theta = theta.detach().clone().requires_grad_(True)
     cur = theta.unsqueeze(0).expand(M, -1)
     inner_kls = []
     clip0 = min_log_std     # step 0 runs distribution_info_sym(params=None): clipped log_std

@@ -1,0 +1,104 @@
+"""ctypes binding of libpromp_b200.so (the C ABI declared in include/promp_b200.h).
+
+PyTorch tensors are used only as device buffers: every call passes raw `data_ptr()` addresses and
+the current CUDA stream handle.  There is NO CPU fallback: if the library is missing or no CUDA
+device is present, the product path raises.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpromp_b200.so')
+
+# enums (mirror include/promp_b200.h)
+ENV_POINT_CORNER, ENV_POINT, ENV_CHEETAH_DIR = 0, 1, 2
+REWARD_SPARSE, REWARD_DENSE, REWARD_DENSE_SQUARED = 0, 1, 2
+OBJ_RATIO, OBJ_LOGLIK, OBJ_CLIP, OBJ_NONE = 0, 1, 2, 3
+BASELINE_ZERO, BASELINE_LINEAR_FEATURE = 0, 1
+
+_P = c_void_p
+_SIGNATURES = {
+    'promp_last_error': (c_char_p, []),
+    'promp_version': (c_int, []),
+    'promp_num_params': (c_int, [c_int, c_int, c_int]),
+    'promp_env_state_dim': (c_int, [c_int]),
+    'promp_env_task_dim': (c_int, [c_int]),
+    'promp_rollout': (c_int, [c_int, c_int, c_float, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P, c_uint64,
+                              c_uint64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'promp_env_step': (c_int, [c_int, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'promp_env_observe': (c_int, [c_int, c_int, _P, _P, _P]),
+    'promp_process_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int]),
+    'promp_process_samples': (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_double, c_double, c_double, c_int, c_int,
+                                      c_int, _P, _P, _P, _P, _P, c_int64, _P]),
+    'promp_adj_avg_rewards': (c_int, [c_int64, _P, c_double, c_double, _P, _P]),
+    'promp_policy_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    'promp_policy_grad': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
+                                  c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, c_int64, _P]),
+    'promp_policy_hvp': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
+                                 c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
+    'promp_reduce_tasks': (c_int, [c_int, c_int, _P, c_float, _P, _P]),
+    'promp_adam_tf1': (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
+    'promp_policy_forward': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class PrompLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "promp_b200: %s is missing. Build it with `python -m promp_b200._build` (needs nvcc; "
+                "sm_100a). There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)        # AttributeError here = header / library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().promp_last_error().decode('utf-8', 'replace')
+
+
+def check(status, what):
+    if status != 0:
+        raise PrompLibraryError("%s failed (status %d): %s" % (what, status, last_error()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL).  Tensors must be contiguous CUDA tensors."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PrompLibraryError("promp_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback"
+                                % t.device)
+    if not t.is_contiguous():
+        raise PrompLibraryError("promp_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise PrompLibraryError("promp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    load()
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,111 @@
+// Shared device/host helpers for the promp_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/promp_b200.h"
+
+namespace promp {
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define PROMP_REQUIRE(cond, ...)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            promp::set_error(__VA_ARGS__);                         \
+            return PROMP_ERR_INVALID_ARG;                          \
+        }                                                          \
+    } while (0)
+
+#define PROMP_CUDA(call)                                           \
+    do {                                                           \
+        int _st = promp::check_cuda((call), #call);                \
+        if (_st != PROMP_OK) return _st;                           \
+    } while (0)
+
+#define PROMP_LAUNCH_CHECK(name)                                   \
+    do {                                                           \
+        int _st = promp::check_cuda(cudaGetLastError(), name);     \
+        if (_st != PROMP_OK) return _st;                           \
+    } while (0)
+
+// ---------------------------------------------------------------- parameter layout
+// Flat parameter vector in the reference's creation order
+// (ref: policies/gaussian_mlp_policy.py:55-80, policies/networks/mlp.py:100):
+//   W0[Do,Hd] b0[Hd] W1[Hd,Hd] b1[Hd] W2[Hd,Da] b2[Da] log_std[Da]
+template <int DO, int DA, int HID>
+struct PLayout {
+    static constexpr int W0 = 0;
+    static constexpr int B0 = W0 + DO * HID;
+    static constexpr int W1 = B0 + HID;
+    static constexpr int B1 = W1 + HID * HID;
+    static constexpr int W2 = B1 + HID;
+    static constexpr int B2 = W2 + HID * DA;
+    static constexpr int LS = B2 + DA;
+    static constexpr int P = LS + DA;
+};
+
+__host__ __device__ inline int num_params(int Do, int Da, int Hd) {
+    return Do * Hd + Hd + Hd * Hd + Hd + Hd * Da + Da + Da;
+}
+
+// ---------------------------------------------------------------- warp helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __host__ __device__ static inline void round(uint32_t c[4], uint32_t k0, uint32_t k1) {
+        uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    // counter = (c0,c1,c2,c3), key = seed
+    __host__ __device__ static inline void gen(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed,
+                                               uint32_t out[4]) {
+        uint32_t c[4] = {c0, c1, c2, c3};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            round(c, k0, k1);
+            k0 += W0;
+            k1 += W1;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+};
+// uniform in (0,1]: never 0 so log() is finite
+__host__ __device__ inline float u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+// two N(0,1) from two uint32 (Box-Muller)
+__device__ inline void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    float r = sqrtf(-2.0f * logf(u01(a)));
+    float s, c;
+    sincospif(2.0f * u01(b), &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+}  // namespace promp

@@ -1,0 +1,184 @@
+// Analytic environments of the ProMP hot path as device functions (float32).
+//   point corner : ref envs/point_envs/point_env_2d_corner.py:22-81
+//   point        : ref envs/point_envs/point_env_2d.py:9-59
+//   cheetah      : MuJoCo-free HalfCheetahRandDirec surrogate; reward / obs / reset / task spec follow
+//                  ref envs/mujoco_envs/half_cheetah_rand_direc.py:14-53, the dynamics are defined in
+//                  DESIGN.md (restated on the CPU in oracle/cheetah_surrogate.py).
+//   NormalizedEnv: ref envs/normalized_env.py:109-117 (action affine map + clip; obs / reward
+//                  normalisation are off by default, :23-24, and out of scope).
+#pragma once
+#include "common.cuh"
+
+namespace promp {
+
+template <int KIND> struct EnvTraits;
+template <> struct EnvTraits<PROMP_ENV_POINT_CORNER> {
+    static constexpr int DO = 2, DA = 2, SD = 2, TD = 2, NINFO = 0;
+};
+template <> struct EnvTraits<PROMP_ENV_POINT> {
+    static constexpr int DO = 2, DA = 2, SD = 2, TD = 1, NINFO = 0;
+};
+template <> struct EnvTraits<PROMP_ENV_CHEETAH_DIR> {
+    static constexpr int DO = 17, DA = 6, SD = 18, TD = 1, NINFO = 2;
+};
+
+// NormalizedEnv.step action map, same evaluation order as the reference expression
+//   lb + (a + scale) * (ub - lb) / (2*scale), then clip to [lb, ub]       (normalization_scale = 10)
+__device__ __forceinline__ float normalized_action(float a, float lb, float ub) {
+    float s = lb + ((a + 10.0f) * (ub - lb)) / 20.0f;
+    return fminf(fmaxf(s, lb), ub);
+}
+
+// ------------------------------------------------------------------ point corner
+struct PointCornerCfg {
+    int reward_type;
+    float radius;
+};
+
+__device__ __forceinline__ float dist2d(float x, float y, float gx, float gy) {
+    float dx = x - gx, dy = y - gy;
+    return sqrtf(dx * dx + dy * dy);
+}
+
+// s (in/out): state; (ax, ay): policy-space action.  Returns reward.
+__device__ __forceinline__ float point_corner_step(float& sx, float& sy, float ax, float ay, float gx, float gy,
+                                                   const PointCornerCfg& cfg) {
+    const float lim = 0.2f;
+    float ex = normalized_action(ax, -lim, lim), ey = normalized_action(ay, -lim, lim);
+    // env-side clip (point_env_2d_corner.py:37) is the identity after the wrapper's clip
+    ex = fminf(fmaxf(ex, -lim), lim);
+    ey = fminf(fmaxf(ey, -lim), lim);
+    float px = sx, py = sy;
+    sx = px + ex;
+    sy = py + ey;
+    float r;
+    if (cfg.reward_type == PROMP_REWARD_DENSE) {
+        r = -dist2d(sx, sy, gx, gy);
+    } else if (cfg.reward_type == PROMP_REWARD_DENSE_SQUARED) {
+        float g = dist2d(sx, sy, gx, gy);
+        r = -(g * g);
+    } else {
+        // sparse (:68-75): 0 inside the L1 radius; progress toward the goal iff the goal is the nearest corner
+        float d0 = dist2d(sx, sy, -2.f, -2.f), d1 = dist2d(sx, sy, 2.f, -2.f);
+        float d2 = dist2d(sx, sy, -2.f, 2.f), d3 = dist2d(sx, sy, 2.f, 2.f);
+        float dmin = fminf(fminf(d0, d1), fminf(d2, d3));
+        float g;   // take the goal distance from the same four values when the goal is a corner (exact ==)
+        if (gx == -2.f && gy == -2.f) g = d0;
+        else if (gx == 2.f && gy == -2.f) g = d1;
+        else if (gx == -2.f && gy == 2.f) g = d2;
+        else if (gx == 2.f && gy == 2.f) g = d3;
+        else g = dist2d(sx, sy, gx, gy);
+        r = 0.f;
+        if (!(fabsf(sx) + fabsf(sy) < cfg.radius) && g == dmin) r = dist2d(px, py, gx, gy) - g;
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------ point (origin goal, early done)
+__device__ __forceinline__ float point_step(float& sx, float& sy, float ax, float ay, bool& done) {
+    const float lim = 0.1f;
+    float ex = normalized_action(ax, -lim, lim), ey = normalized_action(ay, -lim, lim);
+    ex = fminf(fmaxf(ex, -lim), lim);
+    ey = fminf(fmaxf(ey, -lim), lim);
+    sx += ex;
+    sy += ey;
+    done = (fabsf(sx) < 0.01f) && (fabsf(sy) < 0.01f);
+    return -sqrtf(sx * sx + sy * sy);
+}
+
+// ------------------------------------------------------------------ cheetah surrogate
+namespace cheetah {
+constexpr int NJ = 6;
+constexpr float HS = 0.01f, DT = 0.05f;
+constexpr int FRAME_SKIP = 5;
+static __device__ __constant__ const float G[8] = {12.0f, 9.0f, 6.0f, 12.0f, 6.0f, 3.0f, 0.f, 0.f};
+static __device__ __constant__ const float K[8] = {24.0f, 18.0f, 12.0f, 18.0f, 12.0f, 6.0f, 0.f, 0.f};
+static __device__ __constant__ const float D[8] = {4.5f, 3.0f, 1.5f, 3.0f, 1.5f, 0.75f, 0.f, 0.f};
+static __device__ __constant__ const float C[8] = {0.9f, 0.6f, 0.3f, -0.8f, -0.5f, -0.25f, 0.f, 0.f};
+static __device__ __constant__ const float PH[8] = {0.3f, -0.4f, 0.8f, -0.3f, 0.5f, -0.9f, 0.f, 0.f};
+static __device__ __constant__ const float P[8] = {0.6f, 0.4f, 0.2f, -0.6f, -0.4f, -0.2f, 0.f, 0.f};
+constexpr float BX = 1.5f, LZ = 0.1f, KZ = 40.0f, DZ = 6.0f, KP = 30.0f, DP = 5.0f;
+
+struct JointConst {
+    float g, k, d, c, ph, p;
+};
+__device__ __forceinline__ JointConst joint_const(int j) {
+    int i = j < NJ ? j : 7;
+    return JointConst{G[i], K[i], D[i], C[i], PH[i], P[i]};
+}
+
+// root: x, z, pitch, xd, zd, pd
+// Serial version (one thread per env): state = qpos[9] ++ qvel[9]; u[6] already rescaled+clipped.
+__device__ inline void step_serial(float* st, const float* u, float dir, float& reward, float& r_run, float& r_ctrl) {
+    float x0 = st[0];
+    for (int s = 0; s < FRAME_SKIP; ++s) {
+        float thrust = 0.f, lift = 0.f, twist = 0.f;
+        float pitch = st[2];
+        for (int j = 0; j < NJ; ++j) {
+            float q = st[3 + j], qd = st[12 + j];
+            float acc = G[j] * u[j] - K[j] * q - D[j] * qd;
+            qd = qd + HS * acc;
+            q = q + HS * qd;
+            st[3 + j] = q;
+            st[12 + j] = qd;
+            float sn, cs;
+            sincosf(q + pitch + PH[j], &sn, &cs);
+            thrust = thrust + C[j] * qd * sn;
+            lift = lift + C[j] * qd * cs;
+            twist = twist + P[j] * u[j];
+        }
+        float xd = st[9] + HS * (thrust - BX * st[9]);
+        st[9] = xd;
+        st[0] = st[0] + HS * xd;
+        float zd = st[10] + HS * (LZ * lift - KZ * st[1] - DZ * st[10]);
+        st[10] = zd;
+        st[1] = st[1] + HS * zd;
+        float pd = st[11] + HS * (twist - KP * st[2] - DP * st[11]);
+        st[11] = pd;
+        st[2] = st[2] + HS * pd;
+    }
+    float su = 0.f;
+    for (int j = 0; j < NJ; ++j) su += u[j] * u[j];
+    r_ctrl = -0.05f * su;
+    r_run = dir * (st[0] - x0) / DT;
+    reward = r_ctrl + r_run;
+}
+
+// Warp version: lane j < 6 owns joint j (q, qd, torque u); the six root floats are replicated in
+// every lane and stay bit-identical because the 8-lane xor reductions are symmetric.
+__device__ __forceinline__ float sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+__device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& q, float& qd, float (&root)[6], float dir,
+                                          float& reward, float& r_run, float& r_ctrl) {
+    float x0 = root[0];
+#pragma unroll 1
+    for (int s = 0; s < FRAME_SKIP; ++s) {
+        float acc = jc.g * u - jc.k * q - jc.d * qd;
+        qd = qd + HS * acc;
+        q = q + HS * qd;
+        float sn, cs;
+        sincosf(q + root[2] + jc.ph, &sn, &cs);
+        float thrust = sum8(jc.c * qd * sn);
+        float lift = sum8(jc.c * qd * cs);
+        float twist = sum8(jc.p * u);
+        float xd = root[3] + HS * (thrust - BX * root[3]);
+        root[3] = xd;
+        root[0] = root[0] + HS * xd;
+        float zd = root[4] + HS * (LZ * lift - KZ * root[1] - DZ * root[4]);
+        root[4] = zd;
+        root[1] = root[1] + HS * zd;
+        float pd = root[5] + HS * (twist - KP * root[2] - DP * root[5]);
+        root[5] = pd;
+        root[2] = root[2] + HS * pd;
+    }
+    r_ctrl = -0.05f * sum8(u * u);
+    r_run = dir * (root[0] - x0) / DT;
+    reward = r_ctrl + r_run;
+}
+}  // namespace cheetah
+
+}  // namespace promp

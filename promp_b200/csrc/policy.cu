@@ -1,0 +1,905 @@
+// Gaussian-MLP policy kernels: per-task objective gradient (inner adapt step, outer surrogates, KL
+// terms) and the exact Hessian-vector product that carries the MAML meta-gradient through the inner
+// SGD step.  See include/promp_b200.h for the interface and the reference functions replaced.
+//
+// Work decomposition: grid = (chunks, M).  A CTA owns one task's weights in shared memory and walks
+// that task's 64-sample tiles with stride `chunks`; weight-gradient accumulators stay in registers
+// across tiles, are written once per CTA to a per-(task,chunk) partial buffer, and the last CTA of
+// each task (atomic ticket) reduces the partials in fixed chunk order -> bitwise run-to-run
+// deterministic sums.  These kernels are fp32-FMA bound (AI ~ 10^2..10^3 FLOP/B), not HBM bound.
+#include "mlp_tile.cuh"
+
+namespace promp {
+
+template <int DO>
+struct DOPad {
+    static constexpr int V = (DO + 3) / 4 * 4;
+};
+
+constexpr int PSTAT = 4;   // per-partial trailing stats: sum obj, sum kl, sum ratio, unused
+
+struct PolicyArgs {
+    int M, N;
+    const float* params;
+    int64_t param_stride;
+    const float *obs, *act, *adv, *old_mean, *old_ls;
+    int ls_per_sample;
+    int obj_kind;
+    float obj_scale, clip_eps, kl_coeff;
+    int clip_log_std;
+    float min_log_std;
+    // grad kernel
+    float* grad;
+    float* out_params;
+    float sgd_lr;
+    // hvp kernel
+    const float* vec;
+    float* out;
+    float inner_lr;
+    float* stats;
+    float* partial;      // [M][chunks][P + PSTAT]
+    int* counters;       // [M], zero on entry, left zero on exit
+};
+
+template <int DO, int DA, int HID>
+__device__ __forceinline__ void load_head_consts(const float* P, int clip, float min_ls, HeadIn<DA>& hin) {
+    using L = PLayout<DO, DA, HID>;
+#pragma unroll
+    for (int d = 0; d < DA; ++d) {
+        const float raw = P[L::LS + d];
+        const bool clipped = clip && (raw < min_ls);      // tf.maximum: gradient goes to x when x >= y
+        hin.ls[d] = clipped ? min_ls : raw;
+        hin.ls_mask[d] = clipped ? 0.f : 1.f;
+        hin.sig[d] = expf(hin.ls[d]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+template <int DO, int DA, int HID>
+struct GradSmem {
+    using L = PLayout<DO, DA, HID>;
+    using C = TileCfg<HID>;
+    static constexpr int DOP = DOPad<DO>::V;
+    static constexpr int PP = (L::P + 3) / 4 * 4;
+    float P[PP];
+    float W1T[HID * HID];
+    float X[TB * DOP];
+    float H1[TB * C::LD];
+    float H2[TB * C::LD];
+    float DMU[TB * DA];
+    float DLS[TB * DA];
+    float red[3 * (PT_THREADS / 32)];
+    int last;
+};
+
+template <int DO, int DA, int HID>
+__global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
+    using L = PLayout<DO, DA, HID>;
+    using C = TileCfg<HID>;
+    using SM = GradSmem<DO, DA, HID>;
+    constexpr int LD = C::LD, RM = C::RM, RK = C::RK, DOP = SM::DOP;
+    constexpr int NW0 = (DO * HID + PT_THREADS - 1) / PT_THREADS;
+    constexpr int NW2 = (HID * DA + PT_THREADS - 1) / PT_THREADS;
+    constexpr int NU = HID / 32;
+    constexpr int PSTRIDE = L::P + PSTAT;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid % C::TX, ty = tid / C::TX;
+    const int row0 = ty * RM, col0 = tx * 4;
+    const int m = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int N = A.N;
+    const float invN = 1.0f / (float)N;
+    const float* th = A.params + (int64_t)m * A.param_stride;
+    const bool want_grad = A.grad != nullptr;
+
+    for (int i = tid; i < L::P; i += PT_THREADS) S.P[i] = __ldg(th + i);
+    __syncthreads();
+    for (int i = tid; i < HID * HID; i += PT_THREADS) {
+        const int k = i / HID, j = i % HID;
+        S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
+    }
+    HeadIn<DA> hin;
+    load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
+
+    float gW1[RK][4], gB1[4] = {0, 0, 0, 0}, gW0[NW0], gB0 = 0.f, gW2[NW2], gB2 = 0.f, gLS = 0.f;
+#pragma unroll
+    for (int r = 0; r < RK; ++r) gW1[r][0] = gW1[r][1] = gW1[r][2] = gW1[r][3] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
+    float s_obj = 0.f, s_kl = 0.f, s_ratio = 0.f;
+
+    const int ntiles = (N + TB - 1) / TB;
+    for (int tile = chunk; tile < ntiles; tile += nchunks) {
+        const int n0 = tile * TB, nb = min(TB, N - n0);
+        const int64_t g0 = (int64_t)m * N + n0;
+        __syncthreads();
+        for (int i = tid; i < TB * DOP; i += PT_THREADS) {
+            const int b = i / DOP, c = i % DOP;
+            S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+        }
+        __syncthreads();
+        // ---- layer 0: H1 = tanh(X W0 + b0)                      (policies/networks/mlp.py:96-117)
+        {
+            float acc[RM][4];
+            const float4 bv = *reinterpret_cast<const float4*>(S.P + L::B0 + col0);
+#pragma unroll
+            for (int i = 0; i < RM; ++i) acc[i][0] = bv.x, acc[i][1] = bv.y, acc[i][2] = bv.z, acc[i][3] = bv.w;
+            gemm_tile_smallk<DO, DOP, HID, RM>(S.X, S.P + L::W0, row0, col0, acc);
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+                *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) =
+                    make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+        }
+        __syncthreads();
+        // ---- layer 1: H2 = tanh(H1 W1 + b1)
+        {
+            float acc[RM][4];
+            const float4 bv = *reinterpret_cast<const float4*>(S.P + L::B1 + col0);
+#pragma unroll
+            for (int i = 0; i < RM; ++i) acc[i][0] = bv.x, acc[i][1] = bv.y, acc[i][2] = bv.z, acc[i][3] = bv.w;
+            gemm_tile<HID, LD, HID, RM>(S.H1, S.P + L::W1, row0, col0, acc);
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+                *reinterpret_cast<float4*>(S.H2 + (row0 + i) * LD + col0) =
+                    make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+        }
+        __syncthreads();
+        // ---- layer 2 (warp-shuffle reduction) + Gaussian head; warp w owns rows w*8 .. w*8+7
+        for (int r = 0; r < TB / (PT_THREADS / 32); ++r) {
+            const int b = warp * (TB / (PT_THREADS / 32)) + r;
+            float mu[DA];
+#pragma unroll
+            for (int d = 0; d < DA; ++d) mu[d] = 0.f;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int j = lane + 32 * u;
+                const float h = S.H2[b * LD + j];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) mu[d] = fmaf(h, S.P[L::W2 + j * DA + d], mu[d]);
+            }
+#pragma unroll
+            for (int d = 0; d < DA; ++d) mu[d] = warp_sum(mu[d]) + S.P[L::B2 + d];
+            float dmu[DA], dls[DA];
+            if (b < nb) {
+                const int64_t n = g0 + b;
+                float a[DA], mo[DA], lso[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    a[d] = __ldg(A.act + n * DA + d);
+                    mo[d] = __ldg(A.old_mean + n * DA + d);
+                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                }
+                const float adv = __ldg(A.adv + n);
+                HeadOut<DA> o;
+                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    dmu[d] = wt * o.zeta[d] / hin.sig[d] + kc * o.dkl_dmu[d];
+                    dls[d] = (wt * (o.zeta[d] * o.zeta[d] - 1.f) + kc * o.dkl_dls[d]) * hin.ls_mask[d];
+                }
+                s_obj += o.obj;
+                s_kl += o.kl;
+                s_ratio += o.ratio;
+            } else {
+#pragma unroll
+                for (int d = 0; d < DA; ++d) dmu[d] = dls[d] = 0.f;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int d = 0; d < DA; ++d) S.DMU[b * DA + d] = dmu[d], S.DLS[b * DA + d] = dls[d];
+            }
+        }
+        if (!want_grad) continue;
+        __syncthreads();
+        // ---- output layer gradients
+#pragma unroll
+        for (int r = 0; r < NW2; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < HID * DA) {
+                const int j = idx / DA, d = idx % DA;
+                float s = 0.f;
+                for (int b = 0; b < nb; ++b) s = fmaf(S.H2[b * LD + j], S.DMU[b * DA + d], s);
+                gW2[r] += s;
+            }
+        }
+        if (tid < DA) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int b = 0; b < nb; ++b) s1 += S.DMU[b * DA + tid], s2 += S.DLS[b * DA + tid];
+            gB2 += s1;
+            gLS += s2;
+        }
+        __syncthreads();
+        // ---- D2 = (DMU W2^T) * (1 - H2^2), in place over H2
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            const int b = row0 + i;
+            float4 h = *reinterpret_cast<float4*>(S.H2 + b * LD + col0);
+            float hv[4] = {h.x, h.y, h.z, h.w}, o4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float dh = 0.f;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) dh = fmaf(S.DMU[b * DA + d], S.P[L::W2 + (col0 + c) * DA + d], dh);
+                o4[c] = dh * (1.f - hv[c] * hv[c]);
+            }
+            *reinterpret_cast<float4*>(S.H2 + b * LD + col0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+        __syncthreads();
+        // ---- gW1 += H1^T D2, gB1 += colsum(D2); dH1 = D2 W1^T
+        wgrad_tile<LD, RK>(S.H1, S.H2, ty * RK, col0, nb, gW1);
+        if (ty == 0) {
+            for (int b = 0; b < nb; ++b) {
+                const float4 d = *reinterpret_cast<const float4*>(S.H2 + b * LD + col0);
+                gB1[0] += d.x; gB1[1] += d.y; gB1[2] += d.z; gB1[3] += d.w;
+            }
+        }
+        float acc[RM][4];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        gemm_tile<HID, LD, HID, RM>(S.H2, S.W1T, row0, col0, acc);
+        __syncthreads();   // every read of H1 (wgrad) is done before it is overwritten
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            float4 h = *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0);
+            *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) =
+                make_float4(acc[i][0] * (1.f - h.x * h.x), acc[i][1] * (1.f - h.y * h.y), acc[i][2] * (1.f - h.z * h.z),
+                            acc[i][3] * (1.f - h.w * h.w));
+        }
+        __syncthreads();
+        // ---- gW0 += X^T D1, gB0 += colsum(D1)
+#pragma unroll
+        for (int r = 0; r < NW0; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < DO * HID) {
+                const int i = idx / HID, j = idx % HID;
+                float s = 0.f;
+                for (int b = 0; b < nb; ++b) s = fmaf(S.X[b * DOP + i], S.H1[b * LD + j], s);
+                gW0[r] += s;
+            }
+        }
+        if (tid < HID) {
+            float s = 0.f;
+            for (int b = 0; b < nb; ++b) s += S.H1[b * LD + tid];
+            gB0 += s;
+        }
+    }
+
+    // ---- per-CTA partials -> global, last CTA of the task reduces in chunk order
+    float* part = A.partial + ((int64_t)m * nchunks + chunk) * PSTRIDE;
+    if (want_grad) {
+#pragma unroll
+        for (int r = 0; r < NW0; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
+        }
+        if (tid < HID) part[L::B0 + tid] = gB0;
+#pragma unroll
+        for (int r = 0; r < RK; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1[r][c];
+        if (ty == 0)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
+#pragma unroll
+        for (int r = 0; r < NW2; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
+        }
+        if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+    }
+    // head sums are valid in every lane of a warp (computed redundantly); reduce across warps
+    __syncthreads();
+    if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
+    __syncthreads();
+    if (tid < 3) {
+        float s = 0.f;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+        part[L::P + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == nchunks - 1);
+    __syncthreads();
+    if (!S.last) return;
+    __threadfence();
+    const float* pm = A.partial + (int64_t)m * nchunks * PSTRIDE;
+    if (want_grad) {
+        for (int p = tid; p < L::P; p += PT_THREADS) {
+            float s = 0.f;
+            for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + p);
+            A.grad[(int64_t)m * L::P + p] = s;
+            if (A.out_params) A.out_params[(int64_t)m * L::P + p] = S.P[p] - A.sgd_lr * s;   // meta_algos/base.py:209
+        }
+    }
+    if (A.stats && tid < 3) {
+        float s = 0.f;
+        for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + L::P + tid);
+        A.stats[(int64_t)m * 4 + tid] = s * invN;
+    }
+    if (tid == 0) A.counters[m] = 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Exact Hessian-vector product of the inner surrogate (R-operator: forward-mode tangent through the
+// MLP + Gaussian log-likelihood, then the reverse sweep of the tangent), fused with the KL-penalty
+// gradient:  out = vec - inner_lr * H vec + kl_coeff * grad KL.   Notation in the comments:
+//   H1,H2 activations; R1,R2 their tangents; D* = backprop of the surrogate; C* = combined
+//   (-inner_lr * tangent-of-backprop + kl-penalty backprop) signal that is accumulated into `out`.
+template <int DO, int DA, int HID>
+struct HvpSmem {
+    using L = PLayout<DO, DA, HID>;
+    using C = TileCfg<HID>;
+    static constexpr int DOP = DOPad<DO>::V;
+    static constexpr int PP = (L::P + 3) / 4 * 4;
+    float P[PP];
+    float V[PP];
+    float W1T[HID * HID];
+    float V1T[HID * HID];
+    float X[TB * DOP];
+    float H1[TB * C::LD];
+    float R1[TB * C::LD];
+    float H2[TB * C::LD];
+    float R2[TB * C::LD];
+    float DMU[TB * DA];
+    float CMU[TB * DA];
+    float CLS[TB * DA];
+    float red[3 * (PT_THREADS / 32)];
+    int last;
+};
+
+template <int DO, int DA, int HID>
+__global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
+    using L = PLayout<DO, DA, HID>;
+    using C = TileCfg<HID>;
+    using SM = HvpSmem<DO, DA, HID>;
+    constexpr int LD = C::LD, RM = C::RM, RK = C::RK, DOP = SM::DOP;
+    constexpr int NW0 = (DO * HID + PT_THREADS - 1) / PT_THREADS;
+    constexpr int NW2 = (HID * DA + PT_THREADS - 1) / PT_THREADS;
+    constexpr int NU = HID / 32;
+    constexpr int PSTRIDE = L::P + PSTAT;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid % C::TX, ty = tid / C::TX;
+    const int row0 = ty * RM, col0 = tx * 4;
+    const int m = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int N = A.N;
+    const float invN = 1.0f / (float)N;
+    const float ac = -A.inner_lr;                 // coefficient of H vec in `out`
+    const float* th = A.params + (int64_t)m * A.param_stride;
+    const float* vg = A.vec + (int64_t)m * L::P;
+
+    for (int i = tid; i < L::P; i += PT_THREADS) S.P[i] = __ldg(th + i), S.V[i] = __ldg(vg + i);
+    __syncthreads();
+    for (int i = tid; i < HID * HID; i += PT_THREADS) {
+        const int k = i / HID, j = i % HID;
+        S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
+        S.V1T[j * HID + k] = S.V[L::W1 + k * HID + j];
+    }
+    HeadIn<DA> hin;
+    load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
+    float rls[DA];     // tangent of the (clipped) log_std
+#pragma unroll
+    for (int d = 0; d < DA; ++d) rls[d] = S.V[L::LS + d] * hin.ls_mask[d];
+
+    // accumulators: gC* multiply 1, gA* multiply `ac`
+    float gW1c[RK][4], gW1a[RK][4], gB1[4] = {0, 0, 0, 0}, gW0[NW0], gB0 = 0.f, gW2[NW2], gB2 = 0.f, gLS = 0.f;
+#pragma unroll
+    for (int r = 0; r < RK; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gW1c[r][c] = gW1a[r][c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
+    float s_obj = 0.f, s_kl = 0.f, s_ratio = 0.f;
+
+    const int ntiles = (N + TB - 1) / TB;
+    for (int tile = chunk; tile < ntiles; tile += nchunks) {
+        const int n0 = tile * TB, nb = min(TB, N - n0);
+        const int64_t g0 = (int64_t)m * N + n0;
+        __syncthreads();
+        for (int i = tid; i < TB * DOP; i += PT_THREADS) {
+            const int b = i / DOP, c = i % DOP;
+            S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+        }
+        __syncthreads();
+        // ---- layer 0 and its tangent: H1 = tanh(X W0 + b0); R1 = (1-H1^2) * (X V0 + vb0)
+        {
+            float acc[RM][4], racc[RM][4];
+            const float4 bv = *reinterpret_cast<const float4*>(S.P + L::B0 + col0);
+            const float4 rv = *reinterpret_cast<const float4*>(S.V + L::B0 + col0);
+#pragma unroll
+            for (int i = 0; i < RM; ++i) {
+                acc[i][0] = bv.x, acc[i][1] = bv.y, acc[i][2] = bv.z, acc[i][3] = bv.w;
+                racc[i][0] = rv.x, racc[i][1] = rv.y, racc[i][2] = rv.z, racc[i][3] = rv.w;
+            }
+            gemm_tile_smallk<DO, DOP, HID, RM>(S.X, S.P + L::W0, row0, col0, acc);
+            gemm_tile_smallk<DO, DOP, HID, RM>(S.X, S.V + L::W0, row0, col0, racc);
+#pragma unroll
+            for (int i = 0; i < RM; ++i) {
+                float h[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) h[c] = tanhf(acc[i][c]);
+                *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(S.R1 + (row0 + i) * LD + col0) =
+                    make_float4((1.f - h[0] * h[0]) * racc[i][0], (1.f - h[1] * h[1]) * racc[i][1],
+                                (1.f - h[2] * h[2]) * racc[i][2], (1.f - h[3] * h[3]) * racc[i][3]);
+            }
+        }
+        __syncthreads();
+        // ---- layer 1 and its tangent: R2 = (1-H2^2) * (R1 W1 + H1 V1 + vb1)
+        {
+            float acc[RM][4], racc[RM][4];
+            const float4 bv = *reinterpret_cast<const float4*>(S.P + L::B1 + col0);
+            const float4 rv = *reinterpret_cast<const float4*>(S.V + L::B1 + col0);
+#pragma unroll
+            for (int i = 0; i < RM; ++i) {
+                acc[i][0] = bv.x, acc[i][1] = bv.y, acc[i][2] = bv.z, acc[i][3] = bv.w;
+                racc[i][0] = rv.x, racc[i][1] = rv.y, racc[i][2] = rv.z, racc[i][3] = rv.w;
+            }
+            gemm_tile<HID, LD, HID, RM>(S.H1, S.P + L::W1, row0, col0, acc);
+            gemm_tile<HID, LD, HID, RM>(S.R1, S.P + L::W1, row0, col0, racc);
+            gemm_tile<HID, LD, HID, RM>(S.H1, S.V + L::W1, row0, col0, racc);
+#pragma unroll
+            for (int i = 0; i < RM; ++i) {
+                float h[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) h[c] = tanhf(acc[i][c]);
+                *reinterpret_cast<float4*>(S.H2 + (row0 + i) * LD + col0) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(S.R2 + (row0 + i) * LD + col0) =
+                    make_float4((1.f - h[0] * h[0]) * racc[i][0], (1.f - h[1] * h[1]) * racc[i][1],
+                                (1.f - h[2] * h[2]) * racc[i][2], (1.f - h[3] * h[3]) * racc[i][3]);
+            }
+        }
+        __syncthreads();
+        // ---- layer 2, its tangent, and the Gaussian head with its tangent
+        for (int r = 0; r < TB / (PT_THREADS / 32); ++r) {
+            const int b = warp * (TB / (PT_THREADS / 32)) + r;
+            float mu[DA], rmu[DA];
+#pragma unroll
+            for (int d = 0; d < DA; ++d) mu[d] = rmu[d] = 0.f;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int j = lane + 32 * u;
+                const float h = S.H2[b * LD + j], rh = S.R2[b * LD + j];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    const float w2 = S.P[L::W2 + j * DA + d];
+                    mu[d] = fmaf(h, w2, mu[d]);
+                    rmu[d] = fmaf(rh, w2, fmaf(h, S.V[L::W2 + j * DA + d], rmu[d]));
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < DA; ++d) {
+                mu[d] = warp_sum(mu[d]) + S.P[L::B2 + d];
+                rmu[d] = warp_sum(rmu[d]) + S.V[L::B2 + d];
+            }
+            float dmu[DA], cmu[DA], cls[DA];
+            if (b < nb) {
+                const int64_t n = g0 + b;
+                float a[DA], mo[DA], lso[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    a[d] = __ldg(A.act + n * DA + d);
+                    mo[d] = __ldg(A.old_mean + n * DA + d);
+                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                }
+                const float adv = __ldg(A.adv + n);
+                HeadOut<DA> o;
+                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                const float wt = o.w * invN, kc = A.kl_coeff * invN;
+                // tangent of log p:  R l = sum_d (zeta/sig) R mu + (zeta^2 - 1) R ls
+                float rl = 0.f;
+#pragma unroll
+                for (int d = 0; d < DA; ++d)
+                    rl += (o.zeta[d] / hin.sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
+                // d w / d logp: RATIO w = -A r -> R w = w R l ; LOGLIK w = -A -> 0
+                const float rwt = (A.obj_kind == PROMP_OBJ_RATIO) ? wt * rl : 0.f;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    const float is = 1.f / hin.sig[d], z = o.zeta[d];
+                    const float rz = -rmu[d] * is - z * rls[d];
+                    dmu[d] = wt * z * is;
+                    const float rdmu = rwt * z * is + wt * (rz * is - z * rls[d] * is);
+                    const float rdls = rwt * (z * z - 1.f) + wt * 2.f * z * rz;
+                    cmu[d] = ac * rdmu + kc * o.dkl_dmu[d];
+                    cls[d] = (ac * rdls + kc * o.dkl_dls[d]) * hin.ls_mask[d];
+                }
+                s_obj += o.obj;
+                s_kl += o.kl;
+                s_ratio += o.ratio;
+            } else {
+#pragma unroll
+                for (int d = 0; d < DA; ++d) dmu[d] = cmu[d] = cls[d] = 0.f;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int d = 0; d < DA; ++d)
+                    S.DMU[b * DA + d] = dmu[d], S.CMU[b * DA + d] = cmu[d], S.CLS[b * DA + d] = cls[d];
+            }
+        }
+        __syncthreads();
+        // ---- output layer: out_W2 += H2^T CMU + ac * R2^T DMU ; out_b2 += colsum CMU ; out_ls += colsum CLS
+#pragma unroll
+        for (int r = 0; r < NW2; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < HID * DA) {
+                const int j = idx / DA, d = idx % DA;
+                float s = 0.f, sa = 0.f;
+                for (int b = 0; b < nb; ++b) {
+                    s = fmaf(S.H2[b * LD + j], S.CMU[b * DA + d], s);
+                    sa = fmaf(S.R2[b * LD + j], S.DMU[b * DA + d], sa);
+                }
+                gW2[r] += s + ac * sa;
+            }
+        }
+        if (tid < DA) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int b = 0; b < nb; ++b) s1 += S.CMU[b * DA + tid], s2 += S.CLS[b * DA + tid];
+            gB2 += s1;
+            gLS += s2;
+        }
+        __syncthreads();
+        // ---- D2 = dH2 * g2 -> H2 ; C2 = CdH2 * g2 + ac * dH2 * (-2 H2 R2) -> R2
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            const int b = row0 + i;
+            const float4 h4 = *reinterpret_cast<float4*>(S.H2 + b * LD + col0);
+            const float4 r4 = *reinterpret_cast<float4*>(S.R2 + b * LD + col0);
+            const float hv[4] = {h4.x, h4.y, h4.z, h4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+            float d2[4], c2[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float dh = 0.f, ch = 0.f;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    const float w2 = S.P[L::W2 + (col0 + c) * DA + d], v2 = S.V[L::W2 + (col0 + c) * DA + d];
+                    const float dm = S.DMU[b * DA + d];
+                    dh = fmaf(dm, w2, dh);
+                    ch = fmaf(S.CMU[b * DA + d], w2, fmaf(ac * dm, v2, ch));
+                }
+                const float g2 = 1.f - hv[c] * hv[c];
+                d2[c] = dh * g2;
+                c2[c] = ch * g2 + ac * dh * (-2.f * hv[c] * rv[c]);
+            }
+            *reinterpret_cast<float4*>(S.H2 + b * LD + col0) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+            *reinterpret_cast<float4*>(S.R2 + b * LD + col0) = make_float4(c2[0], c2[1], c2[2], c2[3]);
+        }
+        __syncthreads();
+        // ---- out_W1 += H1^T C2 + ac * R1^T D2 ; out_b1 += colsum C2
+        wgrad_tile<LD, RK>(S.H1, S.R2, ty * RK, col0, nb, gW1c);
+        wgrad_tile<LD, RK>(S.R1, S.H2, ty * RK, col0, nb, gW1a);
+        if (ty == 0) {
+            for (int b = 0; b < nb; ++b) {
+                const float4 d = *reinterpret_cast<const float4*>(S.R2 + b * LD + col0);
+                gB1[0] += d.x; gB1[1] += d.y; gB1[2] += d.z; gB1[3] += d.w;
+            }
+        }
+        // ---- dH1 = D2 W1^T ; CdH1 = C2 W1^T + ac * D2 V1^T
+        float dh1[RM][4], ch1[RM][4];
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dh1[i][c] = ch1[i][c] = 0.f;
+        gemm_tile<HID, LD, HID, RM>(S.H2, S.V1T, row0, col0, ch1);
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ch1[i][c] *= ac;
+        gemm_tile<HID, LD, HID, RM>(S.R2, S.W1T, row0, col0, ch1);
+        gemm_tile<HID, LD, HID, RM>(S.H2, S.W1T, row0, col0, dh1);
+        __syncthreads();   // all reads of H1 / R1 by the weight-gradient loops are done
+        // ---- C1 = CdH1 * g1 + ac * dH1 * (-2 H1 R1) -> H1
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            const float4 h4 = *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0);
+            const float4 r4 = *reinterpret_cast<float4*>(S.R1 + (row0 + i) * LD + col0);
+            const float hv[4] = {h4.x, h4.y, h4.z, h4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+            float c1[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                c1[c] = ch1[i][c] * (1.f - hv[c] * hv[c]) + ac * dh1[i][c] * (-2.f * hv[c] * rv[c]);
+            *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) = make_float4(c1[0], c1[1], c1[2], c1[3]);
+        }
+        __syncthreads();
+        // ---- out_W0 += X^T C1 ; out_b0 += colsum C1
+#pragma unroll
+        for (int r = 0; r < NW0; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < DO * HID) {
+                const int i = idx / HID, j = idx % HID;
+                float s = 0.f;
+                for (int b = 0; b < nb; ++b) s = fmaf(S.X[b * DOP + i], S.H1[b * LD + j], s);
+                gW0[r] += s;
+            }
+        }
+        if (tid < HID) {
+            float s = 0.f;
+            for (int b = 0; b < nb; ++b) s += S.H1[b * LD + tid];
+            gB0 += s;
+        }
+    }
+
+    float* part = A.partial + ((int64_t)m * nchunks + chunk) * PSTRIDE;
+#pragma unroll
+    for (int r = 0; r < NW0; ++r) {
+        const int idx = tid + r * PT_THREADS;
+        if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
+    }
+    if (tid < HID) part[L::B0 + tid] = gB0;
+#pragma unroll
+    for (int r = 0; r < RK; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1c[r][c] + ac * gW1a[r][c];
+    if (ty == 0)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
+#pragma unroll
+    for (int r = 0; r < NW2; ++r) {
+        const int idx = tid + r * PT_THREADS;
+        if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
+    }
+    if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+    __syncthreads();
+    if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
+    __syncthreads();
+    if (tid < 3) {
+        float s = 0.f;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+        part[L::P + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == nchunks - 1);
+    __syncthreads();
+    if (!S.last) return;
+    __threadfence();
+    const float* pm = A.partial + (int64_t)m * nchunks * PSTRIDE;
+    for (int p = tid; p < L::P; p += PT_THREADS) {
+        float s = 0.f;
+        for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + p);
+        A.out[(int64_t)m * L::P + p] = S.V[p] + s;
+    }
+    if (A.stats && tid < 3) {
+        float s = 0.f;
+        for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + L::P + tid);
+        A.stats[(int64_t)m * 4 + tid] = s * invN;
+    }
+    if (tid == 0) A.counters[m] = 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward only: mean for arbitrary obs (distribution_info_sym / get_actions without sampling)
+template <int DO, int DA, int HID>
+__global__ void __launch_bounds__(128) policy_forward_kernel(int M, int N, const float* params, int64_t stride,
+                                                              const float* obs, float* mean) {
+    using L = PLayout<DO, DA, HID>;
+    constexpr int NU = HID / 32;
+    __shared__ float sP[L::P];
+    __shared__ float sh[4][HID];
+    const int m = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float* th = params + (int64_t)m * stride;
+    for (int i = threadIdx.x; i < L::P; i += blockDim.x) sP[i] = __ldg(th + i);
+    __syncthreads();
+    for (int n = blockIdx.x * 4 + w; n < N; n += gridDim.x * 4) {
+        const float* o = obs + ((int64_t)m * N + n) * DO;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int j = lane + 32 * u;
+            float z = sP[L::B0 + j];
+            for (int i = 0; i < DO; ++i) z = fmaf(__ldg(o + i), sP[L::W0 + i * HID + j], z);
+            sh[w][j] = tanhf(z);
+        }
+        __syncwarp();
+        float mu[DA];
+#pragma unroll
+        for (int d = 0; d < DA; ++d) mu[d] = 0.f;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int j = lane + 32 * u;
+            float z = sP[L::B1 + j];
+            for (int k = 0; k < HID; ++k) z = fmaf(sh[w][k], sP[L::W1 + k * HID + j], z);
+            const float h2 = tanhf(z);
+#pragma unroll
+            for (int d = 0; d < DA; ++d) mu[d] = fmaf(h2, sP[L::W2 + j * DA + d], mu[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < DA; ++d) {
+            const float s = warp_sum(mu[d]) + sP[L::B2 + d];
+            if (lane == d) mean[((int64_t)m * N + n) * DA + d] = s;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void reduce_tasks_kernel(int M, int P, const float* in, float scale, float* out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += in[(int64_t)m * P + p];
+    out[p] = s * scale;
+}
+
+__global__ void adam_tf1_kernel(int P, float* theta, const float* grad, float* mm, float* vv, int32_t* step, float lr,
+                                float b1, float b2, float eps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = *step + 1;
+    // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)   (tf.train.AdamOptimizer)
+    const float lr_t = lr * sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
+    if (p < P) {
+        const float g = grad[p];
+        const float mn = b1 * mm[p] + (1.f - b1) * g;
+        const float vn = b2 * vv[p] + (1.f - b2) * g * g;
+        mm[p] = mn;
+        vv[p] = vn;
+        theta[p] = theta[p] - lr_t * mn / (sqrtf(vn) + eps);
+    }
+}
+__global__ void adam_step_inc_kernel(int32_t* step) { *step += 1; }
+
+// -------------------------------------------------------------------------------------------------
+static int pick_chunks(int M, int N) {
+    const int ntiles = (N + TB - 1) / TB;
+    int c = (2 * 148 + M - 1) / M;      // ~2 CTAs per SM across the 148 SMs
+    if (c > ntiles) c = ntiles;
+    if (c < 1) c = 1;
+    return c;
+}
+
+template <int DO, int DA, int HID>
+static int launch_grad(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    using L = PLayout<DO, DA, HID>;
+    const int chunks = pick_chunks(A.M, A.N);
+    const int64_t need = (int64_t)A.M * chunks * (L::P + PSTAT) * sizeof(float) + (int64_t)A.M * sizeof(int);
+    if (ws_bytes < need) {
+        set_error("policy workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
+        return PROMP_ERR_WORKSPACE;
+    }
+    A.counters = (int*)ws;
+    A.partial = (float*)((char*)ws + (((int64_t)A.M * sizeof(int) + 15) / 16) * 16);
+    static bool attr_set = false;
+    const int smem = (int)sizeof(GradSmem<DO, DA, HID>);
+    if (!attr_set) {
+        PROMP_CUDA(cudaFuncSetAttribute(policy_grad_kernel<DO, DA, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    policy_grad_kernel<DO, DA, HID><<<dim3(chunks, A.M), PT_THREADS, smem, st>>>(A);
+    PROMP_LAUNCH_CHECK("policy_grad_kernel");
+    return PROMP_OK;
+}
+
+template <int DO, int DA, int HID>
+static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    using L = PLayout<DO, DA, HID>;
+    const int chunks = pick_chunks(A.M, A.N);
+    const int64_t need = (int64_t)A.M * chunks * (L::P + PSTAT) * sizeof(float) + (int64_t)A.M * sizeof(int);
+    if (ws_bytes < need) {
+        set_error("policy workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
+        return PROMP_ERR_WORKSPACE;
+    }
+    A.counters = (int*)ws;
+    A.partial = (float*)((char*)ws + (((int64_t)A.M * sizeof(int) + 15) / 16) * 16);
+    static bool attr_set = false;
+    const int smem = (int)sizeof(HvpSmem<DO, DA, HID>);
+    if (!attr_set) {
+        PROMP_CUDA(cudaFuncSetAttribute(policy_hvp_kernel<DO, DA, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    policy_hvp_kernel<DO, DA, HID><<<dim3(chunks, A.M), PT_THREADS, smem, st>>>(A);
+    PROMP_LAUNCH_CHECK("policy_hvp_kernel");
+    return PROMP_OK;
+}
+
+template <int DO, int DA, int HID>
+static int launch_forward(int M, int N, const float* params, int64_t stride, const float* obs, float* mean,
+                          cudaStream_t st) {
+    int gx = (N + 3) / 4;
+    const int cap = (4 * 148 + M - 1) / M;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    policy_forward_kernel<DO, DA, HID><<<dim3(gx, M), 128, 0, st>>>(M, N, params, stride, obs, mean);
+    PROMP_LAUNCH_CHECK("policy_forward_kernel");
+    return PROMP_OK;
+}
+
+// supported (obs_dim, act_dim, hidden) instantiations
+#define PROMP_DISPATCH_DIMS(FN, ...)                                                           \
+    if (obs_dim == 2 && act_dim == 2 && hidden == 64) return FN<2, 2, 64>(__VA_ARGS__);        \
+    if (obs_dim == 2 && act_dim == 2 && hidden == 32) return FN<2, 2, 32>(__VA_ARGS__);        \
+    if (obs_dim == 17 && act_dim == 6 && hidden == 64) return FN<17, 6, 64>(__VA_ARGS__);      \
+    if (obs_dim == 17 && act_dim == 6 && hidden == 32) return FN<17, 6, 32>(__VA_ARGS__);      \
+    set_error("unsupported (obs_dim, act_dim, hidden) = (%d, %d, %d); built: (2,2,{32,64}), (17,6,{32,64})", \
+              obs_dim, act_dim, hidden);                                                       \
+    return PROMP_ERR_INVALID_ARG;
+
+}  // namespace promp
+
+using namespace promp;
+
+extern "C" int64_t promp_policy_workspace_bytes(int M, int N, int obs_dim, int act_dim, int hidden) {
+    const int chunks = pick_chunks(M, N);
+    const int P = promp::num_params(obs_dim, act_dim, hidden);
+    return (int64_t)M * chunks * (P + PSTAT) * sizeof(float) + (((int64_t)M * sizeof(int) + 15) / 16) * 16 + 16;
+}
+
+static int check_policy_args(const char* who, int M, int N, const void* params, const void* obs, const void* act,
+                             const void* adv, const void* old_mean, const void* old_ls, const void* ws) {
+    PROMP_REQUIRE(M > 0 && N > 0, "%s: M and N must be positive (got %d, %d)", who, M, N);
+    PROMP_REQUIRE(M <= 65535, "%s: M=%d exceeds the grid.y limit", who, M);
+    PROMP_REQUIRE(params && obs && act && adv && old_mean && old_ls && ws, "%s: null pointer argument", who);
+    return PROMP_OK;
+}
+
+extern "C" int promp_policy_grad(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
+                                 int64_t param_stride, const float* obs, const float* act, const float* adv,
+                                 const float* old_mean, const float* old_log_std, int ls_per_sample, int obj_kind,
+                                 float obj_scale, float clip_eps, float kl_coeff, int clip_log_std, float min_log_std,
+                                 float* grad, float* out_params, float sgd_lr, float* stats, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+    int st = check_policy_args("promp_policy_grad", M, N, params, obs, act, adv, old_mean, old_log_std, workspace);
+    if (st != PROMP_OK) return st;
+    PROMP_REQUIRE(obj_kind >= 0 && obj_kind <= 3, "promp_policy_grad: bad obj_kind %d", obj_kind);
+    PROMP_REQUIRE(!(out_params && !grad), "promp_policy_grad: out_params needs grad");
+    PolicyArgs A{};
+    A.M = M; A.N = N; A.params = params; A.param_stride = param_stride;
+    A.obs = obs; A.act = act; A.adv = adv; A.old_mean = old_mean; A.old_ls = old_log_std;
+    A.ls_per_sample = ls_per_sample; A.obj_kind = obj_kind; A.obj_scale = obj_scale; A.clip_eps = clip_eps;
+    A.kl_coeff = kl_coeff; A.clip_log_std = clip_log_std; A.min_log_std = min_log_std;
+    A.grad = grad; A.out_params = out_params; A.sgd_lr = sgd_lr; A.stats = stats;
+    cudaStream_t s = (cudaStream_t)stream;
+    PROMP_DISPATCH_DIMS(launch_grad, A, workspace, workspace_bytes, s)
+}
+
+extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
+                                int64_t param_stride, const float* obs, const float* act, const float* adv,
+                                const float* old_mean, const float* old_log_std, int ls_per_sample, int obj_kind,
+                                float inner_lr, float kl_coeff, int clip_log_std, float min_log_std, const float* vec,
+                                float* out, float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_policy_args("promp_policy_hvp", M, N, params, obs, act, adv, old_mean, old_log_std, workspace);
+    if (st != PROMP_OK) return st;
+    PROMP_REQUIRE(obj_kind == PROMP_OBJ_RATIO || obj_kind == PROMP_OBJ_LOGLIK,
+                  "promp_policy_hvp: inner objective must be RATIO or LOGLIK (got %d)", obj_kind);
+    PROMP_REQUIRE(vec && out, "promp_policy_hvp: vec/out must not be null");
+    PolicyArgs A{};
+    A.M = M; A.N = N; A.params = params; A.param_stride = param_stride;
+    A.obs = obs; A.act = act; A.adv = adv; A.old_mean = old_mean; A.old_ls = old_log_std;
+    A.ls_per_sample = ls_per_sample; A.obj_kind = obj_kind; A.obj_scale = 1.f; A.clip_eps = 0.f;
+    A.kl_coeff = kl_coeff; A.clip_log_std = clip_log_std; A.min_log_std = min_log_std;
+    A.vec = vec; A.out = out; A.inner_lr = inner_lr; A.stats = stats;
+    cudaStream_t s = (cudaStream_t)stream;
+    PROMP_DISPATCH_DIMS(launch_hvp, A, workspace, workspace_bytes, s)
+}
+
+extern "C" int promp_policy_forward(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
+                                    int64_t param_stride, const float* obs, float* mean, void* stream) {
+    PROMP_REQUIRE(M > 0 && N > 0 && params && obs && mean, "promp_policy_forward: bad arguments");
+    PROMP_REQUIRE(M <= 65535, "promp_policy_forward: M=%d exceeds the grid.y limit", M);
+    cudaStream_t s = (cudaStream_t)stream;
+    PROMP_DISPATCH_DIMS(launch_forward, M, N, params, param_stride, obs, mean, s)
+}
+
+extern "C" int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, void* stream) {
+    PROMP_REQUIRE(M > 0 && P > 0 && in && out, "promp_reduce_tasks: bad arguments");
+    reduce_tasks_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, P, in, scale, out);
+    PROMP_LAUNCH_CHECK("reduce_tasks_kernel");
+    return PROMP_OK;
+}
+
+extern "C" int promp_adam_tf1(int P, float* theta, const float* grad, float* m, float* v, int32_t* step, float lr,
+                              float beta1, float beta2, float eps, void* stream) {
+    PROMP_REQUIRE(P > 0 && theta && grad && m && v && step, "promp_adam_tf1: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    adam_tf1_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, theta, grad, m, v, step, lr, beta1, beta2, eps);
+    adam_step_inc_kernel<<<1, 1, 0, s>>>(step);
+    PROMP_LAUNCH_CHECK("adam_tf1_kernel");
+    return PROMP_OK;
+}

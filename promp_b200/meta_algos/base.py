@@ -1,0 +1,155 @@
+"""MAMLAlgo on the GPU (ref: meta_policy_search/meta_algos/base.py:85-313).
+
+The reference builds a TF graph with M replicated per-task sub-graphs and lets tf.gradients
+differentiate through the inner SGD step.  Here the same quantities are produced by three kernels:
+
+  forward chain   theta_{s+1,i} = theta_{s,i} - alpha * grad surr_s,i(theta_{s,i})   promp_policy_grad (+SGD)
+  outer gradient  v_i = grad_{theta'} L_i(theta_{S-1,i})                             promp_policy_grad
+  backward chain  v_i <- v_i - alpha * H_s,i v_i + c_s * grad KL_s,i                 promp_policy_hvp
+  meta-gradient   g = (1/M) sum_i v_i   (+ all-reduce over ranks)                    promp_reduce_tasks
+
+which is exactly d/dtheta of the meta objective for any number of inner steps (the backward chain
+is the transpose of d theta_{s+1} / d theta_s = I - alpha H_s).
+"""
+import numpy as np
+
+from promp_b200 import _lib
+from promp_b200.samplers.device_data import SamplesData, PhaseData
+from promp_b200.utils.dist import allreduce_sum_, world_size  # noqa: F401
+
+
+class MAMLAlgo(object):
+    """
+    Args:
+        policy (MetaGaussianMLPPolicy), inner_lr, meta_batch_size, num_inner_grad_steps,
+        trainable_inner_step_size (must be False, as in every shipped reference config)
+    """
+    inner_obj_kind = _lib.OBJ_RATIO
+
+    def __init__(self, policy, inner_lr=0.1, meta_batch_size=20, num_inner_grad_steps=1,
+                 trainable_inner_step_size=False):
+        assert hasattr(policy, 'sampling_params'), "policy must be a promp_b200 MetaGaussianMLPPolicy"
+        assert type(num_inner_grad_steps) and num_inner_grad_steps >= 0
+        assert type(meta_batch_size) == int
+        if trainable_inner_step_size:
+            raise NotImplementedError("trainable_inner_step_size is not supported (reference: 'it isn't supported "
+                                      "right now', meta_algos/base.py:203)")
+        self.policy = policy
+        self.inner_lr = float(inner_lr)
+        self.meta_batch_size = meta_batch_size
+        self.num_inner_grad_steps = num_inner_grad_steps
+        self.trainable_inner_step_size = trainable_inner_step_size
+        self._optimization_keys = None
+        self._ws = None
+
+    # ------------------------------------------------------------------------------------ helpers
+    def _workspace(self, N):
+        import torch
+        p = self.policy
+        need = _lib.load().promp_policy_workspace_bytes(self.meta_batch_size, N, p.obs_dim, p.action_dim, p.hidden)
+        if self._ws is None or self._ws.numel() * 4 < need:
+            self._ws = torch.zeros((need + 3) // 4, dtype=torch.int32, device=p.device)   # counters start at zero
+        return self._ws
+
+    def _phase_of(self, samples):
+        """samples: list (len M) of per-task dicts -> PhaseData on the device."""
+        import torch
+        assert len(samples) == self.meta_batch_size
+        first = samples[0]
+        if isinstance(first, SamplesData) and all(isinstance(s, SamplesData) and s.phase is first.phase for s in samples):
+            return first.phase
+        # reference-style numpy dicts: upload (ref _extract_input_dict, base.py:245-280)
+        p = self.policy
+        N = len(first['advantages'])
+        E = 1
+        phase = PhaseData(self.meta_batch_size, E, N, p.obs_dim, p.action_dim, p.device)
+
+        def up(key, sub=None):
+            arr = np.stack([np.asarray(s[key] if sub is None else s[key][sub], dtype=np.float32) for s in samples])
+            return torch.from_numpy(np.ascontiguousarray(arr)).to(p.device)
+        phase.obs = up('observations').reshape(self.meta_batch_size, N, p.obs_dim)
+        phase.act = up('actions').reshape(self.meta_batch_size, N, p.action_dim)
+        phase.adv = up('advantages').reshape(self.meta_batch_size, N)
+        phase.mean = up('agent_infos', 'mean').reshape(self.meta_batch_size, N, p.action_dim)
+        phase.log_std_full = up('agent_infos', 'log_std').reshape(self.meta_batch_size, N, p.action_dim)
+        return phase
+
+    def _grad(self, phase, params, stride, obj_kind, obj_scale=1.0, clip_eps=0.0, kl_coeff=0.0, clip_log_std=0,
+              grad=None, out_params=None, sgd_lr=0.0, stats=None):
+        p = self.policy
+        ws = self._workspace(phase.N)
+        full = getattr(phase, 'log_std_full', None)
+        old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
+        _lib.call('promp_policy_grad', p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N,
+                  _lib.ptr(params), stride, _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.adv),
+                  _lib.ptr(phase.mean), _lib.ptr(old_ls), per_sample, obj_kind, float(obj_scale), float(clip_eps),
+                  float(kl_coeff), int(clip_log_std), float(p.min_log_std), _lib.ptr(grad), _lib.ptr(out_params),
+                  float(sgd_lr), _lib.ptr(stats), _lib.ptr(ws), ws.numel() * 4, _lib.stream())
+
+    def _hvp(self, phase, params, stride, vec, out, kl_coeff, clip_log_std, stats=None):
+        p = self.policy
+        ws = self._workspace(phase.N)
+        full = getattr(phase, 'log_std_full', None)
+        old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
+        _lib.call('promp_policy_hvp', p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N,
+                  _lib.ptr(params), stride, _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.adv),
+                  _lib.ptr(phase.mean), _lib.ptr(old_ls), per_sample, self.inner_obj_kind, float(self.inner_lr),
+                  float(kl_coeff), int(clip_log_std), float(p.min_log_std), _lib.ptr(vec), _lib.ptr(out),
+                  _lib.ptr(stats), _lib.ptr(ws), ws.numel() * 4, _lib.stream())
+
+    # ------------------------------------------------------------------------------------ inner step
+    def _adapt(self, samples):
+        """MAMLAlgo._adapt (base.py:217-242): theta_i' = theta_i - alpha * grad surr_i(theta_i), all tasks
+        in one launch, result stays on the device and becomes the sampling policy."""
+        import torch
+        assert len(samples) == self.meta_batch_size
+        phase = self._phase_of(samples)
+        p = self.policy
+        params, stride, _ = p.sampling_params()
+        M, P = self.meta_batch_size, p.num_params
+        grad = torch.empty(M, P, dtype=torch.float32, device=p.device)
+        new = torch.empty(M, P, dtype=torch.float32, device=p.device)
+        # the adapt graph is fed parameter placeholders: no log_std clip (gaussian_mlp_policy.py:164-182)
+        self._grad(phase, params, stride, self.inner_obj_kind, grad=grad, out_params=new, sgd_lr=self.inner_lr)
+        self.last_inner_grad = grad
+        p.update_task_parameters(new)
+
+    # ------------------------------------------------------------------------------------ meta objective
+    def _meta_pass(self, theta, phases, outer_obj_kind, clip_eps, inner_kl_coeffs, want_grad, outer_kl_coeff=0.0,
+                   outer_obj_scale=1.0):
+        """One evaluation of the meta objective (and optionally its gradient) at `theta` [P].
+
+        Returns dict(grad=[P] or None (local sum over tasks / M_global, NOT yet all-reduced),
+                     surr=[M] outer surrogate per task, outer_kl=[M], inner_kl=[S-1, M])."""
+        import torch
+        p = self.policy
+        M, P, S = self.meta_batch_size, p.num_params, len(phases)
+        dev = p.device
+        cur, stride, clip = theta, 0, 1              # step 0 = distribution_info_sym(params=None): clipped log_std
+        chain = []
+        inner_kl = torch.zeros(max(S - 1, 0), M, dtype=torch.float32, device=dev)
+        for s in range(S - 1):
+            g = torch.empty(M, P, dtype=torch.float32, device=dev)
+            nxt = torch.empty(M, P, dtype=torch.float32, device=dev)
+            st = torch.zeros(M, 4, dtype=torch.float32, device=dev)
+            self._grad(phases[s], cur, stride, self.inner_obj_kind, clip_log_std=clip, grad=g, out_params=nxt,
+                       sgd_lr=self.inner_lr, stats=st)
+            inner_kl[s] = st[:, 1]
+            chain.append((cur, stride, clip))
+            cur, stride, clip = nxt, P, 0
+        st = torch.zeros(M, 4, dtype=torch.float32, device=dev)
+        v = torch.empty(M, P, dtype=torch.float32, device=dev) if want_grad else None
+        self._grad(phases[-1], cur, stride, outer_obj_kind, obj_scale=outer_obj_scale, clip_eps=clip_eps,
+                   kl_coeff=outer_kl_coeff, clip_log_std=clip, grad=v, stats=st)
+        out = dict(surr=st[:, 0], outer_kl=st[:, 1], inner_kl=inner_kl, grad=None)
+        if want_grad:
+            for s in range(S - 2, -1, -1):
+                prm, strd, clp = chain[s]
+                self._hvp(phases[s], prm, strd, v, v, inner_kl_coeffs[s], clp)
+            flat = torch.empty(P, dtype=torch.float32, device=dev)
+            _lib.call('promp_reduce_tasks', M, P, _lib.ptr(v), 1.0 / (M * world_size()), _lib.ptr(flat), _lib.stream())
+            out['grad'] = flat
+        return out
+
+    def optimize_policy(self, all_samples_data, log=True):
+        raise NotImplementedError

@@ -1,0 +1,86 @@
+"""ProMP (ref: meta_policy_search/meta_algos/pro_mp.py:9-214) on the GPU."""
+import numpy as np
+
+from promp_b200 import _lib
+from promp_b200.meta_algos.base import MAMLAlgo
+from promp_b200.utils.dist import allreduce_sum_, world_size
+from promp_b200.optimizers.maml_first_order_optimizer import MAMLPPOOptimizer
+from promp_b200.utils import logger
+
+
+class ProMP(MAMLAlgo):
+    """Same constructor arguments as the reference (pro_mp.py:30-57)."""
+
+    def __init__(self, *args, name="ppo_maml", learning_rate=1e-3, num_ppo_steps=5, num_minibatches=1, clip_eps=0.2,
+                 target_inner_step=0.01, init_inner_kl_penalty=1e-2, adaptive_inner_kl_penalty=True,
+                 anneal_factor=1.0, **kwargs):
+        super(ProMP, self).__init__(*args, **kwargs)
+        self.optimizer = MAMLPPOOptimizer(learning_rate=learning_rate, max_epochs=num_ppo_steps,
+                                          num_minibatches=num_minibatches)
+        self.clip_eps = clip_eps
+        self.target_inner_step = target_inner_step
+        self.adaptive_inner_kl_penalty = adaptive_inner_kl_penalty
+        self.inner_kl_coeff = init_inner_kl_penalty * np.ones(self.num_inner_grad_steps)
+        self.anneal_coeff = 1
+        self.anneal_factor = anneal_factor
+        self._optimization_keys = ['observations', 'actions', 'advantages', 'agent_infos']
+        self.name = name
+        self.kl_coeff = [init_inner_kl_penalty] * self.meta_batch_size * self.num_inner_grad_steps
+        self.inner_obj_kind = _lib.OBJ_RATIO                     # _adapt_objective_sym (pro_mp.py:59-65)
+        self.optimizer.build(self.policy)
+
+    def _objective_pass(self, phases, want_grad):
+        """meta_objective = mean_i L_clip,i + mean_s(c_s * mean_i KL_s,i)   (pro_mp.py:151-155)."""
+        S1 = max(self.num_inner_grad_steps, 1)
+        coeffs = [float(c) / S1 for c in self.inner_kl_coeff]      # tf.reduce_mean over the S-1 steps
+        return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, coeffs, want_grad)
+
+    def optimize_policy(self, all_samples_data, log=True):
+        """ProMP.optimize_policy (pro_mp.py:165-199): K Adam epochs on the same data, then a stats pass."""
+        import torch
+        assert len(all_samples_data) == self.num_inner_grad_steps + 1
+        phases = [self._phase_of(s) for s in all_samples_data]
+        if log: logger.log("Optimizing")
+        stats = self.optimizer.optimize(self, phases)
+        if log: logger.log("Computing statistics")
+        # one device->host copy for everything that is logged / decided on the host
+        host = stats.cpu().numpy().astype(np.float64)
+        loss_before, loss_after = host[0], host[1]
+        inner_kls = host[2:2 + self.num_inner_grad_steps]
+        if self.adaptive_inner_kl_penalty:
+            if log: logger.log("Updating inner KL loss coefficients")
+            self.inner_kl_coeff = self.adapt_kl_coeff(self.inner_kl_coeff, inner_kls, self.target_inner_step)
+        self.last_stats = dict(loss_before=loss_before, loss_after=loss_after, inner_kls=inner_kls,
+                               outer_kl=host[2 + self.num_inner_grad_steps])
+        if log:
+            logger.logkv('LossBefore', loss_before)
+            logger.logkv('LossAfter', loss_after)
+            logger.logkv('KLInner', np.mean(inner_kls))
+            logger.logkv('KLCoeffInner', np.mean(self.inner_kl_coeff))
+
+    def loss_terms(self, res):
+        """Scalar meta objective + KLs (global means) from a _meta_pass result, as a device vector
+        [loss, inner_kl_0.., outer_kl]."""
+        import torch
+        Mg = self.meta_batch_size * world_size()
+        S1 = self.num_inner_grad_steps
+        vec = torch.cat([res['surr'].sum().view(1), res['inner_kl'].sum(1).view(-1), res['outer_kl'].sum().view(1)]) / Mg
+        allreduce_sum_(vec)
+        coeff = torch.as_tensor(np.asarray(self.inner_kl_coeff, dtype=np.float32), device=vec.device)
+        penalty = (coeff * vec[1:1 + S1]).mean() if S1 > 0 else vec.new_zeros(())
+        return torch.cat([(vec[0] + penalty).view(1), vec[1:]])
+
+    def adapt_kl_coeff(self, kl_coeff, kl_values, kl_target):
+        """pro_mp.py:201-214."""
+        if hasattr(kl_values, '__iter__'):
+            assert len(kl_coeff) == len(kl_values)
+            return np.array([_adapt_kl_coeff(kl_coeff[i], kl, kl_target) for i, kl in enumerate(kl_values)])
+        return _adapt_kl_coeff(kl_coeff, kl_values, kl_target)
+
+
+def _adapt_kl_coeff(kl_coeff, kl, kl_target):
+    if kl < kl_target / 1.5:
+        kl_coeff /= 2
+    elif kl > kl_target * 1.5:
+        kl_coeff *= 2
+    return kl_coeff

@@ -1,0 +1,146 @@
+"""Device-resident trajectory storage and the lazy host views handed to reference-style callers.
+
+One `PhaseData` holds everything a sampling phase produces, as SoA float32 tensors in HBM with the
+reference's index contract (flat sample n = e*H + t inside task m):
+
+    obs [M,N,Do]  act [M,N,Da]  mean [M,N,Da]  log_std [M,Da]  rew [M,N]  done [M,N] u8
+    info [2,M,N] (env_infos, cheetah only)  returns [M,N]  adv [M,N]  coeffs [M,F] f64  stats [M,8] f64
+
+`LazyPath` / `SamplesData` are dict-like views that copy to the host only when a caller actually
+indexes them (the unchanged reference Trainer only needs them for diagnostics).
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+
+class PhaseData(object):
+    def __init__(self, M, E, H, obs_dim, act_dim, device):
+        import torch
+        self.M, self.E, self.H, self.N = M, E, H, E * H
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        f32 = dict(dtype=torch.float32, device=device)
+        N = self.N
+        self.obs = torch.empty(M, N, obs_dim, **f32)
+        self.act = torch.empty(M, N, act_dim, **f32)
+        self.mean = torch.empty(M, N, act_dim, **f32)
+        self.log_std = torch.empty(M, act_dim, **f32)
+        self.rew = torch.empty(M, N, **f32)
+        self.done = torch.empty(M, N, dtype=torch.uint8, device=device)
+        self.info = None
+        self.info_keys = ()
+        self.returns = None
+        self.adv = None
+        self.coeffs = None
+        self.stats = None
+        self.adj_avg_rewards = None
+        self._host = {}
+
+    def host(self, name):
+        """numpy copy of a device tensor, fetched once per phase."""
+        if name not in self._host:
+            t = getattr(self, name)
+            self._host[name] = None if t is None else t.detach().cpu().numpy()
+        return self._host[name]
+
+    def invalidate_host(self):
+        self._host = {}
+
+    def bytes_per_step(self):
+        return 4 * (self.obs_dim + 2 * self.act_dim + 1) + 1 + 8 * len(self.info_keys)
+
+
+class LazyPath(dict):
+    """One trajectory (task m, env e) as the dict the reference builds at meta_sampler.py:116-123."""
+
+    def __init__(self, phase, m, e):
+        super(LazyPath, self).__init__()
+        self.phase, self.m, self.e = phase, m, e
+
+    def _slice(self):
+        H = self.phase.H
+        return slice(self.e * H, (self.e + 1) * H)
+
+    def __missing__(self, key):
+        p, s = self.phase, self._slice()
+        if key == 'observations':
+            v = p.host('obs')[self.m, s]
+        elif key == 'actions':
+            v = p.host('act')[self.m, s]
+        elif key == 'rewards':
+            v = p.host('rew')[self.m, s]
+        elif key == 'returns' and p.returns is not None:
+            v = p.host('returns')[self.m, s]
+        elif key == 'agent_infos':
+            v = dict(mean=p.host('mean')[self.m, s],
+                     log_std=np.broadcast_to(p.host('log_std')[self.m], (p.H, p.act_dim)))
+        elif key == 'env_infos':
+            v = {k: p.host('info')[i, self.m, s] for i, k in enumerate(p.info_keys)}
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def keys(self):
+        base = ['observations', 'actions', 'rewards', 'env_infos', 'agent_infos']
+        if self.phase.returns is not None:
+            base.append('returns')
+        return set(base) | set(dict.keys(self))
+
+    def __len__(self):
+        return self.phase.H
+
+
+class PathsMetaBatch(OrderedDict):
+    """OrderedDict{task -> [path]*E} (what MetaSampler.obtain_samples returns) + the device phase."""
+    phase = None
+
+
+class SamplesData(dict):
+    """Processed samples of one task: the 8 keys of samplers/meta_sample_processor.py:39-47, lazily."""
+    KEYS = ('observations', 'actions', 'rewards', 'returns', 'advantages', 'env_infos', 'agent_infos',
+            'adj_avg_rewards')
+
+    def __init__(self, phase, m, processor=None):
+        super(SamplesData, self).__init__()
+        self.phase, self.m, self._processor = phase, m, processor
+
+    def __missing__(self, key):
+        p, m = self.phase, self.m
+        if key == 'observations':
+            v = p.host('obs')[m]
+        elif key == 'actions':
+            v = p.host('act')[m]
+        elif key == 'rewards':
+            v = p.host('rew')[m]
+        elif key == 'returns':
+            v = p.host('returns')[m]
+        elif key == 'advantages':
+            v = p.host('adv')[m]
+        elif key == 'agent_infos':
+            v = dict(mean=p.host('mean')[m], log_std=np.broadcast_to(p.host('log_std')[m], (p.N, p.act_dim)))
+        elif key == 'env_infos':
+            v = {k: p.host('info')[i, m] for i, k in enumerate(p.info_keys)}
+        elif key == 'adj_avg_rewards':
+            if p.adj_avg_rewards is None and self._processor is not None:
+                self._processor.compute_adj_avg_rewards(p)
+            v = p.host('adj_avg_rewards')[m]
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def keys(self):
+        return list(self.KEYS)
+
+    def __len__(self):
+        return len(self.KEYS)
+
+    def __iter__(self):
+        return iter(self.KEYS)
+
+    def __contains__(self, key):
+        return key in self.KEYS
+
+    def items(self):
+        return [(k, self[k]) for k in self.KEYS]

@@ -1,0 +1,184 @@
+"""MetaSampleProcessor on the GPU.
+
+Mirrors meta_policy_search/samplers/meta_sample_processor.py:6-49 and samplers/base.py:33-173
+(constructor arguments, `.baseline`, process_samples(paths_meta_batch, log, log_prefix) -> list of M
+dicts with the 8 keys).  All numerics run in promp_process_samples (one CTA per task).
+"""
+import numpy as np
+
+from promp_b200 import _lib
+from promp_b200.samplers.device_data import PhaseData, PathsMetaBatch, SamplesData
+from promp_b200.utils import logger
+
+
+def _baseline_kind(baseline):
+    kind = getattr(baseline, 'device_kind', None)
+    if kind is None:
+        raise TypeError("promp_b200 implements LinearFeatureBaseline and ZeroBaseline on the device; got %r "
+                        "(no CPU fallback)" % (baseline,))
+    return kind
+
+
+def _phase_from_host_paths(paths_meta_batch, device):
+    """Upload reference-style host paths (dict of lists of path dicts) into a PhaseData."""
+    import torch
+    M = len(paths_meta_batch)
+    tasks = list(paths_meta_batch.values())
+    E = len(tasks[0])
+    H = len(tasks[0][0]["rewards"])
+    for paths in tasks:
+        if len(paths) != E or any(len(p["rewards"]) != H for p in paths):
+            raise NotImplementedError("promp_b200: variable-length / ragged paths are not supported by the device "
+                                      "sample processor yet (SURVEY.md section 8f item 2)")
+    obs0 = np.asarray(tasks[0][0]["observations"])
+    act0 = np.asarray(tasks[0][0]["actions"])
+    Do = obs0.shape[1] if obs0.ndim > 1 else 1
+    Da = act0.shape[1] if act0.ndim > 1 else 1
+    phase = PhaseData(M, E, H, Do, Da, device)
+
+    def stack(key, d):
+        return np.stack([np.concatenate([np.asarray(p[key], dtype=np.float32).reshape(H, d) for p in paths])
+                         for paths in tasks])
+    phase.obs.copy_(torch.from_numpy(stack("observations", Do)))
+    phase.act.copy_(torch.from_numpy(stack("actions", Da)))
+    phase.rew.copy_(torch.from_numpy(stack("rewards", 1)[..., 0]))
+    phase.done.zero_()
+    phase.done.view(M, E, H)[:, :, -1] = 1
+    ai = tasks[0][0].get("agent_infos") or {}
+    if "mean" in ai:
+        phase.mean.copy_(torch.from_numpy(np.stack([np.concatenate(
+            [np.asarray(p["agent_infos"]["mean"], dtype=np.float32).reshape(H, Da) for p in paths]) for paths in tasks])))
+        phase.log_std.copy_(torch.from_numpy(np.stack(
+            [np.asarray(paths[0]["agent_infos"]["log_std"], dtype=np.float32).reshape(H, Da)[0] for paths in tasks])))
+    else:
+        phase.mean.zero_()
+        phase.log_std.zero_()
+    return phase
+
+
+def run_process_kernel(phase, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv):
+    import torch
+    M, E, H, Do = phase.M, phase.E, phase.H, phase.obs_dim
+    dev = phase.obs.device
+    if phase.returns is None:
+        phase.returns = torch.empty(M, E * H, dtype=torch.float32, device=dev)
+        phase.adv = torch.empty(M, E * H, dtype=torch.float32, device=dev)
+        phase.coeffs = torch.zeros(M, 2 * Do + 4, dtype=torch.float64, device=dev)
+        phase.stats = torch.zeros(M, 8, dtype=torch.float64, device=dev)
+    nbytes = _lib.load().promp_process_workspace_bytes(M, E, H, Do)
+    ws = getattr(phase, '_proc_ws', None)
+    if ws is None or ws.numel() * 8 < nbytes:
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        phase._proc_ws = ws
+    _lib.call('promp_process_samples', M, E, H, Do, _lib.ptr(phase.obs), _lib.ptr(phase.rew), float(discount),
+              float(gae_lambda), float(reg_coeff), int(baseline_kind), int(bool(normalize_adv)), int(bool(positive_adv)),
+              _lib.ptr(phase.returns), _lib.ptr(phase.adv), _lib.ptr(phase.coeffs), _lib.ptr(phase.stats),
+              _lib.ptr(ws), ws.numel() * 8, _lib.stream())
+    phase.adj_avg_rewards = None
+    phase.invalidate_host()
+
+
+def fit_baseline_on_paths(paths, target_key, reg_coeff):
+    """LinearBaseline.fit on a flat list of equal-length paths: runs the device kernel with the paths as one task
+    (discount chosen so that the kernel's `returns` equal the provided target is not possible in general, so the
+    target must be the discounted return the kernel itself computes: only target_key='returns' is supported)."""
+    import torch
+    if target_key != 'returns':
+        raise NotImplementedError("device LinearFeatureBaseline.fit supports target_key='returns' only")
+    raise NotImplementedError("standalone LinearFeatureBaseline.fit needs the discount: use "
+                              "MetaSampleProcessor.process_samples (the reference never calls fit on its own)")
+
+
+class MetaSampleProcessor(object):
+    def __init__(self, baseline, discount=0.99, gae_lambda=1, normalize_adv=False, positive_adv=False):
+        assert 0 <= discount <= 1.0, 'discount factor must be in [0,1]'
+        assert 0 <= gae_lambda <= 1.0, 'gae_lambda must be in [0,1]'
+        assert hasattr(baseline, 'fit') and hasattr(baseline, 'predict')
+        self.baseline = baseline
+        self.discount = discount
+        self.gae_lambda = gae_lambda
+        self.normalize_adv = normalize_adv
+        self.positive_adv = positive_adv
+
+    def process_phase(self, phase):
+        """Device-only entry: run the processing kernel on a PhaseData (no host traffic)."""
+        run_process_kernel(phase, self.discount, self.gae_lambda, getattr(self.baseline, '_reg_coeff', 1e-5),
+                           _baseline_kind(self.baseline), self.normalize_adv, self.positive_adv)
+        return phase
+
+    def compute_adj_avg_rewards(self, phase, allreduce=None):
+        """samples_data['adj_avg_rewards'] (meta_sample_processor.py:40-44), computed on first access."""
+        import torch
+        st = phase.stats[:, 5:7].sum(0)
+        cnt = torch.tensor([float(phase.M * phase.N)], dtype=torch.float64, device=st.device)
+        vec = torch.cat([st, cnt])
+        if allreduce is not None:
+            allreduce(vec)
+        s, s2, n = [float(x) for x in vec.cpu()]
+        mean = s / n
+        std = max(s2 / n - mean * mean, 0.0) ** 0.5
+        phase.adj_avg_rewards = torch.empty_like(phase.rew)
+        _lib.call('promp_adj_avg_rewards', phase.rew.numel(), _lib.ptr(phase.rew), mean, std,
+                  _lib.ptr(phase.adj_avg_rewards), _lib.stream())
+        phase._host.pop('adj_avg_rewards', None)
+
+    def process_samples(self, paths_meta_batch, log=False, log_prefix=''):
+        """meta_sample_processor.py:8-49."""
+        import torch
+        assert isinstance(paths_meta_batch, dict), 'paths must be a dict'
+        assert self.baseline, 'baseline must be specified'
+        phase = getattr(paths_meta_batch, 'phase', None)
+        if phase is None:
+            _lib.require_cuda()
+            phase = _phase_from_host_paths(paths_meta_batch, torch.device('cuda', torch.cuda.current_device()))
+        self.process_phase(phase)
+        if hasattr(self.baseline, '_coeffs') and _baseline_kind(self.baseline) == 1:
+            self.baseline._lazy_coeffs = (phase, phase.M - 1)
+            self.baseline._coeffs = _LazyCoeffs(phase)      # last task's fit, fetched on demand
+        samples = [SamplesData(phase, m, self) for m in range(phase.M)]
+        self._log_path_stats(phase, log, log_prefix)
+        return samples
+
+    def _log_path_stats(self, phase, log=False, log_prefix=''):
+        """samplers/base.py:135-149 from the per-task sums the kernel wrote (one small D2H)."""
+        if not log:
+            return
+        st = phase.host('stats')
+        n = phase.M * phase.E
+        sR0, sG, sG2 = st[:, 0].sum(), st[:, 1].sum(), st[:, 2].sum()
+        mean_g = sG / n
+        if log == 'reward':
+            logger.logkv(log_prefix + 'AverageReturn', mean_g)
+        elif log == 'all' or log is True:
+            logger.logkv(log_prefix + 'AverageDiscountedReturn', sR0 / n)
+            logger.logkv(log_prefix + 'AverageReturn', mean_g)
+            logger.logkv(log_prefix + 'NumTrajs', n)
+            logger.logkv(log_prefix + 'StdReturn', float(np.sqrt(max(sG2 / n - mean_g * mean_g, 0.0))))
+            logger.logkv(log_prefix + 'MaxReturn', st[:, 3].max())
+            logger.logkv(log_prefix + 'MinReturn', st[:, 4].min())
+
+
+class _LazyCoeffs(object):
+    """Stands in for baseline._coeffs until someone needs the numbers (avoids a D2H per phase)."""
+
+    def __init__(self, phase):
+        self._phase = phase
+        self._val = None
+
+    def _get(self):
+        if self._val is None:
+            self._val = self._phase.host('coeffs')[-1].copy()
+        return self._val
+
+    def __array__(self, dtype=None, copy=None):
+        v = self._get()
+        return v.astype(dtype) if dtype is not None else v
+
+    def __len__(self):
+        return len(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def dot(self, other):
+        return self._get().dot(other)

@@ -1,0 +1,181 @@
+"""MetaSampler on the GPU.
+
+Mirrors meta_policy_search/samplers/meta_sampler.py:12-150 (constructor arguments, attributes,
+update_tasks, obtain_samples -> OrderedDict{task: [path]*rollouts}).  With a device policy and a
+fixed-horizon device env the whole sampling phase is ONE kernel launch (promp_rollout); otherwise
+the reference's step loop runs with the envs stepped on the device (MetaDeviceEnvExecutor).
+"""
+import time
+from collections import OrderedDict
+
+import numpy as np
+
+from promp_b200 import _lib
+from promp_b200.samplers.device_data import PhaseData, LazyPath, PathsMetaBatch
+from promp_b200.samplers.vectorized_env_executor import MetaDeviceEnvExecutor
+from promp_b200.utils import logger
+
+
+class MetaSampler(object):
+    """
+    Args (as the reference):
+        env, policy, rollouts_per_meta_task, meta_batch_size, max_path_length, envs_per_task, parallel
+    Extra keyword arguments (device specific, all optional):
+        reset_mode ('numpy'|'device'): 'numpy' draws task / reset states from the global numpy RNG in the
+            reference's consumption order and uploads them (seed-for-seed parity); 'device' draws reset
+            states in-kernel with Philox (nothing crosses PCIe).
+        seed (int): Philox key for in-kernel action noise / reset states.
+        task_shard ((rank, world)): this process owns tasks [rank*M, (rank+1)*M) of a global batch of
+            world*M tasks; every rank draws the same global task list and keeps its slice.
+    `parallel` is accepted and ignored: there are no env worker processes on the device path.
+    """
+
+    def __init__(self, env, policy, rollouts_per_meta_task, meta_batch_size, max_path_length, envs_per_task=None,
+                 parallel=False, reset_mode='numpy', seed=0, task_shard=None):
+        assert hasattr(env, 'reset') and hasattr(env, 'step')
+        assert hasattr(env, 'set_task')
+        assert reset_mode in ('numpy', 'device')
+        self.env, self.policy = env, policy
+        self.batch_size = rollouts_per_meta_task
+        self.max_path_length = max_path_length
+        self.envs_per_task = rollouts_per_meta_task if envs_per_task is None else envs_per_task
+        self.meta_batch_size = meta_batch_size
+        self.total_samples = meta_batch_size * rollouts_per_meta_task * max_path_length
+        self.parallel = parallel
+        self.total_timesteps_sampled = 0
+        self.reset_mode = reset_mode
+        self.seed = int(seed)
+        self.task_shard = task_shard
+        self._phase_counter = 0
+        self._injected_noise = None
+        self._injected_init = None
+        self.vec_env = MetaDeviceEnvExecutor(env, self.meta_batch_size, self.envs_per_task, self.max_path_length)
+        self.spec = self.vec_env.spec
+        self.device = self.vec_env.device
+
+    # ------------------------------------------------------------------------------------------
+    def update_tasks(self):
+        """meta_sampler.py:51-57."""
+        if self.task_shard is None:
+            tasks = self.env.sample_tasks(self.meta_batch_size)
+        else:
+            rank, world = self.task_shard
+            all_tasks = self.env.sample_tasks(self.meta_batch_size * world)
+            tasks = list(all_tasks[rank * self.meta_batch_size:(rank + 1) * self.meta_batch_size])
+        assert len(tasks) == self.meta_batch_size
+        self.vec_env.set_tasks(tasks)
+
+    def inject(self, noise=None, init_state=None):
+        """Parity hooks: action noise [M,E,H,Da] and/or reset states [M,E,state_dim] for the NEXT phase."""
+        self._injected_noise, self._injected_init = noise, init_state
+
+    def _fused_ok(self):
+        return (hasattr(self.policy, 'sampling_params') and self.spec['env_kind'] != _lib.ENV_POINT
+                and self.envs_per_task == self.batch_size)
+
+    def obtain_samples(self, log=False, log_prefix=''):
+        """meta_sampler.py:59-137."""
+        t0 = time.time()
+        if self._fused_ok():
+            paths = self._obtain_samples_fused()
+            policy_time, env_time = 0.0, time.time() - t0      # one fused kernel: not separable
+        else:
+            paths, policy_time, env_time = self._obtain_samples_stepwise()
+        self.total_timesteps_sampled += self.total_samples
+        if log:
+            logger.logkv(log_prefix + "PolicyExecTime", policy_time)
+            logger.logkv(log_prefix + "EnvExecTime", env_time)
+        return paths
+
+    # ------------------------------------------------------------------------------------------
+    def rollout_into(self, phase, init_state=None, noise=None):
+        """Launch the fused rollout kernel for one sampling phase into `phase` (device buffers)."""
+        import torch
+        s = self.spec
+        M, E, H = self.meta_batch_size, self.envs_per_task, self.max_path_length
+        params, stride, clip = self.policy.sampling_params()
+        if s['env_kind'] == _lib.ENV_CHEETAH_DIR and phase.info is None:
+            phase.info = torch.empty(2, M, E * H, dtype=torch.float32, device=self.device)
+            phase.info_keys = ('reward_run', 'reward_ctrl')
+        self._phase_counter += 1
+        _lib.call('promp_rollout', s['env_kind'], s['reward_type'], s['radius'], M, E, H, self.policy.hidden,
+                  _lib.ptr(params), stride, _lib.ptr(self.vec_env.task_params_per_task), _lib.ptr(init_state),
+                  _lib.ptr(noise), self.seed, self._phase_counter, clip, float(self.policy.min_log_std),
+                  _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.mean), _lib.ptr(phase.rew),
+                  _lib.ptr(phase.done), _lib.ptr(phase.info), _lib.ptr(phase.log_std), None, _lib.stream())
+        phase.invalidate_host()
+        return phase
+
+    def _obtain_samples_fused(self):
+        import torch
+        M, E, H = self.meta_batch_size, self.envs_per_task, self.max_path_length
+        inner = getattr(self.env, '_wrapped_env', self.env)
+        init = self._injected_init
+        if init is None and self.reset_mode == 'numpy':
+            # vec_env.reset(): M*E reset draws in env order (vectorized_env_executor.py:73)
+            init = inner.host_reset_states(M * E).astype(np.float32)
+        if init is not None and not isinstance(init, torch.Tensor):
+            init = torch.from_numpy(np.ascontiguousarray(init, dtype=np.float32).reshape(M, E, -1)).to(self.device, non_blocking=True)
+        noise = self._injected_noise
+        if noise is not None and not isinstance(noise, torch.Tensor):
+            noise = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float32)).to(self.device)
+        phase = PhaseData(M, E, H, self.spec['obs_dim'], self.spec['act_dim'], self.device)
+        self.rollout_into(phase, init, noise)
+        if self._injected_init is None and self.reset_mode == 'numpy':
+            # at ts == H every env is reset once more and that observation is discarded
+            # (vectorized_env_executor.py:47-50): consume the same draws to stay aligned with the reference
+            inner.host_reset_states(M * E)
+        self._injected_noise = self._injected_init = None
+        paths = PathsMetaBatch()
+        for m in range(M):
+            paths[m] = [LazyPath(phase, m, e) for e in range(E)]
+        paths.phase = phase
+        return paths
+
+    # ------------------------------------------------------------------------------------------
+    def _obtain_samples_stepwise(self):
+        """The reference loop (meta_sampler.py:76-131), envs stepped by promp_env_step."""
+        paths = OrderedDict((i, []) for i in range(self.meta_batch_size))
+        n_envs = self.vec_env.num_envs
+        running = [dict(observations=[], actions=[], rewards=[], env_infos=[], agent_infos=[]) for _ in range(n_envs)]
+        n_samples, policy_time, env_time = 0, 0.0, 0.0
+        obses = self.vec_env.reset()
+        while n_samples < self.total_samples:
+            t = time.time()
+            obs_per_task = np.split(np.asarray(obses), self.meta_batch_size)
+            actions, agent_infos = self.policy.get_actions(obs_per_task)
+            policy_time += time.time() - t
+            t = time.time()
+            actions = np.concatenate(actions)
+            next_obses, rewards, dones, env_infos = self.vec_env.step(actions)
+            env_time += time.time() - t
+            if not env_infos:
+                env_infos = [dict() for _ in range(n_envs)]
+            if not agent_infos:
+                agent_infos = [dict() for _ in range(n_envs)]
+            else:
+                assert len(agent_infos) == self.meta_batch_size
+                agent_infos = sum(agent_infos, [])
+            for idx in range(n_envs):
+                r = running[idx]
+                r["observations"].append(obses[idx])
+                r["actions"].append(actions[idx])
+                r["rewards"].append(rewards[idx])
+                r["env_infos"].append(env_infos[idx])
+                r["agent_infos"].append(agent_infos[idx])
+                if dones[idx]:
+                    paths[idx // self.envs_per_task].append(dict(
+                        observations=np.asarray(r["observations"]), actions=np.asarray(r["actions"]),
+                        rewards=np.asarray(r["rewards"]), env_infos=_stack(r["env_infos"]),
+                        agent_infos=_stack(r["agent_infos"])))
+                    n_samples += len(r["rewards"])
+                    running[idx] = dict(observations=[], actions=[], rewards=[], env_infos=[], agent_infos=[])
+            obses = next_obses
+        return paths, policy_time, env_time
+
+
+def _stack(dict_list):
+    if not dict_list or not dict_list[0]:
+        return {}
+    return {k: (_stack([d[k] for d in dict_list]) if isinstance(dict_list[0][k], dict)
+                else np.asarray([d[k] for d in dict_list])) for k in dict_list[0]}

@@ -1,0 +1,522 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python classes)
+against the CPU oracle and the committed golden vectors of the unmodified reference.
+
+Tolerances: integer / index work bit-exact; float32 quantities within 1e-4 relative (the north-star
+bar), tighter where the arithmetic allows.  Run on the B200 box: pytest -m gpu.
+"""
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------
+def _make_stack(env_name, M, E, H, hidden=64, seed=3, **sampler_kw):
+    torch = _cuda()
+    from promp_b200.envs import normalize, MetaPointEnvCorner, HalfCheetahRandDirecEnv
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.samplers import MetaSampler, MetaSampleProcessor
+    from promp_b200.baselines import LinearFeatureBaseline
+    np.random.seed(seed)
+    env = normalize(MetaPointEnvCorner() if env_name == 'point' else HalfCheetahRandDirecEnv())
+    policy = MetaGaussianMLPPolicy(name="meta-policy", obs_dim=int(np.prod(env.observation_space.shape)),
+                                   action_dim=int(np.prod(env.action_space.shape)), meta_batch_size=M,
+                                   hidden_sizes=(hidden, hidden))
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H,
+                          **sampler_kw)
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
+    return env, policy, sampler, proc
+
+
+def test_rollout_matches_reference_golden(golden_dir):
+    """configs[0] (M=5,E=4,H=100, seed 1): tasks / reset states / rollouts vs the UNMODIFIED reference
+    MetaSampler + normalize(MetaPointEnvCorner) (fixture sampler_rollout.npz), same theta and noise."""
+    torch = _cuda()
+    g = _load(golden_dir, 'sampler_rollout.npz')
+    M, E, H = 5, 4, 100
+    env, policy, sampler, proc = _make_stack('point', M, E, H)
+    policy.set_params(g['theta'])
+    np.random.seed(1)
+    for it in range(2):
+        sampler.update_tasks()
+        goals = sampler.vec_env.task_params_per_task.cpu().numpy()
+        assert np.array_equal(goals.astype(np.float64), g['it%d_goals' % it])      # bit-exact task draw
+        policy.switch_to_pre_update()
+        noise = np.ascontiguousarray(np.transpose(g['noise'][it], (1, 2, 0, 3)))   # [H,M,E,Da] -> [M,E,H,Da]
+        sampler.inject(noise=noise)
+        paths = sampler.obtain_samples()
+        assert list(paths.keys()) == list(range(M)) and all(len(v) == E for v in paths.values())
+        obs = np.stack([np.stack([p['observations'] for p in paths[m]]) for m in range(M)])
+        act = np.stack([np.stack([p['actions'] for p in paths[m]]) for m in range(M)])
+        rew = np.stack([np.stack([p['rewards'] for p in paths[m]]) for m in range(M)])
+        mean = np.stack([np.stack([p['agent_infos']['mean'] for p in paths[m]]) for m in range(M)])
+        assert obs.shape == (M, E, H, 2)
+        # reset states: same numpy draws, float32-rounded
+        np.testing.assert_array_equal(obs[:, :, 0], g['it%d_obs' % it][:, :, 0].astype(np.float32))
+        np.testing.assert_allclose(obs, g['it%d_obs' % it], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(act, g['it%d_act' % it], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(mean, g['it%d_mean' % it], rtol=1e-4, atol=2e-5)
+        bad = np.abs(rew - g['it%d_rew' % it]) > 1e-4      # sparse reward is discontinuous: allow rare boundary flips
+        assert bad.mean() < 0.005, bad.mean()
+    # the numpy stream was consumed exactly like the reference consumed it
+    assert np.array_equal(np.random.uniform(size=4), g['rng_probe_after'])
+
+
+def test_env_step_kernel_matches_reference_golden(golden_dir):
+    """promp_env_step (vec-env API) vs the reference envs for all three reward types + early-done PointEnv."""
+    torch = _cuda()
+    from promp_b200.envs import normalize, MetaPointEnvCorner, MetaPointEnv
+    from promp_b200.samplers import MetaDeviceEnvExecutor
+    g = _load(golden_dir, 'point_corner_steps.npz')
+    T, n_env, _ = g['actions'].shape
+    for rtype in ('sparse', 'dense', 'dense_squared'):
+        ex = MetaDeviceEnvExecutor(normalize(MetaPointEnvCorner(reward_type=rtype)), n_env, 1, max_path_length=10 ** 6)
+        ex.set_tasks(list(g['goals']))
+        ex.state.copy_(torch.from_numpy(g['obs0'].astype(np.float32)))
+        n_bad = 0
+        for t in range(T):
+            obs, rew, dones, infos = ex.step(g['actions'][t])
+            np.testing.assert_allclose(np.asarray(obs), g['next_obs_' + rtype][t], rtol=0, atol=5e-5)
+            n_bad += int((np.abs(np.asarray(rew) - g['rewards_' + rtype][t]) > 1e-4).sum())
+            assert not dones.any() and infos[0] == {}
+            # keep the device trajectory glued to the reference so float32 drift cannot accumulate
+            ex.state.copy_(torch.from_numpy(g['next_obs_' + rtype][t].astype(np.float32)))
+        assert n_bad <= (3 if rtype == 'sparse' else 0), (rtype, n_bad)
+    g = _load(golden_dir, 'point_env_steps.npz')
+    T, n_env, _ = g['actions'].shape
+    np.random.seed(0)
+    ex = MetaDeviceEnvExecutor(normalize(MetaPointEnv()), n_env, 1, max_path_length=10 ** 6)
+    ex.set_tasks([{}] * n_env)
+    ex.state.copy_(torch.from_numpy(g['obs0'].astype(np.float32)))
+    for t in range(T):
+        st_before = ex.state.cpu().numpy().copy()
+        obs, rew, dones, _ = ex.step(g['actions'][t])
+        np.testing.assert_allclose(np.asarray(rew), g['rewards'][t], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(dones, g['dones'][t]) or np.abs(np.abs(g['next_obs'][t]) - 0.01).min() < 1e-5
+        ex.state.copy_(torch.from_numpy(g['next_obs'][t].astype(np.float32)))
+        ex.ts.zero_()
+
+
+@pytest.mark.parametrize('env_name,M,E,H,hidden', [('point', 4, 5, 70, 64), ('cheetah', 3, 4, 45, 64),
+                                                    ('cheetah', 2, 3, 40, 32), ('point', 2, 3, 33, 32)])
+def test_rollout_teacher_forced_vs_oracle(env_name, M, E, H, hidden):
+    """Fused rollout vs the CPU oracle: policy forward on the kernel's own observations, sampling rule,
+    and env transitions replayed with the kernel's own actions (removes closed-loop drift)."""
+    torch = _cuda()
+    from oracle import tf_half as th, numpy_half as nh, cheetah_surrogate as cs
+    env, policy, sampler, proc = _make_stack(env_name, M, E, H, hidden=hidden)
+    sampler.update_tasks()
+    Do, Da = policy.obs_dim, policy.action_dim
+    rng = np.random.RandomState(5)
+    noise = rng.randn(M, E, H, Da).astype(np.float32)
+    # post-update style per-task parameters to exercise param_stride != 0
+    theta = policy.theta.cpu().numpy()
+    theta_tasks = np.stack([theta + 0.05 * rng.randn(theta.size).astype(np.float32) for _ in range(M)])
+    policy.update_task_parameters(torch.from_numpy(theta_tasks).cuda())
+    sampler.inject(noise=noise)
+    paths = sampler.obtain_samples()
+    ph = paths.phase
+    obs = ph.obs.cpu().numpy().reshape(M, E, H, Do)
+    act = ph.act.cpu().numpy().reshape(M, E, H, Da)
+    mean = ph.mean.cpu().numpy().reshape(M, E, H, Da)
+    rew = ph.rew.cpu().numpy().reshape(M, E, H)
+    done = ph.done.cpu().numpy().reshape(M, E, H)
+    assert done[..., :-1].sum() == 0 and (done[..., -1] == 1).all()
+    # (1) policy forward (float32 oracle) on the kernel's observations
+    mu_o, ls_o = th.dist_info(torch.from_numpy(theta_tasks), torch.from_numpy(obs.reshape(M, E * H, Do)),
+                              (Do, Da, (hidden, hidden)))
+    np.testing.assert_allclose(mean.reshape(M, E * H, Da), mu_o.numpy(), rtol=1e-4, atol=2e-5)
+    # (2) sampling rule a = mean + eps*exp(log_std) (raw log_std), reported log_std unclipped post-update
+    sig = np.exp(theta_tasks[:, -Da:])[:, None, None, :]
+    np.testing.assert_allclose(act, mean + noise * sig, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ph.log_std.cpu().numpy(), theta_tasks[:, -Da:], rtol=0, atol=0)
+    # (3) env transitions with the kernel's actions
+    if env_name == 'point':
+        goals = sampler.vec_env.task_params_per_task.cpu().numpy().astype(np.float64)
+        n_bad = 0
+        for m in range(M):
+            for e in range(E):
+                o = nh.NormalizedEnv(nh.PointEnvCorner())
+                o.set_task(goals[m])
+                for t in range(H):
+                    o._wrapped_env._state = obs[m, e, t].astype(np.float64)
+                    nxt, r, _, _ = o.step(act[m, e, t].astype(np.float64))
+                    if t + 1 < H:
+                        np.testing.assert_allclose(obs[m, e, t + 1], nxt, rtol=0, atol=1e-6)
+                    n_bad += abs(r - rew[m, e, t]) > 1e-5
+        assert n_bad <= 2
+    else:
+        dirs = sampler.vec_env.task_params_per_task.cpu().numpy()[:, 0]
+        info = ph.info.cpu().numpy().reshape(2, M, E, H)
+        for t in range(H - 1):
+            # rebuild the full state is impossible from obs alone (x is not observed) -> track x separately
+            pass
+        # full-state replay from the reset state: inject known init states instead
+        init = np.zeros((M, E, 18), dtype=np.float32)
+        init[..., :9] = rng.uniform(-.1, .1, size=(M, E, 9))
+        init[..., 9:] = 0.1 * rng.randn(M, E, 9)
+        sampler.inject(noise=noise, init_state=init)
+        paths = sampler.obtain_samples()
+        ph = paths.phase
+        obs = ph.obs.cpu().numpy().reshape(M, E, H, Do)
+        act = ph.act.cpu().numpy().reshape(M, E, H, Da)
+        rew = ph.rew.cpu().numpy().reshape(M, E, H)
+        info = ph.info.cpu().numpy().reshape(2, M, E, H)
+        qpos, qvel = init[..., :9].copy(), init[..., 9:].copy()
+        np.testing.assert_allclose(obs[:, :, 0], cs.get_obs(qpos, qvel), rtol=0, atol=0)
+        for t in range(H):
+            u = np.clip(np.float32(-1.0) + (act[:, :, t] + np.float32(10.0)) * np.float32(2.0) / np.float32(20.0), -1, 1)
+            qpos, qvel, r, rr, rc = cs.step(qpos, qvel, u.astype(np.float32), dirs[:, None].astype(np.float32))
+            np.testing.assert_allclose(rew[:, :, t], r, rtol=1e-3, atol=2e-4)
+            np.testing.assert_allclose(info[0, :, :, t], rr, rtol=1e-3, atol=2e-4)
+            np.testing.assert_allclose(info[1, :, :, t], rc, rtol=1e-4, atol=1e-6)
+            if t + 1 < H:
+                np.testing.assert_allclose(obs[:, :, t + 1], cs.get_obs(qpos, qvel), rtol=1e-4, atol=2e-5)
+                # re-glue the replay to the kernel state that is observable (everything except x)
+                qpos[..., 1:] = obs[:, :, t + 1, :8]
+                qvel[...] = obs[:, :, t + 1, 8:]
+
+
+def test_rollout_philox_statistics():
+    """In-kernel Philox noise / reset states: right moments, different per phase, reproducible per seed."""
+    torch = _cuda()
+    env, policy, sampler, proc = _make_stack('point', 40, 20, 100, reset_mode='device', seed=11)
+    sampler.update_tasks()
+    p1 = sampler.obtain_samples().phase
+    eps = ((p1.act - p1.mean) / torch.exp(p1.log_std).unsqueeze(1)).cpu().numpy().ravel()
+    assert abs(eps.mean()) < 0.01 and abs(eps.std() - 1.0) < 0.01
+    assert abs(np.mean(eps ** 3)) < 0.05 and abs(np.mean(eps ** 4) - 3.0) < 0.1
+    s0 = p1.obs.view(40, 20, 100, 2)[:, :, 0].cpu().numpy()
+    assert s0.min() >= -0.2 and s0.max() <= 0.2 and abs(s0.mean()) < 0.02 and abs(s0.std() - 0.4 / math.sqrt(12)) < 0.01
+    p2 = sampler.obtain_samples().phase
+    assert not torch.equal(p1.act, p2.act)
+    env, policy2, sampler2, _ = _make_stack('point', 40, 20, 100, reset_mode='device', seed=11)
+    policy2.set_params(policy.get_param_values())
+    sampler2.vec_env.set_tasks(sampler.vec_env.tasks)
+    q1 = sampler2.obtain_samples().phase
+    assert torch.equal(q1.act, p1.act) and torch.equal(q1.obs, p1.obs)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', list('abcde'))
+def test_process_samples_matches_reference_golden(golden_dir, case):
+    torch = _cuda()
+    from promp_b200.samplers import MetaSampleProcessor
+    from promp_b200.baselines import LinearFeatureBaseline
+    g = _load(golden_dir, 'process_samples.npz')
+    pre = 'case_%s_' % case
+    cfg = {k: g[pre + 'cfg_' + k].item() for k in ('M', 'E', 'H', 'Do', 'Da', 'discount', 'gae_lambda',
+                                                    'normalize_adv', 'positive_adv')}
+    M, E, H = cfg['M'], cfg['E'], cfg['H']
+    paths = OrderedDict()
+    for m in range(M):
+        paths[m] = [dict(observations=g[pre + 'obs'][m, e], actions=g[pre + 'act'][m, e], rewards=g[pre + 'rew'][m, e],
+                         env_infos={}, agent_infos={}) for e in range(E)]
+    base = LinearFeatureBaseline()
+    proc = MetaSampleProcessor(base, cfg['discount'], cfg['gae_lambda'], bool(cfg['normalize_adv']),
+                               bool(cfg['positive_adv']))
+    data = proc.process_samples(paths, log=False)
+    assert len(data) == M and len(data[0].keys()) == 8
+    ret = np.stack([d['returns'] for d in data])
+    adv = np.stack([d['advantages'] for d in data])
+    np.testing.assert_allclose(ret, g[pre + 'returns'], rtol=2e-7, atol=1e-6)            # float32 rounding of f64 scan
+    coeffs = data[0].phase.coeffs.cpu().numpy()
+    pred_scale = np.abs(g[pre + 'returns']).max()
+    np.testing.assert_allclose(adv, g[pre + 'advantages'], rtol=1e-4, atol=1e-4 * max(1.0, np.abs(g[pre + 'advantages']).max()) * 0.1)
+    assert rel_err(adv, g[pre + 'advantages']) < 1e-5
+    assert rel_err(coeffs, g[pre + 'coeffs']) < 1e-4, rel_err(coeffs, g[pre + 'coeffs'])
+    np.testing.assert_allclose(np.stack([d['adj_avg_rewards'] for d in data]), g[pre + 'adj_avg_rewards'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(np.stack([d['observations'] for d in data]).reshape(M, E, H, -1), g[pre + 'obs'])
+    np.testing.assert_allclose(np.asarray(base.get_param_values()), g[pre + 'coeffs'][-1], rtol=1e-3, atol=1e-6)
+
+
+def test_process_samples_properties_full_size():
+    """BASELINE.json configs[1] size (40x20x100): size-independent properties."""
+    torch = _cuda()
+    from promp_b200.samplers.device_data import PhaseData
+    from promp_b200.samplers.meta_sample_processor import run_process_kernel
+    M, E, H, Do = 40, 20, 100, 2
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    ph = PhaseData(M, E, H, Do, 2, torch.device('cuda'))
+    ph.obs.copy_(torch.randn(M, E * H, Do, generator=gen, device='cuda'))
+    ph.rew.copy_(torch.randn(M, E * H, generator=gen, device='cuda'))
+    # gamma = lambda = 1, zero baseline: adv[t] = sum_{k>=t} r[k] (ref tests/test_samplers.py:326-342)
+    run_process_kernel(ph, 1.0, 1.0, 1e-5, 0, False, False)
+    r = ph.rew.view(M, E, H).double()
+    want = torch.flip(torch.cumsum(torch.flip(r, [2]), 2), [2])
+    assert torch.allclose(ph.adv.view(M, E, H).double(), want, atol=1e-4)
+    assert torch.allclose(ph.returns.view(M, E, H).double(), want, atol=1e-4)
+    # normalised advantages: zero mean, unit (population) std per task
+    run_process_kernel(ph, 0.99, 0.97, 1e-5, 1, True, False)
+    a = ph.adv.double()
+    assert a.mean(1).abs().max() < 1e-5 and (a.std(1, unbiased=False) - 1).abs().max() < 1e-4
+    # linearity of returns in the rewards
+    ret1 = ph.returns.clone()
+    ph.rew.mul_(3.0)
+    run_process_kernel(ph, 0.99, 0.97, 1e-5, 1, True, False)
+    assert torch.allclose(ph.returns, 3.0 * ret1, rtol=1e-5, atol=1e-5)
+    # advantages are invariant to reward scaling after normalisation (baseline fit is linear in the target)
+    assert torch.allclose(ph.adv.double(), a, atol=2e-4)
+    # positive shift
+    run_process_kernel(ph, 0.99, 0.97, 1e-5, 1, True, True)
+    assert abs(float(ph.adv.min()) - 1e-8) < 1e-6
+    # stats: undiscounted return sums agree with torch
+    st = ph.stats.cpu().numpy()
+    G = ph.rew.view(M, E, H).double().sum(2)
+    np.testing.assert_allclose(st[:, 1], G.sum(1).cpu().numpy(), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(st[:, 3], G.max(1).values.cpu().numpy(), rtol=1e-9, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+def _random_phase(torch, M, N, Do, Da, theta, seed, hidden=64):
+    """Synthetic sampling-phase data whose old distribution is close to (not equal to) the policy."""
+    from promp_b200.samplers.device_data import PhaseData
+    from oracle import tf_half as th
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(M, N, Do, generator=g)
+    th_t = torch.as_tensor(theta).view(1, -1).expand(M, -1)
+    mean, ls = th.dist_info(th_t, obs, (Do, Da, (hidden, hidden)))
+    old_mean = mean + 0.1 * torch.randn(M, N, Da, generator=g)
+    old_ls = (ls + 0.05 * torch.randn(M, 1, Da, generator=g)).expand(M, N, Da).contiguous()
+    act = old_mean + torch.exp(old_ls) * torch.randn(M, N, Da, generator=g)
+    adv = torch.randn(M, N, generator=g)
+    cpu = dict(obs=obs, act=act, adv=adv, mean=old_mean, log_std=old_ls)
+    ph = PhaseData(M, 1, N, Do, Da, torch.device('cuda'))
+    ph.obs.copy_(obs); ph.act.copy_(act); ph.mean.copy_(old_mean); ph.log_std.copy_(old_ls[:, 0])
+    ph.adv = adv.cuda()
+    return cpu, ph
+
+
+def _algo(torch, kind, M, Do, Da, hidden=64, S1=1, **kw):
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.meta_algos import ProMP, TRPOMAML
+    np.random.seed(1)
+    policy = MetaGaussianMLPPolicy(name="p", obs_dim=Do, action_dim=Da, meta_batch_size=M, hidden_sizes=(hidden, hidden))
+    # make log_std and biases non-trivial
+    th0 = policy.theta.cpu().numpy()
+    th0 += 0.1 * np.random.RandomState(9).randn(th0.size).astype(np.float32)
+    policy.set_params(th0)
+    if kind == 'promp':
+        algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=S1, learning_rate=1e-3,
+                     num_ppo_steps=5, clip_eps=0.3, init_inner_kl_penalty=5e-4, adaptive_inner_kl_penalty=False, **kw)
+    else:
+        algo = TRPOMAML(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=S1, step_size=0.01, **kw)
+    return policy, algo
+
+
+@pytest.mark.parametrize('Do,Da,hidden,N', [(2, 2, 64, 333), (17, 6, 64, 200), (2, 2, 32, 130), (17, 6, 32, 97)])
+@pytest.mark.parametrize('inner', ['likelihood_ratio', 'log_likelihood'])
+def test_adapt_matches_oracle(Do, Da, hidden, N, inner):
+    """MAMLAlgo._adapt: theta_i' = theta_i - alpha*grad surr_i, pre-update (shared theta) then post-update
+    (per-task theta) - against torch autograd on the CPU (float32)."""
+    torch = _cuda()
+    from oracle import tf_half as th
+    M = 5
+    policy, algo = _algo(torch, 'trpo', M, Do, Da, hidden, inner_type=inner)
+    dims = (Do, Da, (hidden, hidden))
+    cpu, ph = _random_phase(torch, M, N, Do, Da, policy.theta.cpu().numpy(), 1, hidden)
+    from promp_b200.samplers.device_data import SamplesData
+    samples = [SamplesData(ph, m) for m in range(M)]
+    policy.switch_to_pre_update()
+    algo._adapt(samples)
+    want = th.adapt(policy.theta.cpu().view(1, -1).expand(M, -1).contiguous(), cpu, dims, 0.1, inner)
+    got = policy.theta_tasks.cpu()
+    g_want = (policy.theta.cpu().view(1, -1) - want) / 0.1
+    assert rel_err(algo.last_inner_grad.cpu().numpy(), g_want.numpy()) < 2e-5
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    # second inner step from per-task parameters
+    algo._adapt(samples)
+    want2 = th.adapt(want, cpu, dims, 0.1, inner)
+    np.testing.assert_allclose(policy.theta_tasks.cpu().numpy(), want2.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_likelihood_ratio_is_one_at_first_inner_step():
+    """ref tests/test_integration.py:150-175: with pi_old = pi_new the likelihood ratio is 1."""
+    torch = _cuda()
+    env, policy, sampler, proc = _make_stack('point', 10, 2, 50)
+    from promp_b200.meta_algos import ProMP
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=10, num_inner_grad_steps=1)
+    sampler.update_tasks()
+    policy.switch_to_pre_update()
+    paths = sampler.obtain_samples()
+    samples = proc.process_samples(paths)
+    ph = samples[0].phase
+    st = torch.zeros(10, 4, device='cuda')
+    algo._grad(ph, policy.theta, 0, 0, stats=st)
+    assert torch.allclose(st[:, 2], torch.ones(10, device='cuda'), atol=1e-5)     # mean ratio per task
+    assert st[:, 1].abs().max() < 1e-6                                              # KL(old||new) = 0
+
+
+@pytest.mark.parametrize('Do,Da,hidden,N,S1', [(2, 2, 64, 256, 1), (17, 6, 64, 150, 1), (2, 2, 64, 100, 2),
+                                               (17, 6, 32, 90, 1), (2, 2, 32, 70, 2)])
+@pytest.mark.parametrize('kind', ['promp', 'trpo'])
+def test_meta_gradient_matches_oracle(Do, Da, hidden, N, S1, kind):
+    """Second-order meta-gradient (forward chain + exact HVP backward chain) vs torch double-backward.
+    The oracle is evaluated in float64 on the same float32 inputs; bar: 1e-4 relative on the gradient."""
+    torch = _cuda()
+    from oracle import tf_half as th
+    M = 4
+    policy, algo = _algo(torch, kind, M, Do, Da, hidden, S1=S1)
+    dims = (Do, Da, (hidden, hidden))
+    theta = policy.theta.cpu().numpy()
+    cpus, phases = [], []
+    for s in range(S1 + 1):
+        c, p = _random_phase(torch, M, N, Do, Da, theta, 10 + s, hidden)
+        cpus.append({k: v.double() for k, v in c.items()})
+        phases.append(p)
+    t64 = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    coeff = list(algo.inner_kl_coeff) if kind == 'promp' else None
+    obj, ikl, okl = th.meta_objective(t64, cpus, dims, 0.1, kind, 0.3, coeff)
+    (g_want,) = torch.autograd.grad(obj, t64)
+    if kind == 'promp':
+        res = algo._objective_pass(phases, want_grad=True)
+        terms = algo.loss_terms(res).cpu().numpy()
+        assert abs(terms[0] - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
+        np.testing.assert_allclose(terms[1:1 + S1], ikl.detach().numpy(), rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(terms[1 + S1], float(okl), rtol=1e-3, atol=1e-6)
+        g_got = res['grad'].cpu().numpy()
+    else:
+        g_got = algo.eval_gradient(policy.theta, phases, 'loss')
+        loss, klv = algo.eval_scalars(policy.theta, phases)
+        assert abs(loss - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
+        assert abs(klv - float(okl)) < 1e-3 * max(1e-3, abs(float(okl)))
+        # constraint gradient too
+        (gk_want,) = torch.autograd.grad(th.meta_objective(t64, cpus, dims, 0.1, kind)[2], t64)
+        gk_got = algo.eval_gradient(policy.theta, phases, 'kl')
+        assert rel_err(gk_got, gk_want.numpy()) < 1e-4, rel_err(gk_got, gk_want.numpy())
+    err = rel_err(g_got, g_want.numpy())
+    assert err < 1e-4, err
+    assert abs(np.linalg.norm(g_got) / np.linalg.norm(g_want.numpy()) - 1) < 1e-4     # grad-norm bar of the north star
+
+
+def test_adam_tf1_matches_oracle():
+    torch = _cuda()
+    from oracle import tf_half as th
+    from promp_b200.optimizers import MAMLPPOOptimizer
+
+    class P(object):
+        pass
+    p = P()
+    p.num_params, p.device = 1000, torch.device('cuda')
+    g = torch.Generator().manual_seed(0)
+    theta0 = torch.randn(1000, generator=g)
+    p.theta = theta0.clone().cuda()
+    opt = MAMLPPOOptimizer(learning_rate=1e-3)
+    opt.build(p)
+    adam = th.TF1Adam(1000)
+    cur = theta0.clone()
+    for i in range(7):
+        grad = torch.randn(1000, generator=g) * (10.0 ** (i % 3 - 1))
+        opt.apply_gradient(grad.cuda())
+        cur = adam.step(cur, grad)
+    np.testing.assert_allclose(p.theta.cpu().numpy(), cur.numpy(), rtol=1e-5, atol=1e-7)
+    assert int(opt.step.item()) == 7
+
+
+@pytest.mark.parametrize('Do,Da', [(2, 2), (17, 6)])
+def test_promp_optimize_policy_matches_oracle(Do, Da):
+    """ProMP.optimize_policy: 5 Adam epochs + stats pass vs the float32 torch restatement."""
+    torch = _cuda()
+    from oracle import tf_half as th
+    from promp_b200.samplers.device_data import SamplesData
+    M, N = 6, 300
+    policy, algo = _algo(torch, 'promp', M, Do, Da)
+    dims = (Do, Da, (64, 64))
+    theta0 = policy.theta.cpu().clone()
+    cpus, all_samples = [], []
+    for s in range(2):
+        c, p = _random_phase(torch, M, N, Do, Da, theta0.numpy(), 20 + s)
+        cpus.append(c)
+        all_samples.append([SamplesData(p, m) for m in range(M)])
+    adam = th.TF1Adam(theta0.numel())
+    want, st = th.promp_optimize(theta0.clone(), cpus, dims, adam, 0.1, 0.3, list(algo.inner_kl_coeff), 5)
+    algo.optimize_policy(all_samples, log=False)
+    got = policy.theta.cpu()
+    # Adam normalises the step: compare the *update*, which is O(lr) per coordinate
+    assert rel_err((got - theta0).numpy(), (want - theta0).numpy()) < 2e-3
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-5)
+    ls = algo.last_stats
+    assert abs(ls['loss_before'] - st['loss_before']) < 1e-4 * max(1, abs(st['loss_before']))
+    assert abs(ls['loss_after'] - st['loss_after']) < 1e-4 * max(1, abs(st['loss_after']))
+    np.testing.assert_allclose(ls['inner_kls'], st['inner_kls'], rtol=2e-3, atol=1e-6)
+    assert abs(ls['outer_kl'] - st['outer_kl']) < 2e-3 * max(1e-3, abs(st['outer_kl']))
+
+
+def test_trpo_maml_optimize_policy_runs_and_matches_first_quantities():
+    """TRPO-MAML: loss gradient and one finite-difference Hx against the oracle (the CG result itself is
+    dominated by fp32 finite-difference noise), then a full optimize_policy."""
+    torch = _cuda()
+    from oracle import tf_half as th
+    from promp_b200.samplers.device_data import SamplesData
+    M, N, Do, Da = 4, 400, 2, 2
+    policy, algo = _algo(torch, 'trpo', M, Do, Da, inner_type='log_likelihood')
+    dims = (Do, Da, (64, 64))
+    theta0 = policy.theta.cpu().numpy().copy()
+    cpus, phases, all_samples = [], [], []
+    for s in range(2):
+        c, p = _random_phase(torch, M, N, Do, Da, theta0, 30 + s)
+        cpus.append(c); phases.append(p)
+        all_samples.append([SamplesData(p, m) for m in range(M)])
+    orc = th.TRPOMAMLOracle(dims, 0.1, 0.01, 'log_likelihood')
+    g_o = orc.gradient(theta0, cpus)
+    g_d = algo.eval_gradient(policy.theta, phases, 'loss')
+    assert rel_err(g_d, g_o) < 1e-4
+    x = g_o / np.linalg.norm(g_o)
+    hx_o = orc.Hx(theta0, cpus, x.astype(np.float32))
+    hx_d = algo.optimizer.Hx(theta0, phases, x.astype(np.float32))
+    assert rel_err(hx_d, hx_o) < 0.2            # both are fp32 central differences with eps = 1e-5
+    algo.optimize_policy(all_samples, log=False)
+    ls = algo.last_stats
+    assert np.isfinite(ls['loss_after']) and ls['kl'] <= 0.01 + 1e-6
+    assert ls['loss_after'] <= ls['loss_before'] + 1e-7
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('env_name', ['point', 'cheetah'])
+def test_trainer_end_to_end(env_name):
+    """Full meta-iterations through the reference-shaped classes; reference logging keys present."""
+    torch = _cuda()
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    from promp_b200.utils import logger
+    logger.set_quiet(True)
+    M, E, H = 5, 4, 100
+    env, policy, sampler, proc = _make_stack(env_name, M, E, H)
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3,
+                 num_ppo_steps=5, clip_eps=0.3, target_inner_step=0.01, init_inner_kl_penalty=5e-4,
+                 adaptive_inner_kl_penalty=False)
+    trainer = Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=3,
+                      num_inner_grad_steps=1)
+    theta0 = policy.theta.clone()
+    trainer.train()
+    kv = logger.last_dump()
+    for key in ('Step_0-AverageReturn', 'Step_1-AverageReturn', 'Step_0-AveragePolicyStd', 'LossBefore', 'LossAfter',
+                'KLInner', 'KLCoeffInner', 'Time-Sampling', 'Time-OuterStep', 'ItrTime', 'n_timesteps'):
+        assert key in kv, key
+    assert kv['n_timesteps'] == 3 * 2 * M * E * H
+    assert torch.isfinite(policy.theta).all() and not torch.equal(policy.theta, theta0)
+    assert np.isfinite(kv['LossAfter'])
+    # policy pickles through get/set state (policies/base.py:205-215)
+    import pickle
+    pol2 = pickle.loads(pickle.dumps(policy))
+    assert torch.equal(pol2.theta, policy.theta)
