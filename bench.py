@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the ProMP hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload point|cheetah] [--impl reference]
+
+A "step" is ONE FULL META-ITERATION of the hot path over one batch of synthetic tasks
+(BASELINE.json configs[1]: MetaPointEnvCorner, 40 tasks x 20 envs x H=100, ProMP, 2x(64) Gaussian MLP):
+  update_tasks -> [rollout -> returns/baseline/GAE] -> inner adapt -> [rollout -> processing]
+  -> ProMP outer step (5 Adam epochs of the second-order meta-gradient + stats pass).
+metric = env-steps/s = (M*E*H*2 env steps per meta-iteration) / (time per meta-iteration), whole job.
+
+  value : device-resident loop (reset states drawn in-kernel, nothing logged to the host), CUDA events.
+  e2e   : the same iteration through the reference-facing API (Trainer.train_iteration with logging):
+          every sampling phase copies host-drawn tasks + reset states H2D and reads the logged
+          statistics D2H, as the unchanged reference Trainer would.
+  roofline     : dominant kernel (policy_hvp_kernel), algorithmic bytes / CUDA-event time vs the measured
+                 HBM peak (MEASURED_PEAKS.json).  NOTE: that kernel is fp32-FMA bound (AI ~ 500 FLOP/B), so
+                 the HBM fraction is small by construction; `fp32_tflops` gives the compute-side view.
+  cpu_baseline : the CPU oracle port of the reference (oracle/) on the host cores, bounded sample.
+
+--impl reference times the reference's CPU implementation (oracle port: /root/reference is absent on the
+GPU box and TF1 is not installable) on the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'point': dict(env='MetaPointEnvCorner', M=40, E=20, H=100, Do=2, Da=2,
+                  name='ProMP MetaPointEnvCorner meta_batch=40 x envs_per_task=20, H=100 (BASELINE.json configs[1])'),
+    'cheetah': dict(env='HalfCheetahRandDirecEnv', M=40, E=20, H=200, Do=17, Da=6,
+                    name='ProMP HalfCheetahRandDirec-surrogate meta_batch=40 x 20, H=200 (BASELINE.json configs[2])'),
+}
+PROMP = dict(inner_lr=0.1, learning_rate=1e-3, num_ppo_steps=5, clip_eps=0.3, target_inner_step=0.01,
+             init_inner_kl_penalty=5e-4, adaptive_inner_kl_penalty=False, num_inner_grad_steps=1)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, sm_max_mhz=1965.0), 'fallback'
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(max(mx)) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def build_stack(wl, reset_mode, task_shard=None):
+    from promp_b200.envs import normalize, MetaPointEnvCorner, HalfCheetahRandDirecEnv
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.samplers import MetaSampler, MetaSampleProcessor
+    from promp_b200.baselines import LinearFeatureBaseline
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    env = normalize(MetaPointEnvCorner() if wl['env'] == 'MetaPointEnvCorner' else HalfCheetahRandDirecEnv())
+    policy = MetaGaussianMLPPolicy(name="meta-policy", obs_dim=wl['Do'], action_dim=wl['Da'], meta_batch_size=wl['M'],
+                                   hidden_sizes=(64, 64))
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=wl['E'], meta_batch_size=wl['M'],
+                          max_path_length=wl['H'], parallel=True, reset_mode=reset_mode, seed=1, task_shard=task_shard)
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
+    algo = ProMP(policy=policy, inner_lr=PROMP['inner_lr'], meta_batch_size=wl['M'],
+                 num_inner_grad_steps=PROMP['num_inner_grad_steps'], learning_rate=PROMP['learning_rate'],
+                 num_ppo_steps=PROMP['num_ppo_steps'], clip_eps=PROMP['clip_eps'],
+                 target_inner_step=PROMP['target_inner_step'], init_inner_kl_penalty=PROMP['init_inner_kl_penalty'],
+                 adaptive_inner_kl_penalty=PROMP['adaptive_inner_kl_penalty'])
+    trainer = Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1,
+                      num_inner_grad_steps=PROMP['num_inner_grad_steps'])
+    return trainer
+
+
+class LaunchCounter(object):
+    """Counts OUR kernel launches by wrapping the ctypes entry points (kernels per call from the .cu files)."""
+    KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=1,
+                   promp_adj_avg_rewards=1, promp_policy_grad=1, promp_policy_hvp=1, promp_reduce_tasks=1,
+                   promp_adam_tf1=2, promp_policy_forward=1)
+
+    def __init__(self, time_kernels=False):
+        from promp_b200 import _lib
+        self._lib = _lib
+        self.count = 0
+        self.calls = {}
+        self.time_kernels = time_kernels
+        self.events = {}
+        self._orig = _lib.call
+
+    def __enter__(self):
+        import torch
+        orig, me = self._orig, self
+
+        def call(name, *args):
+            k = me.KERNELS.get(name, 0)
+            me.count += k
+            me.calls[name] = me.calls.get(name, 0) + 1
+            if me.time_kernels and k:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                orig(name, *args)
+                b.record()
+                me.events.setdefault(name, []).append((a, b))
+            else:
+                orig(name, *args)
+        self._lib.call = call
+        return self
+
+    def __exit__(self, *exc):
+        self._lib.call = self._orig
+
+    def kernel_ms(self):
+        import torch
+        torch.cuda.synchronize()
+        return {n: [a.elapsed_time(b) for a, b in ev] for n, ev in self.events.items()}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from promp_b200 import _lib
+    from promp_b200.utils import logger
+    logger.set_quiet(True)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    _lib.require_cuda()
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    wl = WORKLOADS[args.workload]
+    M, E, H = wl['M'], wl['E'], wl['H']
+    steps_per_iter = M * E * H * (PROMP['num_inner_grad_steps'] + 1) * world      # weak scaling: M tasks per GPU
+    shard = (rank, world) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(trainer, log, n_warm, n_steps):
+        for i in range(n_warm):
+            trainer.train_iteration(i, log=log)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for i in range(n_steps):
+            trainer.train_iteration(i, log=log)
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = a.elapsed_time(b)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- value: device-resident loop --------------------------------------------------------------
+    np.random.seed(1)
+    tr_dev = build_stack(wl, 'device', shard)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    with LaunchCounter() as lc:
+        ms_dev, wall_dev = timed(tr_dev, False, args.warmup, args.steps)
+    launches = lc.count // (args.warmup + args.steps)
+    clk = clocks.stop() if clocks else None
+    # ---- e2e: reference-facing API with host inputs / logged outputs ------------------------------
+    np.random.seed(1)
+    tr_e2e = build_stack(wl, 'numpy', shard)
+    ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps)
+    sd = tr_e2e.sampler.spec
+    S = PROMP['num_inner_grad_steps'] + 1
+    h2d = 4 * (M * sd['task_dim'] + S * M * E * sd['state_dim'])
+    d2h = S * (M * 8 * 8 + M * sd['act_dim'] * 4 + (2 * M * E * H * 4 * 2 if sd['env_kind'] == 2 else 0)) + 4 * (3 + S - 1)
+
+    out = None
+    if rank == 0:
+        # ---- per-kernel timing pass (instrumented, not part of the timed loops) ----------------------
+        with LaunchCounter(time_kernels=True) as lk:
+            for i in range(3):
+                tr_dev.train_iteration(i, log=False)
+            kms = lk.kernel_ms()
+        per_kernel = {n: dict(launches_per_iter=len(v) // 3, avg_ms=float(np.mean(v)), total_ms_per_iter=float(np.sum(v) / 3))
+                      for n, v in kms.items()}
+        peaks, peak_src = measured_peaks()
+        N = E * H
+        # dominant kernel: policy_hvp_kernel.  Algorithmic bytes per launch (SURVEY.md section 8d "inner adapt /
+        # outer epoch" rows): obs + act + adv + old_mean per sample, once, + per-task params, direction and output.
+        P = _lib.load().promp_num_params(wl['Do'], wl['Da'], 64)
+        hvp_bytes = M * N * 4 * (wl['Do'] + 2 * wl['Da'] + 1) + M * 4 * (wl['Da'] + 3 * P)
+        fwd_flops = 2 * (wl['Do'] * 64 + 64 * 64 + 64 * wl['Da'])
+        hvp_flops = M * N * (8 * 2 * 64 * 64 + 6 * 2 * wl['Do'] * 64 + 8 * 2 * 64 * wl['Da'])
+        hvp_ms = per_kernel.get('promp_policy_hvp', {}).get('avg_ms', float('nan'))
+        achieved = hvp_bytes / (hvp_ms * 1e-3) / 1e9
+        roof = dict(kernel='policy_hvp_kernel', bound='hbm', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
+                    frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_launch=hvp_bytes, avg_launch_ms=hvp_ms,
+                    fp32_tflops=hvp_flops / (hvp_ms * 1e-3) / 1e12,
+                    fp32_peak_tflops=148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12,
+                    note='kernel is fp32-FMA bound (AI ~ %d FLOP/B): the HBM fraction is small by construction; '
+                         'share of the iteration = %.0f%%' % (hvp_flops / hvp_bytes,
+                                                              100 * per_kernel.get('promp_policy_hvp', {}).get('total_ms_per_iter', 0)
+                                                              / max(sum(k['total_ms_per_iter'] for k in per_kernel.values()), 1e-9)))
+        # HBM-bound scan kernel for reference: promp_process_samples reads obs twice + rew twice, writes ret + adv
+        proc_bytes = M * N * (4 * 2 * wl['Do'] + 8 + 8)
+        proc_ms = per_kernel.get('promp_process_samples', {}).get('avg_ms', float('nan'))
+        roof['process_kernel'] = dict(achieved=proc_bytes / (proc_ms * 1e-3) / 1e9, frac=proc_bytes / (proc_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                      algorithmic_bytes_per_launch=proc_bytes, avg_launch_ms=proc_ms)
+        ro_bytes = M * N * (4 * (wl['Do'] + 2 * wl['Da'] + 1) + 1 + (8 if wl['Da'] == 6 else 0))
+        ro_ms = per_kernel.get('promp_rollout', {}).get('avg_ms', float('nan'))
+        roof['rollout_kernel'] = dict(achieved=ro_bytes / (ro_ms * 1e-3) / 1e9, frac=ro_bytes / (ro_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                      algorithmic_bytes_per_launch=ro_bytes, avg_launch_ms=ro_ms,
+                                      env_steps_per_s=M * N / (ro_ms * 1e-3))
+        cpu = run_cpu_baseline(wl, steps=2, warmup=1, m_sample=10) if not args.no_cpu_baseline else None
+        value = steps_per_iter * args.steps / (ms_dev * 1e-3)
+        e2e_val = steps_per_iter * args.steps / (ms_e2e * 1e-3)
+        out = {
+            'metric': 'env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'tasks_per_gpu': M, 'envs_per_task': E, 'max_path_length': H,
+                       'algo': 'ProMP num_promp_steps=5 inner_lr=0.1 lr=1e-3 clip_eps=0.3 (pro-mp_run_point_mass.py defaults)',
+                       'step_definition': 'one full meta-iteration (2 sampling+processing phases, inner adapt, 5 Adam epochs + stats pass)',
+                       'parallelism': 'task-sharded dp%d, one NCCL all-reduce of the flat meta-gradient per Adam epoch' % world,
+                       'l2_note': 'every iteration rewrites all trajectory buffers from fresh rollouts (inputs are produced, not re-read); no L2 flush needed'},
+            'meta_iters_per_sec': world * 0 + args.steps / (ms_dev * 1e-3),
+            'wall_ms_per_step': wall_dev / args.steps,
+            'e2e': {'value': e2e_val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps, 'wall_ms_per_step': wall_e2e / args.steps,
+                    'api': 'promp_b200.meta_trainer.Trainer.train_iteration(log=True), reset_mode=numpy'},
+            'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
+            'clocks': clk, 'roofline': roof, 'kernels': per_kernel, 'cpu_baseline': cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def pick_torch_threads(fn):
+    """The CPU stand-in for TF1's executor is sensitive to the thread count:
+    sweep and keep the fastest."""
+    import torch
+    best, best_t = None, None
+    cands = sorted(set([1, 2, 4, 8, os.cpu_count() or 1]))
+    for nt in cands:
+        if nt > (os.cpu_count() or 1):
+            continue
+        torch.set_num_threads(nt)
+        t = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t
+        if best_t is None or dt < best_t:
+            best, best_t = nt, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_meta_iteration(wl, m_sample, state):
+    """One meta-iteration of the reference algorithm on the CPU (oracle port), m_sample tasks."""
+    import torch
+    from oracle import numpy_half as nh, tf_half as th, cheetah_surrogate as cs
+    Do, Da, E, H = wl['Do'], wl['Da'], wl['E'], wl['H']
+    dims = (Do, Da, (64, 64))
+    if 'sampler' not in state:
+        env = nh.NormalizedEnv(nh.PointEnvCorner() if wl['env'] == 'MetaPointEnvCorner' else cs.HalfCheetahRandDirecSurrogate())
+        policy = th.OraclePolicy(m_sample, Do, Da)
+        state.update(policy=policy, sampler=nh.Sampler(env, policy, E, m_sample, H),
+                     proc=nh.SampleProcessor(nh.LinearFeatureBaseline(), 0.99, 1, True), adam=th.TF1Adam(policy.theta.size))
+    policy, sampler, proc, adam = state['policy'], state['sampler'], state['proc'], state['adam']
+
+    def to_phase(data):
+        f = lambda a: torch.tensor(np.stack(a), dtype=torch.float32)
+        return dict(obs=f([d['observations'] for d in data]), act=f([d['actions'] for d in data]),
+                    adv=f([d['advantages'] for d in data]), mean=f([d['agent_infos']['mean'] for d in data]),
+                    log_std=f([d['agent_infos']['log_std'] for d in data]))
+    spans = {}
+    t0 = time.perf_counter()
+    sampler.update_tasks()
+    policy.switch_to_pre_update()
+    phases = []
+    for step in range(2):
+        t = time.perf_counter()
+        paths = sampler.obtain_samples()
+        spans['sampling'] = spans.get('sampling', 0) + time.perf_counter() - t
+        t = time.perf_counter()
+        data = proc.process_samples(paths)
+        phases.append(to_phase(data))
+        spans['sample_proc'] = spans.get('sample_proc', 0) + time.perf_counter() - t
+        if step == 0:
+            t = time.perf_counter()
+            new = th.adapt(torch.tensor(policy.theta_tasks), phases[0], dims, PROMP['inner_lr'])
+            policy.update_task_parameters(new.numpy())
+            spans['inner_step'] = time.perf_counter() - t
+    t = time.perf_counter()
+    theta, _ = th.promp_optimize(torch.tensor(policy.theta), phases, dims, adam, PROMP['inner_lr'], PROMP['clip_eps'],
+                                 [PROMP['init_inner_kl_penalty']], PROMP['num_ppo_steps'])
+    policy.theta = theta.numpy()
+    spans['outer_step'] = time.perf_counter() - t
+    spans['itr'] = time.perf_counter() - t0
+    return spans
+
+
+def run_cpu_baseline(wl, steps, warmup, m_sample):
+    import torch
+    import warnings
+    warnings.filterwarnings('ignore')
+    state = {}
+    np.random.seed(1)
+    # choose the torch thread count on a gradient evaluation of the right shape
+    from oracle import tf_half as th
+    dims = (wl['Do'], wl['Da'], (64, 64))
+    N = wl['E'] * wl['H']
+    g = torch.Generator().manual_seed(0)
+    fake = dict(obs=torch.randn(m_sample, N, wl['Do'], generator=g), act=torch.randn(m_sample, N, wl['Da'], generator=g),
+                adv=torch.randn(m_sample, N, generator=g), mean=torch.randn(m_sample, N, wl['Da'], generator=g),
+                log_std=torch.zeros(m_sample, N, wl['Da']))
+    theta = torch.tensor(th.init_params(*dims))
+
+    def probe():
+        t = theta.clone().requires_grad_(True)
+        obj, _, _ = th.meta_objective(t, [fake, fake], dims, 0.1, 'promp', 0.3, [5e-4])
+        torch.autograd.grad(obj, t)
+    nthreads = pick_torch_threads(probe)
+    for _ in range(warmup):
+        cpu_meta_iteration(wl, m_sample, state)
+    all_spans = [cpu_meta_iteration(wl, m_sample, state) for _ in range(steps)]
+    itr = float(np.median([s['itr'] for s in all_spans]))
+    steps_per_iter = m_sample * wl['E'] * wl['H'] * 2
+    med = {k: float(np.median([s[k] for s in all_spans])) for k in all_spans[0]}
+    return dict(value=steps_per_iter / itr, unit='env-steps/s', cores=os.cpu_count(), torch_threads=nthreads, kind='port',
+                sample='%d of %d tasks x %d envs x H=%d, full meta-iteration (tasks are independent; numpy half = per-env Python '
+                       'stepping like the reference, TF1 half = PyTorch-CPU restatement batched over tasks), median of %d'
+                       % (m_sample, wl['M'], wl['E'], wl['H'], steps),
+                sec_per_iter=itr, spans_sec=med,
+                sampling_env_steps_per_sec=steps_per_iter / med['sampling'])
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on this box's cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    m_sample = 10
+    cpu = run_cpu_baseline(wl, steps=args.steps, warmup=args.warmup, m_sample=m_sample)
+    out = {
+        'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': cpu['value'], 'unit': 'env-steps/s',
+        'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': cpu['sec_per_iter'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (TF half) / f64 (numpy half)', 'data': 'synthetic',
+        'config': {'workload': wl['name'], 'sample': cpu['sample'],
+                   'note': 'reference = jonasrothfuss/ProMP CPU path; /root/reference and TF1 are absent on the GPU box, so the '
+                           'oracle port (pinned to the reference by tests/golden) is what runs'},
+        'cpu_baseline': cpu,
+        'e2e': {'value': cpu['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='promp_b200', choices=['promp_b200', 'reference'])
+    ap.add_argument('--workload', default='point', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else max(args.warmup, 1)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -288,16 +288,18 @@ def test_process_samples_properties_full_size():
 
 
 # ------------------------------------------------------------------------------------------------
-def _random_phase(torch, M, N, Do, Da, theta, seed, hidden=64):
-    """Synthetic sampling-phase data whose old distribution is close to (not equal to) the policy."""
+def _random_phase(torch, M, N, Do, Da, theta, seed, hidden=64, perturb=1.0):
+    """Synthetic sampling-phase data whose old distribution is close to (perturb=1) or exactly (perturb=0)
+    the policy given by theta ([P] shared or [M,P] per task)."""
     from promp_b200.samplers.device_data import PhaseData
     from oracle import tf_half as th
     g = torch.Generator().manual_seed(seed)
     obs = torch.randn(M, N, Do, generator=g)
-    th_t = torch.as_tensor(theta).view(1, -1).expand(M, -1)
+    th_t = torch.as_tensor(theta)
+    th_t = th_t.view(1, -1).expand(M, -1) if th_t.dim() == 1 else th_t
     mean, ls = th.dist_info(th_t, obs, (Do, Da, (hidden, hidden)))
-    old_mean = mean + 0.1 * torch.randn(M, N, Da, generator=g)
-    old_ls = (ls + 0.05 * torch.randn(M, 1, Da, generator=g)).expand(M, N, Da).contiguous()
+    old_mean = mean + perturb * 0.1 * torch.randn(M, N, Da, generator=g)
+    old_ls = (ls + perturb * 0.05 * torch.randn(M, 1, Da, generator=g)).expand(M, N, Da).contiguous()
     act = old_mean + torch.exp(old_ls) * torch.randn(M, N, Da, generator=g)
     adv = torch.randn(M, N, generator=g)
     cpu = dict(obs=obs, act=act, adv=adv, mean=old_mean, log_std=old_ls)
@@ -473,10 +475,13 @@ def test_trpo_maml_optimize_policy_runs_and_matches_first_quantities():
     dims = (Do, Da, (64, 64))
     theta0 = policy.theta.cpu().numpy().copy()
     cpus, phases, all_samples = [], [], []
-    for s in range(2):
-        c, p = _random_phase(torch, M, N, Do, Da, theta0, 30 + s)
-        cpus.append(c); phases.append(p)
-        all_samples.append([SamplesData(p, m) for m in range(M)])
+    # like real sampling: phase 0 is drawn from pi_theta, phase 1 from the adapted pi_theta_i'
+    c, p = _random_phase(torch, M, N, Do, Da, theta0, 30, perturb=0.0)
+    cpus.append(c); phases.append(p)
+    adapted = th.adapt(torch.from_numpy(theta0).view(1, -1).expand(M, -1).contiguous(), c, dims, 0.1, 'log_likelihood')
+    c, p = _random_phase(torch, M, N, Do, Da, adapted.numpy(), 31, perturb=0.0)
+    cpus.append(c); phases.append(p)
+    all_samples = [[SamplesData(ph, m) for m in range(M)] for ph in phases]
     orc = th.TRPOMAMLOracle(dims, 0.1, 0.01, 'log_likelihood')
     g_o = orc.gradient(theta0, cpus)
     g_d = algo.eval_gradient(policy.theta, phases, 'loss')
@@ -487,8 +492,13 @@ def test_trpo_maml_optimize_policy_runs_and_matches_first_quantities():
     assert rel_err(hx_d, hx_o) < 0.2            # both are fp32 central differences with eps = 1e-5
     algo.optimize_policy(all_samples, log=False)
     ls = algo.last_stats
+    assert ls['kl_before'] < 1e-6
     assert np.isfinite(ls['loss_after']) and ls['kl'] <= 0.01 + 1e-6
-    assert ls['loss_after'] <= ls['loss_before'] + 1e-7
+    assert ls['loss_after'] < ls['loss_before'] and not algo.optimizer.last['rejected']
+    # same decision sequence as the oracle's host loop
+    th_o, st_o = orc.optimize(theta0, cpus)
+    assert st_o['rejected'] is False
+    assert abs(st_o['loss'] - ls['loss_after']) < 0.05 * abs(ls['loss_before'] - ls['loss_after']) + 1e-5
 
 
 # ------------------------------------------------------------------------------------------------
