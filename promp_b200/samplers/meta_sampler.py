@@ -14,6 +14,7 @@ from promp_b200 import _lib
 from promp_b200.samplers.device_data import PhaseData, LazyPath, PathsMetaBatch
 from promp_b200.samplers.vectorized_env_executor import MetaDeviceEnvExecutor
 from promp_b200.utils import logger
+from promp_b200.utils.dist import shard_tasks
 
 
 class MetaSampler(object):
@@ -61,7 +62,7 @@ class MetaSampler(object):
         else:
             rank, world = self.task_shard
             all_tasks = self.env.sample_tasks(self.meta_batch_size * world)
-            tasks = list(all_tasks[rank * self.meta_batch_size:(rank + 1) * self.meta_batch_size])
+            tasks = shard_tasks(all_tasks, rank, world)
         assert len(tasks) == self.meta_batch_size
         self.vec_env.set_tasks(tasks)
 

@@ -24,3 +24,12 @@ def world_size():
 def rank():
     d = _dist()
     return d.get_rank() if d is not None else 0
+
+
+def shard_tasks(all_tasks, rank, world):
+    """Rank `rank` of `world` owns the contiguous slice of the global task list (every rank draws the same
+    list from the same numpy seed, so results do not depend on the number of GPUs)."""
+    n = len(all_tasks)
+    assert n % world == 0, "global meta batch must be divisible by the number of ranks"
+    per = n // world
+    return list(all_tasks[rank * per:(rank + 1) * per])
