@@ -124,7 +124,7 @@ class LaunchCounter(object):
     """Counts OUR kernel launches by wrapping the ctypes entry points (kernels per call from the .cu files)."""
     KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=1,
                    promp_adj_avg_rewards=1, promp_policy_grad=1, promp_policy_hvp=1, promp_reduce_tasks=1,
-                   promp_adam_tf1=2, promp_policy_forward=1)
+                   promp_adam_tf1=2, promp_policy_forward=1, promp_counter_add=1)
 
     def __init__(self, time_kernels=False):
         from promp_b200 import _lib
@@ -187,15 +187,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(trainer, log, n_warm, n_steps):
+    def timed(trainer, log, n_warm, n_steps, step_fn=None):
+        run = step_fn if step_fn is not None else (lambda: trainer.train_iteration(0, log=log))
         for i in range(n_warm):
-            trainer.train_iteration(i, log=log)
+            run()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
         for i in range(n_steps):
-            trainer.train_iteration(i, log=log)
+            run()
         b.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -209,9 +210,16 @@ def run_gpu(args):
     np.random.seed(1)
     tr_dev = build_stack(wl, 'device', shard)
     clocks = ClockSampler(local_rank) if rank == 0 else None
+    use_graph = (world == 1) and not args.no_graph
     with LaunchCounter() as lc:
-        ms_dev, wall_dev = timed(tr_dev, False, args.warmup, args.steps)
+        ms_eager, wall_eager = timed(tr_dev, False, args.warmup, args.steps)
     launches = lc.count // (args.warmup + args.steps)
+    if use_graph:
+        # the same ~40 launches per meta-iteration captured once into a CUDA graph and replayed
+        step_fn = tr_dev.capture_graph(warmup=2)
+        ms_dev, wall_dev = timed(tr_dev, False, args.warmup, args.steps, step_fn)
+    else:
+        ms_dev, wall_dev = ms_eager, wall_eager
     clk = clocks.stop() if clocks else None
     # ---- e2e: reference-facing API with host inputs / logged outputs ------------------------------
     np.random.seed(1)
@@ -274,6 +282,7 @@ def run_gpu(args):
                        'l2_note': 'every iteration rewrites all trajectory buffers from fresh rollouts (inputs are produced, not re-read); no L2 flush needed'},
             'meta_iters_per_sec': world * 0 + args.steps / (ms_dev * 1e-3),
             'wall_ms_per_step': wall_dev / args.steps,
+            'launch_mode': 'cuda_graph_replay' if use_graph else 'eager', 'eager_ms_per_step': ms_eager / args.steps,
             'e2e': {'value': e2e_val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps, 'wall_ms_per_step': wall_e2e / args.steps,
                     'api': 'promp_b200.meta_trainer.Trainer.train_iteration(log=True), reset_mode=numpy'},
@@ -418,6 +427,7 @@ def main():
     ap.add_argument('--impl', default='promp_b200', choices=['promp_b200', 'reference'])
     ap.add_argument('--workload', default='point', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time the device-resident loop eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else max(args.warmup, 1)
     if args.impl == 'reference':

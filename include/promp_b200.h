@@ -74,6 +74,9 @@ int promp_env_task_dim(int env_kind);
  *   init_state  [M, E, state_dim] or NULL  -> NULL draws the reset state in-kernel (Philox4x32-10)
  *   noise       [M, E, H, Da]    or NULL  -> NULL draws N(0,1) action noise in-kernel
  *   seed, stream_id             Philox key / sub-stream (use a fresh stream_id per sampling phase)
+ *   stream_id_dev               optional device uint64 whose value is ADDED to stream_id; the host bumps it with
+ *                               promp_counter_add after each launch, so a captured CUDA graph replays the same
+ *                               launch with fresh noise / reset states every time
  *   clip_reported_log_std       1 = pre-update mode: reported log_std = max(log_std, min_log_std)
  *                               (policies/gaussian_mlp_policy.py:71); sampling always uses the raw one
  * outputs (all written):
@@ -86,10 +89,13 @@ int promp_rollout(int env_kind, int reward_type, float sparse_radius,
                   int M, int E, int H, int hidden,
                   const float* params, int64_t param_stride,
                   const float* task_params, const float* init_state, const float* noise,
-                  uint64_t seed, uint64_t stream_id,
+                  uint64_t seed, uint64_t stream_id, const uint64_t* stream_id_dev,
                   int clip_reported_log_std, float min_log_std,
                   float* obs, float* act, float* mean, float* rew, uint8_t* done, float* info,
                   float* log_std_out, float* final_state, void* stream);
+
+/* *counter += inc on the stream (device-side phase counter for graph-replayed rollouts). */
+int promp_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
 /*
  * One vectorised env step (MetaIterativeEnvExecutor.step, samplers/vectorized_env_executor.py:25-52)

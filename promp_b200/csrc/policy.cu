@@ -2,11 +2,13 @@
 // terms) and the exact Hessian-vector product that carries the MAML meta-gradient through the inner
 // SGD step.  See include/promp_b200.h for the interface and the reference functions replaced.
 //
-// Work decomposition: grid = (chunks, M).  A CTA owns one task's weights in shared memory and walks
-// that task's 64-sample tiles with stride `chunks`; weight-gradient accumulators stay in registers
-// across tiles, are written once per CTA to a per-(task,chunk) partial buffer, and the last CTA of
-// each task (atomic ticket) reduces the partials in fixed chunk order -> bitwise run-to-run
-// deterministic sums.  These kernels are fp32-FMA bound (AI ~ 10^2..10^3 FLOP/B), not HBM bound.
+// Work decomposition: persistent CTAs, one wave.  The M*ceil(N/64) sample tiles form one task-major
+// list; CTA c owns the contiguous range [c*q, (c+1)*q) (q = ceil(T/grid), grid = SMs x resident
+// CTAs), so every SM gets the same number of tiles whatever M and N are.  A CTA keeps the current
+// task's weights in shared memory and its weight-gradient accumulators in registers; when its range
+// crosses a task boundary (or ends) it flushes them to a per-(CTA,task) partial slot, and the last
+// segment of each task to arrive (atomic ticket) reduces that task's slots in CTA order -> bitwise
+// run-to-run deterministic sums.  These kernels are fp32-FMA bound (AI ~ 10^2..10^3 FLOP/B).
 #include "mlp_tile.cuh"
 
 namespace promp {
@@ -37,8 +39,25 @@ struct PolicyArgs {
     float* out;
     float inner_lr;
     float* stats;
-    float* partial;      // [M][chunks][P + PSTAT]
+    float* partial;      // [grid][kmax][P + PSTAT] per-(CTA, task-segment) partial sums
     int* counters;       // [M], zero on entry, left zero on exit
+    int q;               // tiles per CTA
+    int kmax;            // max task segments per CTA
+};
+
+// Tile-range bookkeeping shared by both kernels.
+struct TileSched {
+    int ntiles, T, q, g_lo, g_hi;
+    __device__ __forceinline__ TileSched(int M, int N, int q_) {
+        ntiles = (N + TB - 1) / TB;
+        T = M * ntiles;
+        q = q_;
+        g_lo = blockIdx.x * q;
+        g_hi = min(g_lo + q, T);
+    }
+    __device__ __forceinline__ int first_task(int c) const { return (c * q) / ntiles; }
+    __device__ __forceinline__ int cta_lo(int m) const { return (m * ntiles) / q; }
+    __device__ __forceinline__ int cta_hi(int m) const { return ((m + 1) * ntiles - 1) / q; }
 };
 
 template <int DO, int DA, int HID>
@@ -89,32 +108,107 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % C::TX, ty = tid / C::TX;
     const int row0 = ty * RM, col0 = tx * 4;
-    const int m = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
     const float invN = 1.0f / (float)N;
-    const float* th = A.params + (int64_t)m * A.param_stride;
     const bool want_grad = A.grad != nullptr;
-
-    for (int i = tid; i < L::P; i += PT_THREADS) S.P[i] = __ldg(th + i);
-    __syncthreads();
-    for (int i = tid; i < HID * HID; i += PT_THREADS) {
-        const int k = i / HID, j = i % HID;
-        S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
-    }
+    const float* th = nullptr;
     HeadIn<DA> hin;
-    load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
 
-    float gW1[RK][4], gB1[4] = {0, 0, 0, 0}, gW0[NW0], gB0 = 0.f, gW2[NW2], gB2 = 0.f, gLS = 0.f;
+    float gW1[RK][4], gB1[4], gW0[NW0], gB0, gW2[NW2], gB2, gLS;
+    float s_obj, s_kl, s_ratio;
+    auto zero_acc = [&]() {
 #pragma unroll
-    for (int r = 0; r < RK; ++r) gW1[r][0] = gW1[r][1] = gW1[r][2] = gW1[r][3] = 0.f;
+        for (int r = 0; r < RK; ++r) gW1[r][0] = gW1[r][1] = gW1[r][2] = gW1[r][3] = 0.f;
+        gB1[0] = gB1[1] = gB1[2] = gB1[3] = 0.f;
 #pragma unroll
-    for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
+        for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
 #pragma unroll
-    for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
-    float s_obj = 0.f, s_kl = 0.f, s_ratio = 0.f;
+        for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
+        gB0 = gB2 = gLS = 0.f;
+        s_obj = s_kl = s_ratio = 0.f;
+    };
+    auto load_task = [&](int m, bool first) {
+        th = A.params + (int64_t)m * A.param_stride;
+        if (!first && A.param_stride == 0) return;       // shared theta: weights already resident
+        __syncthreads();
+        for (int i = tid; i < L::P; i += PT_THREADS) S.P[i] = __ldg(th + i);
+        __syncthreads();
+        for (int i = tid; i < HID * HID; i += PT_THREADS) {
+            const int k = i / HID, j = i % HID;
+            S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
+        }
+        load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
+    };
+    // write this CTA's partial sums for task m; the last segment of the task reduces them in CTA order
+    auto flush = [&](int m) {
+        float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+        if (want_grad) {
+#pragma unroll
+            for (int r = 0; r < NW0; ++r) {
+                const int idx = tid + r * PT_THREADS;
+                if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
+            }
+            if (tid < HID) part[L::B0 + tid] = gB0;
+#pragma unroll
+            for (int r = 0; r < RK; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1[r][c];
+            if (ty == 0)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
+#pragma unroll
+            for (int r = 0; r < NW2; ++r) {
+                const int idx = tid + r * PT_THREADS;
+                if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
+            }
+            if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+        }
+        // head sums are valid in every lane of a warp (computed redundantly); reduce across warps
+        __syncthreads();
+        if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
+        __syncthreads();
+        if (tid < 3) {
+            float s = 0.f;
+            for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+            part[L::P + tid] = s;
+        }
+        __threadfence();
+        __syncthreads();
+        const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
+        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
+        __syncthreads();
+        if (S.last) {
+            __threadfence();
+            if (want_grad) {
+                for (int p = tid; p < L::P; p += PT_THREADS) {
+                    float s = 0.f;
+                    for (int c = c_lo; c <= c_hi; ++c)
+                        s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + p);
+                    A.grad[(int64_t)m * L::P + p] = s;
+                    if (A.out_params) A.out_params[(int64_t)m * L::P + p] = S.P[p] - A.sgd_lr * s;   // meta_algos/base.py:209
+                }
+            }
+            if (A.stats && tid < 3) {
+                float s = 0.f;
+                for (int c = c_lo; c <= c_hi; ++c)
+                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + L::P + tid);
+                A.stats[(int64_t)m * 4 + tid] = s * invN;
+            }
+            if (tid == 0) A.counters[m] = 0;
+        }
+        __syncthreads();
+    };
 
-    const int ntiles = (N + TB - 1) / TB;
-    for (int tile = chunk; tile < ntiles; tile += nchunks) {
+    int cur_m = -1;
+    for (int g = ts.g_lo; g < ts.g_hi; ++g) {
+        const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+        if (m != cur_m) {
+            if (cur_m >= 0) flush(cur_m);
+            load_task(m, cur_m < 0);
+            zero_acc();
+            cur_m = m;
+        }
         const int n0 = tile * TB, nb = min(TB, N - n0);
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
@@ -270,59 +364,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
         }
     }
 
-    // ---- per-CTA partials -> global, last CTA of the task reduces in chunk order
-    float* part = A.partial + ((int64_t)m * nchunks + chunk) * PSTRIDE;
-    if (want_grad) {
-#pragma unroll
-        for (int r = 0; r < NW0; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
-        }
-        if (tid < HID) part[L::B0 + tid] = gB0;
-#pragma unroll
-        for (int r = 0; r < RK; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1[r][c];
-        if (ty == 0)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
-#pragma unroll
-        for (int r = 0; r < NW2; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
-        }
-        if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
-    }
-    // head sums are valid in every lane of a warp (computed redundantly); reduce across warps
-    __syncthreads();
-    if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
-    __syncthreads();
-    if (tid < 3) {
-        float s = 0.f;
-        for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
-        part[L::P + tid] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == nchunks - 1);
-    __syncthreads();
-    if (!S.last) return;
-    __threadfence();
-    const float* pm = A.partial + (int64_t)m * nchunks * PSTRIDE;
-    if (want_grad) {
-        for (int p = tid; p < L::P; p += PT_THREADS) {
-            float s = 0.f;
-            for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + p);
-            A.grad[(int64_t)m * L::P + p] = s;
-            if (A.out_params) A.out_params[(int64_t)m * L::P + p] = S.P[p] - A.sgd_lr * s;   // meta_algos/base.py:209
-        }
-    }
-    if (A.stats && tid < 3) {
-        float s = 0.f;
-        for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + L::P + tid);
-        A.stats[(int64_t)m * 4 + tid] = s * invN;
-    }
-    if (tid == 0) A.counters[m] = 0;
+    if (cur_m >= 0) flush(cur_m);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -370,40 +412,111 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % C::TX, ty = tid / C::TX;
     const int row0 = ty * RM, col0 = tx * 4;
-    const int m = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
     const float invN = 1.0f / (float)N;
     const float ac = -A.inner_lr;                 // coefficient of H vec in `out`
-    const float* th = A.params + (int64_t)m * A.param_stride;
-    const float* vg = A.vec + (int64_t)m * L::P;
-
-    for (int i = tid; i < L::P; i += PT_THREADS) S.P[i] = __ldg(th + i), S.V[i] = __ldg(vg + i);
-    __syncthreads();
-    for (int i = tid; i < HID * HID; i += PT_THREADS) {
-        const int k = i / HID, j = i % HID;
-        S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
-        S.V1T[j * HID + k] = S.V[L::W1 + k * HID + j];
-    }
+    const float* th = nullptr;
     HeadIn<DA> hin;
-    load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
     float rls[DA];     // tangent of the (clipped) log_std
-#pragma unroll
-    for (int d = 0; d < DA; ++d) rls[d] = S.V[L::LS + d] * hin.ls_mask[d];
 
     // accumulators: gC* multiply 1, gA* multiply `ac`
-    float gW1c[RK][4], gW1a[RK][4], gB1[4] = {0, 0, 0, 0}, gW0[NW0], gB0 = 0.f, gW2[NW2], gB2 = 0.f, gLS = 0.f;
+    float gW1c[RK][4], gW1a[RK][4], gB1[4], gW0[NW0], gB0, gW2[NW2], gB2, gLS;
+    float s_obj, s_kl, s_ratio;
+    auto zero_acc = [&]() {
 #pragma unroll
-    for (int r = 0; r < RK; ++r)
+        for (int r = 0; r < RK; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gW1c[r][c] = gW1a[r][c] = 0.f;
+            for (int c = 0; c < 4; ++c) gW1c[r][c] = gW1a[r][c] = 0.f;
+        gB1[0] = gB1[1] = gB1[2] = gB1[3] = 0.f;
 #pragma unroll
-    for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
+        for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
 #pragma unroll
-    for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
-    float s_obj = 0.f, s_kl = 0.f, s_ratio = 0.f;
+        for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
+        gB0 = gB2 = gLS = 0.f;
+        s_obj = s_kl = s_ratio = 0.f;
+    };
+    auto load_task = [&](int m, bool first) {
+        th = A.params + (int64_t)m * A.param_stride;
+        const float* vg = A.vec + (int64_t)m * L::P;
+        const bool reload_p = first || A.param_stride != 0;      // shared theta stays resident across tasks
+        __syncthreads();
+        for (int i = tid; i < L::P; i += PT_THREADS) {
+            if (reload_p) S.P[i] = __ldg(th + i);
+            S.V[i] = __ldcg(vg + i);                             // written by the previous kernel on this stream
+        }
+        __syncthreads();
+        for (int i = tid; i < HID * HID; i += PT_THREADS) {
+            const int k = i / HID, j = i % HID;
+            if (reload_p) S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
+            S.V1T[j * HID + k] = S.V[L::W1 + k * HID + j];
+        }
+        load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
+#pragma unroll
+        for (int d = 0; d < DA; ++d) rls[d] = S.V[L::LS + d] * hin.ls_mask[d];
+    };
+    auto flush = [&](int m) {
+        float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+#pragma unroll
+        for (int r = 0; r < NW0; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
+        }
+        if (tid < HID) part[L::B0 + tid] = gB0;
+#pragma unroll
+        for (int r = 0; r < RK; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1c[r][c] + ac * gW1a[r][c];
+        if (ty == 0)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
+#pragma unroll
+        for (int r = 0; r < NW2; ++r) {
+            const int idx = tid + r * PT_THREADS;
+            if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
+        }
+        if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+        __syncthreads();
+        if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
+        __syncthreads();
+        if (tid < 3) {
+            float s = 0.f;
+            for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+            part[L::P + tid] = s;
+        }
+        __threadfence();
+        __syncthreads();
+        const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
+        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
+        __syncthreads();
+        if (S.last) {
+            __threadfence();
+            for (int p = tid; p < L::P; p += PT_THREADS) {
+                float s = 0.f;
+                for (int c = c_lo; c <= c_hi; ++c)
+                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + p);
+                A.out[(int64_t)m * L::P + p] = S.V[p] + s;
+            }
+            if (A.stats && tid < 3) {
+                float s = 0.f;
+                for (int c = c_lo; c <= c_hi; ++c)
+                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + L::P + tid);
+                A.stats[(int64_t)m * 4 + tid] = s * invN;
+            }
+            if (tid == 0) A.counters[m] = 0;
+        }
+        __syncthreads();
+    };
 
-    const int ntiles = (N + TB - 1) / TB;
-    for (int tile = chunk; tile < ntiles; tile += nchunks) {
+    int cur_m = -1;
+    for (int g = ts.g_lo; g < ts.g_hi; ++g) {
+        const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+        if (m != cur_m) {
+            if (cur_m >= 0) flush(cur_m);
+            load_task(m, cur_m < 0);
+            zero_acc();
+            cur_m = m;
+        }
         const int n0 = tile * TB, nb = min(TB, N - n0);
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
@@ -629,52 +742,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
         }
     }
 
-    float* part = A.partial + ((int64_t)m * nchunks + chunk) * PSTRIDE;
-#pragma unroll
-    for (int r = 0; r < NW0; ++r) {
-        const int idx = tid + r * PT_THREADS;
-        if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
-    }
-    if (tid < HID) part[L::B0 + tid] = gB0;
-#pragma unroll
-    for (int r = 0; r < RK; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1c[r][c] + ac * gW1a[r][c];
-    if (ty == 0)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
-#pragma unroll
-    for (int r = 0; r < NW2; ++r) {
-        const int idx = tid + r * PT_THREADS;
-        if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
-    }
-    if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
-    __syncthreads();
-    if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
-    __syncthreads();
-    if (tid < 3) {
-        float s = 0.f;
-        for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
-        part[L::P + tid] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == nchunks - 1);
-    __syncthreads();
-    if (!S.last) return;
-    __threadfence();
-    const float* pm = A.partial + (int64_t)m * nchunks * PSTRIDE;
-    for (int p = tid; p < L::P; p += PT_THREADS) {
-        float s = 0.f;
-        for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + p);
-        A.out[(int64_t)m * L::P + p] = S.V[p] + s;
-    }
-    if (A.stats && tid < 3) {
-        float s = 0.f;
-        for (int c = 0; c < nchunks; ++c) s += __ldcg(pm + (int64_t)c * PSTRIDE + L::P + tid);
-        A.stats[(int64_t)m * 4 + tid] = s * invN;
-    }
-    if (tid == 0) A.counters[m] = 0;
+    if (cur_m >= 0) flush(cur_m);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -747,56 +815,71 @@ __global__ void adam_tf1_kernel(int P, float* theta, const float* grad, float* m
 __global__ void adam_step_inc_kernel(int32_t* step) { *step += 1; }
 
 // -------------------------------------------------------------------------------------------------
-static int pick_chunks(int M, int N) {
+struct TilePlan {
+    int grid, q, kmax;
+    int64_t partial_floats;
+};
+// One-wave persistent plan: `slots` resident CTAs share the T tiles as evenly as possible.
+static TilePlan plan_tiles(int M, int N, int slots, int P) {
     const int ntiles = (N + TB - 1) / TB;
-    int c = (2 * 148 + M - 1) / M;      // ~2 CTAs per SM across the 148 SMs
-    if (c > ntiles) c = ntiles;
-    if (c < 1) c = 1;
-    return c;
+    const int64_t T = (int64_t)M * ntiles;
+    TilePlan p;
+    int g = (int)(T < slots ? T : slots);
+    if (g < 1) g = 1;
+    p.q = (int)((T + g - 1) / g);
+    p.grid = (int)((T + p.q - 1) / p.q);
+    p.kmax = (p.q + ntiles - 1) / ntiles + 1;
+    p.partial_floats = (int64_t)p.grid * p.kmax * (P + PSTAT);
+    return p;
+}
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+static int64_t counters_bytes(int M) { return (((int64_t)M * sizeof(int) + 15) / 16) * 16; }
+
+template <typename Kernel>
+static int launch_policy(Kernel kernel, int smem, int& occ_cache, PolicyArgs& A, int P, void* ws, int64_t ws_bytes,
+                         cudaStream_t st, const char* name) {
+    if (occ_cache == 0) {
+        PROMP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        PROMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PT_THREADS, smem));
+        occ_cache = occ < 1 ? 1 : occ;
+    }
+    const TilePlan p = plan_tiles(A.M, A.N, sm_count() * occ_cache, P);
+    const int64_t need = counters_bytes(A.M) + p.partial_floats * (int64_t)sizeof(float);
+    if (ws_bytes < need) {
+        set_error("policy workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
+        return PROMP_ERR_WORKSPACE;
+    }
+    A.counters = (int*)ws;
+    A.partial = (float*)((char*)ws + counters_bytes(A.M));
+    A.q = p.q;
+    A.kmax = p.kmax;
+    kernel<<<p.grid, PT_THREADS, smem, st>>>(A);
+    PROMP_LAUNCH_CHECK(name);
+    return PROMP_OK;
 }
 
 template <int DO, int DA, int HID>
 static int launch_grad(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
-    using L = PLayout<DO, DA, HID>;
-    const int chunks = pick_chunks(A.M, A.N);
-    const int64_t need = (int64_t)A.M * chunks * (L::P + PSTAT) * sizeof(float) + (int64_t)A.M * sizeof(int);
-    if (ws_bytes < need) {
-        set_error("policy workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
-        return PROMP_ERR_WORKSPACE;
-    }
-    A.counters = (int*)ws;
-    A.partial = (float*)((char*)ws + (((int64_t)A.M * sizeof(int) + 15) / 16) * 16);
-    static bool attr_set = false;
-    const int smem = (int)sizeof(GradSmem<DO, DA, HID>);
-    if (!attr_set) {
-        PROMP_CUDA(cudaFuncSetAttribute(policy_grad_kernel<DO, DA, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    policy_grad_kernel<DO, DA, HID><<<dim3(chunks, A.M), PT_THREADS, smem, st>>>(A);
-    PROMP_LAUNCH_CHECK("policy_grad_kernel");
-    return PROMP_OK;
+    static int occ = 0;
+    return launch_policy(policy_grad_kernel<DO, DA, HID>, (int)sizeof(GradSmem<DO, DA, HID>), occ, A,
+                         PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_kernel");
 }
 
 template <int DO, int DA, int HID>
 static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
-    using L = PLayout<DO, DA, HID>;
-    const int chunks = pick_chunks(A.M, A.N);
-    const int64_t need = (int64_t)A.M * chunks * (L::P + PSTAT) * sizeof(float) + (int64_t)A.M * sizeof(int);
-    if (ws_bytes < need) {
-        set_error("policy workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
-        return PROMP_ERR_WORKSPACE;
-    }
-    A.counters = (int*)ws;
-    A.partial = (float*)((char*)ws + (((int64_t)A.M * sizeof(int) + 15) / 16) * 16);
-    static bool attr_set = false;
-    const int smem = (int)sizeof(HvpSmem<DO, DA, HID>);
-    if (!attr_set) {
-        PROMP_CUDA(cudaFuncSetAttribute(policy_hvp_kernel<DO, DA, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    policy_hvp_kernel<DO, DA, HID><<<dim3(chunks, A.M), PT_THREADS, smem, st>>>(A);
-    PROMP_LAUNCH_CHECK("policy_hvp_kernel");
-    return PROMP_OK;
+    static int occ = 0;
+    return launch_policy(policy_hvp_kernel<DO, DA, HID>, (int)sizeof(HvpSmem<DO, DA, HID>), occ, A,
+                         PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_kernel");
 }
 
 template <int DO, int DA, int HID>
@@ -826,16 +909,22 @@ static int launch_forward(int M, int N, const float* params, int64_t stride, con
 using namespace promp;
 
 extern "C" int64_t promp_policy_workspace_bytes(int M, int N, int obs_dim, int act_dim, int hidden) {
-    const int chunks = pick_chunks(M, N);
+    // upper bound over the occupancies the kernels can have (1..4 CTAs per SM on 148..160 SMs)
     const int P = promp::num_params(obs_dim, act_dim, hidden);
-    return (int64_t)M * chunks * (P + PSTAT) * sizeof(float) + (((int64_t)M * sizeof(int) + 15) / 16) * 16 + 16;
+    int64_t worst = 0;
+    for (int occ = 1; occ <= 4; ++occ) {
+        const TilePlan p = plan_tiles(M, N, 160 * occ, P);
+        if (p.partial_floats > worst) worst = p.partial_floats;
+        const TilePlan p2 = plan_tiles(M, N, 148 * occ, P);
+        if (p2.partial_floats > worst) worst = p2.partial_floats;
+    }
+    return counters_bytes(M) + worst * (int64_t)sizeof(float) + 16;
 }
 
 static int check_policy_args(const char* who, int M, int N, const void* params, const void* obs, const void* act,
                              const void* adv, const void* old_mean, const void* old_ls, const void* ws) {
     PROMP_REQUIRE(M > 0 && N > 0, "%s: M and N must be positive (got %d, %d)", who, M, N);
-    PROMP_REQUIRE(M <= 65535, "%s: M=%d exceeds the grid.y limit", who, M);
-    PROMP_REQUIRE(params && obs && act && adv && old_mean && old_ls && ws, "%s: null pointer argument", who);
+        PROMP_REQUIRE(params && obs && act && adv && old_mean && old_ls && ws, "%s: null pointer argument", who);
     return PROMP_OK;
 }
 

@@ -26,6 +26,7 @@ struct RolloutArgs {
     const float* init_state;
     const float* noise;
     uint64_t seed, stream_id;
+    const uint64_t* stream_id_dev;
     int clip_reported;
     float min_log_std;
     float *obs, *act, *mean, *rew;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
     RolloutSmem<KIND, HID>& S = smem_all[w];
 
     const float* th = A.params + (int64_t)m * A.param_stride;
+    if (A.stream_id_dev) A.stream_id += *A.stream_id_dev;   // device-side phase counter (CUDA-graph replays)
     const int64_t env_id = (int64_t)m * A.E + e;     // global env index
     const int64_t base = env_id * A.H;               // flat sample offset of this env (n = e*H + t)
 
@@ -412,7 +414,7 @@ extern "C" int promp_env_task_dim(int env_kind) {
 extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius, int M, int E, int H, int hidden,
                              const float* params, int64_t param_stride, const float* task_params,
                              const float* init_state, const float* noise, uint64_t seed, uint64_t stream_id,
-                             int clip_reported_log_std, float min_log_std, float* obs, float* act, float* mean,
+                             const uint64_t* stream_id_dev, int clip_reported_log_std, float min_log_std, float* obs, float* act, float* mean,
                              float* rew, uint8_t* done, float* info, float* log_std_out, float* final_state,
                              void* stream) {
     PROMP_REQUIRE(M > 0 && E > 0 && H > 0, "promp_rollout: M, E, H must be positive (got %d, %d, %d)", M, E, H);
@@ -422,7 +424,7 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
     PROMP_REQUIRE(hidden == 64 || hidden == 32, "promp_rollout: hidden size %d unsupported (32 or 64)", hidden);
     PROMP_REQUIRE(reward_type >= 0 && reward_type <= 2, "promp_rollout: bad reward_type %d", reward_type);
     RolloutArgs A{reward_type, sparse_radius, M, E, H, params, param_stride, task_params, init_state, noise, seed,
-                  stream_id, clip_reported_log_std, min_log_std, obs, act, mean, rew, done, info, log_std_out,
+                  stream_id, stream_id_dev, clip_reported_log_std, min_log_std, obs, act, mean, rew, done, info, log_std_out,
                   final_state};
     cudaStream_t st = (cudaStream_t)stream;
     switch (env_kind) {
@@ -440,6 +442,14 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
     }
     set_error("promp_rollout: unknown env_kind %d", env_kind);
     return PROMP_ERR_INVALID_ARG;
+}
+
+__global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
+extern "C" int promp_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+    PROMP_REQUIRE(counter != nullptr, "promp_counter_add: null counter");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+    PROMP_LAUNCH_CHECK("counter_add_kernel");
+    return PROMP_OK;
 }
 
 extern "C" int promp_env_step(int env_kind, int reward_type, float sparse_radius, int n_env, int H, float* state,

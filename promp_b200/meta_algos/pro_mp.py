@@ -42,21 +42,29 @@ class ProMP(MAMLAlgo):
         phases = [self._phase_of(s) for s in all_samples_data]
         if log: logger.log("Optimizing")
         stats = self.optimizer.optimize(self, phases)
+        self.last_stats_device = stats           # [loss_before, loss_after, inner_kl_0.., outer_kl] on the device
+        self._last_stats = None
+        if not (log or self.adaptive_inner_kl_penalty):
+            return                               # nothing is decided or logged on the host: no synchronisation
         if log: logger.log("Computing statistics")
-        # one device->host copy for everything that is logged / decided on the host
-        host = stats.cpu().numpy().astype(np.float64)
-        loss_before, loss_after = host[0], host[1]
-        inner_kls = host[2:2 + self.num_inner_grad_steps]
+        ls = self.last_stats                     # one device->host copy for everything logged / decided on the host
         if self.adaptive_inner_kl_penalty:
             if log: logger.log("Updating inner KL loss coefficients")
-            self.inner_kl_coeff = self.adapt_kl_coeff(self.inner_kl_coeff, inner_kls, self.target_inner_step)
-        self.last_stats = dict(loss_before=loss_before, loss_after=loss_after, inner_kls=inner_kls,
-                               outer_kl=host[2 + self.num_inner_grad_steps])
+            self.inner_kl_coeff = self.adapt_kl_coeff(self.inner_kl_coeff, ls['inner_kls'], self.target_inner_step)
         if log:
-            logger.logkv('LossBefore', loss_before)
-            logger.logkv('LossAfter', loss_after)
-            logger.logkv('KLInner', np.mean(inner_kls))
+            logger.logkv('LossBefore', ls['loss_before'])
+            logger.logkv('LossAfter', ls['loss_after'])
+            logger.logkv('KLInner', np.mean(ls['inner_kls']))
             logger.logkv('KLCoeffInner', np.mean(self.inner_kl_coeff))
+
+    @property
+    def last_stats(self):
+        if self._last_stats is None:
+            host = self.last_stats_device.cpu().numpy().astype(np.float64)
+            S1 = self.num_inner_grad_steps
+            self._last_stats = dict(loss_before=host[0], loss_after=host[1], inner_kls=host[2:2 + S1],
+                                    outer_kl=host[2 + S1])
+        return self._last_stats
 
     def loss_terms(self, res):
         """Scalar meta objective + KLs (global means) from a _meta_pass result, as a device vector
@@ -66,7 +74,11 @@ class ProMP(MAMLAlgo):
         S1 = self.num_inner_grad_steps
         vec = torch.cat([res['surr'].sum().view(1), res['inner_kl'].sum(1).view(-1), res['outer_kl'].sum().view(1)]) / Mg
         allreduce_sum_(vec)
-        coeff = torch.as_tensor(np.asarray(self.inner_kl_coeff, dtype=np.float32), device=vec.device)
+        key = tuple(float(c) for c in self.inner_kl_coeff)
+        if getattr(self, '_coeff_key', None) != key:          # cached on the device (no H2D inside a graph capture)
+            self._coeff_dev = torch.tensor(key, dtype=torch.float32, device=vec.device)
+            self._coeff_key = key
+        coeff = self._coeff_dev
         penalty = (coeff * vec[1:1 + S1]).mean() if S1 > 0 else vec.new_zeros(())
         return torch.cat([(vec[0] + penalty).view(1), vec[1:]])
 

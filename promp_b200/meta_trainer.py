@@ -56,6 +56,49 @@ class Trainer(object):
             logger.logkv('ItrTime', time.time() - t_itr)
         return all_samples_data
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the device part
+    def capture_graph(self, warmup=3):
+        """Capture everything of a meta-iteration that runs on the device (2x rollout + processing, inner adapt,
+        K Adam epochs + stats pass: ~40 kernel launches) into ONE CUDA graph.  Returns step(): draws the tasks
+        on the host (numpy RNG, as the reference), uploads them, replays the graph.  Requires in-kernel reset
+        states (reset_mode='device'), no host logging and a fixed KL coefficient; world_size 1."""
+        import torch
+        assert self.sampler.reset_mode == 'device', "graph replay needs reset_mode='device'"
+        assert not getattr(self.algo, 'adaptive_inner_kl_penalty', False), "adaptive KL coefficient is a host decision"
+        self.sampler.enable_device_phase_counter()
+
+        def device_part():
+            self.policy.switch_to_pre_update()
+            all_samples = []
+            for step in range(self.num_inner_grad_steps + 1):
+                paths = self.sampler.obtain_samples(log=False)
+                samples = self.sample_processor.process_samples(paths, log=False)
+                all_samples.append(samples)
+                if step < self.num_inner_grad_steps:
+                    self.algo._adapt(samples)
+            self.algo.optimize_policy(all_samples, log=False)
+            return all_samples
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.sampler.update_tasks()
+                device_part()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        self.sampler.update_tasks()
+        with torch.cuda.graph(graph):
+            self._graph_samples = device_part()
+        self._graph = graph
+
+        def step():
+            self.sampler.update_tasks()
+            graph.replay()
+            return self._graph_samples
+        return step
+
     def train(self):
         start = time.time()
         for itr in range(self.start_itr, self.n_itr):

@@ -48,6 +48,7 @@ class MetaSampler(object):
         self.seed = int(seed)
         self.task_shard = task_shard
         self._phase_counter = 0
+        self._phase_counter_dev = None      # device uint64 phase counter (graph mode)
         self._injected_noise = None
         self._injected_init = None
         self.vec_env = MetaDeviceEnvExecutor(env, self.meta_batch_size, self.envs_per_task, self.max_path_length)
@@ -101,11 +102,21 @@ class MetaSampler(object):
         self._phase_counter += 1
         _lib.call('promp_rollout', s['env_kind'], s['reward_type'], s['radius'], M, E, H, self.policy.hidden,
                   _lib.ptr(params), stride, _lib.ptr(self.vec_env.task_params_per_task), _lib.ptr(init_state),
-                  _lib.ptr(noise), self.seed, self._phase_counter, clip, float(self.policy.min_log_std),
+                  _lib.ptr(noise), self.seed, self._phase_counter, _lib.ptr(self._phase_counter_dev), clip,
+                  float(self.policy.min_log_std),
                   _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.mean), _lib.ptr(phase.rew),
                   _lib.ptr(phase.done), _lib.ptr(phase.info), _lib.ptr(phase.log_std), None, _lib.stream())
+        if self._phase_counter_dev is not None:
+            _lib.call('promp_counter_add', _lib.ptr(self._phase_counter_dev), 1 << 20, _lib.stream())
         phase.invalidate_host()
         return phase
+
+    def enable_device_phase_counter(self):
+        """Keep the Philox phase counter in device memory so that a captured CUDA graph draws fresh
+        noise / reset states on every replay."""
+        import torch
+        if self._phase_counter_dev is None:
+            self._phase_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     def _obtain_samples_fused(self):
         import torch
