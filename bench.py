@@ -176,7 +176,8 @@ def run_gpu(args):
     _lib.require_cuda()
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=120))
     wl = WORKLOADS[args.workload]
     M, E, H = wl['M'], wl['E'], wl['H']
     steps_per_iter = M * E * H * (PROMP['num_inner_grad_steps'] + 1) * world      # weak scaling: M tasks per GPU
@@ -231,12 +232,14 @@ def run_gpu(args):
     d2h = S * (M * 8 * 8 + M * sd['act_dim'] * 4 + (2 * M * E * H * 4 * 2 if sd['env_kind'] == 2 else 0)) + 4 * (3 + S - 1)
 
     out = None
+    # ---- per-kernel timing pass (instrumented, not part of the timed loops; every rank runs it because the
+    #      iteration contains the all-reduce) --------------------------------------------------------------
+    with LaunchCounter(time_kernels=True) as lk:
+        for i in range(3):
+            tr_dev.train_iteration(i, log=False)
+        kms = lk.kernel_ms()
+    barrier()
     if rank == 0:
-        # ---- per-kernel timing pass (instrumented, not part of the timed loops) ----------------------
-        with LaunchCounter(time_kernels=True) as lk:
-            for i in range(3):
-                tr_dev.train_iteration(i, log=False)
-            kms = lk.kernel_ms()
         per_kernel = {n: dict(launches_per_iter=len(v) // 3, avg_ms=float(np.mean(v)), total_ms_per_iter=float(np.sum(v) / 3))
                       for n, v in kms.items()}
         peaks, peak_src = measured_peaks()
