@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpromp_b200.so')
+LIB_PATH = os.environ.get('PROMP_B200_LIB', os.path.join(_HERE, 'libpromp_b200.so'))   # override: kernel experiments
 
 # enums (mirror include/promp_b200.h)
 ENV_POINT_CORNER, ENV_POINT, ENV_CHEETAH_DIR = 0, 1, 2

@@ -51,6 +51,15 @@ __host__ __device__ inline int num_params(int Do, int Da, int Hd) {
     return Do * Hd + Hd + Hd * Hd + Hd + Hd * Da + Da + Da;
 }
 
+// ---------------------------------------------------------------- math
+// tanh via one ex2.approx + one fast division: |abs error| <= ~2e-7 over the whole range (saturates to +-1
+// exactly for |x| > 10), ~4x fewer instructions than tanhf.  MUFU.TANH (tanh.approx) is only 2^-11 accurate
+// and would break the 1e-4 parity bar on gradients.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -27,6 +27,9 @@ struct TileCfg {
 template <int K, int LDA, int LDW, int RM>
 __device__ __forceinline__ void gemm_tile(const float* __restrict__ A, const float* __restrict__ W, int row0, int col0,
                                           float (&acc)[RM][4]) {
+#ifdef PROMP_EXP_NO_GEMM   // kernel-time experiments only (tools/kernel_time.py)
+    return;
+#endif
 #pragma unroll 4
     for (int k = 0; k < K; k += 4) {
         float4 a[RM], w[4];
@@ -68,6 +71,9 @@ __device__ __forceinline__ void gemm_tile_smallk(const float* __restrict__ A, co
 template <int LD, int RK>
 __device__ __forceinline__ void wgrad_tile(const float* __restrict__ A, const float* __restrict__ D, int k0, int col0,
                                            int nb, float (&g)[RK][4]) {
+#ifdef PROMP_EXP_NO_GEMM
+    return;
+#endif
 #pragma unroll 4
     for (int b = 0; b < nb; ++b) {
         const float4 d = *reinterpret_cast<const float4*>(D + b * LD + col0);

@@ -60,6 +60,27 @@ struct TileSched {
     __device__ __forceinline__ int cta_hi(int m) const { return ((m + 1) * ntiles - 1) / q; }
 };
 
+
+// Sum one float4 column of a task's partial slots over its CTA segments [c_lo, c_hi] in CTA order, with eight
+// independent L2 loads in flight (the naive dependent loop costs ~50 us of serial latency at the kernel tail).
+__device__ __forceinline__ float4 reduce_segments4(const float* partial, const TileSched& ts, int kmax, int pstride, int m,
+                                                   int c_lo, int c_hi, int p) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = c_lo; c0 <= c_hi; c0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u;
+            v[u] = (c <= c_hi) ? __ldcg(reinterpret_cast<const float4*>(
+                                     partial + ((int64_t)c * kmax + (m - ts.first_task(c))) * pstride + p))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s.x += v[u].x, s.y += v[u].y, s.z += v[u].z, s.w += v[u].w;
+    }
+    return s;
+}
+
 template <int DO, int DA, int HID>
 __device__ __forceinline__ void load_head_consts(const float* P, int clip, float min_ls, HeadIn<DA>& hin) {
     using L = PLayout<DO, DA, HID>;
@@ -74,6 +95,19 @@ __device__ __forceinline__ void load_head_consts(const float* P, int clip, float
 }
 
 // -------------------------------------------------------------------------------------------------
+// Thread roles inside a 256-thread CTA working on a 64-sample tile:
+//   GEMM role      (tx, ty): 4 (HID=64) or 2 (HID=32) rows x 4 columns of every [64 x HID] product
+//   row role       (rb, rq): 4 threads per sample row, each owns a quarter of the hidden units (layer 2 + head)
+//   column role    (cj, cp): thread owns hidden unit cj for the sample slice cp (small weight gradients)
+// Small reductions (bias / W0 / W2 gradients) are accumulated per thread in registers across tiles and
+// only combined through shared memory when the CTA flushes a task segment.
+template <int HID>
+struct RoleCfg {
+    static constexpr int NPART = PT_THREADS / HID;    // sample slices for the column role (4 | 8)
+    static constexpr int BPP = TB / NPART;            // samples per slice (16 | 8)
+    static constexpr int QW = HID / 4;                // hidden units per row-role thread (16 | 8)
+};
+
 template <int DO, int DA, int HID>
 struct GradSmem {
     using L = PLayout<DO, DA, HID>;
@@ -83,7 +117,7 @@ struct GradSmem {
     float P[PP];
     float W1T[HID * HID];
     float X[TB * DOP];
-    float H1[TB * C::LD];
+    float H1[TB * C::LD];     // also: flush scratch
     float H2[TB * C::LD];
     float DMU[TB * DA];
     float DLS[TB * DA];
@@ -91,15 +125,17 @@ struct GradSmem {
     int last;
 };
 
+// Combine per-thread partial sums through shared memory: out[idx] = sum_p scratch[p][idx], idx < n.
+// `mine(i)` yields this thread's partial for its i-th element; thread `tid` holds elements idx = base(tid) .. ; generic
+// helper used only at flush time (once per task segment), so simplicity beats speed here.
 template <int DO, int DA, int HID>
-__global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
+__global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A) {
     using L = PLayout<DO, DA, HID>;
     using C = TileCfg<HID>;
+    using R = RoleCfg<HID>;
     using SM = GradSmem<DO, DA, HID>;
     constexpr int LD = C::LD, RM = C::RM, RK = C::RK, DOP = SM::DOP;
-    constexpr int NW0 = (DO * HID + PT_THREADS - 1) / PT_THREADS;
-    constexpr int NW2 = (HID * DA + PT_THREADS - 1) / PT_THREADS;
-    constexpr int NU = HID / 32;
+    constexpr int NPART = R::NPART, BPP = R::BPP, QW = R::QW;
     constexpr int PSTRIDE = L::P + PSTAT;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -108,6 +144,8 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % C::TX, ty = tid / C::TX;
     const int row0 = ty * RM, col0 = tx * 4;
+    const int rb = tid >> 2, rq = tid & 3;           // row role
+    const int cj = tid % HID, cp = tid / HID;        // column role
     const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
     const float invN = 1.0f / (float)N;
@@ -115,17 +153,22 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
     const float* th = nullptr;
     HeadIn<DA> hin;
 
-    float gW1[RK][4], gB1[4], gW0[NW0], gB0, gW2[NW2], gB2, gLS;
-    float s_obj, s_kl, s_ratio;
+    // register accumulators (per task segment)
+    float gW1[RK][4];        // GEMM role: H1^T D2 block
+    float gB1p[4], gB0p[4];  // GEMM role: column sums over this thread's rows
+    float gW0p[DO], gW2p[DA];   // column role: X^T D1 / H2^T DMU for unit cj over sample slice cp
+    float gB2 = 0.f, gLS = 0.f; // thread tid < DA
+    float s_obj, s_kl, s_ratio; // row role, rq == 0
     auto zero_acc = [&]() {
 #pragma unroll
         for (int r = 0; r < RK; ++r) gW1[r][0] = gW1[r][1] = gW1[r][2] = gW1[r][3] = 0.f;
-        gB1[0] = gB1[1] = gB1[2] = gB1[3] = 0.f;
 #pragma unroll
-        for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
+        for (int c = 0; c < 4; ++c) gB1p[c] = gB0p[c] = 0.f;
 #pragma unroll
-        for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
-        gB0 = gB2 = gLS = 0.f;
+        for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
+        gB2 = gLS = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -135,7 +178,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
         for (int i = tid; i < L::P; i += PT_THREADS) S.P[i] = __ldg(th + i);
         __syncthreads();
         for (int i = tid; i < HID * HID; i += PT_THREADS) {
-            const int k = i / HID, j = i % HID;
+            const int j = i / HID, k = i % HID;      // consecutive threads -> consecutive W1T addresses
             S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
         }
         load_head_consts<DO, DA, HID>(S.P, A.clip_log_std, A.min_log_std, hin);
@@ -143,30 +186,57 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
     // write this CTA's partial sums for task m; the last segment of the task reduces them in CTA order
     auto flush = [&](int m) {
         float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+        float* scr = S.H1;      // free between tiles
+        __syncthreads();
         if (want_grad) {
-#pragma unroll
-            for (int r = 0; r < NW0; ++r) {
-                const int idx = tid + r * PT_THREADS;
-                if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
-            }
-            if (tid < HID) part[L::B0 + tid] = gB0;
 #pragma unroll
             for (int r = 0; r < RK; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1[r][c];
-            if (ty == 0)
+            // column sums: reduce the C::TY row groups
 #pragma unroll
-                for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
+            for (int c = 0; c < 4; ++c) scr[ty * HID + col0 + c] = gB1p[c];
+            __syncthreads();
+            if (tid < HID) {
+                float s = 0.f;
+                for (int y = 0; y < C::TY; ++y) s += scr[y * HID + tid];
+                part[L::B1 + tid] = s;
+            }
+            __syncthreads();
 #pragma unroll
-            for (int r = 0; r < NW2; ++r) {
-                const int idx = tid + r * PT_THREADS;
-                if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
+            for (int c = 0; c < 4; ++c) scr[ty * HID + col0 + c] = gB0p[c];
+            __syncthreads();
+            if (tid < HID) {
+                float s = 0.f;
+                for (int y = 0; y < C::TY; ++y) s += scr[y * HID + tid];
+                part[L::B0 + tid] = s;
+            }
+            __syncthreads();
+            // W0 / W2 gradients: reduce the NPART sample slices
+#pragma unroll
+            for (int i = 0; i < DO; ++i) scr[(cp * DO + i) * HID + cj] = gW0p[i];
+            __syncthreads();
+            for (int idx = tid; idx < DO * HID; idx += PT_THREADS) {
+                float s = 0.f;
+                for (int p = 0; p < NPART; ++p) s += scr[p * DO * HID + idx];
+                part[L::W0 + idx] = s;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < DA; ++d) scr[(cp * HID + cj) * DA + d] = gW2p[d];
+            __syncthreads();
+            for (int idx = tid; idx < HID * DA; idx += PT_THREADS) {
+                float s = 0.f;
+                for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
+                part[L::W2 + idx] = s;
             }
             if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
         }
-        // head sums are valid in every lane of a warp (computed redundantly); reduce across warps
+        // head statistics (held by the rq == 0 threads)
+        const float v0 = warp_sum(rq == 0 ? s_obj : 0.f), v1 = warp_sum(rq == 0 ? s_kl : 0.f),
+                    v2 = warp_sum(rq == 0 ? s_ratio : 0.f);
         __syncthreads();
-        if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
+        if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
         __syncthreads();
         if (tid < 3) {
             float s = 0.f;
@@ -181,12 +251,14 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
         if (S.last) {
             __threadfence();
             if (want_grad) {
-                for (int p = tid; p < L::P; p += PT_THREADS) {
-                    float s = 0.f;
-                    for (int c = c_lo; c <= c_hi; ++c)
-                        s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + p);
-                    A.grad[(int64_t)m * L::P + p] = s;
-                    if (A.out_params) A.out_params[(int64_t)m * L::P + p] = S.P[p] - A.sgd_lr * s;   // meta_algos/base.py:209
+                static_assert(L::P % 4 == 0 && PSTRIDE % 4 == 0, "float4 reduction needs P % 4 == 0");
+                for (int p = 4 * tid; p < L::P; p += 4 * PT_THREADS) {
+                    const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                    *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
+                    if (A.out_params)      // meta_algos/base.py:209
+                        *reinterpret_cast<float4*>(A.out_params + (int64_t)m * L::P + p) =
+                            make_float4(S.P[p] - A.sgd_lr * s.x, S.P[p + 1] - A.sgd_lr * s.y, S.P[p + 2] - A.sgd_lr * s.z,
+                                        S.P[p + 3] - A.sgd_lr * s.w);
                 }
             }
             if (A.stats && tid < 3) {
@@ -227,7 +299,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
 #pragma unroll
             for (int i = 0; i < RM; ++i)
                 *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) =
-                    make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+                    make_float4(tanh_fast(acc[i][0]), tanh_fast(acc[i][1]), tanh_fast(acc[i][2]), tanh_fast(acc[i][3]));
         }
         __syncthreads();
         // ---- layer 1: H2 = tanh(H1 W1 + b1)
@@ -240,76 +312,86 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
 #pragma unroll
             for (int i = 0; i < RM; ++i)
                 *reinterpret_cast<float4*>(S.H2 + (row0 + i) * LD + col0) =
-                    make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+                    make_float4(tanh_fast(acc[i][0]), tanh_fast(acc[i][1]), tanh_fast(acc[i][2]), tanh_fast(acc[i][3]));
         }
         __syncthreads();
-        // ---- layer 2 (warp-shuffle reduction) + Gaussian head; warp w owns rows w*8 .. w*8+7
-        for (int r = 0; r < TB / (PT_THREADS / 32); ++r) {
-            const int b = warp * (TB / (PT_THREADS / 32)) + r;
+        // ---- layer 2 + Gaussian head: 4 threads per sample row, quarter dot products + 2 shuffles
+#ifndef PROMP_EXP_NO_HEAD
+        {
             float mu[DA];
 #pragma unroll
             for (int d = 0; d < DA; ++d) mu[d] = 0.f;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                const int j = lane + 32 * u;
-                const float h = S.H2[b * LD + j];
-#pragma unroll
-                for (int d = 0; d < DA; ++d) mu[d] = fmaf(h, S.P[L::W2 + j * DA + d], mu[d]);
-            }
-#pragma unroll
-            for (int d = 0; d < DA; ++d) mu[d] = warp_sum(mu[d]) + S.P[L::B2 + d];
-            float dmu[DA], dls[DA];
-            if (b < nb) {
-                const int64_t n = g0 + b;
-                float a[DA], mo[DA], lso[DA];
+            for (int k4 = 0; k4 < QW / 4; ++k4) {
+                const int j = rq * QW + 4 * k4;
+                const float4 h = *reinterpret_cast<const float4*>(S.H2 + rb * LD + j);
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
-                    a[d] = __ldg(A.act + n * DA + d);
-                    mo[d] = __ldg(A.old_mean + n * DA + d);
-                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    mu[d] = fmaf(h.x, S.P[L::W2 + (j + 0) * DA + d], mu[d]);
+                    mu[d] = fmaf(h.y, S.P[L::W2 + (j + 1) * DA + d], mu[d]);
+                    mu[d] = fmaf(h.z, S.P[L::W2 + (j + 2) * DA + d], mu[d]);
+                    mu[d] = fmaf(h.w, S.P[L::W2 + (j + 3) * DA + d], mu[d]);
                 }
-                const float adv = __ldg(A.adv + n);
-                HeadOut<DA> o;
-                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
-                const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
-#pragma unroll
-                for (int d = 0; d < DA; ++d) {
-                    dmu[d] = wt * o.zeta[d] / hin.sig[d] + kc * o.dkl_dmu[d];
-                    dls[d] = (wt * (o.zeta[d] * o.zeta[d] - 1.f) + kc * o.dkl_dls[d]) * hin.ls_mask[d];
-                }
-                s_obj += o.obj;
-                s_kl += o.kl;
-                s_ratio += o.ratio;
-            } else {
-#pragma unroll
-                for (int d = 0; d < DA; ++d) dmu[d] = dls[d] = 0.f;
             }
-            if (lane == 0) {
 #pragma unroll
-                for (int d = 0; d < DA; ++d) S.DMU[b * DA + d] = dmu[d], S.DLS[b * DA + d] = dls[d];
+            for (int d = 0; d < DA; ++d) {
+                mu[d] += __shfl_xor_sync(0xffffffffu, mu[d], 1);
+                mu[d] += __shfl_xor_sync(0xffffffffu, mu[d], 2);
+                mu[d] += S.P[L::B2 + d];
+            }
+            if (rq == 0) {
+                float dmu[DA], dls[DA];
+                if (rb < nb) {
+                    const int64_t n = g0 + rb;
+                    float a[DA], mo[DA], lso[DA];
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        a[d] = __ldg(A.act + n * DA + d);
+                        mo[d] = __ldg(A.old_mean + n * DA + d);
+                        lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    }
+                    const float adv = __ldg(A.adv + n);
+                    HeadOut<DA> o;
+                    gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                    const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        dmu[d] = wt * o.zeta[d] / hin.sig[d] + kc * o.dkl_dmu[d];
+                        dls[d] = (wt * (o.zeta[d] * o.zeta[d] - 1.f) + kc * o.dkl_dls[d]) * hin.ls_mask[d];
+                    }
+                    s_obj += o.obj;
+                    s_kl += o.kl;
+                    s_ratio += o.ratio;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) dmu[d] = dls[d] = 0.f;
+                }
+#pragma unroll
+                for (int d = 0; d < DA; ++d) S.DMU[rb * DA + d] = dmu[d], S.DLS[rb * DA + d] = dls[d];
             }
         }
+#endif
         if (!want_grad) continue;
         __syncthreads();
-        // ---- output layer gradients
+        // ---- output layer gradients (column role): gW2[cj][d] += sum_{b in slice} H2[b][cj] * DMU[b][d]
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float h = S.H2[b * LD + cj];
 #pragma unroll
-        for (int r = 0; r < NW2; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < HID * DA) {
-                const int j = idx / DA, d = idx % DA;
-                float s = 0.f;
-                for (int b = 0; b < nb; ++b) s = fmaf(S.H2[b * LD + j], S.DMU[b * DA + d], s);
-                gW2[r] += s;
+                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.DMU[b * DA + d], gW2p[d]);
+            }
+            if (tid < DA) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int b = 0; b < nb; ++b) s1 += S.DMU[b * DA + tid], s2 += S.DLS[b * DA + tid];
+                gB2 += s1;
+                gLS += s2;
             }
         }
-        if (tid < DA) {
-            float s1 = 0.f, s2 = 0.f;
-            for (int b = 0; b < nb; ++b) s1 += S.DMU[b * DA + tid], s2 += S.DLS[b * DA + tid];
-            gB2 += s1;
-            gLS += s2;
-        }
         __syncthreads();
-        // ---- D2 = (DMU W2^T) * (1 - H2^2), in place over H2
+        // ---- D2 = (DMU W2^T) * (1 - H2^2), in place over H2; bias gradient accumulates on the fly
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
             const int b = row0 + i;
@@ -321,18 +403,13 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
 #pragma unroll
                 for (int d = 0; d < DA; ++d) dh = fmaf(S.DMU[b * DA + d], S.P[L::W2 + (col0 + c) * DA + d], dh);
                 o4[c] = dh * (1.f - hv[c] * hv[c]);
+                gB1p[c] += o4[c];
             }
             *reinterpret_cast<float4*>(S.H2 + b * LD + col0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
         __syncthreads();
-        // ---- gW1 += H1^T D2, gB1 += colsum(D2); dH1 = D2 W1^T
+        // ---- gW1 += H1^T D2 ; dH1 = D2 W1^T
         wgrad_tile<LD, RK>(S.H1, S.H2, ty * RK, col0, nb, gW1);
-        if (ty == 0) {
-            for (int b = 0; b < nb; ++b) {
-                const float4 d = *reinterpret_cast<const float4*>(S.H2 + b * LD + col0);
-                gB1[0] += d.x; gB1[1] += d.y; gB1[2] += d.z; gB1[3] += d.w;
-            }
-        }
         float acc[RM][4];
 #pragma unroll
         for (int i = 0; i < RM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -341,29 +418,24 @@ __global__ void __launch_bounds__(PT_THREADS) policy_grad_kernel(PolicyArgs A) {
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
             float4 h = *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0);
-            *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) =
-                make_float4(acc[i][0] * (1.f - h.x * h.x), acc[i][1] * (1.f - h.y * h.y), acc[i][2] * (1.f - h.z * h.z),
-                            acc[i][3] * (1.f - h.w * h.w));
+            const float4 d1 = make_float4(acc[i][0] * (1.f - h.x * h.x), acc[i][1] * (1.f - h.y * h.y),
+                                          acc[i][2] * (1.f - h.z * h.z), acc[i][3] * (1.f - h.w * h.w));
+            gB0p[0] += d1.x; gB0p[1] += d1.y; gB0p[2] += d1.z; gB0p[3] += d1.w;
+            *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) = d1;
         }
         __syncthreads();
-        // ---- gW0 += X^T D1, gB0 += colsum(D1)
+        // ---- gW0 += X^T D1 (column role)
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float d1 = S.H1[b * LD + cj];
 #pragma unroll
-        for (int r = 0; r < NW0; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < DO * HID) {
-                const int i = idx / HID, j = idx % HID;
-                float s = 0.f;
-                for (int b = 0; b < nb; ++b) s = fmaf(S.X[b * DOP + i], S.H1[b * LD + j], s);
-                gW0[r] += s;
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(S.X[b * DOP + i], d1, gW0p[i]);
             }
         }
-        if (tid < HID) {
-            float s = 0.f;
-            for (int b = 0; b < nb; ++b) s += S.H1[b * LD + tid];
-            gB0 += s;
-        }
     }
-
     if (cur_m >= 0) flush(cur_m);
 }
 
@@ -384,7 +456,7 @@ struct HvpSmem {
     float W1T[HID * HID];
     float V1T[HID * HID];
     float X[TB * DOP];
-    float H1[TB * C::LD];
+    float H1[TB * C::LD];     // also: flush scratch
     float R1[TB * C::LD];
     float H2[TB * C::LD];
     float R2[TB * C::LD];
@@ -399,11 +471,10 @@ template <int DO, int DA, int HID>
 __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     using L = PLayout<DO, DA, HID>;
     using C = TileCfg<HID>;
+    using R = RoleCfg<HID>;
     using SM = HvpSmem<DO, DA, HID>;
     constexpr int LD = C::LD, RM = C::RM, RK = C::RK, DOP = SM::DOP;
-    constexpr int NW0 = (DO * HID + PT_THREADS - 1) / PT_THREADS;
-    constexpr int NW2 = (HID * DA + PT_THREADS - 1) / PT_THREADS;
-    constexpr int NU = HID / 32;
+    constexpr int NPART = R::NPART, BPP = R::BPP, QW = R::QW;
     constexpr int PSTRIDE = L::P + PSTAT;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -412,6 +483,8 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid % C::TX, ty = tid / C::TX;
     const int row0 = ty * RM, col0 = tx * 4;
+    const int rb = tid >> 2, rq = tid & 3;
+    const int cj = tid % HID, cp = tid / HID;
     const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
     const float invN = 1.0f / (float)N;
@@ -420,20 +493,22 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     HeadIn<DA> hin;
     float rls[DA];     // tangent of the (clipped) log_std
 
-    // accumulators: gC* multiply 1, gA* multiply `ac`
-    float gW1c[RK][4], gW1a[RK][4], gB1[4], gW0[NW0], gB0, gW2[NW2], gB2, gLS;
+    // accumulators: gW1c multiplies 1, gW1a multiplies `ac`
+    float gW1c[RK][4], gW1a[RK][4], gB1p[4], gB0p[4], gW0p[DO], gW2p[DA];
+    float gB2 = 0.f, gLS = 0.f;
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
         for (int r = 0; r < RK; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) gW1c[r][c] = gW1a[r][c] = 0.f;
-        gB1[0] = gB1[1] = gB1[2] = gB1[3] = 0.f;
 #pragma unroll
-        for (int r = 0; r < NW0; ++r) gW0[r] = 0.f;
+        for (int c = 0; c < 4; ++c) gB1p[c] = gB0p[c] = 0.f;
 #pragma unroll
-        for (int r = 0; r < NW2; ++r) gW2[r] = 0.f;
-        gB0 = gB2 = gLS = 0.f;
+        for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
+        gB2 = gLS = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -447,7 +522,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
         }
         __syncthreads();
         for (int i = tid; i < HID * HID; i += PT_THREADS) {
-            const int k = i / HID, j = i % HID;
+            const int j = i / HID, k = i % HID;      // consecutive threads -> consecutive addresses of the transposes
             if (reload_p) S.W1T[j * HID + k] = S.P[L::W1 + k * HID + j];
             S.V1T[j * HID + k] = S.V[L::W1 + k * HID + j];
         }
@@ -457,27 +532,52 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     };
     auto flush = [&](int m) {
         float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
-#pragma unroll
-        for (int r = 0; r < NW0; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < DO * HID) part[L::W0 + idx] = gW0[r];
-        }
-        if (tid < HID) part[L::B0 + tid] = gB0;
+        float* scr = S.H1;
+        __syncthreads();
 #pragma unroll
         for (int r = 0; r < RK; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) part[L::W1 + (ty * RK + r) * HID + col0 + c] = gW1c[r][c] + ac * gW1a[r][c];
-        if (ty == 0)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) part[L::B1 + col0 + c] = gB1[c];
+        for (int c = 0; c < 4; ++c) scr[ty * HID + col0 + c] = gB1p[c];
+        __syncthreads();
+        if (tid < HID) {
+            float s = 0.f;
+            for (int y = 0; y < C::TY; ++y) s += scr[y * HID + tid];
+            part[L::B1 + tid] = s;
+        }
+        __syncthreads();
 #pragma unroll
-        for (int r = 0; r < NW2; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < HID * DA) part[L::W2 + idx] = gW2[r];
+        for (int c = 0; c < 4; ++c) scr[ty * HID + col0 + c] = gB0p[c];
+        __syncthreads();
+        if (tid < HID) {
+            float s = 0.f;
+            for (int y = 0; y < C::TY; ++y) s += scr[y * HID + tid];
+            part[L::B0 + tid] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < DO; ++i) scr[(cp * DO + i) * HID + cj] = gW0p[i];
+        __syncthreads();
+        for (int idx = tid; idx < DO * HID; idx += PT_THREADS) {
+            float s = 0.f;
+            for (int p = 0; p < NPART; ++p) s += scr[p * DO * HID + idx];
+            part[L::W0 + idx] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < DA; ++d) scr[(cp * HID + cj) * DA + d] = gW2p[d];
+        __syncthreads();
+        for (int idx = tid; idx < HID * DA; idx += PT_THREADS) {
+            float s = 0.f;
+            for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
+            part[L::W2 + idx] = s;
         }
         if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+        const float v0 = warp_sum(rq == 0 ? s_obj : 0.f), v1 = warp_sum(rq == 0 ? s_kl : 0.f),
+                    v2 = warp_sum(rq == 0 ? s_ratio : 0.f);
         __syncthreads();
-        if (lane == 0) S.red[warp] = s_obj, S.red[8 + warp] = s_kl, S.red[16 + warp] = s_ratio;
+        if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
         __syncthreads();
         if (tid < 3) {
             float s = 0.f;
@@ -491,11 +591,11 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
         __syncthreads();
         if (S.last) {
             __threadfence();
-            for (int p = tid; p < L::P; p += PT_THREADS) {
-                float s = 0.f;
-                for (int c = c_lo; c <= c_hi; ++c)
-                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + p);
-                A.out[(int64_t)m * L::P + p] = S.V[p] + s;
+            static_assert(L::P % 4 == 0 && PSTRIDE % 4 == 0, "float4 reduction needs P % 4 == 0");
+            for (int p = 4 * tid; p < L::P; p += 4 * PT_THREADS) {
+                const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) =
+                    make_float4(S.V[p] + s.x, S.V[p + 1] + s.y, S.V[p + 2] + s.z, S.V[p + 3] + s.w);
             }
             if (A.stats && tid < 3) {
                 float s = 0.f;
@@ -541,7 +641,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
             for (int i = 0; i < RM; ++i) {
                 float h[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) h[c] = tanhf(acc[i][c]);
+                for (int c = 0; c < 4; ++c) h[c] = tanh_fast(acc[i][c]);
                 *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(S.R1 + (row0 + i) * LD + col0) =
                     make_float4((1.f - h[0] * h[0]) * racc[i][0], (1.f - h[1] * h[1]) * racc[i][1],
@@ -566,7 +666,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
             for (int i = 0; i < RM; ++i) {
                 float h[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) h[c] = tanhf(acc[i][c]);
+                for (int c = 0; c < 4; ++c) h[c] = tanh_fast(acc[i][c]);
                 *reinterpret_cast<float4*>(S.H2 + (row0 + i) * LD + col0) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(S.R2 + (row0 + i) * LD + col0) =
                     make_float4((1.f - h[0] * h[0]) * racc[i][0], (1.f - h[1] * h[1]) * racc[i][1],
@@ -574,95 +674,101 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
             }
         }
         __syncthreads();
-        // ---- layer 2, its tangent, and the Gaussian head with its tangent
-        for (int r = 0; r < TB / (PT_THREADS / 32); ++r) {
-            const int b = warp * (TB / (PT_THREADS / 32)) + r;
+        // ---- layer 2, its tangent, and the Gaussian head with its tangent (row role)
+#ifndef PROMP_EXP_NO_HEAD
+        {
             float mu[DA], rmu[DA];
 #pragma unroll
             for (int d = 0; d < DA; ++d) mu[d] = rmu[d] = 0.f;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                const int j = lane + 32 * u;
-                const float h = S.H2[b * LD + j], rh = S.R2[b * LD + j];
+            for (int k4 = 0; k4 < QW / 4; ++k4) {
+                const int j = rq * QW + 4 * k4;
+                const float4 h4 = *reinterpret_cast<const float4*>(S.H2 + rb * LD + j);
+                const float4 r4 = *reinterpret_cast<const float4*>(S.R2 + rb * LD + j);
+                const float hv[4] = {h4.x, h4.y, h4.z, h4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-                for (int d = 0; d < DA; ++d) {
-                    const float w2 = S.P[L::W2 + j * DA + d];
-                    mu[d] = fmaf(h, w2, mu[d]);
-                    rmu[d] = fmaf(rh, w2, fmaf(h, S.V[L::W2 + j * DA + d], rmu[d]));
-                }
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        const float w2 = S.P[L::W2 + (j + e) * DA + d];
+                        mu[d] = fmaf(hv[e], w2, mu[d]);
+                        rmu[d] = fmaf(rv[e], w2, fmaf(hv[e], S.V[L::W2 + (j + e) * DA + d], rmu[d]));
+                    }
             }
 #pragma unroll
             for (int d = 0; d < DA; ++d) {
-                mu[d] = warp_sum(mu[d]) + S.P[L::B2 + d];
-                rmu[d] = warp_sum(rmu[d]) + S.V[L::B2 + d];
+                mu[d] += __shfl_xor_sync(0xffffffffu, mu[d], 1);
+                mu[d] += __shfl_xor_sync(0xffffffffu, mu[d], 2);
+                rmu[d] += __shfl_xor_sync(0xffffffffu, rmu[d], 1);
+                rmu[d] += __shfl_xor_sync(0xffffffffu, rmu[d], 2);
+                mu[d] += S.P[L::B2 + d];
+                rmu[d] += S.V[L::B2 + d];
             }
-            float dmu[DA], cmu[DA], cls[DA];
-            if (b < nb) {
-                const int64_t n = g0 + b;
-                float a[DA], mo[DA], lso[DA];
+            if (rq == 0) {
+                float dmu[DA], cmu[DA], cls[DA];
+                if (rb < nb) {
+                    const int64_t n = g0 + rb;
+                    float a[DA], mo[DA], lso[DA];
 #pragma unroll
-                for (int d = 0; d < DA; ++d) {
-                    a[d] = __ldg(A.act + n * DA + d);
-                    mo[d] = __ldg(A.old_mean + n * DA + d);
-                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    for (int d = 0; d < DA; ++d) {
+                        a[d] = __ldg(A.act + n * DA + d);
+                        mo[d] = __ldg(A.old_mean + n * DA + d);
+                        lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    }
+                    const float adv = __ldg(A.adv + n);
+                    HeadOut<DA> o;
+                    gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                    const float wt = o.w * invN, kc = A.kl_coeff * invN;
+                    // tangent of log p:  R l = sum_d (zeta/sig) R mu + (zeta^2 - 1) R ls
+                    float rl = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d)
+                        rl += (o.zeta[d] / hin.sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
+                    // d w / d logp: RATIO w = -A r -> R w = w R l ; LOGLIK w = -A -> 0
+                    const float rwt = (A.obj_kind == PROMP_OBJ_RATIO) ? wt * rl : 0.f;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        const float is = 1.f / hin.sig[d], z = o.zeta[d];
+                        const float rz = -rmu[d] * is - z * rls[d];
+                        dmu[d] = wt * z * is;
+                        const float rdmu = rwt * z * is + wt * (rz * is - z * rls[d] * is);
+                        const float rdls = rwt * (z * z - 1.f) + wt * 2.f * z * rz;
+                        cmu[d] = ac * rdmu + kc * o.dkl_dmu[d];
+                        cls[d] = (ac * rdls + kc * o.dkl_dls[d]) * hin.ls_mask[d];
+                    }
+                    s_obj += o.obj;
+                    s_kl += o.kl;
+                    s_ratio += o.ratio;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) dmu[d] = cmu[d] = cls[d] = 0.f;
                 }
-                const float adv = __ldg(A.adv + n);
-                HeadOut<DA> o;
-                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
-                const float wt = o.w * invN, kc = A.kl_coeff * invN;
-                // tangent of log p:  R l = sum_d (zeta/sig) R mu + (zeta^2 - 1) R ls
-                float rl = 0.f;
 #pragma unroll
                 for (int d = 0; d < DA; ++d)
-                    rl += (o.zeta[d] / hin.sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
-                // d w / d logp: RATIO w = -A r -> R w = w R l ; LOGLIK w = -A -> 0
-                const float rwt = (A.obj_kind == PROMP_OBJ_RATIO) ? wt * rl : 0.f;
-#pragma unroll
-                for (int d = 0; d < DA; ++d) {
-                    const float is = 1.f / hin.sig[d], z = o.zeta[d];
-                    const float rz = -rmu[d] * is - z * rls[d];
-                    dmu[d] = wt * z * is;
-                    const float rdmu = rwt * z * is + wt * (rz * is - z * rls[d] * is);
-                    const float rdls = rwt * (z * z - 1.f) + wt * 2.f * z * rz;
-                    cmu[d] = ac * rdmu + kc * o.dkl_dmu[d];
-                    cls[d] = (ac * rdls + kc * o.dkl_dls[d]) * hin.ls_mask[d];
-                }
-                s_obj += o.obj;
-                s_kl += o.kl;
-                s_ratio += o.ratio;
-            } else {
-#pragma unroll
-                for (int d = 0; d < DA; ++d) dmu[d] = cmu[d] = cls[d] = 0.f;
+                    S.DMU[rb * DA + d] = dmu[d], S.CMU[rb * DA + d] = cmu[d], S.CLS[rb * DA + d] = cls[d];
             }
-            if (lane == 0) {
+        }
+#endif
+        __syncthreads();
+        // ---- output layer (column role): out_W2 += H2^T CMU + ac * R2^T DMU ; out_b2 += colsum CMU ; out_ls += colsum CLS
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float h = S.H2[b * LD + cj], r = ac * S.R2[b * LD + cj];
 #pragma unroll
-                for (int d = 0; d < DA; ++d)
-                    S.DMU[b * DA + d] = dmu[d], S.CMU[b * DA + d] = cmu[d], S.CLS[b * DA + d] = cls[d];
+                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.CMU[b * DA + d], fmaf(r, S.DMU[b * DA + d], gW2p[d]));
+            }
+            if (tid < DA) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int b = 0; b < nb; ++b) s1 += S.CMU[b * DA + tid], s2 += S.CLS[b * DA + tid];
+                gB2 += s1;
+                gLS += s2;
             }
         }
         __syncthreads();
-        // ---- output layer: out_W2 += H2^T CMU + ac * R2^T DMU ; out_b2 += colsum CMU ; out_ls += colsum CLS
-#pragma unroll
-        for (int r = 0; r < NW2; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < HID * DA) {
-                const int j = idx / DA, d = idx % DA;
-                float s = 0.f, sa = 0.f;
-                for (int b = 0; b < nb; ++b) {
-                    s = fmaf(S.H2[b * LD + j], S.CMU[b * DA + d], s);
-                    sa = fmaf(S.R2[b * LD + j], S.DMU[b * DA + d], sa);
-                }
-                gW2[r] += s + ac * sa;
-            }
-        }
-        if (tid < DA) {
-            float s1 = 0.f, s2 = 0.f;
-            for (int b = 0; b < nb; ++b) s1 += S.CMU[b * DA + tid], s2 += S.CLS[b * DA + tid];
-            gB2 += s1;
-            gLS += s2;
-        }
-        __syncthreads();
-        // ---- D2 = dH2 * g2 -> H2 ; C2 = CdH2 * g2 + ac * dH2 * (-2 H2 R2) -> R2
+        // ---- D2 = dH2 * g2 -> H2 ; C2 = CdH2 * g2 + ac * dH2 * (-2 H2 R2) -> R2 ; out_b1 accumulates C2 on the fly
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
             const int b = row0 + i;
@@ -683,20 +789,15 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
                 const float g2 = 1.f - hv[c] * hv[c];
                 d2[c] = dh * g2;
                 c2[c] = ch * g2 + ac * dh * (-2.f * hv[c] * rv[c]);
+                gB1p[c] += c2[c];
             }
             *reinterpret_cast<float4*>(S.H2 + b * LD + col0) = make_float4(d2[0], d2[1], d2[2], d2[3]);
             *reinterpret_cast<float4*>(S.R2 + b * LD + col0) = make_float4(c2[0], c2[1], c2[2], c2[3]);
         }
         __syncthreads();
-        // ---- out_W1 += H1^T C2 + ac * R1^T D2 ; out_b1 += colsum C2
+        // ---- out_W1 += H1^T C2 + ac * R1^T D2
         wgrad_tile<LD, RK>(S.H1, S.R2, ty * RK, col0, nb, gW1c);
         wgrad_tile<LD, RK>(S.R1, S.H2, ty * RK, col0, nb, gW1a);
-        if (ty == 0) {
-            for (int b = 0; b < nb; ++b) {
-                const float4 d = *reinterpret_cast<const float4*>(S.R2 + b * LD + col0);
-                gB1[0] += d.x; gB1[1] += d.y; gB1[2] += d.z; gB1[3] += d.w;
-            }
-        }
         // ---- dH1 = D2 W1^T ; CdH1 = C2 W1^T + ac * D2 V1^T
         float dh1[RM][4], ch1[RM][4];
 #pragma unroll
@@ -711,7 +812,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
         gemm_tile<HID, LD, HID, RM>(S.R2, S.W1T, row0, col0, ch1);
         gemm_tile<HID, LD, HID, RM>(S.H2, S.W1T, row0, col0, dh1);
         __syncthreads();   // all reads of H1 / R1 by the weight-gradient loops are done
-        // ---- C1 = CdH1 * g1 + ac * dH1 * (-2 H1 R1) -> H1
+        // ---- C1 = CdH1 * g1 + ac * dH1 * (-2 H1 R1) -> H1 ; out_b0 accumulates C1 on the fly
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
             const float4 h4 = *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0);
@@ -719,29 +820,25 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
             const float hv[4] = {h4.x, h4.y, h4.z, h4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
             float c1[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 4; ++c) {
                 c1[c] = ch1[i][c] * (1.f - hv[c] * hv[c]) + ac * dh1[i][c] * (-2.f * hv[c] * rv[c]);
+                gB0p[c] += c1[c];
+            }
             *reinterpret_cast<float4*>(S.H1 + (row0 + i) * LD + col0) = make_float4(c1[0], c1[1], c1[2], c1[3]);
         }
         __syncthreads();
-        // ---- out_W0 += X^T C1 ; out_b0 += colsum C1
+        // ---- out_W0 += X^T C1 (column role)
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float c1 = S.H1[b * LD + cj];
 #pragma unroll
-        for (int r = 0; r < NW0; ++r) {
-            const int idx = tid + r * PT_THREADS;
-            if (idx < DO * HID) {
-                const int i = idx / HID, j = idx % HID;
-                float s = 0.f;
-                for (int b = 0; b < nb; ++b) s = fmaf(S.X[b * DOP + i], S.H1[b * LD + j], s);
-                gW0[r] += s;
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(S.X[b * DOP + i], c1, gW0p[i]);
             }
         }
-        if (tid < HID) {
-            float s = 0.f;
-            for (int b = 0; b < nb; ++b) s += S.H1[b * LD + tid];
-            gB0 += s;
-        }
     }
-
     if (cur_m >= 0) flush(cur_m);
 }
 
@@ -765,7 +862,7 @@ __global__ void __launch_bounds__(128) policy_forward_kernel(int M, int N, const
             const int j = lane + 32 * u;
             float z = sP[L::B0 + j];
             for (int i = 0; i < DO; ++i) z = fmaf(__ldg(o + i), sP[L::W0 + i * HID + j], z);
-            sh[w][j] = tanhf(z);
+            sh[w][j] = tanh_fast(z);
         }
         __syncwarp();
         float mu[DA];
@@ -776,7 +873,7 @@ __global__ void __launch_bounds__(128) policy_forward_kernel(int M, int N, const
             const int j = lane + 32 * u;
             float z = sP[L::B1 + j];
             for (int k = 0; k < HID; ++k) z = fmaf(sh[w][k], sP[L::W1 + k * HID + j], z);
-            const float h2 = tanhf(z);
+            const float h2 = tanh_fast(z);
 #pragma unroll
             for (int d = 0; d < DA; ++d) mu[d] = fmaf(h2, sP[L::W2 + j * DA + d], mu[d]);
         }

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                 float z = b0[u];
 #pragma unroll
                 for (int i = 0; i < DO; ++i) z = fmaf(ob[i], w0[i][u], z);
-                S.h1[lane + 32 * u] = tanhf(z);
+                S.h1[lane + 32 * u] = tanh_fast(z);
             }
             // stage obs_t (the observation the action is computed from)
             if (lane < DO) S.st_obs[tt * DO + lane] = S.obs[lane];
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
             for (int d = 0; d < DA; ++d) mu[d] = 0.f;
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
-                const float h2 = tanhf(acc[u][0] + acc[u][1]);
+                const float h2 = tanh_fast(acc[u][0] + acc[u][1]);
 #pragma unroll
                 for (int d = 0; d < DA; ++d) mu[d] = fmaf(h2, w2[u][d], mu[d]);
             }
