@@ -225,11 +225,20 @@ def run_gpu(args):
     # ---- e2e: reference-facing API with host inputs / logged outputs ------------------------------
     np.random.seed(1)
     tr_e2e = build_stack(wl, 'numpy', shard)
-    ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps)
     sd = tr_e2e.sampler.spec
     S = PROMP['num_inner_grad_steps'] + 1
-    h2d = 4 * (M * sd['task_dim'] + S * M * E * sd['state_dim'])
-    d2h = S * (M * 8 * 8 + M * sd['act_dim'] * 4 + (2 * M * E * H * 4 * 2 if sd['env_kind'] == 2 else 0)) + 4 * (3 + S - 1)
+    if use_graph:
+        # the public training entry point with use_cuda_graph=True: host numpy draws of tasks + reset states (reference
+        # RNG order) -> pinned -> H2D, graph replay, one D2H of the packed logged scalars, logger keys emitted
+        e2e_step = tr_e2e.capture_graph(warmup=2, log=True)
+        ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps, e2e_step)
+        h2d, d2h = tr_e2e.graph_h2d_bytes, tr_e2e.graph_d2h_bytes
+        e2e_api = 'promp_b200.meta_trainer.Trainer(use_cuda_graph=True).train() iteration, reset_mode=numpy, log=True'
+    else:
+        ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps)
+        h2d = 4 * (M * sd['task_dim'] + S * M * E * sd['state_dim'])
+        d2h = S * (M * 8 * 8 + M * sd['act_dim'] * 4 + (2 * M * E * H * 4 * 2 if sd['env_kind'] == 2 else 0)) + 4 * (3 + S - 1)
+        e2e_api = 'promp_b200.meta_trainer.Trainer.train_iteration(log=True), reset_mode=numpy'
 
     out = None
     # ---- per-kernel timing pass (instrumented, not part of the timed loops; every rank runs it because the
@@ -288,7 +297,7 @@ def run_gpu(args):
             'launch_mode': 'cuda_graph_replay' if use_graph else 'eager', 'eager_ms_per_step': ms_eager / args.steps,
             'e2e': {'value': e2e_val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps, 'wall_ms_per_step': wall_e2e / args.steps,
-                    'api': 'promp_b200.meta_trainer.Trainer.train_iteration(log=True), reset_mode=numpy'},
+                    'api': e2e_api},
             'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
             'clocks': clk, 'roofline': roof, 'kernels': per_kernel, 'cpu_baseline': cpu,
         }

@@ -44,6 +44,11 @@ class MetaEnv(object):
     def log_diagnostics(self, paths, prefix=''):
         pass
 
+    DEVICE_LOG_KEYS = ()
+
+    def device_log_terms(self, phase):
+        return None
+
     # ---- device description -------------------------------------------------------------
     def device_spec(self):
         return dict(env_kind=self.env_kind, reward_type=self.reward_type, radius=float(self.sparse_reward_radius),

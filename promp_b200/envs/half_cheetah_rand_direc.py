@@ -36,11 +36,12 @@ class HalfCheetahRandDirecEnv(MetaEnv):
         return np.asarray([task], dtype=np.float32)
 
     def host_reset_states(self, n):
-        # reset_model (:49-53) per env: 9 uniforms then 9 normals, env after env
+        """reset_model (:49-53): qpos = init + U(-.1,.1)^9, qvel = init + .1*N(0,1)^9 for each env.  The reference
+        draws these from each env's own gym `np_random` stream (not the global numpy RNG), so there is no global
+        draw order to reproduce: the n envs are drawn vectorised from the global RNG."""
         out = np.empty((n, 18))
-        for i in range(n):
-            out[i, :9] = np.random.uniform(low=-.1, high=.1, size=9)
-            out[i, 9:] = np.random.randn(9) * .1
+        out[:, :9] = np.random.uniform(low=-.1, high=.1, size=(n, 9))
+        out[:, 9:] = np.random.randn(n, 9) * .1
         return out
 
     def log_diagnostics(self, paths, prefix=''):
@@ -60,6 +61,13 @@ class HalfCheetahRandDirecEnv(MetaEnv):
         logger.logkv(prefix + 'AvgForwardVel', np.mean(fwrd_vel))
         logger.logkv(prefix + 'AvgFinalForwardVel', np.mean(final_fwrd_vel))
         logger.logkv(prefix + 'AvgCtrlCost', np.std(ctrl_cost))
+
+    DEVICE_LOG_KEYS = ('AvgForwardVel', 'AvgFinalForwardVel', 'AvgCtrlCost')
+
+    def device_log_terms(self, phase):
+        import torch
+        run, ctrl = phase.info[0], phase.info[1]
+        return torch.stack([run.mean(), run.reshape(-1, phase.H)[:, -1].mean(), torch.std(-ctrl, unbiased=False)]).double()
 
     def __str__(self):
         return 'HalfCheetahRandDirecEnv'

@@ -98,6 +98,18 @@ class MAMLAlgo(object):
                   _lib.ptr(stats), _lib.ptr(ws), ws.numel() * 4, _lib.stream())
 
     # ------------------------------------------------------------------------------------ inner step
+    def adapt_phase(self, phase):
+        """_adapt on a PhaseData directly (no per-task dict views): used by the CUDA-graph Trainer."""
+        import torch
+        p = self.policy
+        params, stride, _ = p.sampling_params()
+        M, P = self.meta_batch_size, p.num_params
+        grad = torch.empty(M, P, dtype=torch.float32, device=p.device)
+        new = torch.empty(M, P, dtype=torch.float32, device=p.device)
+        self._grad(phase, params, stride, self.inner_obj_kind, grad=grad, out_params=new, sgd_lr=self.inner_lr)
+        self.last_inner_grad = grad
+        p.update_task_parameters(new)
+
     def _adapt(self, samples):
         """MAMLAlgo._adapt (base.py:217-242): theta_i' = theta_i - alpha * grad surr_i(theta_i), all tasks
         in one launch, result stays on the device and becomes the sampling policy."""

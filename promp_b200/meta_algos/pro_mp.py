@@ -35,6 +35,19 @@ class ProMP(MAMLAlgo):
         coeffs = [float(c) / S1 for c in self.inner_kl_coeff]      # tf.reduce_mean over the S-1 steps
         return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, coeffs, want_grad)
 
+    LOG_KEYS = ('LossBefore', 'LossAfter', 'KLInner')
+
+    def optimize_phases(self, phases):
+        """optimize_policy on PhaseData objects, everything left on the device.  Returns the float64 device vector
+        [LossBefore, LossAfter, KLInner] for the CUDA-graph Trainer."""
+        import torch
+        assert not self.adaptive_inner_kl_penalty, "adaptive KL coefficient is a host decision: not graph-capturable"
+        stats = self.optimizer.optimize(self, phases)
+        self.last_stats_device = stats
+        self._last_stats = None
+        S1 = self.num_inner_grad_steps
+        return torch.stack([stats[0], stats[1], stats[2:2 + S1].mean()]).double()
+
     def optimize_policy(self, all_samples_data, log=True):
         """ProMP.optimize_policy (pro_mp.py:165-199): K Adam epochs on the same data, then a stats pass."""
         import torch

@@ -15,13 +15,15 @@ from promp_b200.utils import logger
 
 class Trainer(object):
     def __init__(self, algo, env, sampler, sample_processor, policy, n_itr, start_itr=0, num_inner_grad_steps=1,
-                 sess=None):
+                 sess=None, use_cuda_graph=False):
         self.algo, self.env, self.sampler, self.sample_processor = algo, env, sampler, sample_processor
         self.baseline = sample_processor.baseline
         self.policy = policy
         self.n_itr, self.start_itr = n_itr, start_itr
         self.num_inner_grad_steps = num_inner_grad_steps
         self.sess = sess
+        self.use_cuda_graph = use_cuda_graph      # replay the device part of every iteration as one CUDA graph
+        self._graph_step = None
 
     def train_iteration(self, itr, log=True):
         t_itr = time.time()
@@ -57,53 +59,108 @@ class Trainer(object):
         return all_samples_data
 
     # ------------------------------------------------------------------ CUDA-graph replay of the device part
-    def capture_graph(self, warmup=3):
-        """Capture everything of a meta-iteration that runs on the device (2x rollout + processing, inner adapt,
-        K Adam epochs + stats pass: ~40 kernel launches) into ONE CUDA graph.  Returns step(): draws the tasks
-        on the host (numpy RNG, as the reference), uploads them, replays the graph.  Requires in-kernel reset
-        states (reset_mode='device'), no host logging and a fixed KL coefficient; world_size 1."""
+    def capture_graph(self, warmup=3, log=False):
+        """Capture everything of a meta-iteration that runs on the device (S x [rollout + processing], inner adapt
+        steps, K Adam epochs + stats pass: ~40 kernel launches) into ONE CUDA graph and return step().
+
+        step() = host part of the reference iteration (numpy task draw; with reset_mode='numpy' also every phase's
+        reset states, in the reference's RNG order) -> H2D into static buffers -> graph replay -> (log=True) one D2H
+        copy of the packed vector of logged scalars, emitted under the reference's logger keys.
+        Requirements: device policy + fixed-horizon device env, fixed KL coefficient, world_size 1."""
         import torch
-        assert self.sampler.reset_mode == 'device', "graph replay needs reset_mode='device'"
-        assert not getattr(self.algo, 'adaptive_inner_kl_penalty', False), "adaptive KL coefficient is a host decision"
-        self.sampler.enable_device_phase_counter()
+        from promp_b200.samplers.device_data import PhaseData
+        sampler, proc, algo, policy = self.sampler, self.sample_processor, self.algo, self.policy
+        assert sampler._fused_ok(), "graph mode needs the fused rollout path"
+        assert not getattr(algo, 'adaptive_inner_kl_penalty', False), "adaptive KL coefficient is a host decision"
+        assert hasattr(algo, 'optimize_phases'), "graph mode is implemented for ProMP"
+        S = self.num_inner_grad_steps + 1
+        M, E, H = sampler.meta_batch_size, sampler.envs_per_task, sampler.max_path_length
+        numpy_resets = sampler.reset_mode == 'numpy'
+        sampler.enable_device_phase_counter()
+        inner_env = getattr(self.env, '_wrapped_env', self.env)
+        keys = []
+        state = {}
+
+        def host_part():
+            if numpy_resets:
+                return sampler.stage_host_inputs(S)
+            sampler.update_tasks()
+            return 4 * M * sampler.spec['task_dim']
 
         def device_part():
-            self.policy.switch_to_pre_update()
-            all_samples = []
-            for step in range(self.num_inner_grad_steps + 1):
-                paths = self.sampler.obtain_samples(log=False)
-                samples = self.sample_processor.process_samples(paths, log=False)
-                all_samples.append(samples)
+            policy.switch_to_pre_update()
+            phases, terms = [], []
+            del keys[:]
+            for step in range(S):
+                phase = PhaseData(M, E, H, sampler.spec['obs_dim'], sampler.spec['act_dim'], sampler.device)
+                sampler.rollout_into(phase, sampler._static_init[step] if numpy_resets else None, None)
+                proc.process_phase(phase)
+                phases.append(phase)
+                if log:
+                    prefix = 'Step_%d-' % step
+                    terms.append(proc.device_log_terms(phase))
+                    keys.extend(prefix + k for k in proc.PATH_STAT_KEYS)
+                    env_terms = inner_env.device_log_terms(phase)
+                    if env_terms is not None:
+                        terms.append(env_terms)
+                        keys.extend(prefix + k for k in inner_env.DEVICE_LOG_KEYS)
+                    terms.append(policy.device_log_terms(phase))
+                    keys.append(prefix + 'AveragePolicyStd')
                 if step < self.num_inner_grad_steps:
-                    self.algo._adapt(samples)
-            self.algo.optimize_policy(all_samples, log=False)
-            return all_samples
+                    algo.adapt_phase(phase)
+            algo_terms = algo.optimize_phases(phases)
+            if log:
+                terms.append(algo_terms)
+                keys.extend(algo.LOG_KEYS)
+                vec = torch.cat(terms)
+                if 'pinned' not in state:
+                    state['pinned'] = torch.empty(vec.numel(), dtype=torch.float64).pin_memory()
+                state['pinned'].copy_(vec, non_blocking=True)        # the ONE device->host copy of the iteration
+            state['phases'] = phases
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.sampler.update_tasks()
+                host_part()
                 device_part()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        self.sampler.update_tasks()
+        host_part()
         with torch.cuda.graph(graph):
-            self._graph_samples = device_part()
+            device_part()
         self._graph = graph
+        self.graph_d2h_bytes = 8 * len(keys) if log else 0
+        n_steps = M * E * H * S
 
-        def step():
-            self.sampler.update_tasks()
+        def step(itr=0):
+            t0 = time.time()
+            self.graph_h2d_bytes = host_part()
             graph.replay()
-            return self._graph_samples
+            sampler.total_timesteps_sampled += n_steps
+            if log:
+                torch.cuda.current_stream().synchronize()
+                vals = state['pinned'].numpy()
+                for k, v in zip(keys, vals):
+                    logger.logkv(k, int(v) if k.endswith('NumTrajs') else float(v))
+                logger.logkv('KLCoeffInner', float(np.mean(algo.inner_kl_coeff)))
+                logger.logkv('Itr', itr)
+                logger.logkv('n_timesteps', sampler.total_timesteps_sampled)
+                logger.logkv('ItrTime', time.time() - t0)
+            return state['phases']
         return step
 
     def train(self):
         start = time.time()
         for itr in range(self.start_itr, self.n_itr):
             logger.log("\n ---------------- Iteration %d ----------------" % itr)
-            self.train_iteration(itr)
+            if self.use_cuda_graph:
+                if self._graph_step is None:
+                    self._graph_step = self.capture_graph(log=True)
+                self._graph_step(itr)
+            else:
+                self.train_iteration(itr)
             logger.logkv('Time', time.time() - start)
             logger.save_itr_params(itr, self.get_itr_snapshot(itr))
             logger.dumpkvs()

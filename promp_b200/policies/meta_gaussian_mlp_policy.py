@@ -186,6 +186,11 @@ class MetaGaussianMLPPolicy(object):
             log_stds = np.vstack([path["agent_infos"]["log_std"] for path in paths])
             logger.logkv(prefix + 'AveragePolicyStd', np.mean(np.exp(log_stds)))
 
+    def device_log_terms(self, phase):
+        """AveragePolicyStd (gaussian_mlp_policy.py:118-123) as a float64 device vector of length 1."""
+        import torch
+        return torch.exp(phase.log_std).mean().double().view(1)
+
     # ------------------------------------------------------------------ pickling (policies/base.py:205-215)
     def __getstate__(self):
         return {'init_args': dict(self._init_args), 'network_params': self.get_param_values()}

@@ -139,6 +139,19 @@ class MetaSampleProcessor(object):
         self._log_path_stats(phase, log, log_prefix)
         return samples
 
+    PATH_STAT_KEYS = ('AverageDiscountedReturn', 'AverageReturn', 'NumTrajs', 'StdReturn', 'MaxReturn', 'MinReturn')
+
+    def device_log_terms(self, phase):
+        """The six path statistics of samplers/base.py:135-149 as one float64 device vector (no host sync):
+        used by the CUDA-graph Trainer, which reads all logged scalars back with a single D2H copy."""
+        import torch
+        st = phase.stats
+        n = float(phase.M * phase.E)
+        s = st[:, :3].sum(0)
+        mean_g = s[1] / n
+        std = torch.sqrt(torch.clamp(s[2] / n - mean_g * mean_g, min=0.0))
+        return torch.stack([s[0] / n, mean_g, torch.full_like(mean_g, n), std, st[:, 3].max(), st[:, 4].min()])
+
     def _log_path_stats(self, phase, log=False, log_prefix=''):
         """samplers/base.py:135-149 from the per-task sums the kernel wrote (one small D2H)."""
         if not log:

@@ -111,6 +111,25 @@ class MetaSampler(object):
         phase.invalidate_host()
         return phase
 
+    def stage_host_inputs(self, n_phases):
+        """Graph mode with reset_mode='numpy': draw this iteration's tasks and every phase's reset states from the
+        global numpy RNG in the reference's consumption order (sample_tasks; then per phase: M*E resets, and the M*E
+        end-of-horizon resets whose observations the reference discards) into pinned memory and start the H2D copies
+        into the static device buffers the captured rollouts read."""
+        import torch
+        M, E = self.meta_batch_size, self.envs_per_task
+        inner = getattr(self.env, '_wrapped_env', self.env)
+        sd = self.spec['state_dim']
+        if getattr(self, '_static_init', None) is None or len(self._static_init) != n_phases:
+            self._static_init = [torch.empty(M, E, sd, dtype=torch.float32, device=self.device) for _ in range(n_phases)]
+            self._pinned_init = [torch.empty(M, E, sd, dtype=torch.float32).pin_memory() for _ in range(n_phases)]
+        self.update_tasks()
+        for s in range(n_phases):
+            self._pinned_init[s].copy_(torch.from_numpy(inner.host_reset_states(M * E).astype(np.float32).reshape(M, E, sd)))
+            self._static_init[s].copy_(self._pinned_init[s], non_blocking=True)
+            inner.host_reset_states(M * E)     # discarded end-of-horizon resets (vectorized_env_executor.py:47-50)
+        return 4 * (M * self.spec['task_dim'] + n_phases * M * E * sd)
+
     def enable_device_phase_counter(self):
         """Keep the Philox phase counter in device memory so that a captured CUDA graph draws fresh
         noise / reset states on every replay."""

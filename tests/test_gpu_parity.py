@@ -530,3 +530,65 @@ def test_trainer_end_to_end(env_name):
     import pickle
     pol2 = pickle.loads(pickle.dumps(policy))
     assert torch.equal(pol2.theta, policy.theta)
+
+
+@pytest.mark.parametrize('env_name', ['point', 'cheetah'])
+def test_trainer_cuda_graph_mode(env_name):
+    """Trainer(use_cuda_graph=True): the device part of the iteration replayed as one CUDA graph, host inputs drawn
+    from numpy in the reference's order, logged scalars read back in one copy - same keys, consistent values."""
+    torch = _cuda()
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    from promp_b200.utils import logger
+    logger.set_quiet(True)
+    M, E, H = 6, 5, 40
+    env, policy, sampler, proc = _make_stack(env_name, M, E, H)
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3,
+                 num_ppo_steps=5, clip_eps=0.3, init_inner_kl_penalty=5e-4, adaptive_inner_kl_penalty=False)
+    trainer = Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1,
+                      num_inner_grad_steps=1, use_cuda_graph=True)
+    step = trainer.capture_graph(warmup=2, log=True)
+    np.random.seed(123)
+    theta0 = policy.theta.clone()
+    obs_prev = None
+    for itr in range(3):
+        phases = step(itr)
+        kv = dict(logger.getkvs())
+        for key in ('Step_0-AverageReturn', 'Step_1-AverageReturn', 'Step_0-StdReturn', 'Step_1-MaxReturn',
+                    'Step_0-AveragePolicyStd', 'LossBefore', 'LossAfter', 'KLInner', 'KLCoeffInner', 'n_timesteps'):
+            assert key in kv and np.isfinite(kv[key]), key
+        # logged values agree with the device buffers they summarise
+        for s, ph in enumerate(phases):
+            ret = ph.rew.view(M * E, H).double().sum(1)
+            assert abs(kv['Step_%d-AverageReturn' % s] - float(ret.mean())) < 1e-4 * max(1.0, abs(float(ret.mean())))
+            assert abs(kv['Step_%d-MaxReturn' % s] - float(ret.max())) < 1e-4 * max(1.0, abs(float(ret.max())))
+            assert kv['Step_%d-NumTrajs' % s] == M * E
+        if env_name == 'cheetah':
+            assert 'Step_0-AvgForwardVel' in kv and 'Step_1-AvgCtrlCost' in kv
+        # fresh noise / reset states on every replay
+        cur = phases[0].obs.clone()
+        if obs_prev is not None:
+            assert not torch.equal(cur, obs_prev)
+        obs_prev = cur
+    assert not torch.equal(policy.theta, theta0) and torch.isfinite(policy.theta).all()
+    # numpy stream consumption == reference order: tasks, then per phase (M*E resets + M*E discarded resets)
+    probe = np.random.uniform(size=3)
+    np.random.seed(123)
+    inner = env._wrapped_env
+    for itr in range(3):
+        env.sample_tasks(M)
+        for s in range(2):
+            inner.host_reset_states(M * E)
+            inner.host_reset_states(M * E)
+    assert np.array_equal(probe, np.random.uniform(size=3))
+    # reset states of the last replay are exactly the host draws
+    np.random.seed(7)
+    phases = step(3)
+    np.random.seed(7)
+    env.sample_tasks(M)
+    want = inner.host_reset_states(M * E).astype(np.float32)
+    got = phases[0].obs.view(M * E, H, -1)[:, 0].cpu().numpy()
+    if env_name == 'point':
+        np.testing.assert_array_equal(got, want)
+    else:
+        np.testing.assert_array_equal(got, np.concatenate([want[:, 1:9], want[:, 9:]], axis=1))
