@@ -122,7 +122,7 @@ def build_stack(wl, reset_mode, task_shard=None):
 
 class LaunchCounter(object):
     """Counts OUR kernel launches by wrapping the ctypes entry points (kernels per call from the .cu files)."""
-    KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=1,
+    KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=2,
                    promp_adj_avg_rewards=1, promp_policy_grad=1, promp_policy_hvp=1, promp_reduce_tasks=1,
                    promp_adam_tf1=2, promp_policy_forward=1, promp_counter_add=1)
 

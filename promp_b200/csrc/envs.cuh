@@ -122,7 +122,7 @@ __device__ inline void step_serial(float* st, const float* u, float dir, float& 
             st[3 + j] = q;
             st[12 + j] = qd;
             float sn, cs;
-            sincosf(q + pitch + PH[j], &sn, &cs);
+            __sincosf(q + pitch + PH[j], &sn, &cs);   // |angle| stays O(1): fast path error ~5e-7
             thrust = thrust + C[j] * qd * sn;
             lift = lift + C[j] * qd * cs;
             twist = twist + P[j] * u[j];
@@ -161,7 +161,7 @@ __device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& 
         qd = qd + HS * acc;
         q = q + HS * qd;
         float sn, cs;
-        sincosf(q + root[2] + jc.ph, &sn, &cs);
+        __sincosf(q + root[2] + jc.ph, &sn, &cs);   // |angle| stays O(1): fast path error ~5e-7
         float thrust = sum8(jc.c * qd * sn);
         float lift = sum8(jc.c * qd * cs);
         float twist = sum8(jc.p * u);

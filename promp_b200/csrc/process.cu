@@ -1,6 +1,7 @@
 // Sample processing: returns -> linear-feature baseline fit/predict -> GAE -> normalisation -> stats.
-// One CTA per task (tasks are independent: the reference re-fits the shared baseline inside its
-// task loop, samplers/meta_sample_processor.py:31-34).  The scans, Gram matrix, Cholesky solve and
+// Tasks are independent (the reference re-fits the shared baseline inside its task loop,
+// samplers/meta_sample_processor.py:31-34); a task is split over C CTAs for the returns + Gram stage and
+// finished by one CTA.  The scans, Gram matrix, Cholesky solve and
 // moments run in float64 like the reference's numpy/LAPACK path; inputs/outputs are float32.
 //
 // HBM-bound stage (AI < 1 FLOP/B): per env-step it reads obs (4*Do B) twice + rew (4 B) twice and
@@ -59,7 +60,10 @@ struct ProcArgs {
     float* adv;
     double* coeffs;
     double* stats;
-    double* ws;   // [M][2][N] float64: returns, baseline->advantages
+    double* ws;      // [M][2][N] float64 (returns, baseline->advantages), then partials
+    double* gram_p;  // [M][C][PS_MAXPAIR] partial Gram matrices
+    double* stat_p;  // [M][C][8] partial path statistics
+    int C, EPC;      // trajectory chunks per task, trajectories per chunk
 };
 
 // LinearFeatureBaseline._features (baselines/linear_baseline.py:101-106) for one sample, float64:
@@ -77,28 +81,36 @@ __device__ __forceinline__ void features(const float* o, int Do, int step, doubl
     f[2 * Do + 3] = 1.0;
 }
 
-__global__ void __launch_bounds__(PS_THREADS) process_kernel(ProcArgs A) {
-    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+__device__ __forceinline__ void pair_tables(int NC, int n_pairs, unsigned char* pair_i, unsigned char* pair_j) {
+    for (int p = threadIdx.x; p < n_pairs; p += PS_THREADS) {   // packed (i<=j) index tables
+        int i = 0, rem = p;
+        while (rem >= NC - i) { rem -= NC - i; ++i; }
+        pair_i[p] = (unsigned char)i;
+        pair_j[p] = (unsigned char)(i + rem);
+    }
+}
+
+// Stage 1, grid (C, M): CTA (c, m) owns trajectories [c*EPC, (c+1)*EPC) of task m: discounted returns, path
+// statistics, and its slice of the Gram matrix Phi^T [Phi | y] in float64.  Splitting a task over C CTAs puts
+// ~2 CTAs on every SM (a task-per-CTA launch uses only M of the 148 SMs and is fp64-FMA bound for F = 38).
+__global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
+    const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x;
     const int E = A.E, H = A.H, Do = A.Do, N = E * H;
-    const int F = 2 * Do + 4, NC = F + 1;            // NC columns: features + target
+    const int F = 2 * Do + 4, NC = F + 1;
     const int n_pairs = NC * (NC + 1) / 2;
+    const int e_lo = c * A.EPC, e_hi = min(E, e_lo + A.EPC);
     const float* obs = A.obs + (int64_t)m * N * Do;
     const float* rew = A.rew + (int64_t)m * N;
     double* ret64 = A.ws + (int64_t)m * 2 * N;
-    double* adv64 = ret64 + N;
 
     __shared__ double red[PS_THREADS / 32];
     __shared__ double tile[PS_TS * PS_MAXCOL];
-    __shared__ double gram[PS_MAXPAIR];                 // packed upper triangle over NC columns
-    __shared__ double Lm[(PS_MAXCOL - 1) * (PS_MAXCOL - 1)];
-    __shared__ double wv[PS_MAXCOL];
+    __shared__ double gram[PS_MAXPAIR];
     __shared__ unsigned char pair_i[PS_MAXPAIR], pair_j[PS_MAXPAIR];
-    __shared__ int s_flag;
-    __shared__ double s_reg;
 
-    // ---- (1) discounted returns R_t = r_t + g R_{t+1}  (utils/utils.py:74-81) + path statistics
+    // ---- discounted returns R_t = r_t + g R_{t+1}  (utils/utils.py:74-81) + path statistics
     double sR0 = 0, sG = 0, sG2 = 0, mxG = -1e300, mnG = 1e300, sr = 0, sr2 = 0;
-    for (int e = tid; e < E; e += PS_THREADS) {
+    for (int e = e_lo + tid; e < e_hi; e += PS_THREADS) {
         double R = 0.0, G = 0.0;
         for (int t = H - 1; t >= 0; --t) {
             const double r = (double)rew[e * H + t];
@@ -117,56 +129,97 @@ __global__ void __launch_bounds__(PS_THREADS) process_kernel(ProcArgs A) {
     sR0 = block_sum(sR0, red); sG = block_sum(sG, red); sG2 = block_sum(sG2, red);
     sr = block_sum(sr, red); sr2 = block_sum(sr2, red);
     mxG = block_max(mxG, red); mnG = block_min(mnG, red);
-    __syncthreads();   // ret64 visible to the whole CTA
-    for (int n = tid; n < N; n += PS_THREADS) A.returns[(int64_t)m * N + n] = (float)ret64[n];
+    if (tid == 0) {
+        double* sp = A.stat_p + ((int64_t)m * A.C + c) * 8;
+        sp[0] = sR0; sp[1] = sG; sp[2] = sG2; sp[3] = mxG; sp[4] = mnG; sp[5] = sr; sp[6] = sr2; sp[7] = 0.0;
+    }
+    __syncthreads();   // ret64 of this CTA's trajectories visible to the whole CTA
+    const int n_lo = e_lo * H, n_hi = e_hi * H;
+    for (int n = n_lo + tid; n < n_hi; n += PS_THREADS) A.returns[(int64_t)m * N + n] = (float)ret64[n];
+    if (A.baseline_kind != PROMP_BASELINE_LINEAR_FEATURE) return;
+
+    // ---- partial Gram matrix over this CTA's samples (baselines/linear_baseline.py:66-73)
+    pair_tables(NC, n_pairs, pair_i, pair_j);
+    const int G = max(1, PS_THREADS / n_pairs);        // sample groups per pair
+    const int n_items = n_pairs * G;
+    double acc[PS_MAXITEM] = {0, 0, 0, 0};
+    for (int n0 = n_lo; n0 < n_hi; n0 += PS_TS) {
+        const int ns = min(PS_TS, n_hi - n0);
+        __syncthreads();
+        for (int s = tid; s < ns; s += PS_THREADS) {     // one thread builds one sample's feature row
+            const int n = n0 + s;
+            features(obs + (int64_t)n * Do, Do, n % H, &tile[s * NC]);
+            tile[s * NC + F] = ret64[n];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < PS_MAXITEM; ++it) {
+            const int item = tid + it * PS_THREADS;
+            if (item < n_items) {
+                const int p = item % n_pairs, g = item / n_pairs;
+                const int i = pair_i[p], j = pair_j[p];
+                double a = acc[it];
+                for (int s = g; s < ns; s += G) a = fma(tile[s * NC + i], tile[s * NC + j], a);
+                acc[it] = a;
+            }
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < n_pairs; p += PS_THREADS) gram[p] = 0.0;
+    __syncthreads();
+    for (int g = 0; g < G; ++g) {      // deterministic group reduction: groups added in order g = 0..G-1
+#pragma unroll
+        for (int it = 0; it < PS_MAXITEM; ++it) {
+            const int item = tid + it * PS_THREADS;
+            if (item < n_items && item / n_pairs == g) gram[item % n_pairs] += acc[it];
+        }
+        __syncthreads();
+    }
+    double* gp = A.gram_p + ((int64_t)m * A.C + c) * PS_MAXPAIR;
+    for (int p = tid; p < n_pairs; p += PS_THREADS) gp[p] = gram[p];
+}
+
+// Stage 2, one CTA per task: reduce the partials (fixed chunk order), Cholesky solve with the reference's
+// ridge / NaN-retry rule, predict, GAE scan, per-task moments, advantages.
+__global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) {
+    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int E = A.E, H = A.H, Do = A.Do, N = E * H;
+    const int F = 2 * Do + 4, NC = F + 1;
+    const int n_pairs = NC * (NC + 1) / 2;
+    const float* obs = A.obs + (int64_t)m * N * Do;
+    const float* rew = A.rew + (int64_t)m * N;
+    double* adv64 = A.ws + (int64_t)m * 2 * N + N;
+
+    __shared__ double red[PS_THREADS / 32];
+    __shared__ double gram[PS_MAXPAIR];                 // packed upper triangle over NC columns
+    __shared__ double Lm[(PS_MAXCOL - 1) * (PS_MAXCOL - 1)];
+    __shared__ double wv[PS_MAXCOL];
+    __shared__ unsigned char pair_i[PS_MAXPAIR], pair_j[PS_MAXPAIR];
+    __shared__ int s_flag;
+    __shared__ double s_reg;
+
+    if (tid < 8) {   // path statistics: sums for 0,1,2,5,6; max for 3; min for 4
+        const double* sp = A.stat_p + (int64_t)m * A.C * 8 + tid;
+        double v = sp[0];
+        for (int c = 1; c < A.C; ++c) {
+            const double x = sp[c * 8];
+            v = (tid == 3) ? fmax(v, x) : (tid == 4) ? fmin(v, x) : v + x;
+        }
+        if (A.stats && tid < 7) A.stats[(int64_t)m * 8 + tid] = v;
+    }
 
     double reg_used = 0.0;
     if (A.baseline_kind == PROMP_BASELINE_LINEAR_FEATURE) {
-        // ---- (2) Gram matrix Phi^T [Phi | y] in float64 (baselines/linear_baseline.py:66-73)
-        for (int p = tid; p < n_pairs; p += PS_THREADS) {   // packed (i<=j) index tables
-            int i = 0, rem = p;
-            while (rem >= NC - i) { rem -= NC - i; ++i; }
-            pair_i[p] = (unsigned char)i;
-            pair_j[p] = (unsigned char)(i + rem);
-        }
-        const int G = max(1, PS_THREADS / n_pairs);        // sample groups per pair
-        const int n_items = n_pairs * G;
-        double acc[PS_MAXITEM] = {0, 0, 0, 0};
-        for (int n0 = 0; n0 < N; n0 += PS_TS) {
-            const int ns = min(PS_TS, N - n0);
-            __syncthreads();
-            for (int s = tid; s < ns; s += PS_THREADS) {     // one thread builds one sample's feature row
-                const int n = n0 + s;
-                features(obs + (int64_t)n * Do, Do, n % H, &tile[s * NC]);
-                tile[s * NC + F] = ret64[n];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int it = 0; it < PS_MAXITEM; ++it) {
-                const int item = tid + it * PS_THREADS;
-                if (item < n_items) {
-                    const int p = item % n_pairs, g = item / n_pairs;
-                    const int i = pair_i[p], j = pair_j[p];
-                    double a = acc[it];
-                    for (int s = g; s < ns; s += G) a = fma(tile[s * NC + i], tile[s * NC + j], a);
-                    acc[it] = a;
-                }
-            }
+        pair_tables(NC, n_pairs, pair_i, pair_j);
+        for (int p = tid; p < n_pairs; p += PS_THREADS) {
+            const double* gp = A.gram_p + (int64_t)m * A.C * PS_MAXPAIR + p;
+            double v = 0.0;
+            for (int c = 0; c < A.C; ++c) v += gp[(int64_t)c * PS_MAXPAIR];
+            gram[p] = v;
         }
         __syncthreads();
-        for (int p = tid; p < n_pairs; p += PS_THREADS) gram[p] = 0.0;
-        __syncthreads();
-        // deterministic group reduction: groups added in order g = 0..G-1
-        for (int g = 0; g < G; ++g) {
-#pragma unroll
-            for (int it = 0; it < PS_MAXITEM; ++it) {
-                const int item = tid + it * PS_THREADS;
-                if (item < n_items && item / n_pairs == g) gram[item % n_pairs] += acc[it];
-            }
-            __syncthreads();
-        }
 
-        // ---- (3) solve (Phi^T Phi + reg I) w = Phi^T y; retry with 10x reg on NaN, up to 5 tries (:68-77)
+        // ---- solve (Phi^T Phi + reg I) w = Phi^T y; retry with 10x reg on NaN, up to 5 tries (:68-77)
         if (tid == 0) { s_reg = A.reg_coeff; s_flag = 0; }
         __syncthreads();
         for (int attempt = 0; attempt < 5; ++attempt) {
@@ -223,7 +276,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_kernel(ProcArgs A) {
         }
         if (A.coeffs)
             for (int i = tid; i < F; i += PS_THREADS) A.coeffs[(int64_t)m * F + i] = wv[i];
-        // ---- (4) predict b_n = phi_n . w (baselines/linear_baseline.py:17-33)
+        // ---- predict b_n = phi_n . w (baselines/linear_baseline.py:17-33)
         for (int n = tid; n < N; n += PS_THREADS) {
             double f[PS_MAXCOL];
             features(obs + (int64_t)n * Do, Do, n % H, f);
@@ -236,7 +289,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_kernel(ProcArgs A) {
     }
     __syncthreads();
 
-    // ---- (5) GAE: delta_t = r_t + g b_{t+1} - b_t (b_H = 0); A_t = delta_t + g*lam A_{t+1}  (samplers/base.py:151-162)
+    // ---- GAE: delta_t = r_t + g b_{t+1} - b_t (b_H = 0); A_t = delta_t + g*lam A_{t+1}  (samplers/base.py:151-162)
     const double gl = A.discount * A.gae_lambda;
     double s1 = 0.0;
     for (int e = tid; e < E; e += PS_THREADS) {
@@ -253,7 +306,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_kernel(ProcArgs A) {
     }
     __syncthreads();
 
-    // ---- (6) per-task normalisation / positive shift (utils/utils.py:59-71; population std)
+    // ---- per-task normalisation / positive shift (utils/utils.py:59-71; population std)
     double mean = 0.0, inv = 1.0;
     if (A.normalize_adv) {
         mean = block_sum(s1, red) / (double)N;
@@ -276,11 +329,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_kernel(ProcArgs A) {
         if (A.positive_adv) a = (a - mn) + 1e-8;
         A.adv[(int64_t)m * N + n] = (float)a;
     }
-
-    if (A.stats && tid == 0) {
-        double* st = A.stats + (int64_t)m * 8;
-        st[0] = sR0; st[1] = sG; st[2] = sG2; st[3] = mxG; st[4] = mnG; st[5] = sr; st[6] = sr2; st[7] = reg_used;
-    }
+    if (A.stats && tid == 0) A.stats[(int64_t)m * 8 + 7] = reg_used;
 }
 
 __global__ void adj_avg_rewards_kernel(int64_t n, const float* rew, double mean, double inv, float* out) {
@@ -292,9 +341,19 @@ __global__ void adj_avg_rewards_kernel(int64_t n, const float* rew, double mean,
 
 using namespace promp;
 
+static void proc_chunks(int M, int E, int* C, int* EPC) {
+    int target = (2 * 148 + M - 1) / M;          // ~2 CTAs per SM
+    if (target > E) target = E;
+    if (target < 1) target = 1;
+    *EPC = (E + target - 1) / target;
+    *C = (E + *EPC - 1) / *EPC;
+}
+
 extern "C" int64_t promp_process_workspace_bytes(int M, int E, int H, int obs_dim) {
     (void)obs_dim;
-    return (int64_t)M * 2 * E * H * (int64_t)sizeof(double);
+    int C, EPC;
+    proc_chunks(M, E, &C, &EPC);
+    return ((int64_t)M * 2 * E * H + (int64_t)M * C * (PS_MAXPAIR + 8)) * (int64_t)sizeof(double);
 }
 
 extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const float* obs, const float* rew,
@@ -302,6 +361,7 @@ extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const flo
                                      int normalize_adv, int positive_adv, float* returns, float* adv, double* coeffs,
                                      double* stats, void* workspace, int64_t workspace_bytes, void* stream) {
     PROMP_REQUIRE(M > 0 && E > 0 && H > 0 && obs_dim > 0, "promp_process_samples: dimensions must be positive");
+    PROMP_REQUIRE(M <= 65535, "promp_process_samples: M=%d exceeds the grid.y limit", M);
     PROMP_REQUIRE(2 * obs_dim + 5 <= PS_MAXCOL, "promp_process_samples: obs_dim %d too large (max %d)", obs_dim,
                   (PS_MAXCOL - 5) / 2);
     PROMP_REQUIRE(obs && rew && returns && adv && workspace, "promp_process_samples: null pointer argument");
@@ -314,10 +374,17 @@ extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const flo
                   (long long)promp_process_workspace_bytes(M, E, H, obs_dim));
         return PROMP_ERR_WORKSPACE;
     }
+    int C, EPC;
+    proc_chunks(M, E, &C, &EPC);
+    double* ws = (double*)workspace;
+    double* gram_p = ws + (int64_t)M * 2 * E * H;
+    double* stat_p = gram_p + (int64_t)M * C * PS_MAXPAIR;
     ProcArgs A{M, E, H, obs_dim, obs, rew, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv,
-               returns, adv, coeffs, stats, (double*)workspace};
-    process_kernel<<<M, PS_THREADS, 0, (cudaStream_t)stream>>>(A);
-    PROMP_LAUNCH_CHECK("process_kernel");
+               returns, adv, coeffs, stats, ws, gram_p, stat_p, C, EPC};
+    process_gram_kernel<<<dim3(C, M), PS_THREADS, 0, (cudaStream_t)stream>>>(A);
+    PROMP_LAUNCH_CHECK("process_gram_kernel");
+    process_finish_kernel<<<M, PS_THREADS, 0, (cudaStream_t)stream>>>(A);
+    PROMP_LAUNCH_CHECK("process_finish_kernel");
     return PROMP_OK;
 }
 
