@@ -70,6 +70,8 @@ int promp_env_task_dim(int env_kind);
  * all M*E envs in one launch.  One warp per env; weights live in registers; trajectory records are
  * staged in shared memory and flushed as coalesced float32 rows.
  *
+ *   normalize_actions           1 = env wrapped by NormalizedEnv (affine map from [-10,10] + clip, envs/normalized_env.py:109-117),
+ *                               0 = raw env (only the env's own action clip)
  *   task_params [M, task_dim]   goal (x,y) / direction
  *   init_state  [M, E, state_dim] or NULL  -> NULL draws the reset state in-kernel (Philox4x32-10)
  *   noise       [M, E, H, Da]    or NULL  -> NULL draws N(0,1) action noise in-kernel
@@ -85,7 +87,7 @@ int promp_env_task_dim(int env_kind);
  *   log_std_out [M,Da]  the per-task reported log_std (constant over the phase)
  *   final_state [M,E,state_dim] or NULL
  */
-int promp_rollout(int env_kind, int reward_type, float sparse_radius,
+int promp_rollout(int env_kind, int reward_type, float sparse_radius, int normalize_actions,
                   int M, int E, int H, int hidden,
                   const float* params, int64_t param_stride,
                   const float* task_params, const float* init_state, const float* noise,
@@ -100,13 +102,13 @@ int promp_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 /*
  * One vectorised env step (MetaIterativeEnvExecutor.step, samplers/vectorized_env_executor.py:25-52)
  * for policies that are not device-resident: state [n_env, state_dim] is updated in place.
- *   actions [n_env, Da] policy-space actions (NormalizedEnv rescale+clip applied inside)
+ *   actions [n_env, Da] policy-space actions (NormalizedEnv rescale+clip applied inside when normalize_actions = 1)
  *   task_params [n_env, task_dim] (already expanded per env)
  *   ts [n_env] int32 step counters, incremented; when ts reaches H (or the env is done) the env is
  *   reset from reset_state [n_env, state_dim] (caller-provided fresh reset states) and ts = 0.
  *   next_obs [n_env, Do], rew [n_env], done [n_env] uint8, info [2, n_env] or NULL
  */
-int promp_env_step(int env_kind, int reward_type, float sparse_radius, int n_env, int H,
+int promp_env_step(int env_kind, int reward_type, float sparse_radius, int normalize_actions, int n_env, int H,
                    float* state, int32_t* ts, const float* actions, const float* task_params,
                    const float* reset_state, float* next_obs, float* rew, uint8_t* done, float* info,
                    void* stream);

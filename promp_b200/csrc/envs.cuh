@@ -28,11 +28,17 @@ __device__ __forceinline__ float normalized_action(float a, float lb, float ub) 
     float s = lb + ((a + 10.0f) * (ub - lb)) / 20.0f;
     return fminf(fmaxf(s, lb), ub);
 }
+// wrapped (normalize(env), every reference run script) or raw env (the reference's tests): the raw env receives the
+// policy action unchanged and applies only its own clip
+__device__ __forceinline__ float env_action(float a, float lb, float ub, bool normalized) {
+    return normalized ? normalized_action(a, lb, ub) : a;
+}
 
 // ------------------------------------------------------------------ point corner
 struct PointCornerCfg {
     int reward_type;
     float radius;
+    bool normalized;
 };
 
 __device__ __forceinline__ float dist2d(float x, float y, float gx, float gy) {
@@ -44,8 +50,8 @@ __device__ __forceinline__ float dist2d(float x, float y, float gx, float gy) {
 __device__ __forceinline__ float point_corner_step(float& sx, float& sy, float ax, float ay, float gx, float gy,
                                                    const PointCornerCfg& cfg) {
     const float lim = 0.2f;
-    float ex = normalized_action(ax, -lim, lim), ey = normalized_action(ay, -lim, lim);
-    // env-side clip (point_env_2d_corner.py:37) is the identity after the wrapper's clip
+    float ex = env_action(ax, -lim, lim, cfg.normalized), ey = env_action(ay, -lim, lim, cfg.normalized);
+    // env-side clip (point_env_2d_corner.py:37); the identity after the wrapper's clip
     ex = fminf(fmaxf(ex, -lim), lim);
     ey = fminf(fmaxf(ey, -lim), lim);
     float px = sx, py = sy;
@@ -75,9 +81,9 @@ __device__ __forceinline__ float point_corner_step(float& sx, float& sy, float a
 }
 
 // ------------------------------------------------------------------ point (origin goal, early done)
-__device__ __forceinline__ float point_step(float& sx, float& sy, float ax, float ay, bool& done) {
+__device__ __forceinline__ float point_step(float& sx, float& sy, float ax, float ay, bool& done, bool normalized) {
     const float lim = 0.1f;
-    float ex = normalized_action(ax, -lim, lim), ey = normalized_action(ay, -lim, lim);
+    float ex = env_action(ax, -lim, lim, normalized), ey = env_action(ay, -lim, lim, normalized);
     ex = fminf(fmaxf(ex, -lim), lim);
     ey = fminf(fmaxf(ey, -lim), lim);
     sx += ex;

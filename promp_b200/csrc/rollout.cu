@@ -19,6 +19,7 @@ constexpr int RO_WARPS = 4;    // env-warps per CTA
 struct RolloutArgs {
     int reward_type;
     float radius;
+    int normalized;
     int M, E, H;
     const float* params;
     int64_t param_stride;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
     write_obs();
     __syncwarp();
 
-    const PointCornerCfg pcfg{A.reward_type, A.radius};
+    const PointCornerCfg pcfg{A.reward_type, A.radius, A.normalized != 0};
 
     for (int t0 = 0; t0 < A.H; t0 += T_CH) {
         const int nt = min(T_CH, A.H - t0);
@@ -253,14 +254,15 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                 r = point_corner_step(sx, sy, a[0], a[1], task[0], task[1], pcfg);
             } else if (KIND == PROMP_ENV_POINT) {
                 bool dn;
-                r = point_step(sx, sy, a[0], a[1], dn);   // early `done` is ignored by the fused kernel
+                r = point_step(sx, sy, a[0], a[1], dn, A.normalized != 0);   // early `done` is ignored by the fused kernel
             } else {
                 float al = 0.f;
                 const int jl = lane & 7;
 #pragma unroll
                 for (int d = 0; d < DA; ++d)
                     if (jl == d) al = a[d];
-                const float u_l = jl < 6 ? normalized_action(al, -1.f, 1.f) : 0.f;
+                // raw MuJoCo env: ctrlrange clips the torque to [-1, 1] inside the simulator
+                const float u_l = jl < 6 ? (A.normalized ? normalized_action(al, -1.f, 1.f) : fminf(fmaxf(al, -1.f), 1.f)) : 0.f;
                 float r_run, r_ctrl;
                 cheetah::step_warp(jc, u_l, q, qd, root, task[0], r, r_run, r_ctrl);
                 if (lane == 0) {
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
 
 // ---------------------------------------------------------------------------- single-step kernels
 template <int KIND>
-__global__ void env_step_kernel(int reward_type, float radius, int n_env, int H, float* state, int32_t* ts,
+__global__ void env_step_kernel(int reward_type, float radius, int normalized, int n_env, int H, float* state, int32_t* ts,
                                 const float* actions, const float* task_params, const float* reset_state,
                                 float* next_obs, float* rew, uint8_t* done, float* info) {
     using T = EnvTraits<KIND>;
@@ -331,14 +333,14 @@ __global__ void env_step_kernel(int reward_type, float radius, int n_env, int H,
     float r;
     bool dn = false;
     if (KIND == PROMP_ENV_POINT_CORNER) {
-        PointCornerCfg cfg{reward_type, radius};
+        PointCornerCfg cfg{reward_type, radius, normalized != 0};
         r = point_corner_step(st[0], st[1], a[0], a[1], task_params[(int64_t)i * TD], task_params[(int64_t)i * TD + 1], cfg);
     } else if (KIND == PROMP_ENV_POINT) {
-        r = point_step(st[0], st[1], a[0], a[1], dn);
+        r = point_step(st[0], st[1], a[0], a[1], dn, normalized != 0);
     } else {
         float u[DA], rr, rc;
 #pragma unroll
-        for (int k = 0; k < DA; ++k) u[k] = normalized_action(a[k], -1.f, 1.f);
+        for (int k = 0; k < DA; ++k) u[k] = normalized ? normalized_action(a[k], -1.f, 1.f) : fminf(fmaxf(a[k], -1.f), 1.f);
         cheetah::step_serial(st, u, task_params[(int64_t)i * TD], r, rr, rc);
         if (info) {
             info[i] = rr;
@@ -411,7 +413,8 @@ extern "C" int promp_env_task_dim(int env_kind) {
     return -1;
 }
 
-extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius, int M, int E, int H, int hidden,
+extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius, int normalize_actions, int M, int E, int H,
+                             int hidden,
                              const float* params, int64_t param_stride, const float* task_params,
                              const float* init_state, const float* noise, uint64_t seed, uint64_t stream_id,
                              const uint64_t* stream_id_dev, int clip_reported_log_std, float min_log_std, float* obs, float* act, float* mean,
@@ -423,7 +426,7 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
                   "promp_rollout: null pointer argument");
     PROMP_REQUIRE(hidden == 64 || hidden == 32, "promp_rollout: hidden size %d unsupported (32 or 64)", hidden);
     PROMP_REQUIRE(reward_type >= 0 && reward_type <= 2, "promp_rollout: bad reward_type %d", reward_type);
-    RolloutArgs A{reward_type, sparse_radius, M, E, H, params, param_stride, task_params, init_state, noise, seed,
+    RolloutArgs A{reward_type, sparse_radius, normalize_actions, M, E, H, params, param_stride, task_params, init_state, noise, seed,
                   stream_id, stream_id_dev, clip_reported_log_std, min_log_std, obs, act, mean, rew, done, info, log_std_out,
                   final_state};
     cudaStream_t st = (cudaStream_t)stream;
@@ -452,7 +455,8 @@ extern "C" int promp_counter_add(uint64_t* counter, uint64_t inc, void* stream) 
     return PROMP_OK;
 }
 
-extern "C" int promp_env_step(int env_kind, int reward_type, float sparse_radius, int n_env, int H, float* state,
+extern "C" int promp_env_step(int env_kind, int reward_type, float sparse_radius, int normalize_actions, int n_env, int H,
+                              float* state,
                               int32_t* ts, const float* actions, const float* task_params,
                               const float* reset_state, float* next_obs, float* rew, uint8_t* done, float* info,
                               void* stream) {
@@ -463,16 +467,16 @@ extern "C" int promp_env_step(int env_kind, int reward_type, float sparse_radius
     const int bs = 128, gs = (n_env + bs - 1) / bs;
     switch (env_kind) {
         case PROMP_ENV_POINT_CORNER:
-            env_step_kernel<PROMP_ENV_POINT_CORNER><<<gs, bs, 0, st>>>(reward_type, sparse_radius, n_env, H, state, ts,
+            env_step_kernel<PROMP_ENV_POINT_CORNER><<<gs, bs, 0, st>>>(reward_type, sparse_radius, normalize_actions, n_env, H, state, ts,
                                                                        actions, task_params, reset_state, next_obs,
                                                                        rew, done, info);
             break;
         case PROMP_ENV_POINT:
-            env_step_kernel<PROMP_ENV_POINT><<<gs, bs, 0, st>>>(reward_type, sparse_radius, n_env, H, state, ts, actions,
+            env_step_kernel<PROMP_ENV_POINT><<<gs, bs, 0, st>>>(reward_type, sparse_radius, normalize_actions, n_env, H, state, ts, actions,
                                                                 task_params, reset_state, next_obs, rew, done, info);
             break;
         case PROMP_ENV_CHEETAH_DIR:
-            env_step_kernel<PROMP_ENV_CHEETAH_DIR><<<gs, bs, 0, st>>>(reward_type, sparse_radius, n_env, H, state, ts,
+            env_step_kernel<PROMP_ENV_CHEETAH_DIR><<<gs, bs, 0, st>>>(reward_type, sparse_radius, normalize_actions, n_env, H, state, ts,
                                                                       actions, task_params, reset_state, next_obs, rew,
                                                                       done, info);
             break;

@@ -31,8 +31,8 @@ class MetaGaussianMLPPolicy(object):
         import torch
         _lib.require_cuda()
         hidden_sizes = tuple(int(h) for h in hidden_sizes)
-        if len(hidden_sizes) != 2 or hidden_sizes[0] != hidden_sizes[1] or hidden_sizes[0] not in (32, 64):
-            raise NotImplementedError("promp_b200 kernels are built for two equal hidden layers of 32 or 64 units "
+        if len(hidden_sizes) != 2 or max(hidden_sizes) > 64 or min(hidden_sizes) < 1:
+            raise NotImplementedError("promp_b200 kernels are built for two tanh hidden layers of up to 64 units each "
                                       "(got hidden_sizes=%r)" % (hidden_sizes,))
         if not _is_tanh(hidden_nonlinearity) or output_nonlinearity is not None:
             raise NotImplementedError("promp_b200 kernels implement tanh hidden / identity output non-linearities")
@@ -44,17 +44,30 @@ class MetaGaussianMLPPolicy(object):
                                min_std=min_std)
         self.meta_batch_size = meta_batch_size
         self.obs_dim, self.action_dim, self.name = int(obs_dim), int(action_dim), name
-        self.hidden_sizes, self.hidden = hidden_sizes, hidden_sizes[0]
+        # The kernels are instantiated for 32 and 64 hidden units; other widths run zero-padded: a padded unit has
+        # zero incoming and outgoing weights, so it outputs tanh(0) = 0, receives exactly zero gradient (and zero
+        # Hessian-vector product), and therefore stays zero under SGD / Adam / TRPO steps.
+        self.hidden_sizes, self.hidden = hidden_sizes, (32 if max(hidden_sizes) <= 32 else 64)
         self.learn_std = learn_std
         self.min_log_std = math.log(min_std)
         self.init_log_std = math.log(init_std)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self._dist = DiagonalGaussian(self.action_dim)
+        h0, h1, Hd = hidden_sizes[0], hidden_sizes[1], self.hidden
         self.param_shapes = OrderedDict(zip(PARAM_NAMES, (
-            (self.obs_dim, self.hidden), (self.hidden,), (self.hidden, self.hidden), (self.hidden,),
-            (self.hidden, self.action_dim), (self.action_dim,), (1, self.action_dim))))
-        self.num_params = int(sum(np.prod(s) for s in self.param_shapes.values()))
+            (self.obs_dim, h0), (h0,), (h0, h1), (h1,), (h1, self.action_dim), (self.action_dim,), (1, self.action_dim))))
+        self.num_params_logical = int(sum(np.prod(sh) for sh in self.param_shapes.values()))
+        dev_shapes = ((self.obs_dim, Hd), (Hd,), (Hd, Hd), (Hd,), (Hd, self.action_dim), (self.action_dim,),
+                      (1, self.action_dim))
+        self.num_params = int(sum(np.prod(sh) for sh in dev_shapes))          # device (padded) vector length
         assert self.num_params == _lib.load().promp_num_params(self.obs_dim, self.action_dim, self.hidden)
+        # positions of the logical parameters inside the padded device vector
+        idx, off = [], 0
+        for (key, shape), dshape in zip(self.param_shapes.items(), dev_shapes):
+            grid = np.arange(int(np.prod(dshape))).reshape(dshape) + off
+            idx.append(grid[tuple(slice(0, n) for n in shape)].reshape(-1))
+            off += int(np.prod(dshape))
+        self._pad_index_np = np.concatenate(idx)
         self.policy_params_keys = list(PARAM_NAMES)
         # Xavier-uniform kernels, zero biases, log_std = log(init_std)
         # (policies/networks/mlp.py:12-13, gaussian_mlp_policy.py:64-69); drawn from the numpy global RNG
@@ -67,7 +80,9 @@ class MetaGaussianMLPPolicy(object):
                 flat.append(np.zeros(int(np.prod(shape))))
             else:
                 flat.append(np.full(int(np.prod(shape)), self.init_log_std))
-        self.theta = torch.tensor(np.concatenate(flat), dtype=torch.float32, device=self.device)
+        self._pad_index = torch.from_numpy(self._pad_index_np).to(self.device)
+        self.theta = torch.zeros(self.num_params, dtype=torch.float32, device=self.device)
+        self.theta[self._pad_index] = torch.tensor(np.concatenate(flat), dtype=torch.float32, device=self.device)
         self.theta_tasks = None            # [M, P] post-update parameters
         self._pre_update_mode = True
 
@@ -77,8 +92,8 @@ class MetaGaussianMLPPolicy(object):
         return self._dist
 
     def get_params(self):
-        """Reference returns the tf.Variables; here: name -> view into the flat device vector."""
-        return self._unflatten_torch(self.theta)
+        """Reference returns the tf.Variables; here: name -> device tensor (copy of the logical parameters)."""
+        return self._unflatten_torch(self.theta[self._pad_index])
 
     def _unflatten_torch(self, flat):
         out, off = OrderedDict(), 0
@@ -87,6 +102,18 @@ class MetaGaussianMLPPolicy(object):
             out[key] = flat[off:off + n].view(*shape)
             off += n
         return out
+
+    def pad_flat(self, flat):
+        """logical flat vector(s) [.., P_logical] (numpy) -> padded device layout [.., P] (numpy)."""
+        flat = np.asarray(flat, dtype=np.float32)
+        if flat.shape[-1] == self.num_params and self.num_params != self.num_params_logical:
+            return flat
+        out = np.zeros(flat.shape[:-1] + (self.num_params,), dtype=np.float32)
+        out[..., self._pad_index_np] = flat
+        return out
+
+    def unpad_flat(self, flat):
+        return np.asarray(flat)[..., self._pad_index_np]
 
     def _unflatten_np(self, flat):
         out, off = OrderedDict(), 0
@@ -98,7 +125,7 @@ class MetaGaussianMLPPolicy(object):
 
     def get_param_values(self):
         """OrderedDict name -> ndarray (policies/base.py:176-184)."""
-        return self._unflatten_np(self.theta.detach().cpu().numpy().copy())
+        return self._unflatten_np(self.unpad_flat(self.theta.detach().cpu().numpy()).copy())
 
     def set_params(self, policy_params):
         """policies/base.py:186-203; accepts the OrderedDict or a flat vector."""
@@ -109,8 +136,8 @@ class MetaGaussianMLPPolicy(object):
             flat = np.concatenate([np.asarray(v, dtype=np.float32).reshape(-1) for v in policy_params.values()])
         else:
             flat = np.asarray(policy_params, dtype=np.float32).reshape(-1)
-        assert flat.size == self.num_params
-        self.theta.copy_(torch.from_numpy(flat).to(self.device))
+        assert flat.size in (self.num_params_logical, self.num_params)
+        self.theta.copy_(torch.from_numpy(self.pad_flat(flat)).to(self.device))
 
     # ------------------------------------------------------------------ pre / post update bookkeeping
     def switch_to_pre_update(self):
@@ -129,7 +156,7 @@ class MetaGaussianMLPPolicy(object):
             assert len(updated_policies_parameters) == self.meta_batch_size
             flat = np.stack([np.concatenate([np.asarray(v, dtype=np.float32).reshape(-1) for v in d.values()])
                              for d in updated_policies_parameters])
-            self.theta_tasks = torch.from_numpy(flat).to(self.device)
+            self.theta_tasks = torch.from_numpy(self.pad_flat(flat)).to(self.device)
         self._pre_update_mode = False
 
     @property
@@ -137,7 +164,7 @@ class MetaGaussianMLPPolicy(object):
         if self.theta_tasks is None:
             vals = self.get_param_values()
             return [vals for _ in range(self.meta_batch_size)]
-        host = self.theta_tasks.detach().cpu().numpy()
+        host = self.unpad_flat(self.theta_tasks.detach().cpu().numpy())
         return [self._unflatten_np(host[i]) for i in range(self.meta_batch_size)]
 
     def sampling_params(self):

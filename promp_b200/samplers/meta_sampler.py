@@ -100,7 +100,8 @@ class MetaSampler(object):
             phase.info = torch.empty(2, M, E * H, dtype=torch.float32, device=self.device)
             phase.info_keys = ('reward_run', 'reward_ctrl')
         self._phase_counter += 1
-        _lib.call('promp_rollout', s['env_kind'], s['reward_type'], s['radius'], M, E, H, self.policy.hidden,
+        _lib.call('promp_rollout', s['env_kind'], s['reward_type'], s['radius'], int(s.get('normalized', False)), M, E, H,
+                  self.policy.hidden,
                   _lib.ptr(params), stride, _lib.ptr(self.vec_env.task_params_per_task), _lib.ptr(init_state),
                   _lib.ptr(noise), self.seed, self._phase_counter, _lib.ptr(self._phase_counter_dev), clip,
                   float(self.policy.min_log_std),

@@ -19,9 +19,6 @@ class MetaDeviceEnvExecutor(object):
                             "arbitrary Python envs are not stepped on the CPU (no CPU fallback). Got %r" % (env,))
         self.env = env
         self.spec = env.device_spec()
-        if not self.spec.get('normalized', False):
-            raise NotImplementedError("promp_b200 env kernels include the NormalizedEnv action map; wrap the env with "
-                                      "promp_b200.envs.normalize(env) like the reference run scripts do")
         self.meta_batch_size, self.envs_per_task = meta_batch_size, envs_per_task
         self.n_envs = meta_batch_size * envs_per_task
         self.max_path_length = max_path_length
@@ -76,7 +73,8 @@ class MetaDeviceEnvExecutor(object):
         assert len(actions) == self.num_envs
         act = torch.from_numpy(np.asarray(actions, dtype=np.float32).reshape(self.n_envs, -1)).to(self.device)
         s = self.spec
-        _lib.call('promp_env_step', s['env_kind'], s['reward_type'], s['radius'], self.n_envs, self.max_path_length,
+        _lib.call('promp_env_step', s['env_kind'], s['reward_type'], s['radius'], int(s.get('normalized', False)), self.n_envs,
+                  self.max_path_length,
                   _lib.ptr(self.state), _lib.ptr(self.ts), _lib.ptr(act), _lib.ptr(self.task_params),
                   _lib.ptr(self._dummy_reset), _lib.ptr(self._obs), _lib.ptr(self._rew), _lib.ptr(self._done),
                   _lib.ptr(self._info), _lib.stream())

