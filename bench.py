@@ -261,8 +261,16 @@ def run_gpu(args):
         hvp_flops = M * N * (8 * 2 * 64 * 64 + 6 * 2 * wl['Do'] * 64 + 8 * 2 * 64 * wl['Da'])
         hvp_ms = per_kernel.get('promp_policy_hvp', {}).get('avg_ms', float('nan'))
         achieved = hvp_bytes / (hvp_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/profile_all.sh)
+            km = json.load(open(os.path.join(ROOT, 'profiles', 'r01_kernel_metrics.json')))[args.workload]
+            kk = [k for k in km if k.startswith('policy_hvp_kernel')][0]
+            traffic = km[kk].get('dram_read_bytes', 0.0) + km[kk].get('dram_write_bytes', 0.0)
+            traffic_src = 'profiles/r01_kernel_metrics.json (cold-cache ncu replay; in the live loop the inputs are L2 hits)'
+        except Exception:
+            pass
         roof = dict(kernel='policy_hvp_kernel', bound='hbm', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
-                    frac=achieved / peaks['hbm_gbs'], traffic=None, peak_source=peak_src,
+                    frac=achieved / peaks['hbm_gbs'], traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                     algorithmic_bytes_per_launch=hvp_bytes, avg_launch_ms=hvp_ms,
                     fp32_tflops=hvp_flops / (hvp_ms * 1e-3) / 1e12,
                     fp32_peak_tflops=148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12,
