@@ -178,6 +178,8 @@ def run_gpu(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         import datetime
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=120))
+        from promp_b200.utils.dist import enable_p2p_allreduce
+        p2p = enable_p2p_allreduce()
     wl = WORKLOADS[args.workload]
     M, E, H = wl['M'], wl['E'], wl['H']
     steps_per_iter = M * E * H * (PROMP['num_inner_grad_steps'] + 1) * world      # weak scaling: M tasks per GPU
@@ -211,7 +213,7 @@ def run_gpu(args):
     np.random.seed(1)
     tr_dev = build_stack(wl, 'device', shard)
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph       # N > 1: the all-reduce inside the graph is the P2P kernel (promp_allreduce_p2p)
     with LaunchCounter() as lc:
         ms_eager, wall_eager = timed(tr_dev, False, args.warmup, args.steps)
     launches = lc.count // (args.warmup + args.steps)
@@ -298,7 +300,7 @@ def run_gpu(args):
             'config': {'workload': wl['name'], 'tasks_per_gpu': M, 'envs_per_task': E, 'max_path_length': H,
                        'algo': 'ProMP num_promp_steps=5 inner_lr=0.1 lr=1e-3 clip_eps=0.3 (pro-mp_run_point_mass.py defaults)',
                        'step_definition': 'one full meta-iteration (2 sampling+processing phases, inner adapt, 5 Adam epochs + stats pass)',
-                       'parallelism': 'task-sharded dp%d, one NCCL all-reduce of the flat meta-gradient per Adam epoch' % world,
+                       'parallelism': 'task-sharded dp%d, one all-reduce of the flat meta-gradient per Adam epoch (P2P peer-memory kernel over NVLink, inside the CUDA graph)' % world,
                        'l2_note': 'every iteration rewrites all trajectory buffers from fresh rollouts (inputs are produced, not re-read); no L2 flush needed'},
             'meta_iters_per_sec': world * 0 + args.steps / (ms_dev * 1e-3),
             'wall_ms_per_step': wall_dev / args.steps,
@@ -310,6 +312,7 @@ def run_gpu(args):
             'clocks': clk, 'roofline': roof, 'kernels': per_kernel, 'cpu_baseline': cpu,
         }
     if world > 1:
+        p2p.check()
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:

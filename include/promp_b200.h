@@ -206,6 +206,24 @@ int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, v
 int promp_adam_tf1(int P, float* theta, const float* grad, float* m, float* v, int32_t* step,
                    float lr, float beta1, float beta2, float eps, void* stream);
 
+/*
+ * One-shot all-reduce (sum * scale) of a small float vector over NVLink peer memory, rank-ordered (bitwise identical
+ * on every rank) and graph-capturable; replaces the single collective of the path, the all-reduce of the flat
+ * meta-gradient.  Setup: every rank allocates a buffer of promp_comm_buffer_bytes() with
+ * promp_comm_alloc (the one allocation the library performs: IPC export needs a whole cudaMalloc block), exchanges
+ * promp_ipc_get_handle() blobs (64 bytes, e.g. via torch.distributed.all_gather_object), opens the peers' blobs with
+ * promp_ipc_open_handle and passes the world-sized DEVICE array of buffer pointers (own buffer at index `rank`).
+ *   epoch_dev, error_flag_dev: device uint32, zero-initialised; error_flag becomes 1 if a peer did not arrive in ~2 s.
+ */
+int64_t promp_comm_buffer_bytes(int world, int capacity_floats);
+int promp_comm_alloc(int64_t bytes, void** dev_ptr_host);
+int promp_comm_free(void* dev_ptr);
+int promp_ipc_get_handle(void* dev_ptr, void* handle64_host);
+int promp_ipc_open_handle(const void* handle64_host, void** dev_ptr_host);
+int promp_ipc_close_handle(void* dev_ptr);
+int promp_allreduce_p2p(int world, int rank, int n, int capacity_floats, const float* in, float* out, float scale,
+                        void* const* peers_dev, uint32_t* epoch_dev, uint32_t* error_flag_dev, void* stream);
+
 /* Policy forward only (MetaGaussianMLPPolicy.get_actions without sampling / distribution_info_sym):
  * mean [M,N,Da] for obs [M,N,Do]. */
 int promp_policy_forward(int obs_dim, int act_dim, int hidden, int M, int N,

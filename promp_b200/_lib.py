@@ -41,6 +41,13 @@ _SIGNATURES = {
     'promp_reduce_tasks': (c_int, [c_int, c_int, _P, c_float, _P, _P]),
     'promp_adam_tf1': (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
     'promp_policy_forward': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),
+    'promp_comm_buffer_bytes': (c_int64, [c_int, c_int]),
+    'promp_comm_alloc': (c_int, [c_int64, _P]),
+    'promp_comm_free': (c_int, [_P]),
+    'promp_ipc_get_handle': (c_int, [_P, _P]),
+    'promp_ipc_open_handle': (c_int, [_P, _P]),
+    'promp_ipc_close_handle': (c_int, [_P]),
+    'promp_allreduce_p2p': (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

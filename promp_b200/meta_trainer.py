@@ -66,7 +66,8 @@ class Trainer(object):
         step() = host part of the reference iteration (numpy task draw; with reset_mode='numpy' also every phase's
         reset states, in the reference's RNG order) -> H2D into static buffers -> graph replay -> (log=True) one D2H
         copy of the packed vector of logged scalars, emitted under the reference's logger keys.
-        Requirements: device policy + fixed-horizon device env, fixed KL coefficient, world_size 1."""
+        Requirements: device policy + fixed-horizon device env, fixed KL coefficient.  With world_size > 1 the
+        NCCL all-reduces of the meta-gradient are captured into the graph as well."""
         import torch
         from promp_b200.samplers.device_data import PhaseData
         sampler, proc, algo, policy = self.sampler, self.sample_processor, self.algo, self.policy

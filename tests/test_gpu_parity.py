@@ -658,3 +658,18 @@ def test_raw_env_without_normalize_wrapper(golden_dir):
     want = obs0.astype(np.float32) + np.clip(act, -0.1, 0.1).astype(np.float32)
     np.testing.assert_allclose(np.asarray(obs), want, atol=1e-6)
     np.testing.assert_allclose(np.asarray(rew), -np.sqrt((want ** 2).sum(1)), rtol=1e-5)
+
+
+def test_p2p_allreduce_two_gpus():
+    """promp_allreduce_p2p (NVLink peer memory, rank-ordered, graph-capturable) vs NCCL on 2 GPUs; skipped on a
+    single-GPU box."""
+    torch = _cuda()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29547', os.path.join(root, 'tests', '_p2p_worker.py')]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0 and 'rank 0 p2p ok' in r.stdout and 'rank 1 p2p ok' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
