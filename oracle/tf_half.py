@@ -125,7 +125,7 @@ def adapt(theta_tasks, d, dims, inner_lr, inner_type='likelihood_ratio'):
 
 
 def meta_objective(theta, all_data, dims, inner_lr, algo='promp', clip_eps=0.3, inner_kl_coeff=None,
-                   inner_type='likelihood_ratio', min_log_std=math.log(1e-6)):
+                   inner_type='likelihood_ratio', min_log_std=math.log(1e-6), exploration=False):
     """The outer objective with the inner steps kept symbolic (second order).
     ProMP: ref meta_algos/pro_mp.py:88-163.  TRPO-MAML: ref meta_algos/trpo_maml.py:100-159.
     theta [P] (requires_grad).  all_data: list (len S = num_inner_grad_steps+1) of phase dicts.
@@ -153,7 +153,14 @@ def meta_objective(theta, all_data, dims, inner_lr, algo='promp', clip_eps=0.3, 
         penalty = torch.mean(coeff * inner_kls_t) if inner_kls else torch.zeros((), dtype=theta.dtype)
         obj = torch.mean(surr) + penalty
     elif algo == 'trpo':
-        obj = torch.mean(-torch.mean(lr * d['adv'], -1))
+        surr = -torch.mean(lr * d['adv'], -1)
+        if exploration:
+            # E-MAML (ref meta_algos/trpo_maml.py:137-144): - mean(adj_avg_rewards of the last phase) *
+            # mean(log-likelihood of the INITIAL actions under the pre-update policy)
+            d0 = all_data[0]
+            mean0, ls0 = dist_info(theta.unsqueeze(0).expand(M, -1), d0['obs'], dims, min_log_std)
+            surr = surr - torch.mean(d['adj_avg_rewards'], -1) * torch.mean(log_likelihood(d0['act'], mean0, ls0), -1)
+        obj = torch.mean(surr)
         inner_kls_t = torch.stack(inner_kls) if inner_kls else torch.zeros(0, dtype=theta.dtype)
     else:
         raise NotImplementedError(algo)

@@ -17,8 +17,6 @@ class TRPOMAML(MAMLAlgo):
         assert inner_type in ["log_likelihood", "likelihood_ratio", "dice"]
         if inner_type == 'dice':
             raise NotImplementedError("inner_type='dice' (reference raises NotImplementedError too, trpo_maml.py:64)")
-        if exploration:
-            raise NotImplementedError("E-MAML (exploration=True) is a 'next' row (SURVEY.md section 8f item 1)")
         self.step_size = step_size
         self.inner_type = inner_type
         self.name = name
@@ -28,10 +26,44 @@ class TRPOMAML(MAMLAlgo):
         self.optimizer = ConjugateGradientOptimizer()
         self.optimizer.build(self, step_size)
 
+    # ---- E-MAML exploration term (:137-144): surr_i += -mean(adj_avg_rewards_i) * mean(logp_theta(a0 | x0))
+    def _exploration_coeff(self, phases):
+        """c_i = mean_n adj_avg_rewards_i of the LAST phase = (mean r_i - mean r_all) / (std r_all + 1e-8), on the
+        device from the processing kernel's per-task sums (global over ranks)."""
+        import torch
+        last = phases[-1]
+        if getattr(last, '_explore_adv', None) is None:
+            st = last.stats[:, 5:7]                                    # per task: sum r, sum r^2
+            tot = torch.cat([st.sum(0), torch.tensor([float(last.M * last.N)], dtype=torch.float64, device=st.device)])
+            allreduce_sum_(tot)
+            mean_all = tot[0] / tot[2]
+            std_all = torch.sqrt(torch.clamp(tot[1] / tot[2] - mean_all * mean_all, min=0.0))
+            c = ((st[:, 0] / last.N - mean_all) / (std_all + 1e-8)).float()
+            last._explore_adv = c.view(-1, 1).expand(last.M, phases[0].N).contiguous()
+        return last._explore_adv
+
+    def _exploration_term(self, theta, phases, want_grad):
+        """(-c_i * mean logp) per task [M] and, optionally, its gradient w.r.t. theta per task [M,P]: the LOGLIK
+        objective of promp_policy_grad on the phase-0 data with the constant c_i in place of the advantages."""
+        import torch
+        p = self.policy
+        ph0 = phases[0]
+        adv_saved = ph0.adv
+        ph0.adv = self._exploration_coeff(phases)
+        st = torch.zeros(self.meta_batch_size, 4, dtype=torch.float32, device=p.device)
+        g = torch.empty(self.meta_batch_size, p.num_params, dtype=torch.float32, device=p.device) if want_grad else None
+        try:
+            self._grad(ph0, theta, 0, _lib.OBJ_LOGLIK, clip_log_std=1, grad=g, stats=st)
+        finally:
+            ph0.adv = adv_saved
+        return st[:, 0], g
+
     # meta objective = mean_i -mean(ratio*adv) (:135,152); constraint = mean_i mean KL(old || theta_i') (:133,149)
     def eval_scalars(self, theta, phases):
         import torch
         res = self._meta_pass(theta, phases, _lib.OBJ_RATIO, 0.0, [0.0] * self.num_inner_grad_steps, want_grad=False)
+        if self.exploration:
+            res['surr'] = res['surr'] + self._exploration_term(theta, phases, False)[0]
         vec = torch.stack([res['surr'].sum(), res['outer_kl'].sum()]) / (self.meta_batch_size * world_size())
         allreduce_sum_(vec)
         host = vec.cpu().numpy()
@@ -41,6 +73,13 @@ class TRPOMAML(MAMLAlgo):
         zeros = [0.0] * self.num_inner_grad_steps
         if which == 'loss':
             res = self._meta_pass(theta, phases, _lib.OBJ_RATIO, 0.0, zeros, want_grad=True)
+            if self.exploration:
+                import torch
+                _, g = self._exploration_term(theta, phases, True)
+                extra = torch.empty_like(res['grad'])
+                _lib.call('promp_reduce_tasks', self.meta_batch_size, self.policy.num_params, _lib.ptr(g),
+                          1.0 / (self.meta_batch_size * world_size()), _lib.ptr(extra), _lib.stream())
+                res['grad'] += extra
         else:
             res = self._meta_pass(theta, phases, _lib.OBJ_NONE, 0.0, zeros, want_grad=True, outer_kl_coeff=1.0)
         allreduce_sum_(res['grad'])

@@ -673,3 +673,38 @@ def test_p2p_allreduce_two_gpus():
            '--master-port', '29547', os.path.join(root, 'tests', '_p2p_worker.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
     assert r.returncode == 0 and 'rank 0 p2p ok' in r.stdout and 'rank 1 p2p ok' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_emaml_exploration_term_matches_oracle():
+    """TRPOMAML(exploration=True) = E-MAML (ref meta_algos/trpo_maml.py:137-144): objective and gradient incl. the
+    initial-log-likelihood term weighted by the last phase's mean adjusted reward."""
+    torch = _cuda()
+    from oracle import tf_half as th
+    from promp_b200.samplers.meta_sample_processor import run_process_kernel
+    M, N, Do, Da = 4, 200, 2, 2
+    policy, algo = _algo(torch, 'trpo', M, Do, Da, exploration=True)
+    dims = (Do, Da, (64, 64))
+    theta = policy.theta.cpu().numpy()
+    cpus, phases = [], []
+    for s in range(2):
+        c, p = _random_phase(torch, M, N, Do, Da, theta, 70 + s)
+        # rewards -> the processing kernel's per-task sums feed adj_avg_rewards
+        g = torch.Generator().manual_seed(90 + s)
+        rew = torch.randn(M, N, generator=g) + torch.arange(M).view(-1, 1).float()
+        p.rew.copy_(rew)
+        adv_keep = p.adv.clone()
+        run_process_kernel(p, 0.99, 1.0, 1e-5, 1, True, False)
+        p.adv = adv_keep
+        r64 = rew.double()
+        c = {k: v.double() for k, v in c.items()}
+        c['adj_avg_rewards'] = (r64 - r64.mean()) / (r64.std(unbiased=False) + 1e-8)
+        cpus.append(c); phases.append(p)
+    t64 = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    obj, _, okl = th.meta_objective(t64, cpus, dims, 0.1, 'trpo', exploration=True)
+    (g_want,) = torch.autograd.grad(obj, t64)
+    obj_plain = th.meta_objective(t64, cpus, dims, 0.1, 'trpo')[0]
+    assert abs(float(obj) - float(obj_plain)) > 1e-3          # the term is actually exercised
+    loss, klv = algo.eval_scalars(policy.theta, phases)
+    assert abs(loss - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
+    g_got = algo.eval_gradient(policy.theta, phases, 'loss')
+    assert rel_err(g_got, g_want.detach().numpy()) < 1e-4
