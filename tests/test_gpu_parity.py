@@ -708,3 +708,56 @@ def test_emaml_exploration_term_matches_oracle():
     assert abs(loss - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
     g_got = algo.eval_gradient(policy.theta, phases, 'loss')
     assert rel_err(g_got, g_want.detach().numpy()) < 1e-4
+
+
+def test_policy_kernels_deterministic_and_batch_independent():
+    """(i) Two launches on the same inputs are bitwise identical (fixed-order reductions, no atomics on data);
+    (ii) a task's adapted parameters / HVP do not depend on which other tasks share the launch (tile scheduling
+    crosses task boundaries inside CTAs): M = 96 tasks vs the same tasks run 6 at a time."""
+    torch = _cuda()
+    Do, Da, N = 2, 2, 1000
+    M = 96
+    policy, algo = _algo(torch, 'promp', M, Do, Da)
+    theta = policy.theta.cpu().numpy()
+    _, ph = _random_phase(torch, M, N, Do, Da, theta, 3)
+    P = policy.num_params
+    vec = 0.01 * torch.randn(M, P, generator=torch.Generator().manual_seed(1)).cuda()
+    outs = []
+    for rep in range(2):
+        g = torch.empty(M, P, device='cuda'); newp = torch.empty(M, P, device='cuda'); hv = torch.empty(M, P, device='cuda')
+        st = torch.zeros(M, 4, device='cuda')
+        algo._grad(ph, policy.theta, 0, 0, clip_log_std=1, grad=g, out_params=newp, sgd_lr=0.1, stats=st)
+        algo._hvp(ph, newp, P, vec, hv, 5e-4, 0)
+        outs.append((g, newp, hv, st))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    # the same tasks in small launches
+    from promp_b200.samplers.device_data import PhaseData
+    sub = 6
+    pol2, algo2 = _algo(torch, 'promp', sub, Do, Da)
+    pol2.set_params(policy.get_param_values())
+    for m0 in (0, 42, 90):
+        p2 = PhaseData(sub, 1, N, Do, Da, torch.device('cuda'))
+        sl = slice(m0, m0 + sub)
+        p2.obs.copy_(ph.obs[sl]); p2.act.copy_(ph.act[sl]); p2.mean.copy_(ph.mean[sl]); p2.log_std.copy_(ph.log_std[sl])
+        p2.adv = ph.adv[sl].contiguous()
+        g = torch.empty(sub, P, device='cuda'); newp = torch.empty(sub, P, device='cuda'); hv = torch.empty(sub, P, device='cuda')
+        algo2._grad(p2, pol2.theta, 0, 0, clip_log_std=1, grad=g, out_params=newp, sgd_lr=0.1)
+        algo2._hvp(p2, newp, P, vec[sl].contiguous(), hv, 5e-4, 0)
+        # different tile->CTA assignment changes the summation order of the partials: equal to fp32 round-off
+        assert rel_err(g.cpu().numpy(), outs[0][0][sl].cpu().numpy()) < 2e-6
+        assert rel_err(hv.cpu().numpy(), outs[0][2][sl].cpu().numpy()) < 2e-6
+
+
+def test_ragged_paths_are_rejected_loudly():
+    """Variable-length paths are a 'next' row: the device processor must refuse them, not silently mis-process."""
+    _cuda()
+    from promp_b200.samplers import MetaSampleProcessor
+    from promp_b200.baselines import LinearFeatureBaseline, ZeroBaseline
+    rng = np.random.RandomState(0)
+    paths = {0: [dict(observations=rng.randn(L, 2), actions=rng.randn(L, 2), rewards=rng.randn(L), env_infos={}, agent_infos={})
+                 for L in (5, 7)]}
+    with pytest.raises(NotImplementedError):
+        MetaSampleProcessor(LinearFeatureBaseline()).process_samples(paths)
+    with pytest.raises(AssertionError):
+        MetaSampleProcessor(ZeroBaseline()).process_samples([paths[0]])       # must be a dict (meta_sample_processor.py:25)
