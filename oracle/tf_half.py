@@ -152,8 +152,11 @@ def meta_objective(theta, all_data, dims, inner_lr, algo='promp', clip_eps=0.3, 
         inner_kls_t = torch.stack(inner_kls) if inner_kls else torch.zeros(0, dtype=theta.dtype)
         penalty = torch.mean(coeff * inner_kls_t) if inner_kls else torch.zeros((), dtype=theta.dtype)
         obj = torch.mean(surr) + penalty
-    elif algo == 'trpo':
-        surr = -torch.mean(lr * d['adv'], -1)
+    elif algo in ('trpo', 'vpg'):
+        if algo == 'trpo':
+            surr = -torch.mean(lr * d['adv'], -1)
+        else:   # VPG-MAML outer objective (ref meta_algos/vpg_maml.py:128-130)
+            surr = -torch.mean(log_likelihood(d['act'], mean, ls) * d['adv'], -1)
         if exploration:
             # E-MAML (ref meta_algos/trpo_maml.py:137-144): - mean(adj_avg_rewards of the last phase) *
             # mean(log-likelihood of the INITIAL actions under the pre-update policy)

@@ -761,3 +761,44 @@ def test_ragged_paths_are_rejected_loudly():
         MetaSampleProcessor(LinearFeatureBaseline()).process_samples(paths)
     with pytest.raises(AssertionError):
         MetaSampleProcessor(ZeroBaseline()).process_samples([paths[0]])       # must be a dict (meta_sample_processor.py:25)
+
+
+@pytest.mark.parametrize('exploration', [False, True])
+def test_vpg_maml_matches_oracle(exploration):
+    """VPGMAML (ref meta_algos/vpg_maml.py): meta objective / gradient and the single TF1-Adam step."""
+    torch = _cuda()
+    from oracle import tf_half as th
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.meta_algos import VPGMAML
+    from promp_b200.samplers.device_data import SamplesData
+    from promp_b200.samplers.meta_sample_processor import run_process_kernel
+    M, N, Do, Da = 4, 180, 2, 2
+    np.random.seed(4)
+    policy = MetaGaussianMLPPolicy(name="p", obs_dim=Do, action_dim=Da, meta_batch_size=M, hidden_sizes=(64, 64))
+    algo = VPGMAML(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3,
+                   inner_type='log_likelihood', exploration=exploration)
+    dims = (Do, Da, (64, 64))
+    theta = policy.theta.cpu().numpy().copy()
+    cpus, phases = [], []
+    for s in range(2):
+        c, p = _random_phase(torch, M, N, Do, Da, theta, 110 + s)
+        rew = torch.randn(M, N, generator=torch.Generator().manual_seed(5 + s)) + torch.arange(M).view(-1, 1).float()
+        p.rew.copy_(rew)
+        keep = p.adv.clone()
+        run_process_kernel(p, 0.99, 1.0, 1e-5, 1, True, False)
+        p.adv = keep
+        c = {k: v.double() for k, v in c.items()}
+        r64 = rew.double()
+        c['adj_avg_rewards'] = (r64 - r64.mean()) / (r64.std(unbiased=False) + 1e-8)
+        cpus.append(c); phases.append(p)
+    t64 = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+    obj, _, _ = th.meta_objective(t64, cpus, dims, 0.1, 'vpg', inner_type='log_likelihood', exploration=exploration)
+    (g_want,) = torch.autograd.grad(obj, t64)
+    res = algo._objective_pass(phases, want_grad=True)
+    assert rel_err(res['grad'].cpu().numpy(), g_want.numpy()) < 1e-4
+    assert abs(float(algo.loss_terms(res)[0]) - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
+    algo.optimize_policy([[SamplesData(p, m) for m in range(M)] for p in phases], log=False)
+    adam = th.TF1Adam(theta.size)
+    want = adam.step(torch.tensor(theta), g_want.float())
+    np.testing.assert_allclose(policy.theta.cpu().numpy(), want.numpy(), rtol=0, atol=2e-5)
+    assert abs(algo.last_stats['loss_before'] - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
