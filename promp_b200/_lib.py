@@ -41,6 +41,7 @@ _SIGNATURES = {
     'promp_reduce_tasks': (c_int, [c_int, c_int, _P, c_float, _P, _P]),
     'promp_adam_tf1': (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
     'promp_policy_forward': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),
+    'promp_set_option': (c_int, [c_char_p, c_int]),
     'promp_comm_buffer_bytes': (c_int64, [c_int, c_int]),
     'promp_comm_alloc': (c_int, [c_int64, _P]),
     'promp_comm_free': (c_int, [_P]),
@@ -106,6 +107,10 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise PrompLibraryError("promp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     load()
+
+
+def set_option(name, value):
+    check(load().promp_set_option(name.encode(), int(value)), 'promp_set_option')
 
 
 def call(name, *args):

@@ -27,7 +27,7 @@ struct TileCfg {
 template <int K, int LDA, int LDW, int RM>
 __device__ __forceinline__ void gemm_tile(const float* __restrict__ A, const float* __restrict__ W, int row0, int col0,
                                           float (&acc)[RM][4]) {
-#ifdef PROMP_EXP_NO_GEMM   // kernel-time experiments only (tools/kernel_time.py)
+#if defined(PROMP_EXP_NO_GEMM) || defined(PROMP_EXP_NO_LAYER_GEMM)   // kernel-time experiments only (tools/kernel_time.py)
     return;
 #endif
 #pragma unroll 4

@@ -9,6 +9,7 @@
 // crosses a task boundary (or ends) it flushes them to a per-(CTA,task) partial slot, and the last
 // segment of each task to arrive (atomic ticket) reduces that task's slots in CTA order -> bitwise
 // run-to-run deterministic sums.  These kernels are fp32-FMA bound (AI ~ 10^2..10^3 FLOP/B).
+#include <string.h>
 #include "mlp_tile.cuh"
 
 namespace promp {
@@ -48,8 +49,8 @@ struct PolicyArgs {
 // Tile-range bookkeeping shared by both kernels.
 struct TileSched {
     int ntiles, T, q, g_lo, g_hi;
-    __device__ __forceinline__ TileSched(int M, int N, int q_) {
-        ntiles = (N + TB - 1) / TB;
+    __device__ __forceinline__ TileSched(int M, int N, int q_, int tb = TB) {
+        ntiles = (N + tb - 1) / tb;
         T = M * ntiles;
         q = q_;
         g_lo = blockIdx.x * q;
@@ -842,6 +843,10 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     if (cur_m >= 0) flush(cur_m);
 }
 
+}  // namespace promp
+#include "policy_tc.cuh"
+namespace promp {
+
 // -------------------------------------------------------------------------------------------------
 // forward only: mean for arbitrary obs (distribution_info_sym / get_actions without sampling)
 template <int DO, int DA, int HID>
@@ -917,8 +922,8 @@ struct TilePlan {
     int64_t partial_floats;
 };
 // One-wave persistent plan: `slots` resident CTAs share the T tiles as evenly as possible.
-static TilePlan plan_tiles(int M, int N, int slots, int P) {
-    const int ntiles = (N + TB - 1) / TB;
+static TilePlan plan_tiles(int M, int N, int slots, int P, int tb = TB) {
+    const int ntiles = (N + tb - 1) / tb;
     const int64_t T = (int64_t)M * ntiles;
     TilePlan p;
     int g = (int)(T < slots ? T : slots);
@@ -943,14 +948,14 @@ static int64_t counters_bytes(int M) { return (((int64_t)M * sizeof(int) + 15) /
 
 template <typename Kernel>
 static int launch_policy(Kernel kernel, int smem, int& occ_cache, PolicyArgs& A, int P, void* ws, int64_t ws_bytes,
-                         cudaStream_t st, const char* name) {
+                         cudaStream_t st, const char* name, int tb = TB) {
     if (occ_cache == 0) {
         PROMP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
         PROMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PT_THREADS, smem));
         occ_cache = occ < 1 ? 1 : occ;
     }
-    const TilePlan p = plan_tiles(A.M, A.N, sm_count() * occ_cache, P);
+    const TilePlan p = plan_tiles(A.M, A.N, sm_count() * occ_cache, P, tb);
     const int64_t need = counters_bytes(A.M) + p.partial_floats * (int64_t)sizeof(float);
     if (ws_bytes < need) {
         set_error("policy workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
@@ -970,6 +975,20 @@ static int launch_grad(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t s
     static int occ = 0;
     return launch_policy(policy_grad_kernel<DO, DA, HID>, (int)sizeof(GradSmem<DO, DA, HID>), occ, A,
                          PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_kernel");
+}
+
+static int g_use_tc = 0;     // promp_set_option("tensor_cores", 1): route HID = 64 policy kernels through tcgen05
+
+template <int DO, int DA, int HID>
+static int launch_grad_any(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    if constexpr (HID == TC_HID) {
+        if (g_use_tc) {
+            static int occ = 0;
+            return launch_policy(policy_grad_tc_kernel<DO, DA>, (int)sizeof(GradTcSmem<DO, DA>), occ, A,
+                                 PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_tc_kernel", TBT);
+        }
+    }
+    return launch_grad<DO, DA, HID>(A, ws, ws_bytes, st);
 }
 
 template <int DO, int DA, int HID>
@@ -1042,7 +1061,7 @@ extern "C" int promp_policy_grad(int obs_dim, int act_dim, int hidden, int M, in
     A.kl_coeff = kl_coeff; A.clip_log_std = clip_log_std; A.min_log_std = min_log_std;
     A.grad = grad; A.out_params = out_params; A.sgd_lr = sgd_lr; A.stats = stats;
     cudaStream_t s = (cudaStream_t)stream;
-    PROMP_DISPATCH_DIMS(launch_grad, A, workspace, workspace_bytes, s)
+    PROMP_DISPATCH_DIMS(launch_grad_any, A, workspace, workspace_bytes, s)
 }
 
 extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
@@ -1063,6 +1082,16 @@ extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int
     A.vec = vec; A.out = out; A.inner_lr = inner_lr; A.stats = stats;
     cudaStream_t s = (cudaStream_t)stream;
     PROMP_DISPATCH_DIMS(launch_hvp, A, workspace, workspace_bytes, s)
+}
+
+extern "C" int promp_set_option(const char* name, int value) {
+    PROMP_REQUIRE(name != nullptr, "promp_set_option: null name");
+    if (strcmp(name, "tensor_cores") == 0) {
+        g_use_tc = value ? 1 : 0;
+        return PROMP_OK;
+    }
+    set_error("promp_set_option: unknown option '%s'", name);
+    return PROMP_ERR_INVALID_ARG;
 }
 
 extern "C" int promp_policy_forward(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,

@@ -1,0 +1,496 @@
+// Tensor-core (tcgen05 / TMEM) variant of policy_grad_kernel for HID = 64.
+//
+// The two [128 x 64] x [64 x 64] layer GEMMs of a tile (forward H1.W1 and backward D2.W1^T) run on the 5th-gen tensor
+// cores as tcgen05.mma.kind::tf32 with the 3-term split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (a_hi = the fp32
+// value itself, which the tensor core truncates to TF32; a_lo = a - trunc_tf32(a)), i.e. fp32-level accuracy
+// (1.5e-6 relative, tools/ubench/umma_test.cu) at 24 MMAs per GEMM.  Accumulators live in TMEM (2 x 64 columns) and
+// are read back with tcgen05.ld (one sample row per thread, 32 columns each); operands are written by the epilogue
+// threads straight into the UMMA canonical K-major layout WITHOUT swizzle: 8x4-float core matrices (128 contiguous
+// bytes, rows 16 B apart), next 8 rows at +128 B (SBO), next 4 columns at +S_c (LBO).  S_c = rows*16 + 16 bytes: the
+// extra 16 B make both the row-wise 16-byte stores of the epilogue and the column-wise scalar reads of the SIMT
+// reductions bank-conflict free, and the same bytes stay readable as a plain fp32 tile by the CUDA-core code.
+// The weight-gradient GEMM H1^T.D2 contracts over samples, i.e. needs MN-major operands, which for tf32 exist only
+// in the 128B_BASE32B layout (a second copy of every tile): it stays on the CUDA cores and runs CONCURRENTLY with the
+// backward MMA (different pipes).  One elected thread issues the MMAs; completion is an mbarrier (tcgen05.commit).
+#pragma once
+#include "mlp_tile.cuh"
+
+namespace promp {
+
+constexpr int TBT = 128;                      // samples per tile = UMMA M
+constexpr int TC_HID = 64;
+constexpr int SCA = TBT * 16 + 16;            // bytes between 4-column chunks of a [128 x 64] activation tile
+constexpr int SCW = TC_HID * 16 + 16;         // ... of a [64 x 64] weight tile
+constexpr int TILE_A_BYTES = 16 * SCA;        // 33 024
+constexpr int TILE_W_BYTES = 16 * SCW;        // 16 640
+
+__device__ __forceinline__ int core_off(int r, int c, int sc) {      // byte offset of element (r, c)
+    return (c >> 2) * sc + (r >> 3) * 128 + (r & 7) * 16 + ((c & 3) << 2);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// K-major, no swizzle: LBO = byte distance between core matrices adjacent in K, SBO = ... adjacent in M/N
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;        // descriptor version (sm_100)
+    return d;                      // layout type 0 = no swizzle
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // D f32, A/B tf32, K-major
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tMBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra MBAR_DONE_%=;\n\tbra MBAR_WAIT_%=;\n\tMBAR_DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// D[128 x 64] (TMEM columns d_tmem..+63) = A[128 x 64] . B^T with B [64(N) x 64(K)], 3-term TF32 split, issued by ONE thread.
+__device__ __forceinline__ void issue_gemm_3xtf32(uint32_t d_tmem, const unsigned char* a_hi, const unsigned char* a_lo,
+                                                  const unsigned char* b_hi, const unsigned char* b_lo) {
+    const uint32_t idesc = umma_idesc_tf32(TBT, TC_HID);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {                 // lo*hi, hi*lo (small terms first), hi*hi
+        const unsigned char* a = (term == 0) ? a_lo : a_hi;
+        const unsigned char* b = (term == 1) ? b_lo : b_hi;
+        const uint32_t a0 = smem_u32(a), b0 = smem_u32(b);
+#pragma unroll
+        for (int s = 0; s < TC_HID / 8; ++s) {             // K = 8 per MMA = two 4-column chunks
+            umma_tf32(d_tmem, umma_desc(a0 + 2 * s * SCA, SCA, 128), umma_desc(b0 + 2 * s * SCW, SCW, 128), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+template <int DO, int DA>
+struct SmallLayout {      // the parameters other than W1, compact
+    static constexpr int W0 = 0;
+    static constexpr int B0 = W0 + DO * TC_HID;
+    static constexpr int B1 = B0 + TC_HID;
+    static constexpr int W2 = B1 + TC_HID;
+    static constexpr int B2 = W2 + TC_HID * DA;
+    static constexpr int LS = B2 + DA;
+    static constexpr int SIZE = (LS + DA + 3) / 4 * 4;
+};
+
+template <int DO, int DA>
+struct GradTcSmem {
+    static constexpr int DOP = DOPad<DO>::V;
+    alignas(16) unsigned char W1T_hi[TILE_W_BYTES];   // B of the forward GEMM: rows n = output unit, K = k
+    alignas(16) unsigned char W1T_lo[TILE_W_BYTES];
+    alignas(16) unsigned char W1_hi[TILE_W_BYTES];    // B of the backward GEMM: rows n = k', K = j
+    alignas(16) unsigned char W1_lo[TILE_W_BYTES];
+    alignas(16) unsigned char A0[TILE_A_BYTES];       // H1 -> D1
+    alignas(16) unsigned char A1[TILE_A_BYTES];       // H2 -> D2 (hi)
+    alignas(16) unsigned char LO[TILE_A_BYTES];       // H1_lo -> D2_lo ; flush scratch
+    alignas(16) float Ps[SmallLayout<DO, DA>::SIZE];
+    alignas(16) float X[TBT * DOP];
+    float MUP[2 * TBT * DA];
+    float DMU[TBT * DA];
+    float DLS[TBT * DA];
+    float red[3 * (PT_THREADS / 32)];
+    alignas(8) uint64_t bar;
+    uint32_t tmem_base;
+    int last;
+};
+
+template <int DO, int DA>
+__global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArgs A) {
+    constexpr int HID = TC_HID;
+    using L = PLayout<DO, DA, HID>;
+    using SL = SmallLayout<DO, DA>;
+    using SM = GradTcSmem<DO, DA>;
+    constexpr int DOP = SM::DOP;
+    constexpr int PSTRIDE = L::P + PSTAT;
+    constexpr int NPART = PT_THREADS / HID, BPP = TBT / NPART;     // column role: 4 slices of 32 rows
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qd = warp & 3, half = warp >> 2;
+    const int r = qd * 32 + lane, c0 = 32 * half;          // row-half role: sample row r, hidden units [c0, c0+32)
+    const int ky = tid >> 4, txw = tid & 15;               // SIMT weight-gradient role: 4 k-rows x 4 j-cols
+    const int cj = tid & (HID - 1), cp = tid / HID;        // column role
+    const TileSched ts(A.M, A.N, A.q, TBT);
+    const int N = A.N;
+    const float invN = 1.0f / (float)N;
+    const bool want_grad = A.grad != nullptr;
+    const float* th = nullptr;
+    HeadIn<DA> hin;
+    uint32_t phase = 0;
+
+    // ---- TMEM + mbarrier setup
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&S.tmem_base)), "n"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (tid == 0) mbar_init(&S.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
+
+    float gW1[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2, gLS;
+    float s_obj, s_kl, s_ratio;
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) gW1[a][0] = gW1[a][1] = gW1[a][2] = gW1[a][3] = 0.f;
+#pragma unroll
+        for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
+        gB1c = gB0c = gB2 = gLS = 0.f;
+        s_obj = s_kl = s_ratio = 0.f;
+    };
+    auto load_task = [&](int m, bool first) {
+        th = A.params + (int64_t)m * A.param_stride;
+        if (!first && A.param_stride == 0) return;
+        __syncthreads();
+        for (int i = tid; i < DO * HID + HID; i += PT_THREADS) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);          // W0, b0
+        for (int i = tid; i < HID; i += PT_THREADS) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
+        for (int i = tid; i < HID * DA + 2 * DA; i += PT_THREADS) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);       // W2, b2, ls
+        for (int i = tid; i < HID * HID; i += PT_THREADS) {
+            const int k = i / HID, j = i % HID;
+            const float w = __ldg(th + L::W1 + i), wl = w - tf32_trunc(w);
+            *reinterpret_cast<float*>(S.W1_hi + core_off(k, j, SCW)) = w;
+            *reinterpret_cast<float*>(S.W1_lo + core_off(k, j, SCW)) = wl;
+            *reinterpret_cast<float*>(S.W1T_hi + core_off(j, k, SCW)) = w;
+            *reinterpret_cast<float*>(S.W1T_lo + core_off(j, k, SCW)) = wl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < DA; ++d) {
+            const float raw = S.Ps[SL::LS + d];
+            const bool clipped = A.clip_log_std && (raw < A.min_log_std);
+            hin.ls[d] = clipped ? A.min_log_std : raw;
+            hin.ls_mask[d] = clipped ? 0.f : 1.f;
+            hin.sig[d] = expf(hin.ls[d]);
+        }
+    };
+    auto flush = [&](int m) {
+        float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+        float* scr = reinterpret_cast<float*>(S.LO);      // free between tiles (all MMAs have completed)
+        __syncthreads();
+        if (want_grad) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) part[L::W1 + (4 * ky + a) * HID + 4 * txw + c] = gW1[a][c];
+            scr[cp * HID + cj] = gB1c;
+            scr[NPART * HID + cp * HID + cj] = gB0c;
+            __syncthreads();
+            if (tid < 2 * HID) {
+                const int which = tid / HID, j = tid % HID;
+                float s = 0.f;
+                for (int p = 0; p < NPART; ++p) s += scr[which * NPART * HID + p * HID + j];
+                part[(which ? L::B0 : L::B1) + j] = s;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < DO; ++i) scr[(cp * DO + i) * HID + cj] = gW0p[i];
+            __syncthreads();
+            for (int idx = tid; idx < DO * HID; idx += PT_THREADS) {
+                float s = 0.f;
+                for (int p = 0; p < NPART; ++p) s += scr[p * DO * HID + idx];
+                part[L::W0 + idx] = s;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < DA; ++d) scr[(cp * HID + cj) * DA + d] = gW2p[d];
+            __syncthreads();
+            for (int idx = tid; idx < HID * DA; idx += PT_THREADS) {
+                float s = 0.f;
+                for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
+                part[L::W2 + idx] = s;
+            }
+            if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+        }
+        const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);   // held by half == 0 threads, 0 elsewhere
+        __syncthreads();
+        if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
+        __syncthreads();
+        if (tid < 3) {
+            float s = 0.f;
+            for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+            part[L::P + tid] = s;
+        }
+        __threadfence();
+        __syncthreads();
+        const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
+        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
+        __syncthreads();
+        if (S.last) {
+            __threadfence();
+            if (want_grad) {
+                for (int p = 4 * tid; p < L::P; p += 4 * PT_THREADS) {
+                    const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                    *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
+                    if (A.out_params) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(th + p));
+                        *reinterpret_cast<float4*>(A.out_params + (int64_t)m * L::P + p) =
+                            make_float4(t4.x - A.sgd_lr * s.x, t4.y - A.sgd_lr * s.y, t4.z - A.sgd_lr * s.z, t4.w - A.sgd_lr * s.w);
+                    }
+                }
+            }
+            if (A.stats && tid < 3) {
+                float s = 0.f;
+                for (int c = c_lo; c <= c_hi; ++c)
+                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + L::P + tid);
+                A.stats[(int64_t)m * 4 + tid] = s * invN;
+            }
+            if (tid == 0) A.counters[m] = 0;
+        }
+        __syncthreads();
+    };
+
+    int cur_m = -1;
+    for (int g = ts.g_lo; g < ts.g_hi; ++g) {
+        const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+        if (m != cur_m) {
+            if (cur_m >= 0) flush(cur_m);
+            load_task(m, cur_m < 0);
+            zero_acc();
+            cur_m = m;
+        }
+        const int n0 = tile * TBT, nb = min(TBT, N - n0);
+        const int64_t g0 = (int64_t)m * N + n0;
+        __syncthreads();
+        for (int i = tid; i < TBT * DOP; i += PT_THREADS) {
+            const int b = i / DOP, c = i % DOP;
+            S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+        }
+        __syncthreads();
+        // ---- layer 0 (CUDA cores, row-half role): H1 = tanh(X W0 + b0) -> A0 (fp32 = TF32 "hi" operand) and LO
+        {
+            float x[DO];
+#pragma unroll
+            for (int i = 0; i < DO; ++i) x[i] = S.X[r * DOP + i];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float h[4], hl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = c0 + 4 * c4 + e;
+                    float z = S.Ps[SL::B0 + c];
+#pragma unroll
+                    for (int i = 0; i < DO; ++i) z = fmaf(x[i], S.Ps[SL::W0 + i * HID + c], z);
+                    h[e] = tanh_fast(z);
+                    hl[e] = h[e] - tf32_trunc(h[e]);
+                }
+                const int off = core_off(r, c0 + 4 * c4, SCA);
+                *reinterpret_cast<float4*>(S.A0 + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(S.LO + off) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+            }
+        }
+        // ---- layer 1 on the tensor cores: Z2 = H1 W1 -> TMEM columns [0, 64)
+        proxy_fence_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_3xtf32(tmem, S.A0, S.LO, S.W1T_hi, S.W1T_lo);
+            umma_commit(&S.bar);
+        }
+        mbar_wait(&S.bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float h2[32];
+        tmem_ld32(tmem_row + c0, h2);
+        float mup[DA];
+#pragma unroll
+        for (int d = 0; d < DA; ++d) mup[d] = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * c4 + e;
+                h2[c] = tanh_fast(h2[c] + S.Ps[SL::B1 + c0 + c]);
+#pragma unroll
+                for (int d = 0; d < DA; ++d) mup[d] = fmaf(h2[c], S.Ps[SL::W2 + (c0 + c) * DA + d], mup[d]);
+            }
+            *reinterpret_cast<float4*>(S.A1 + core_off(r, c0 + 4 * c4, SCA)) =
+                make_float4(h2[4 * c4], h2[4 * c4 + 1], h2[4 * c4 + 2], h2[4 * c4 + 3]);
+        }
+#pragma unroll
+        for (int d = 0; d < DA; ++d) S.MUP[(half * TBT + r) * DA + d] = mup[d];
+        tc_fence_before();
+        __syncthreads();
+        // ---- Gaussian head: one thread per sample row (half == 0)
+        if (half == 0) {
+            float dmu[DA], dls[DA];
+            if (r < nb) {
+                const int64_t n = g0 + r;
+                float mu[DA], a[DA], mo[DA], lso[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    mu[d] = S.MUP[r * DA + d] + S.MUP[(TBT + r) * DA + d] + S.Ps[SL::B2 + d];
+                    a[d] = __ldg(A.act + n * DA + d);
+                    mo[d] = __ldg(A.old_mean + n * DA + d);
+                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                }
+                const float adv = __ldg(A.adv + n);
+                HeadOut<DA> o;
+                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    dmu[d] = wt * o.zeta[d] / hin.sig[d] + kc * o.dkl_dmu[d];
+                    dls[d] = (wt * (o.zeta[d] * o.zeta[d] - 1.f) + kc * o.dkl_dls[d]) * hin.ls_mask[d];
+                }
+                s_obj += o.obj;
+                s_kl += o.kl;
+                s_ratio += o.ratio;
+            } else {
+#pragma unroll
+                for (int d = 0; d < DA; ++d) dmu[d] = dls[d] = 0.f;
+            }
+#pragma unroll
+            for (int d = 0; d < DA; ++d) S.DMU[r * DA + d] = dmu[d], S.DLS[r * DA + d] = dls[d];
+        }
+        if (!want_grad) continue;
+        __syncthreads();
+        // ---- output-layer gradients (column role) from the fp32 H2 tile
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float h = *reinterpret_cast<const float*>(S.A1 + core_off(b, cj, SCA));
+#pragma unroll
+                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.DMU[b * DA + d], gW2p[d]);
+            }
+            if (tid < DA) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int b = 0; b < nb; ++b) s1 += S.DMU[b * DA + tid], s2 += S.DLS[b * DA + tid];
+                gB2 += s1;
+                gLS += s2;
+            }
+        }
+        __syncthreads();
+        // ---- D2 = (DMU W2^T) * (1 - H2^2) from the h2 registers -> A1 (hi) / LO (lo)
+        {
+            float dm[DA];
+#pragma unroll
+            for (int d = 0; d < DA; ++d) dm[d] = S.DMU[r * DA + d];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float v[4], vl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * c4 + e;
+                    float dh = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) dh = fmaf(dm[d], S.Ps[SL::W2 + (c0 + c) * DA + d], dh);
+                    v[e] = dh * (1.f - h2[c] * h2[c]);
+                    vl[e] = v[e] - tf32_trunc(v[e]);
+                }
+                const int off = core_off(r, c0 + 4 * c4, SCA);
+                *reinterpret_cast<float4*>(S.A1 + off) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(S.LO + off) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+            }
+        }
+        // ---- backward GEMM on the tensor cores: dH1 = D2 W1^T -> TMEM columns [64, 128) ...
+        proxy_fence_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_3xtf32(tmem + 64, S.A1, S.LO, S.W1_hi, S.W1_lo);
+            umma_commit(&S.bar);
+        }
+        // ---- ... while the CUDA cores do the weight gradient gW1 += H1^T D2 and the bias column sums
+        {
+            const unsigned char* ap = S.A0 + ky * SCA;        // chunk ky  = H1 columns 4ky..4ky+3
+            const unsigned char* dp = S.A1 + txw * SCA;       // chunk txw = D2 columns 4txw..4txw+3
+#pragma unroll 4
+            for (int b = 0; b < TBT; ++b) {
+                const int ro = (b >> 3) * 128 + (b & 7) * 16;
+                const float4 av = *reinterpret_cast<const float4*>(ap + ro);
+                const float4 dv = *reinterpret_cast<const float4*>(dp + ro);
+                const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    gW1[a][0] = fmaf(a4[a], dv.x, gW1[a][0]); gW1[a][1] = fmaf(a4[a], dv.y, gW1[a][1]);
+                    gW1[a][2] = fmaf(a4[a], dv.z, gW1[a][2]); gW1[a][3] = fmaf(a4[a], dv.w, gW1[a][3]);
+                }
+            }
+            const int b0 = cp * BPP;
+            float s = 0.f;
+#pragma unroll 8
+            for (int bb = 0; bb < BPP; ++bb) s += *reinterpret_cast<const float*>(S.A1 + core_off(b0 + bb, cj, SCA));
+            gB1c += s;
+        }
+        mbar_wait(&S.bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float dh1[32];
+        tmem_ld32(tmem_row + 64 + c0, dh1);
+        tc_fence_before();
+        __syncthreads();       // every CUDA-core read of H1 (weight gradient) is done before A0 is overwritten
+        // ---- D1 = dH1 * (1 - H1^2) -> A0 in place
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float4* p = reinterpret_cast<float4*>(S.A0 + core_off(r, c0 + 4 * c4, SCA));
+            const float4 h = *p;
+            *p = make_float4(dh1[4 * c4] * (1.f - h.x * h.x), dh1[4 * c4 + 1] * (1.f - h.y * h.y),
+                             dh1[4 * c4 + 2] * (1.f - h.z * h.z), dh1[4 * c4 + 3] * (1.f - h.w * h.w));
+        }
+        __syncthreads();
+        // ---- gW0 += X^T D1, gB0 += colsum(D1) (column role)
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float d1 = *reinterpret_cast<const float*>(S.A0 + core_off(b, cj, SCA));
+                gB0c += d1;
+#pragma unroll
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(S.X[b * DOP + i], d1, gW0p[i]);
+            }
+        }
+    }
+    if (cur_m >= 0) flush(cur_m);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(128));
+}
+
+}  // namespace promp

@@ -802,3 +802,51 @@ def test_vpg_maml_matches_oracle(exploration):
     want = adam.step(torch.tensor(theta), g_want.float())
     np.testing.assert_allclose(policy.theta.cpu().numpy(), want.numpy(), rtol=0, atol=2e-5)
     assert abs(algo.last_stats['loss_before'] - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
+
+
+@pytest.mark.parametrize('Do,Da,N', [(2, 2, 2000), (17, 6, 700), (2, 2, 130)])
+def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
+    """promp_set_option("tensor_cores", 1): the tcgen05/TMEM 3xTF32 path of policy_grad (layer GEMMs on the tensor
+    cores) gives the CUDA-core path's results to fp32 round-off, for shared and per-task parameters, grad and
+    eval-only modes."""
+    torch = _cuda()
+    from promp_b200 import _lib
+    from oracle import tf_half as th
+    M = 7
+    policy, algo = _algo(torch, 'promp', M, Do, Da)
+    theta = policy.theta.cpu().numpy()
+    cpu, ph = _random_phase(torch, M, N, Do, Da, theta, 8)
+    P = policy.num_params
+    theta_t = (policy.theta.view(1, -1) + 0.05 * torch.randn(M, P, generator=torch.Generator().manual_seed(3)).cuda()).contiguous()
+    res = {}
+    try:
+        for tc in (0, 1):
+            _lib.set_option('tensor_cores', tc)
+            out = []
+            for params, stride in ((policy.theta, 0), (theta_t, P)):
+                for obj in (0, 1, 2):
+                    g = torch.empty(M, P, device='cuda'); newp = torch.empty(M, P, device='cuda'); st = torch.zeros(M, 4, device='cuda')
+                    algo._grad(ph, params, stride, obj, clip_eps=0.3, kl_coeff=0.01, clip_log_std=1, grad=g, out_params=newp,
+                               sgd_lr=0.1, stats=st)
+                    st2 = torch.zeros(M, 4, device='cuda')
+                    algo._grad(ph, params, stride, obj, clip_eps=0.3, kl_coeff=0.01, clip_log_std=1, stats=st2)   # eval only
+                    out.append((g.cpu().numpy(), newp.cpu().numpy(), st.cpu().numpy(), st2.cpu().numpy()))
+            res[tc] = out
+    finally:
+        _lib.set_option('tensor_cores', 0)
+    for a, b in zip(res[0], res[1]):
+        assert rel_err(b[0], a[0]) < 2e-5, rel_err(b[0], a[0])
+        np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(b[2][:, :3], a[2][:, :3], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(b[3][:, :3], a[2][:, :3], rtol=1e-5, atol=1e-6)
+    # and against the fp64 oracle: the inner adapt step with shared theta, likelihood-ratio objective, no KL term
+    try:
+        _lib.set_option('tensor_cores', 1)
+        g = torch.empty(M, P, device='cuda'); newp = torch.empty(M, P, device='cuda')
+        algo._grad(ph, policy.theta, 0, 0, grad=g, out_params=newp, sgd_lr=0.1)
+    finally:
+        _lib.set_option('tensor_cores', 0)
+    c64 = {k: v.double() for k, v in cpu.items()}
+    want = th.adapt(torch.tensor(theta, dtype=torch.float64).view(1, -1).expand(M, -1).contiguous(), c64, (Do, Da, (64, 64)), 0.1)
+    g_want = (torch.tensor(theta, dtype=torch.float64).view(1, -1) - want) / 0.1
+    assert rel_err(g.cpu().numpy(), g_want.numpy()) < 1e-4
