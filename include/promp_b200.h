@@ -224,8 +224,8 @@ int promp_ipc_close_handle(void* dev_ptr);
 int promp_allreduce_p2p(int world, int rank, int n, int capacity_floats, const float* in, float* out, float scale,
                         void* const* peers_dev, uint32_t* epoch_dev, uint32_t* error_flag_dev, void* stream);
 
-/* Runtime options.  "tensor_cores" = 1 routes the hidden-64 policy kernels through the tcgen05 / TMEM path (3xTF32
- * layer GEMMs, same results to fp32 round-off); 0 (default) = CUDA-core fp32 path. */
+/* Runtime options.  "tensor_cores" = 1 (default) runs the hidden-64 promp_policy_grad on the tcgen05 / TMEM path (3xTF32
+ * layer GEMMs, same results to fp32 round-off); 0 = CUDA-core fp32 path. */
 int promp_set_option(const char* name, int value);
 
 /* Policy forward only (MetaGaussianMLPPolicy.get_actions without sampling / distribution_info_sym):

@@ -977,7 +977,7 @@ static int launch_grad(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t s
                          PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_kernel");
 }
 
-static int g_use_tc = 0;     // promp_set_option("tensor_cores", 1): route HID = 64 policy kernels through tcgen05
+static int g_use_tc = 1;     // promp_set_option("tensor_cores", 0|1): HID = 64 policy_grad on tcgen05 (default) or CUDA cores
 
 template <int DO, int DA, int HID>
 static int launch_grad_any(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {

@@ -833,7 +833,7 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
                     out.append((g.cpu().numpy(), newp.cpu().numpy(), st.cpu().numpy(), st2.cpu().numpy()))
             res[tc] = out
     finally:
-        _lib.set_option('tensor_cores', 0)
+        _lib.set_option('tensor_cores', 1)
     for a, b in zip(res[0], res[1]):
         assert rel_err(b[0], a[0]) < 2e-5, rel_err(b[0], a[0])
         np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6)
@@ -845,7 +845,7 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
         g = torch.empty(M, P, device='cuda'); newp = torch.empty(M, P, device='cuda')
         algo._grad(ph, policy.theta, 0, 0, grad=g, out_params=newp, sgd_lr=0.1)
     finally:
-        _lib.set_option('tensor_cores', 0)
+        _lib.set_option('tensor_cores', 1)
     c64 = {k: v.double() for k, v in cpu.items()}
     want = th.adapt(torch.tensor(theta, dtype=torch.float64).view(1, -1).expand(M, -1).contiguous(), c64, (Do, Da, (64, 64)), 0.1)
     g_want = (torch.tensor(theta, dtype=torch.float64).view(1, -1) - want) / 0.1
