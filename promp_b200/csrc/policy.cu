@@ -917,6 +917,8 @@ __global__ void adam_tf1_kernel(int P, float* theta, const float* grad, float* m
 __global__ void adam_step_inc_kernel(int32_t* step) { *step += 1; }
 
 // -------------------------------------------------------------------------------------------------
+static int g_use_tc = 1;     // promp_set_option("tensor_cores", 0|1): HID = 64 policy kernels on tcgen05 (default) or CUDA cores
+
 struct TilePlan {
     int grid, q, kmax;
     int64_t partial_floats;
@@ -977,8 +979,6 @@ static int launch_grad(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t s
                          PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_kernel");
 }
 
-static int g_use_tc = 1;     // promp_set_option("tensor_cores", 0|1): HID = 64 policy_grad on tcgen05 (default) or CUDA cores
-
 template <int DO, int DA, int HID>
 static int launch_grad_any(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
     if constexpr (HID == TC_HID) {
@@ -993,6 +993,13 @@ static int launch_grad_any(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream
 
 template <int DO, int DA, int HID>
 static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    if constexpr (HID == TC_HID && sizeof(HvpTcSmem<DO, DA>) <= 227 * 1024) {     // fits the 227 KB of one SM
+        if (g_use_tc) {
+            static int occ_tc = 0;
+            return launch_policy(policy_hvp_tc_kernel<DO, DA>, (int)sizeof(HvpTcSmem<DO, DA>), occ_tc, A,
+                                 PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_tc_kernel", TBT);
+        }
+    }
     static int occ = 0;
     return launch_policy(policy_hvp_kernel<DO, DA, HID>, (int)sizeof(HvpSmem<DO, DA, HID>), occ, A,
                          PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_kernel");

@@ -493,4 +493,510 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(128));
 }
 
+
+// =================================================================================================================
+// Tensor-core variant of policy_hvp_kernel (HID = 64).  All six layer GEMMs of the exact Hessian-vector product
+//   forward :  Z2 = H1 W1            RZ2 = R1 W1 + H1 V1
+//   backward:  dH1 = D2 W1^T         CdH1 = C2 W1^T + D2 (ac V1)^T
+// run as tcgen05.mma.kind::tf32 with the 3-term split.  Shared memory cannot hold hi+lo copies of four activation
+// tiles next to hi+lo copies of four weight tiles, so
+//   * the "lo" A operands live in TENSOR MEMORY (tcgen05.st by the thread that owns the row; MMA with A from TMEM),
+//   * the B (weight) buffer is time-multiplexed: [W1^T, V1^T] for the forward MMAs, re-filled with [W1, ac V1] for the
+//     backward MMAs (66 KB from L2 twice per 128-row tile: ~1 % of the tile time).
+// The two weight-gradient GEMMs (H1^T C2, R1^T D2) contract over samples (MN-major operands) and stay on the CUDA
+// cores, overlapped with the backward MMAs.  TMEM map (512 columns allocated): Z2 0-63, RZ2 64-127, dH1 128-191,
+// CdH1 192-255, lo-A 256-319, lo-B 320-383.
+template <int DO, int DA>
+struct HvpTcSmem {
+    static constexpr int DOP = DOPad<DO>::V;
+    alignas(16) unsigned char WB[4][TILE_W_BYTES];    // fwd: W1T_hi, W1T_lo, V1T_hi, V1T_lo ; bwd: W1_hi, W1_lo, aV1_hi, aV1_lo
+    alignas(16) unsigned char H1[TILE_A_BYTES];       // H1 -> C1
+    alignas(16) unsigned char R1[TILE_A_BYTES];
+    alignas(16) unsigned char T2a[TILE_A_BYTES];      // H2 -> D2
+    alignas(16) unsigned char T2b[TILE_A_BYTES];      // R2 -> C2 ; flush scratch
+    alignas(16) float Ps[SmallLayout<DO, DA>::SIZE];
+    alignas(16) float Vs[SmallLayout<DO, DA>::SIZE];
+    alignas(16) float X[TBT * DOP];
+    float MUP[2 * TBT * 2 * DA];
+    float DMU[TBT * DA];
+    float CMU[TBT * DA];
+    float CLS[TBT * DA];
+    float red[3 * (PT_THREADS / 32)];
+    alignas(8) uint64_t bar;
+    uint32_t tmem_base;
+    int last;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D (+)= A.B^T over K = 64 with the A "lo" part in TMEM: a_lo(TMEM).b_hi + a_hi(smem).b_lo + a_hi.b_hi
+__device__ __forceinline__ void issue_gemm_3xtf32_ts(uint32_t d_tmem, const unsigned char* a_hi, uint32_t a_lo_tmem,
+                                                     const unsigned char* b_hi, const unsigned char* b_lo, uint32_t acc) {
+    const uint32_t idesc = umma_idesc_tf32(TBT, TC_HID);
+    const uint32_t a0 = smem_u32(a_hi), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+    for (int s = 0; s < TC_HID / 8; ++s) {
+        umma_tf32_ts(d_tmem, a_lo_tmem + 8 * s, umma_desc(bh + 2 * s * SCW, SCW, 128), idesc, acc);
+        acc = 1;
+    }
+#pragma unroll
+    for (int s = 0; s < TC_HID / 8; ++s)
+        umma_tf32(d_tmem, umma_desc(a0 + 2 * s * SCA, SCA, 128), umma_desc(bl + 2 * s * SCW, SCW, 128), idesc, 1);
+#pragma unroll
+    for (int s = 0; s < TC_HID / 8; ++s)
+        umma_tf32(d_tmem, umma_desc(a0 + 2 * s * SCA, SCA, 128), umma_desc(bh + 2 * s * SCW, SCW, 128), idesc, 1);
+}
+
+template <int DO, int DA>
+__global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs A) {
+    constexpr int HID = TC_HID;
+    using L = PLayout<DO, DA, HID>;
+    using SL = SmallLayout<DO, DA>;
+    using SM = HvpTcSmem<DO, DA>;
+    constexpr int DOP = SM::DOP;
+    constexpr int PSTRIDE = L::P + PSTAT;
+    constexpr int NPART = PT_THREADS / HID, BPP = TBT / NPART;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qd = warp & 3, half = warp >> 2;
+    const int r = qd * 32 + lane, c0 = 32 * half;
+    const int ky = tid >> 4, txw = tid & 15;
+    const int cj = tid & (HID - 1), cp = tid / HID;
+    const TileSched ts(A.M, A.N, A.q, TBT);
+    const int N = A.N;
+    const float invN = 1.0f / (float)N;
+    const float ac = -A.inner_lr;
+    const float* th = nullptr;
+    const float* vg = nullptr;
+    HeadIn<DA> hin;
+    float rls[DA];
+    uint32_t phase = 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&S.tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (tid == 0) mbar_init(&S.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
+    constexpr uint32_t C_Z2 = 0, C_RZ2 = 64, C_DH1 = 128, C_CH1 = 192, C_LOA = 256, C_LOB = 320;
+
+    float gW1c[4][4], gW1a[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2, gLS;
+    float s_obj, s_kl, s_ratio;
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gW1c[a][c] = gW1a[a][c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
+        gB1c = gB0c = gB2 = gLS = 0.f;
+        s_obj = s_kl = s_ratio = 0.f;
+    };
+    auto load_task = [&](int m, bool first) {
+        th = A.params + (int64_t)m * A.param_stride;
+        vg = A.vec + (int64_t)m * L::P;
+        __syncthreads();
+        const bool reload_p = first || A.param_stride != 0;
+        for (int i = tid; i < DO * HID + HID; i += PT_THREADS) {
+            if (reload_p) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);
+            S.Vs[SL::W0 + i] = __ldcg(vg + L::W0 + i);
+        }
+        for (int i = tid; i < HID; i += PT_THREADS) {
+            if (reload_p) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
+            S.Vs[SL::B1 + i] = __ldcg(vg + L::B1 + i);
+        }
+        for (int i = tid; i < HID * DA + 2 * DA; i += PT_THREADS) {
+            if (reload_p) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);
+            S.Vs[SL::W2 + i] = __ldcg(vg + L::W2 + i);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < DA; ++d) {
+            const float raw = S.Ps[SL::LS + d];
+            const bool clipped = A.clip_log_std && (raw < A.min_log_std);
+            hin.ls[d] = clipped ? A.min_log_std : raw;
+            hin.ls_mask[d] = clipped ? 0.f : 1.f;
+            hin.sig[d] = expf(hin.ls[d]);
+            rls[d] = S.Vs[SL::LS + d] * hin.ls_mask[d];
+        }
+    };
+    // (re)fill the weight buffer from L2: forward = [W1^T, V1^T], backward = [W1, ac*V1], each as hi (fp32) + lo
+    auto load_weights = [&](bool fwd) {
+        for (int i = tid; i < HID * HID; i += PT_THREADS) {
+            const int k = i / HID, j = i % HID;
+            const float w = __ldg(th + L::W1 + i);
+            const float v = (fwd ? 1.f : ac) * __ldcg(vg + L::W1 + i);
+            const int off = fwd ? core_off(j, k, SCW) : core_off(k, j, SCW);
+            *reinterpret_cast<float*>(S.WB[0] + off) = w;
+            *reinterpret_cast<float*>(S.WB[1] + off) = w - tf32_trunc(w);
+            *reinterpret_cast<float*>(S.WB[2] + off) = v;
+            *reinterpret_cast<float*>(S.WB[3] + off) = v - tf32_trunc(v);
+        }
+    };
+    auto flush = [&](int m) {
+        float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+        float* scr = reinterpret_cast<float*>(S.T2b);
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[L::W1 + (4 * ky + a) * HID + 4 * txw + c] = gW1c[a][c] + ac * gW1a[a][c];
+        scr[cp * HID + cj] = gB1c;
+        scr[NPART * HID + cp * HID + cj] = gB0c;
+        __syncthreads();
+        if (tid < 2 * HID) {
+            const int which = tid / HID, j = tid % HID;
+            float s = 0.f;
+            for (int p = 0; p < NPART; ++p) s += scr[which * NPART * HID + p * HID + j];
+            part[(which ? L::B0 : L::B1) + j] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < DO; ++i) scr[(cp * DO + i) * HID + cj] = gW0p[i];
+        __syncthreads();
+        for (int idx = tid; idx < DO * HID; idx += PT_THREADS) {
+            float s = 0.f;
+            for (int p = 0; p < NPART; ++p) s += scr[p * DO * HID + idx];
+            part[L::W0 + idx] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < DA; ++d) scr[(cp * HID + cj) * DA + d] = gW2p[d];
+        __syncthreads();
+        for (int idx = tid; idx < HID * DA; idx += PT_THREADS) {
+            float s = 0.f;
+            for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
+            part[L::W2 + idx] = s;
+        }
+        if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+        const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);
+        __syncthreads();
+        if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
+        __syncthreads();
+        if (tid < 3) {
+            float s = 0.f;
+            for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+            part[L::P + tid] = s;
+        }
+        __threadfence();
+        __syncthreads();
+        const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
+        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
+        __syncthreads();
+        if (S.last) {
+            __threadfence();
+            for (int p = 4 * tid; p < L::P; p += 4 * PT_THREADS) {
+                const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(vg + p));
+                *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) = make_float4(v4.x + s.x, v4.y + s.y, v4.z + s.z, v4.w + s.w);
+            }
+            if (A.stats && tid < 3) {
+                float s = 0.f;
+                for (int c = c_lo; c <= c_hi; ++c)
+                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + L::P + tid);
+                A.stats[(int64_t)m * 4 + tid] = s * invN;
+            }
+            if (tid == 0) A.counters[m] = 0;
+        }
+        __syncthreads();
+    };
+
+    int cur_m = -1;
+    for (int g = ts.g_lo; g < ts.g_hi; ++g) {
+        const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+        if (m != cur_m) {
+            if (cur_m >= 0) flush(cur_m);
+            load_task(m, cur_m < 0);
+            zero_acc();
+            cur_m = m;
+        }
+        const int n0 = tile * TBT, nb = min(TBT, N - n0);
+        const int64_t g0 = (int64_t)m * N + n0;
+        __syncthreads();
+        for (int i = tid; i < TBT * DOP; i += PT_THREADS) {
+            const int b = i / DOP, c = i % DOP;
+            S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+        }
+        load_weights(true);
+        __syncthreads();
+        // ---- layer 0 and its tangent (CUDA cores, row-half role); lo parts of H1 / R1 -> TMEM
+        {
+            float x[DO], hl[32], rl[32];
+#pragma unroll
+            for (int i = 0; i < DO; ++i) x[i] = S.X[r * DOP + i];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float h[4], r1[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = c0 + 4 * c4 + e;
+                    float z = S.Ps[SL::B0 + c], rz = S.Vs[SL::B0 + c];
+#pragma unroll
+                    for (int i = 0; i < DO; ++i) {
+                        z = fmaf(x[i], S.Ps[SL::W0 + i * HID + c], z);
+                        rz = fmaf(x[i], S.Vs[SL::W0 + i * HID + c], rz);
+                    }
+                    h[e] = tanh_fast(z);
+                    r1[e] = (1.f - h[e] * h[e]) * rz;
+                    hl[4 * c4 + e] = h[e] - tf32_trunc(h[e]);
+                    rl[4 * c4 + e] = r1[e] - tf32_trunc(r1[e]);
+                }
+                const int off = core_off(r, c0 + 4 * c4, SCA);
+                *reinterpret_cast<float4*>(S.H1 + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(S.R1 + off) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+            }
+            tmem_st32(tmem_row + C_LOA + c0, hl);
+            tmem_st32(tmem_row + C_LOB + c0, rl);
+        }
+        // ---- forward MMAs: Z2 = H1 W1 ; RZ2 = R1 W1 + H1 V1
+        proxy_fence_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_3xtf32_ts(tmem + C_Z2, S.H1, tmem + C_LOA, S.WB[0], S.WB[1], 0);
+            issue_gemm_3xtf32_ts(tmem + C_RZ2, S.R1, tmem + C_LOB, S.WB[0], S.WB[1], 0);
+            issue_gemm_3xtf32_ts(tmem + C_RZ2, S.H1, tmem + C_LOA, S.WB[2], S.WB[3], 1);
+            umma_commit(&S.bar);
+        }
+        mbar_wait(&S.bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float h2[32], r2[32];
+        tmem_ld32(tmem_row + C_Z2 + c0, h2);
+        tmem_ld32(tmem_row + C_RZ2 + c0, r2);
+        {
+            float mup[DA], rmup[DA];
+#pragma unroll
+            for (int d = 0; d < DA; ++d) mup[d] = rmup[d] = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * c4 + e;
+                    h2[c] = tanh_fast(h2[c] + S.Ps[SL::B1 + c0 + c]);
+                    r2[c] = (1.f - h2[c] * h2[c]) * (r2[c] + S.Vs[SL::B1 + c0 + c]);
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        const float w2 = S.Ps[SL::W2 + (c0 + c) * DA + d];
+                        mup[d] = fmaf(h2[c], w2, mup[d]);
+                        rmup[d] = fmaf(r2[c], w2, fmaf(h2[c], S.Vs[SL::W2 + (c0 + c) * DA + d], rmup[d]));
+                    }
+                }
+                const int off = core_off(r, c0 + 4 * c4, SCA);
+                *reinterpret_cast<float4*>(S.T2a + off) = make_float4(h2[4 * c4], h2[4 * c4 + 1], h2[4 * c4 + 2], h2[4 * c4 + 3]);
+                *reinterpret_cast<float4*>(S.T2b + off) = make_float4(r2[4 * c4], r2[4 * c4 + 1], r2[4 * c4 + 2], r2[4 * c4 + 3]);
+            }
+#pragma unroll
+            for (int d = 0; d < DA; ++d) {
+                S.MUP[((half * TBT + r) * 2 + 0) * DA + d] = mup[d];
+                S.MUP[((half * TBT + r) * 2 + 1) * DA + d] = rmup[d];
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // the forward MMAs are complete: re-fill the weight buffer for the backward MMAs (all threads)
+        load_weights(false);
+        // ---- Gaussian head and its tangent: one thread per sample row (half == 0)
+        if (half == 0) {
+            float dmu[DA], cmu[DA], cls[DA];
+            if (r < nb) {
+                const int64_t n = g0 + r;
+                float mu[DA], rmu[DA], a[DA], mo[DA], lso[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    mu[d] = S.MUP[(r * 2 + 0) * DA + d] + S.MUP[((TBT + r) * 2 + 0) * DA + d] + S.Ps[SL::B2 + d];
+                    rmu[d] = S.MUP[(r * 2 + 1) * DA + d] + S.MUP[((TBT + r) * 2 + 1) * DA + d] + S.Vs[SL::B2 + d];
+                    a[d] = __ldg(A.act + n * DA + d);
+                    mo[d] = __ldg(A.old_mean + n * DA + d);
+                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                }
+                const float adv = __ldg(A.adv + n);
+                HeadOut<DA> o;
+                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                const float wt = o.w * invN, kc = A.kl_coeff * invN;
+                float rl_ = 0.f;
+#pragma unroll
+                for (int d = 0; d < DA; ++d)
+                    rl_ += (o.zeta[d] / hin.sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
+                const float rwt = (A.obj_kind == PROMP_OBJ_RATIO) ? wt * rl_ : 0.f;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    const float is = 1.f / hin.sig[d], z = o.zeta[d];
+                    const float rz = -rmu[d] * is - z * rls[d];
+                    dmu[d] = wt * z * is;
+                    const float rdmu = rwt * z * is + wt * (rz * is - z * rls[d] * is);
+                    const float rdls = rwt * (z * z - 1.f) + wt * 2.f * z * rz;
+                    cmu[d] = ac * rdmu + kc * o.dkl_dmu[d];
+                    cls[d] = (ac * rdls + kc * o.dkl_dls[d]) * hin.ls_mask[d];
+                }
+                s_obj += o.obj;
+                s_kl += o.kl;
+                s_ratio += o.ratio;
+            } else {
+#pragma unroll
+                for (int d = 0; d < DA; ++d) dmu[d] = cmu[d] = cls[d] = 0.f;
+            }
+#pragma unroll
+            for (int d = 0; d < DA; ++d) S.DMU[r * DA + d] = dmu[d], S.CMU[r * DA + d] = cmu[d], S.CLS[r * DA + d] = cls[d];
+        }
+        __syncthreads();
+        // ---- output layer (column role): out_W2 += H2^T CMU + ac R2^T DMU ; out_b2 += colsum CMU ; out_ls += colsum CLS
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const int off = core_off(b, cj, SCA);
+                const float h = *reinterpret_cast<const float*>(S.T2a + off);
+                const float rr = ac * *reinterpret_cast<const float*>(S.T2b + off);
+#pragma unroll
+                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.CMU[b * DA + d], fmaf(rr, S.DMU[b * DA + d], gW2p[d]));
+            }
+            if (tid < DA) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int b = 0; b < nb; ++b) s1 += S.CMU[b * DA + tid], s2 += S.CLS[b * DA + tid];
+                gB2 += s1;
+                gLS += s2;
+            }
+        }
+        __syncthreads();
+        // ---- D2 = dH2 g2 -> T2a ; C2 = CdH2 g2 + ac dH2 (-2 H2 R2) -> T2b ; lo parts -> TMEM
+        {
+            float dm[DA], cm[DA], dl[32], cl[32];
+#pragma unroll
+            for (int d = 0; d < DA; ++d) dm[d] = S.DMU[r * DA + d], cm[d] = S.CMU[r * DA + d];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float d2[4], c2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * c4 + e;
+                    float dh = 0.f, ch = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) {
+                        const float w2 = S.Ps[SL::W2 + (c0 + c) * DA + d], v2 = S.Vs[SL::W2 + (c0 + c) * DA + d];
+                        dh = fmaf(dm[d], w2, dh);
+                        ch = fmaf(cm[d], w2, fmaf(ac * dm[d], v2, ch));
+                    }
+                    const float g2 = 1.f - h2[c] * h2[c];
+                    d2[e] = dh * g2;
+                    c2[e] = ch * g2 + ac * dh * (-2.f * h2[c] * r2[c]);
+                    dl[c] = d2[e] - tf32_trunc(d2[e]);
+                    cl[c] = c2[e] - tf32_trunc(c2[e]);
+                }
+                const int off = core_off(r, c0 + 4 * c4, SCA);
+                *reinterpret_cast<float4*>(S.T2a + off) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+                *reinterpret_cast<float4*>(S.T2b + off) = make_float4(c2[0], c2[1], c2[2], c2[3]);
+            }
+            tmem_st32(tmem_row + C_LOA + c0, dl);
+            tmem_st32(tmem_row + C_LOB + c0, cl);
+        }
+        // ---- backward MMAs: dH1 = D2 W1^T ; CdH1 = C2 W1^T + D2 (ac V1)^T ...
+        proxy_fence_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_3xtf32_ts(tmem + C_DH1, S.T2a, tmem + C_LOA, S.WB[0], S.WB[1], 0);
+            issue_gemm_3xtf32_ts(tmem + C_CH1, S.T2b, tmem + C_LOB, S.WB[0], S.WB[1], 0);
+            issue_gemm_3xtf32_ts(tmem + C_CH1, S.T2a, tmem + C_LOA, S.WB[2], S.WB[3], 1);
+            umma_commit(&S.bar);
+        }
+        // ---- ... overlapped with the CUDA-core weight gradients out_W1 += H1^T C2 + ac R1^T D2 and colsum(C2)
+        {
+            const unsigned char* hp = S.H1 + ky * SCA;
+            const unsigned char* rp = S.R1 + ky * SCA;
+            const unsigned char* dp = S.T2a + txw * SCA;
+            const unsigned char* cpp = S.T2b + txw * SCA;
+#pragma unroll 2
+            for (int b = 0; b < TBT; ++b) {
+                const int ro = (b >> 3) * 128 + (b & 7) * 16;
+                const float4 hv = *reinterpret_cast<const float4*>(hp + ro);
+                const float4 rv = *reinterpret_cast<const float4*>(rp + ro);
+                const float4 dv = *reinterpret_cast<const float4*>(dp + ro);
+                const float4 cv = *reinterpret_cast<const float4*>(cpp + ro);
+                const float h4[4] = {hv.x, hv.y, hv.z, hv.w}, r4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    gW1c[a][0] = fmaf(h4[a], cv.x, gW1c[a][0]); gW1c[a][1] = fmaf(h4[a], cv.y, gW1c[a][1]);
+                    gW1c[a][2] = fmaf(h4[a], cv.z, gW1c[a][2]); gW1c[a][3] = fmaf(h4[a], cv.w, gW1c[a][3]);
+                    gW1a[a][0] = fmaf(r4[a], dv.x, gW1a[a][0]); gW1a[a][1] = fmaf(r4[a], dv.y, gW1a[a][1]);
+                    gW1a[a][2] = fmaf(r4[a], dv.z, gW1a[a][2]); gW1a[a][3] = fmaf(r4[a], dv.w, gW1a[a][3]);
+                }
+            }
+            const int b0 = cp * BPP;
+            float s = 0.f;
+#pragma unroll 8
+            for (int bb = 0; bb < BPP; ++bb) s += *reinterpret_cast<const float*>(S.T2b + core_off(b0 + bb, cj, SCA));
+            gB1c += s;
+        }
+        mbar_wait(&S.bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float dh1[32], ch1[32];
+        tmem_ld32(tmem_row + C_DH1 + c0, dh1);
+        tmem_ld32(tmem_row + C_CH1 + c0, ch1);
+        tc_fence_before();
+        __syncthreads();       // all CUDA-core reads of H1 / R1 are done before H1 is overwritten
+        // ---- C1 = CdH1 g1 + ac dH1 (-2 H1 R1) -> H1 in place
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            const int off = core_off(r, c0 + 4 * c4, SCA);
+            float4* p = reinterpret_cast<float4*>(S.H1 + off);
+            const float4 h = *p;
+            const float4 rr = *reinterpret_cast<const float4*>(S.R1 + off);
+            const float hv[4] = {h.x, h.y, h.z, h.w}, rv[4] = {rr.x, rr.y, rr.z, rr.w};
+            float c1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                c1[e] = ch1[4 * c4 + e] * (1.f - hv[e] * hv[e]) + ac * dh1[4 * c4 + e] * (-2.f * hv[e] * rv[e]);
+            *p = make_float4(c1[0], c1[1], c1[2], c1[3]);
+        }
+        __syncthreads();
+        // ---- out_W0 += X^T C1 ; out_b0 += colsum C1 (column role)
+        {
+            const int b0 = cp * BPP;
+#pragma unroll 4
+            for (int bb = 0; bb < BPP; ++bb) {
+                const int b = b0 + bb;
+                const float c1 = *reinterpret_cast<const float*>(S.H1 + core_off(b, cj, SCA));
+                gB0c += c1;
+#pragma unroll
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(S.X[b * DOP + i], c1, gW0p[i]);
+            }
+        }
+    }
+    if (cur_m >= 0) flush(cur_m);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+}
+
 }  // namespace promp

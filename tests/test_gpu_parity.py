@@ -850,3 +850,38 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
     want = th.adapt(torch.tensor(theta, dtype=torch.float64).view(1, -1).expand(M, -1).contiguous(), c64, (Do, Da, (64, 64)), 0.1)
     g_want = (torch.tensor(theta, dtype=torch.float64).view(1, -1) - want) / 0.1
     assert rel_err(g.cpu().numpy(), g_want.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize('N,stride_mode', [(2000, 'shared'), (2000, 'per_task'), (130, 'shared')])
+def test_tensor_core_policy_hvp_matches_simt(N, stride_mode):
+    """The tcgen05 path of policy_hvp (PointEnv shapes: forward and backward layer GEMMs as 3xTF32 MMAs with the "lo"
+    A operands in tensor memory) gives the CUDA-core path's backward-chain vector to fp32 round-off, for both inner
+    objectives, with and without the KL term, and with the log_std clip mask active."""
+    torch = _cuda()
+    from promp_b200 import _lib
+    M, Do, Da = 7, 2, 2
+    res = {}
+    for inner in ('likelihood_ratio', 'log_likelihood'):
+        policy, algo = _algo(torch, 'promp', M, Do, Da, inner_type=inner)
+        theta = policy.theta.cpu().numpy()
+        cpu, ph = _random_phase(torch, M, N, Do, Da, theta, 11)
+        P = policy.num_params
+        gen = torch.Generator().manual_seed(5)
+        theta_t = (policy.theta.view(1, -1) + 0.05 * torch.randn(M, P, generator=gen).cuda()).contiguous()
+        vec = torch.randn(M, P, generator=gen).cuda().contiguous()
+        params, stride = (policy.theta, 0) if stride_mode == 'shared' else (theta_t, P)
+        try:
+            for tc in (0, 1):
+                _lib.set_option('tensor_cores', tc)
+                out = []
+                for klc, clip in ((0.0, 0), (5e-3, 0), (5e-3, 1)):
+                    hv = torch.empty(M, P, device='cuda'); st = torch.zeros(M, 4, device='cuda')
+                    algo._hvp(ph, params, stride, vec, hv, klc, clip, stats=st)
+                    out.append((hv.cpu().numpy(), st.cpu().numpy()))
+                res[(inner, tc)] = out
+        finally:
+            _lib.set_option('tensor_cores', 1)
+        for a, b in zip(res[(inner, 0)], res[(inner, 1)]):
+            d = rel_err(b[0] - vec.cpu().numpy(), a[0] - vec.cpu().numpy())      # compare the H v part, not v + ...
+            assert d < 5e-5, d
+            np.testing.assert_allclose(b[1][:, :3], a[1][:, :3], rtol=1e-5, atol=1e-6)

@@ -85,6 +85,25 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // mode 0: T1, mode 1: T2, mode 2: T3.  split: 0 single pass, 1 three-term.
@@ -117,7 +136,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(const float* A, const fl
         *reinterpret_cast<float*>(sWl + tile_off(r, c, 64, layout)) = w - tf32_hi(w);
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     if (tid == 0) mbar_init(&bar, 1);
@@ -126,11 +145,34 @@ __global__ void __launch_bounds__(128) umma_test_kernel(const float* A, const fl
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = tmem_base_s;
+    if (mode == 3) {       // A_lo operand from TMEM: lane = row, column = k
+        for (int hb = 0; hb < 2; ++hb) {
+            float v[32];
+            for (int c = 0; c < 32; ++c) { const float a = A[tid * 64 + hb * 32 + c]; v[c] = a - tf32_hi(a); }
+            tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 128 + hb * 32, v);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
 
     if (tid == 0) {
         const int nterm = split ? 3 : 1;
         uint32_t acc = 0;
-        if (layout == 1) {
+        if (mode == 3) {
+            // D = A.W^T, K-major smem operands (no-swizzle core tiles) except the A_lo term, which comes from TMEM
+            const uint32_t ScA = 128 * 16, ScW = 64 * 16, Sr = 128;
+            const uint32_t idesc = make_idesc(128, 64, 0, 0);
+            for (int s = 0; s < 8; ++s) {     // lo(TMEM) * hi
+                umma_tf32_ts(tmem, tmem + 128 + 8 * s, make_desc(smem_u32(sW) + 2 * s * ScW, ScW, Sr, 0), idesc, acc);
+                acc = 1;
+            }
+            for (int term = 1; term < 3; ++term) {
+                const uint8_t* w = (term == 1) ? sWl : sW;
+                for (int s = 0; s < 8; ++s)
+                    umma_tf32(tmem, make_desc(smem_u32(sA) + 2 * s * ScA, ScA, Sr, 0), make_desc(smem_u32(w) + 2 * s * ScW, ScW, Sr, 0), idesc, 1);
+            }
+        } else if (layout == 1) {
             // no-swizzle core-matrix tiles: S_r = 128 B (next 8 rows), S_c = rows*16 B (next 4 columns)
             const uint32_t ScA = 128 * 16, ScW = 64 * 16, Sr = 128;
             if (mode == 0 || mode == 1) {
@@ -198,7 +240,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(const float* A, const fl
     for (int c = 0; c < 64; ++c) out[tid * 64 + c] = v[c];      // lane (= tid) major dump of all 128 lanes x 64 cols
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(64));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(256));
 }
 
 static float tf32h(float x) {
@@ -222,9 +264,9 @@ int main() {
     cudaMemcpy(dE, E.data(), E.size() * 4, cudaMemcpyHostToDevice);
     const int smem = 163840 + 1024;
     cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    for (int layout = 0; layout < 2; ++layout)
-    for (int mode = 0; mode < 3; ++mode)
-        for (int split = 0; split < 2; ++split) {
+    for (int layout = 1; layout < 2; ++layout)
+    for (int mode = 1; mode < 4; mode += 2)
+        for (int split = 1; split < 2; ++split) {
             cudaMemset(dO, 0, out.size() * 4);
             umma_test_kernel<<<1, 128, smem>>>(dA, dW, dE, dO, mode, split, layout);
             cudaError_t err = cudaDeviceSynchronize();
@@ -241,7 +283,7 @@ int main() {
                         for (int k = 0; k < K; ++k) {
                             float a, b;
                             if (mode == 0) { a = A[m * 64 + k]; b = W[k * 64 + n]; }
-                            else if (mode == 1) { a = A[m * 64 + k]; b = W[n * 64 + k]; }
+                            else if (mode == 1 || mode == 3) { a = A[m * 64 + k]; b = W[n * 64 + k]; }
                             else { a = A[k * 64 + m]; b = E[k * 64 + n]; }
                             ref += (double)a * b;
                             ref_tf += (double)tf32h(a) * tf32h(b);
