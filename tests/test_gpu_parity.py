@@ -862,7 +862,7 @@ def test_tensor_core_policy_hvp_matches_simt(N, stride_mode):
     M, Do, Da = 7, 2, 2
     res = {}
     for inner in ('likelihood_ratio', 'log_likelihood'):
-        policy, algo = _algo(torch, 'promp', M, Do, Da, inner_type=inner)
+        policy, algo = _algo(torch, 'trpo', M, Do, Da, inner_type=inner)
         theta = policy.theta.cpu().numpy()
         cpu, ph = _random_phase(torch, M, N, Do, Da, theta, 11)
         P = policy.num_params
