@@ -1125,3 +1125,15 @@ extern "C" int promp_adam_tf1(int P, float* theta, const float* grad, float* m, 
     PROMP_LAUNCH_CHECK("adam_tf1_kernel");
     return PROMP_OK;
 }
+
+#ifdef PROMP_EXP_CLOCKS
+extern "C" int promp_debug_phase_clocks(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, promp::g_phase_clk, 16 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(promp::g_phase_clk, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

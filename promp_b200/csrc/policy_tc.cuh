@@ -49,6 +49,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -122,13 +127,82 @@ struct GradTcSmem {
     alignas(16) float X[TBT * DOP];
     float MUP[2 * TBT * DA];
     float DMU[TBT * DA];
-    float DLS[TBT * DA];
     float red[3 * (PT_THREADS / 32)];
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
     int last;
 };
 
+
+// -------------------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM  acc[k][j] += sum_b A[b][k] * (scale * D[b][j])  over the 128 rows of two fp32 tiles in the
+// K-major core-matrix layout, on the warp-level tensor-core path (mma.sync m16n8k8 tf32, 3xTF32 split).  This GEMM
+// contracts over SAMPLES, i.e. both tcgen05 operands would be MN-major, which kind::tf32 supports only in the
+// 128B_BASE32B layout - incompatible with the K-major use of the same tiles by the layer MMAs.  The CUDA-core version
+// was bound by shared-memory wavefronts (every LDS.128 costs 4, 8 per sample row per warp for 16 FFMA); the fragment
+// loads below are 12 conflict-free LDS.32 per 8 sample rows and the math leaves the FP32 pipe.
+//   warp w owns the 16 x 32 block  k in [16 (w&3), +16), j in [32 (w>>2), +32)  as 4 n-tiles of m16n8.
+//   fragment column t (t+4) <-> sample 8s+2t (8s+2t+1): with the 16-byte chunk padding this makes every fragment
+//   load hit 32 distinct banks (bank = 4 (g>>2) + (g&3) + 8 t).
+__device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void wgrad_mma_tile(const unsigned char* __restrict__ At, const unsigned char* __restrict__ Dt,
+                                               float scale, int warp, int lane, float (&acc)[4][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int k0 = 16 * (warp & 3) + g, j0 = 32 * (warp >> 2) + g;
+    const unsigned char* ap = At + (k0 >> 2) * SCA + (k0 & 3) * 4 + t * 32;     // rows k0 (and k0+8: two chunks further)
+    const unsigned char* dp = Dt + (j0 >> 2) * SCA + (j0 & 3) * 4 + t * 32;     // n-tile nt: two chunks further each
+#pragma unroll 2
+    for (int s = 0; s < TBT / 8; ++s) {
+        float av[4];
+        av[0] = *reinterpret_cast<const float*>(ap + s * 128);
+        av[1] = *reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA);
+        av[2] = *reinterpret_cast<const float*>(ap + s * 128 + 16);
+        av[3] = *reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA + 16);
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ah[i] = __float_as_uint(av[i]) & 0xffffe000u;
+            al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float d0 = scale * *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128);
+            const float d1 = scale * *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128 + 16);
+            uint32_t bh[2], bl[2];
+            bh[0] = __float_as_uint(d0) & 0xffffe000u;
+            bh[1] = __float_as_uint(d1) & 0xffffe000u;
+            bl[0] = __float_as_uint(d0 - __uint_as_float(bh[0]));
+            bl[1] = __float_as_uint(d1 - __uint_as_float(bh[1]));
+            mma_tf32_16n8k8(acc[nt], al, bh);
+            mma_tf32_16n8k8(acc[nt], ah, bl);
+            mma_tf32_16n8k8(acc[nt], ah, bh);
+        }
+    }
+}
+// accumulator element (nt, i) of wgrad_mma_tile -> flat index into the [HID, HID] weight (row k, column j)
+__device__ __forceinline__ int wgrad_mma_index(int warp, int lane, int nt, int i) {
+    const int g = lane >> 2, t = lane & 3;
+    return (16 * (warp & 3) + g + 8 * (i >> 1)) * TC_HID + 32 * (warp >> 2) + 8 * nt + 2 * t + (i & 1);
+}
+
+#ifdef PROMP_EXP_CLOCKS
+// experiment build only: per-phase clock64 totals of CTA 0 (tools/kernel_time.py --clocks)
+__device__ unsigned long long g_phase_clk[16];
+#define PCLK(i)                                                   \
+    do {                                                          \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                \
+            const long long t_ = clock64();                       \
+            s_clk[i] += (unsigned long long)(t_ - s_last);        \
+            s_last = t_;                                          \
+        }                                                         \
+    } while (0)
+#else
+#define PCLK(i)
+#endif
 template <int DO, int DA>
 __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArgs A) {
     constexpr int HID = TC_HID;
@@ -141,11 +215,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
+#ifdef PROMP_EXP_CLOCKS
+    __shared__ unsigned long long s_clk[16];
+    __shared__ long long s_last;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) s_clk[i] = 0;
+        s_last = clock64();
+    }
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform copy for the MMA-issue branch
     const int qd = warp & 3, half = warp >> 2;
     const int r = qd * 32 + lane, c0 = 32 * half;          // row-half role: sample row r, hidden units [c0, c0+32)
-    const int ky = tid >> 4, txw = tid & 15;               // SIMT weight-gradient role: 4 k-rows x 4 j-cols
     const int cj = tid & (HID - 1), cp = tid / HID;        // column role
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
@@ -168,7 +250,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
 
-    float gW1[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2, gLS;
+    float gW1[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
@@ -177,7 +259,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
-        gB1c = gB0c = gB2 = gLS = 0.f;
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gB2w[d] = gLSw[d] = 0.f;
+        gB1c = gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -211,9 +295,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         __syncthreads();
         if (want_grad) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) part[L::W1 + (4 * ky + a) * HID + 4 * txw + c] = gW1[a][c];
+                for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index(warp, lane, nt, i)] = gW1[nt][i];
             scr[cp * HID + cj] = gB1c;
             scr[NPART * HID + cp * HID + cj] = gB0c;
             __syncthreads();
@@ -241,7 +325,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
                 for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
                 part[L::W2 + idx] = s;
             }
-            if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+            __syncthreads();
+            if (half == 0 && lane == 0) {
+#pragma unroll
+                for (int d = 0; d < DA; ++d) scr[qd * 2 * DA + d] = gB2w[d], scr[qd * 2 * DA + DA + d] = gLSw[d];
+            }
+            __syncthreads();
+            if (tid < 2 * DA) part[L::B2 + tid] = scr[tid] + scr[2 * DA + tid] + scr[4 * DA + tid] + scr[6 * DA + tid];   // b2 then log_std
         }
         const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);   // held by half == 0 threads, 0 elsewhere
         __syncthreads();
@@ -254,9 +344,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         }
         __threadfence();
         __syncthreads();
+        PCLK(14);
         const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
         if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
         __syncthreads();
+        PCLK(15);
         if (S.last) {
             __threadfence();
             if (want_grad) {
@@ -284,11 +376,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
     int cur_m = -1;
     for (int g = ts.g_lo; g < ts.g_hi; ++g) {
         const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+        PCLK(10);
         if (m != cur_m) {
             if (cur_m >= 0) flush(cur_m);
+            PCLK(11);
             load_task(m, cur_m < 0);
             zero_acc();
             cur_m = m;
+            PCLK(12);
         }
         const int n0 = tile * TBT, nb = min(TBT, N - n0);
         const int64_t g0 = (int64_t)m * N + n0;
@@ -298,6 +393,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
             S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
         }
         __syncthreads();
+        PCLK(0);
         // ---- layer 0 (CUDA cores, row-half role): H1 = tanh(X W0 + b0) -> A0 (fp32 = TF32 "hi" operand) and LO
         {
             float x[DO];
@@ -320,18 +416,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
                 *reinterpret_cast<float4*>(S.LO + off) = make_float4(hl[0], hl[1], hl[2], hl[3]);
             }
         }
+        PCLK(1);
         // ---- layer 1 on the tensor cores: Z2 = H1 W1 -> TMEM columns [0, 64)
         proxy_fence_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {      // warp-uniform branch + elect: descriptors go straight to uniform registers
             tc_fence_after();
             issue_gemm_3xtf32(tmem, S.A0, S.LO, S.W1T_hi, S.W1T_lo);
             umma_commit(&S.bar);
+            PCLK(13);
         }
         mbar_wait(&S.bar, phase);
         phase ^= 1;
         tc_fence_after();
+        PCLK(2);
         float h2[32];
         tmem_ld32(tmem_row + c0, h2);
         float mup[DA];
@@ -353,6 +452,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         for (int d = 0; d < DA; ++d) S.MUP[(half * TBT + r) * DA + d] = mup[d];
         tc_fence_before();
         __syncthreads();
+        PCLK(3);
         // ---- Gaussian head: one thread per sample row (half == 0)
         if (half == 0) {
             float dmu[DA], dls[DA];
@@ -383,10 +483,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
                 for (int d = 0; d < DA; ++d) dmu[d] = dls[d] = 0.f;
             }
 #pragma unroll
-            for (int d = 0; d < DA; ++d) S.DMU[r * DA + d] = dmu[d], S.DLS[r * DA + d] = dls[d];
+            for (int d = 0; d < DA; ++d) {
+                S.DMU[r * DA + d] = dmu[d];
+                if (want_grad) {                                               // gB2 / g_log_std column sums
+                    const float s1 = warp_sum(dmu[d]), s2 = warp_sum(dls[d]);
+                    if (lane == 0) gB2w[d] += s1, gLSw[d] += s2;
+                }
+            }
         }
         if (!want_grad) continue;
         __syncthreads();
+        PCLK(4);
         // ---- output-layer gradients (column role) from the fp32 H2 tile
         {
             const int b0 = cp * BPP;
@@ -397,14 +504,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 #pragma unroll
                 for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.DMU[b * DA + d], gW2p[d]);
             }
-            if (tid < DA) {
-                float s1 = 0.f, s2 = 0.f;
-                for (int b = 0; b < nb; ++b) s1 += S.DMU[b * DA + tid], s2 += S.DLS[b * DA + tid];
-                gB2 += s1;
-                gLS += s2;
-            }
         }
         __syncthreads();
+        PCLK(5);
         // ---- D2 = (DMU W2^T) * (1 - H2^2) from the h2 registers -> A1 (hi) / LO (lo)
         {
             float dm[DA];
@@ -431,33 +533,22 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         proxy_fence_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {      // warp-uniform branch + elect: descriptors go straight to uniform registers
             tc_fence_after();
             issue_gemm_3xtf32(tmem + 64, S.A1, S.LO, S.W1_hi, S.W1_lo);
             umma_commit(&S.bar);
         }
-        // ---- ... while the CUDA cores do the weight gradient gW1 += H1^T D2 and the bias column sums
+        PCLK(6);
+        // ---- ... while the warps do the weight gradient gW1 += H1^T D2 (mma.sync 3xTF32) and the bias column sums
         {
-            const unsigned char* ap = S.A0 + ky * SCA;        // chunk ky  = H1 columns 4ky..4ky+3
-            const unsigned char* dp = S.A1 + txw * SCA;       // chunk txw = D2 columns 4txw..4txw+3
-#pragma unroll 4
-            for (int b = 0; b < TBT; ++b) {
-                const int ro = (b >> 3) * 128 + (b & 7) * 16;
-                const float4 av = *reinterpret_cast<const float4*>(ap + ro);
-                const float4 dv = *reinterpret_cast<const float4*>(dp + ro);
-                const float a4[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    gW1[a][0] = fmaf(a4[a], dv.x, gW1[a][0]); gW1[a][1] = fmaf(a4[a], dv.y, gW1[a][1]);
-                    gW1[a][2] = fmaf(a4[a], dv.z, gW1[a][2]); gW1[a][3] = fmaf(a4[a], dv.w, gW1[a][3]);
-                }
-            }
+            wgrad_mma_tile(S.A0, S.A1, 1.f, warp, lane, gW1);
             const int b0 = cp * BPP;
             float s = 0.f;
 #pragma unroll 8
             for (int bb = 0; bb < BPP; ++bb) s += *reinterpret_cast<const float*>(S.A1 + core_off(b0 + bb, cj, SCA));
             gB1c += s;
         }
+        PCLK(7);
         mbar_wait(&S.bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -465,6 +556,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         tmem_ld32(tmem_row + 64 + c0, dh1);
         tc_fence_before();
         __syncthreads();       // every CUDA-core read of H1 (weight gradient) is done before A0 is overwritten
+        PCLK(8);
         // ---- D1 = dH1 * (1 - H1^2) -> A0 in place
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
@@ -474,6 +566,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
                              dh1[4 * c4 + 2] * (1.f - h.z * h.z), dh1[4 * c4 + 3] * (1.f - h.w * h.w));
         }
         __syncthreads();
+        PCLK(9);
         // ---- gW0 += X^T D1, gB0 += colsum(D1) (column role)
         {
             const int b0 = cp * BPP;
@@ -487,10 +580,16 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
             }
         }
     }
+    PCLK(10);
     if (cur_m >= 0) flush(cur_m);
+    PCLK(11);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(128));
+#ifdef PROMP_EXP_CLOCKS
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int i = 0; i < 16; ++i) g_phase_clk[i] += s_clk[i];
+#endif
 }
 
 
@@ -516,11 +615,10 @@ struct HvpTcSmem {
     alignas(16) unsigned char T2b[TILE_A_BYTES];      // R2 -> C2 ; flush scratch
     alignas(16) float Ps[SmallLayout<DO, DA>::SIZE];
     alignas(16) float Vs[SmallLayout<DO, DA>::SIZE];
-    alignas(16) float X[TBT * DOP];
-    float MUP[2 * TBT * 2 * DA];
+    // X (observations) aliases T2a (needed only before H2 is written and, re-read from L2, after D2 is dead);
+    // MUP (per-half partial means) aliases WB[0] between the forward MMAs and the backward weight re-fill.
     float DMU[TBT * DA];
     float CMU[TBT * DA];
-    float CLS[TBT * DA];
     float red[3 * (PT_THREADS / 32)];
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
@@ -575,11 +673,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
+    float* const sX = reinterpret_cast<float*>(S.T2a);
+    float* const sMUP = reinterpret_cast<float*>(S.WB[0]);
+    static_assert(TBT * DOP * 4 <= TILE_A_BYTES && 2 * TBT * 2 * DA * 4 <= TILE_W_BYTES, "aliased buffers must fit");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform copy for the MMA-issue branch
     const int qd = warp & 3, half = warp >> 2;
     const int r = qd * 32 + lane, c0 = 32 * half;
-    const int ky = tid >> 4, txw = tid & 15;
     const int cj = tid & (HID - 1), cp = tid / HID;
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
@@ -604,18 +705,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     constexpr uint32_t C_Z2 = 0, C_RZ2 = 64, C_DH1 = 128, C_CH1 = 192, C_LOA = 256, C_LOB = 320;
 
-    float gW1c[4][4], gW1a[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2, gLS;
+    float gW1[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2w[DA], gLSw[DA];
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) gW1c[a][c] = gW1a[a][c] = 0.f;
+            for (int c = 0; c < 4; ++c) gW1[a][c] = 0.f;
 #pragma unroll
         for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
-        gB1c = gB0c = gB2 = gLS = 0.f;
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gB2w[d] = gLSw[d] = 0.f;
+        gB1c = gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -664,9 +767,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         float* scr = reinterpret_cast<float*>(S.T2b);
         __syncthreads();
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) part[L::W1 + (4 * ky + a) * HID + 4 * txw + c] = gW1c[a][c] + ac * gW1a[a][c];
+            for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index(warp, lane, nt, i)] = gW1[nt][i];
         scr[cp * HID + cj] = gB1c;
         scr[NPART * HID + cp * HID + cj] = gB0c;
         __syncthreads();
@@ -694,7 +797,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
             for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
             part[L::W2 + idx] = s;
         }
-        if (tid < DA) part[L::B2 + tid] = gB2, part[L::LS + tid] = gLS;
+        __syncthreads();
+        if (half == 0 && lane == 0) {
+#pragma unroll
+            for (int d = 0; d < DA; ++d) scr[qd * 2 * DA + d] = gB2w[d], scr[qd * 2 * DA + DA + d] = gLSw[d];
+        }
+        __syncthreads();
+        if (tid < 2 * DA) part[L::B2 + tid] = scr[tid] + scr[2 * DA + tid] + scr[4 * DA + tid] + scr[6 * DA + tid];
         const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);
         __syncthreads();
         if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
@@ -739,17 +848,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         const int n0 = tile * TBT, nb = min(TBT, N - n0);
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
-        for (int i = tid; i < TBT * DOP; i += PT_THREADS) {
-            const int b = i / DOP, c = i % DOP;
-            S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
-        }
+        auto load_x = [&]() {
+            for (int i = tid; i < TBT * DOP; i += PT_THREADS) {
+                const int b = i / DOP, c = i % DOP;
+                sX[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+            }
+        };
+        load_x();
         load_weights(true);
         __syncthreads();
         // ---- layer 0 and its tangent (CUDA cores, row-half role); lo parts of H1 / R1 -> TMEM
         {
             float x[DO], hl[32], rl[32];
 #pragma unroll
-            for (int i = 0; i < DO; ++i) x[i] = S.X[r * DOP + i];
+            for (int i = 0; i < DO; ++i) x[i] = sX[r * DOP + i];
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
                 float h[4], r1[4];
@@ -778,7 +890,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         proxy_fence_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {      // warp-uniform branch + elect: descriptors go straight to uniform registers
             tc_fence_after();
             issue_gemm_3xtf32_ts(tmem + C_Z2, S.H1, tmem + C_LOA, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_RZ2, S.R1, tmem + C_LOB, S.WB[0], S.WB[1], 0);
@@ -815,14 +927,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
             }
 #pragma unroll
             for (int d = 0; d < DA; ++d) {
-                S.MUP[((half * TBT + r) * 2 + 0) * DA + d] = mup[d];
-                S.MUP[((half * TBT + r) * 2 + 1) * DA + d] = rmup[d];
+                sMUP[((half * TBT + r) * 2 + 0) * DA + d] = mup[d];
+                sMUP[((half * TBT + r) * 2 + 1) * DA + d] = rmup[d];
             }
         }
         tc_fence_before();
         __syncthreads();
-        // the forward MMAs are complete: re-fill the weight buffer for the backward MMAs (all threads)
-        load_weights(false);
         // ---- Gaussian head and its tangent: one thread per sample row (half == 0)
         if (half == 0) {
             float dmu[DA], cmu[DA], cls[DA];
@@ -831,8 +941,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 float mu[DA], rmu[DA], a[DA], mo[DA], lso[DA];
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
-                    mu[d] = S.MUP[(r * 2 + 0) * DA + d] + S.MUP[((TBT + r) * 2 + 0) * DA + d] + S.Ps[SL::B2 + d];
-                    rmu[d] = S.MUP[(r * 2 + 1) * DA + d] + S.MUP[((TBT + r) * 2 + 1) * DA + d] + S.Vs[SL::B2 + d];
+                    mu[d] = sMUP[(r * 2 + 0) * DA + d] + sMUP[((TBT + r) * 2 + 0) * DA + d] + S.Ps[SL::B2 + d];
+                    rmu[d] = sMUP[(r * 2 + 1) * DA + d] + sMUP[((TBT + r) * 2 + 1) * DA + d] + S.Vs[SL::B2 + d];
                     a[d] = __ldg(A.act + n * DA + d);
                     mo[d] = __ldg(A.old_mean + n * DA + d);
                     lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
@@ -864,9 +974,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 for (int d = 0; d < DA; ++d) dmu[d] = cmu[d] = cls[d] = 0.f;
             }
 #pragma unroll
-            for (int d = 0; d < DA; ++d) S.DMU[r * DA + d] = dmu[d], S.CMU[r * DA + d] = cmu[d], S.CLS[r * DA + d] = cls[d];
+            for (int d = 0; d < DA; ++d) {
+                S.DMU[r * DA + d] = dmu[d], S.CMU[r * DA + d] = cmu[d];
+                const float s1 = warp_sum(cmu[d]), s2 = warp_sum(cls[d]);
+                if (lane == 0) gB2w[d] += s1, gLSw[d] += s2;
+            }
         }
         __syncthreads();
+        // the forward MMAs are complete and MUP is consumed: re-fill the weight buffer for the backward MMAs
+        load_weights(false);
         // ---- output layer (column role): out_W2 += H2^T CMU + ac R2^T DMU ; out_b2 += colsum CMU ; out_ls += colsum CLS
         {
             const int b0 = cp * BPP;
@@ -878,12 +994,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 const float rr = ac * *reinterpret_cast<const float*>(S.T2b + off);
 #pragma unroll
                 for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.CMU[b * DA + d], fmaf(rr, S.DMU[b * DA + d], gW2p[d]));
-            }
-            if (tid < DA) {
-                float s1 = 0.f, s2 = 0.f;
-                for (int b = 0; b < nb; ++b) s1 += S.CMU[b * DA + tid], s2 += S.CLS[b * DA + tid];
-                gB2 += s1;
-                gLS += s2;
             }
         }
         __syncthreads();
@@ -922,35 +1032,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         proxy_fence_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one()) {      // warp-uniform branch + elect: descriptors go straight to uniform registers
             tc_fence_after();
             issue_gemm_3xtf32_ts(tmem + C_DH1, S.T2a, tmem + C_LOA, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_CH1, S.T2b, tmem + C_LOB, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_CH1, S.T2a, tmem + C_LOA, S.WB[2], S.WB[3], 1);
             umma_commit(&S.bar);
         }
-        // ---- ... overlapped with the CUDA-core weight gradients out_W1 += H1^T C2 + ac R1^T D2 and colsum(C2)
+        // ---- ... overlapped with the weight gradients out_W1 += H1^T C2 + R1^T (ac D2) (mma.sync 3xTF32) and colsum(C2)
         {
-            const unsigned char* hp = S.H1 + ky * SCA;
-            const unsigned char* rp = S.R1 + ky * SCA;
-            const unsigned char* dp = S.T2a + txw * SCA;
-            const unsigned char* cpp = S.T2b + txw * SCA;
-#pragma unroll 2
-            for (int b = 0; b < TBT; ++b) {
-                const int ro = (b >> 3) * 128 + (b & 7) * 16;
-                const float4 hv = *reinterpret_cast<const float4*>(hp + ro);
-                const float4 rv = *reinterpret_cast<const float4*>(rp + ro);
-                const float4 dv = *reinterpret_cast<const float4*>(dp + ro);
-                const float4 cv = *reinterpret_cast<const float4*>(cpp + ro);
-                const float h4[4] = {hv.x, hv.y, hv.z, hv.w}, r4[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    gW1c[a][0] = fmaf(h4[a], cv.x, gW1c[a][0]); gW1c[a][1] = fmaf(h4[a], cv.y, gW1c[a][1]);
-                    gW1c[a][2] = fmaf(h4[a], cv.z, gW1c[a][2]); gW1c[a][3] = fmaf(h4[a], cv.w, gW1c[a][3]);
-                    gW1a[a][0] = fmaf(r4[a], dv.x, gW1a[a][0]); gW1a[a][1] = fmaf(r4[a], dv.y, gW1a[a][1]);
-                    gW1a[a][2] = fmaf(r4[a], dv.z, gW1a[a][2]); gW1a[a][3] = fmaf(r4[a], dv.w, gW1a[a][3]);
-                }
-            }
+            wgrad_mma_tile(S.H1, S.T2b, 1.f, warp, lane, gW1);
+            wgrad_mma_tile(S.R1, S.T2a, ac, warp, lane, gW1);
             const int b0 = cp * BPP;
             float s = 0.f;
 #pragma unroll 8
@@ -979,6 +1071,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 c1[e] = ch1[4 * c4 + e] * (1.f - hv[e] * hv[e]) + ac * dh1[4 * c4 + e] * (-2.f * hv[e] * rv[e]);
             *p = make_float4(c1[0], c1[1], c1[2], c1[3]);
         }
+        load_x();              // D2 (T2a) is dead: bring the observations back for the input-layer gradient
         __syncthreads();
         // ---- out_W0 += X^T C1 ; out_b0 += colsum C1 (column role)
         {
@@ -989,7 +1082,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 const float c1 = *reinterpret_cast<const float*>(S.H1 + core_off(b, cj, SCA));
                 gB0c += c1;
 #pragma unroll
-                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(S.X[b * DOP + i], c1, gW0p[i]);
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(sX[b * DOP + i], c1, gW0p[i]);
             }
         }
     }

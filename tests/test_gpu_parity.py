@@ -852,14 +852,15 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
     assert rel_err(g.cpu().numpy(), g_want.numpy()) < 1e-4
 
 
-@pytest.mark.parametrize('N,stride_mode', [(2000, 'shared'), (2000, 'per_task'), (130, 'shared')])
-def test_tensor_core_policy_hvp_matches_simt(N, stride_mode):
-    """The tcgen05 path of policy_hvp (PointEnv shapes: forward and backward layer GEMMs as 3xTF32 MMAs with the "lo"
-    A operands in tensor memory) gives the CUDA-core path's backward-chain vector to fp32 round-off, for both inner
+@pytest.mark.parametrize('Do,Da,N,stride_mode', [(2, 2, 2000, 'shared'), (2, 2, 2000, 'per_task'), (2, 2, 130, 'shared'),
+                                                  (17, 6, 700, 'per_task'), (17, 6, 129, 'shared')])
+def test_tensor_core_policy_hvp_matches_simt(Do, Da, N, stride_mode):
+    """The tcgen05 path of policy_hvp (forward and backward layer GEMMs as 3xTF32 MMAs with the "lo" A operands in
+    tensor memory) gives the CUDA-core path's backward-chain vector to fp32 round-off, for both inner
     objectives, with and without the KL term, and with the log_std clip mask active."""
     torch = _cuda()
     from promp_b200 import _lib
-    M, Do, Da = 7, 2, 2
+    M = 7
     res = {}
     for inner in ('likelihood_ratio', 'log_likelihood'):
         policy, algo = _algo(torch, 'trpo', M, Do, Da, inner_type=inner)

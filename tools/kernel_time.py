@@ -57,6 +57,23 @@ def main():
     print('  grad eval-only     %.1f us' % timeit(lambda: grad_call(P, True)))
     print('  hvp  shared-theta  %.1f us' % timeit(lambda: hvp_call(0)))
     print('  hvp  per-task      %.1f us' % timeit(lambda: hvp_call(P)))
+    lib = _lib.load()
+    if hasattr(lib, 'promp_debug_phase_clocks'):          # -DPROMP_EXP_CLOCKS experiment build only
+        import ctypes
+        buf = (ctypes.c_ulonglong * 16)()
+        lib.promp_debug_phase_clocks(buf, 1)
+        n = 20
+        for _ in range(n):
+            grad_call(P)
+        lib.promp_debug_phase_clocks(buf, 1)
+        names = ['load X', 'layer0 (SIMT)', 'fwd MMA (sync+issue+wait)', 'tanh/MUP/A1 + sync', 'head + sync', 'gW2 col role + sync',
+                 'D2 + fences + sync', 'wgrad SIMT (overlaps bwd MMA)', 'bwd MMA wait + ld + sync', 'D1 + sync', 'gW0 col role',
+                 'flush: last-arriver reduce', 'load_task', 'fwd MMA sync+issue (part of fwd MMA)', 'flush: partials + fence',
+                 'flush: atomic + sync']
+        tot = sum(buf[i] for i in range(16))
+        print('  CTA 0 phase clocks per launch (grad per-task), total %.0f clk:' % (tot / n))
+        for i, nm in enumerate(names):
+            print('    %-34s %8.0f clk  %5.1f %%' % (nm, buf[i] / n, 100.0 * buf[i] / max(tot, 1)))
 
 
 if __name__ == '__main__':
