@@ -138,6 +138,63 @@ def gen_process_samples():
     np.savez_compressed(os.path.join(OUT, 'process_samples.npz'), **out)
 
 
+def gen_process_samples_ragged():
+    """MetaSampleProcessor + LinearFeatureBaseline on VARIABLE-LENGTH paths (early termination,
+    meta_sampler.py:116-125): per task a different number of paths and samples.  Stored flat with offsets."""
+    from meta_policy_search.samplers.meta_sample_processor import MetaSampleProcessor
+    from meta_policy_search.baselines.linear_baseline import LinearFeatureBaseline
+    from collections import OrderedDict
+    out = {}
+    cases = dict(
+        r1=dict(M=3, Do=2, Da=2, discount=0.99, gae_lambda=1.0, normalize_adv=True, positive_adv=False,
+                lens=[[5, 17, 1, 30, 12], [40, 3], [9, 9, 9, 25, 2, 2, 31]]),
+        r2=dict(M=2, Do=17, Da=6, discount=0.95, gae_lambda=0.9, normalize_adv=True, positive_adv=True,
+                lens=[[60, 45, 80, 100, 33], [100, 100, 7, 64]]),
+        r3=dict(M=4, Do=2, Da=2, discount=0.99, gae_lambda=0.97, normalize_adv=False, positive_adv=False,
+                lens=[[100] * 3, [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 50], [77], [20, 20, 20, 20, 20, 20]]),
+    )
+    for name, c in cases.items():
+        rng = np.random.RandomState(sum(map(ord, name)))
+        M, Do, Da = c['M'], c['Do'], c['Da']
+        paths = OrderedDict()
+        flat = dict(obs=[], act=[], rew=[], mean=[])
+        log_std = (rng.randn(M, Da) * 0.1).astype(np.float32)
+        for m in range(M):
+            paths[m] = []
+            for L in c['lens'][m]:
+                obs = np.cumsum(0.3 * rng.randn(L, Do), axis=0).astype(np.float32).astype(np.float64)
+                act = rng.randn(L, Da).astype(np.float32).astype(np.float64)
+                rew = (rng.randn(L) * (rng.rand(L) < 0.7)).astype(np.float32).astype(np.float64)
+                mean = rng.randn(L, Da).astype(np.float32).astype(np.float64)
+                paths[m].append(dict(observations=obs, actions=act, rewards=rew, env_infos={},
+                                     agent_infos=dict(mean=mean, log_std=np.tile(log_std[m].astype(np.float64), (L, 1)))))
+                for k, v in (('obs', obs), ('act', act), ('rew', rew), ('mean', mean)):
+                    flat[k].append(v.astype(np.float32))
+        proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=c['discount'], gae_lambda=c['gae_lambda'],
+                                   normalize_adv=c['normalize_adv'], positive_adv=c['positive_adv'])
+        coeffs = []
+        orig_fit = proc.baseline.fit
+
+        def fit_and_record(paths_, target_key='returns'):
+            orig_fit(paths_, target_key=target_key)
+            coeffs.append(np.array(proc.baseline._coeffs))
+        proc.baseline.fit = fit_and_record
+        data = proc.process_samples(paths, log=False)
+        pre = 'case_%s_' % name
+        for k in ('M', 'Do', 'Da', 'discount', 'gae_lambda', 'normalize_adv', 'positive_adv'):
+            out[pre + 'cfg_' + k] = np.asarray(c[k])
+        out[pre + 'n_paths'] = np.asarray([len(l) for l in c['lens']], dtype=np.int32)
+        out[pre + 'path_len'] = np.concatenate([np.asarray(l, dtype=np.int32) for l in c['lens']])
+        out[pre + 'log_std'] = log_std
+        for k in flat:
+            out[pre + k] = np.concatenate(flat[k])
+        out[pre + 'returns'] = np.concatenate([d['returns'] for d in data])
+        out[pre + 'advantages'] = np.concatenate([d['advantages'] for d in data])
+        out[pre + 'observations_stacked'] = np.concatenate([d['observations'] for d in data]).astype(np.float32)
+        out[pre + 'coeffs'] = np.stack(coeffs)
+    np.savez_compressed(os.path.join(OUT, 'process_samples_ragged.npz'), **out)
+
+
 def gen_sampler_rollout():
     """Reference MetaSampler(parallel=False) + normalize(MetaPointEnvCorner) driven by the oracle's
     numpy policy with injected action noise: pins RNG consumption order, index mapping, rollouts."""
@@ -193,5 +250,6 @@ if __name__ == '__main__':
     gen_process_samples()
     gen_sampler_rollout()
     gen_baseline_known()
+    gen_process_samples_ragged()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

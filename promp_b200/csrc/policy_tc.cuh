@@ -149,38 +149,41 @@ __device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const uint32_t (&
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// COLSUM: also accumulate the column sums of D (unscaled) from the B fragments: csum[nt] holds, per lane, the partial
+// over this lane's sample rows for column 32 (warp>>2) + 8 nt + (lane>>2); reduce over lane&3 at flush time.
+template <bool COLSUM>
 __device__ __forceinline__ void wgrad_mma_tile(const unsigned char* __restrict__ At, const unsigned char* __restrict__ Dt,
-                                               float scale, int warp, int lane, float (&acc)[4][4]) {
+                                               float scale, int warp, int lane, float (&acc)[4][4], float (&csum)[4]) {
     const int g = lane >> 2, t = lane & 3;
     const int k0 = 16 * (warp & 3) + g, j0 = 32 * (warp >> 2) + g;
     const unsigned char* ap = At + (k0 >> 2) * SCA + (k0 & 3) * 4 + t * 32;     // rows k0 (and k0+8: two chunks further)
     const unsigned char* dp = Dt + (j0 >> 2) * SCA + (j0 & 3) * 4 + t * 32;     // n-tile nt: two chunks further each
 #pragma unroll 2
     for (int s = 0; s < TBT / 8; ++s) {
-        float av[4];
-        av[0] = *reinterpret_cast<const float*>(ap + s * 128);
-        av[1] = *reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA);
-        av[2] = *reinterpret_cast<const float*>(ap + s * 128 + 16);
-        av[3] = *reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA + 16);
-        uint32_t ah[4], al[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            ah[i] = __float_as_uint(av[i]) & 0xffffe000u;
-            al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
-        }
+        uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+        split_tf32(*reinterpret_cast<const float*>(ap + s * 128), ah[0], al[0]);
+        split_tf32(*reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA), ah[1], al[1]);
+        split_tf32(*reinterpret_cast<const float*>(ap + s * 128 + 16), ah[2], al[2]);
+        split_tf32(*reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA + 16), ah[3], al[3]);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            const float d0 = scale * *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128);
-            const float d1 = scale * *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128 + 16);
-            uint32_t bh[2], bl[2];
-            bh[0] = __float_as_uint(d0) & 0xffffe000u;
-            bh[1] = __float_as_uint(d1) & 0xffffe000u;
-            bl[0] = __float_as_uint(d0 - __uint_as_float(bh[0]));
-            bl[1] = __float_as_uint(d1 - __uint_as_float(bh[1]));
-            mma_tf32_16n8k8(acc[nt], al, bh);
-            mma_tf32_16n8k8(acc[nt], ah, bl);
-            mma_tf32_16n8k8(acc[nt], ah, bh);
+            const float d0 = *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128);
+            const float d1 = *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128 + 16);
+            if (COLSUM) csum[nt] += d0 + d1;
+            split_tf32(scale * d0, bh[nt][0], bl[nt][0]);
+            split_tf32(scale * d1, bh[nt][1], bl[nt][1]);
         }
+        // term-major order: consecutive MMAs hit different accumulators (no back-to-back dependent issue)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_16n8k8(acc[nt], al, bh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_16n8k8(acc[nt], ah, bl[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_16n8k8(acc[nt], ah, bh[nt]);
     }
 }
 // accumulator element (nt, i) of wgrad_mma_tile -> flat index into the [HID, HID] weight (row k, column j)
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
 
-    float gW1[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
+    float gW1[4][4], gB1f[4], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gB2w[d] = gLSw[d] = 0.f;
-        gB1c = gB0c = 0.f;
+        gB1f[0] = gB1f[1] = gB1f[2] = gB1f[3] = gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -298,14 +301,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index(warp, lane, nt, i)] = gW1[nt][i];
-            scr[cp * HID + cj] = gB1c;
-            scr[NPART * HID + cp * HID + cj] = gB0c;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {            // b1 gradient: fragment column sums, reduced over the 4 lanes of a column
+                float c = gB1f[nt];
+                c += __shfl_xor_sync(0xffffffffu, c, 1);
+                c += __shfl_xor_sync(0xffffffffu, c, 2);
+                if ((lane & 3) == 0 && (warp & 3) == 0) part[L::B1 + 32 * (warp >> 2) + 8 * nt + (lane >> 2)] = c;
+            }
+            scr[cp * HID + cj] = gB0c;
             __syncthreads();
-            if (tid < 2 * HID) {
-                const int which = tid / HID, j = tid % HID;
+            if (tid < HID) {
                 float s = 0.f;
-                for (int p = 0; p < NPART; ++p) s += scr[which * NPART * HID + p * HID + j];
-                part[(which ? L::B0 : L::B1) + j] = s;
+                for (int p = 0; p < NPART; ++p) s += scr[p * HID + tid];
+                part[L::B0 + tid] = s;
             }
             __syncthreads();
 #pragma unroll
@@ -541,12 +549,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         PCLK(6);
         // ---- ... while the warps do the weight gradient gW1 += H1^T D2 (mma.sync 3xTF32) and the bias column sums
         {
-            wgrad_mma_tile(S.A0, S.A1, 1.f, warp, lane, gW1);
-            const int b0 = cp * BPP;
-            float s = 0.f;
-#pragma unroll 8
-            for (int bb = 0; bb < BPP; ++bb) s += *reinterpret_cast<const float*>(S.A1 + core_off(b0 + bb, cj, SCA));
-            gB1c += s;
+            wgrad_mma_tile<true>(S.A0, S.A1, 1.f, warp, lane, gW1, gB1f);
         }
         PCLK(7);
         mbar_wait(&S.bar, phase);
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     constexpr uint32_t C_Z2 = 0, C_RZ2 = 64, C_DH1 = 128, C_CH1 = 192, C_LOA = 256, C_LOB = 320;
 
-    float gW1[4][4], gW0p[DO], gW2p[DA], gB1c, gB0c, gB2w[DA], gLSw[DA];
+    float gW1[4][4], gB1f[4], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gB2w[d] = gLSw[d] = 0.f;
-        gB1c = gB0c = 0.f;
+        gB1f[0] = gB1f[1] = gB1f[2] = gB1f[3] = gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -770,14 +773,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index(warp, lane, nt, i)] = gW1[nt][i];
-        scr[cp * HID + cj] = gB1c;
-        scr[NPART * HID + cp * HID + cj] = gB0c;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float c = gB1f[nt];
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            if ((lane & 3) == 0 && (warp & 3) == 0) part[L::B1 + 32 * (warp >> 2) + 8 * nt + (lane >> 2)] = c;
+        }
+        scr[cp * HID + cj] = gB0c;
         __syncthreads();
-        if (tid < 2 * HID) {
-            const int which = tid / HID, j = tid % HID;
+        if (tid < HID) {
             float s = 0.f;
-            for (int p = 0; p < NPART; ++p) s += scr[which * NPART * HID + p * HID + j];
-            part[(which ? L::B0 : L::B1) + j] = s;
+            for (int p = 0; p < NPART; ++p) s += scr[p * HID + tid];
+            part[L::B0 + tid] = s;
         }
         __syncthreads();
 #pragma unroll
@@ -1041,13 +1049,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         }
         // ---- ... overlapped with the weight gradients out_W1 += H1^T C2 + R1^T (ac D2) (mma.sync 3xTF32) and colsum(C2)
         {
-            wgrad_mma_tile(S.H1, S.T2b, 1.f, warp, lane, gW1);
-            wgrad_mma_tile(S.R1, S.T2a, ac, warp, lane, gW1);
-            const int b0 = cp * BPP;
-            float s = 0.f;
-#pragma unroll 8
-            for (int bb = 0; bb < BPP; ++bb) s += *reinterpret_cast<const float*>(S.T2b + core_off(b0 + bb, cj, SCA));
-            gB1c += s;
+            float unused[4] = {0.f, 0.f, 0.f, 0.f};
+            wgrad_mma_tile<true>(S.H1, S.T2b, 1.f, warp, lane, gW1, gB1f);
+            wgrad_mma_tile<false>(S.R1, S.T2a, ac, warp, lane, gW1, unused);
         }
         mbar_wait(&S.bar, phase);
         phase ^= 1;

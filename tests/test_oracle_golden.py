@@ -93,6 +93,43 @@ def test_process_samples_matches_reference(golden_dir, case):
         np.testing.assert_array_equal(data[0]['observations'], obs[0].reshape(-1, cfg['Do']))
 
 
+def ragged_paths_from_golden(g, pre):
+    """Rebuild the per-task path lists of a process_samples_ragged.npz case (float64 like the reference's inputs)."""
+    M = int(g[pre + 'cfg_M'])
+    n_paths, path_len = g[pre + 'n_paths'], g[pre + 'path_len']
+    obs, act, rew, mean = (g[pre + k].astype(np.float64) for k in ('obs', 'act', 'rew', 'mean'))
+    paths, off, pi = OrderedDict(), 0, 0
+    for m in range(M):
+        paths[m] = []
+        for _ in range(int(n_paths[m])):
+            L = int(path_len[pi]); pi += 1
+            sl = slice(off, off + L); off += L
+            paths[m].append(dict(observations=obs[sl], actions=act[sl], rewards=rew[sl], env_infos={},
+                                 agent_infos=dict(mean=mean[sl], log_std=np.tile(g[pre + 'log_std'][m].astype(np.float64), (L, 1)))))
+    return paths
+
+
+@pytest.mark.parametrize('case', ['r1', 'r2', 'r3'])
+def test_process_samples_ragged_matches_reference(golden_dir, case):
+    """Variable-length paths (early termination): the oracle's per-path scans, feature time index and ragged fit
+    reproduce the reference MetaSampleProcessor."""
+    g = _load(golden_dir, 'process_samples_ragged.npz')
+    pre = 'case_%s_' % case
+    paths = ragged_paths_from_golden(g, pre)
+    base = nh.LinearFeatureBaseline()
+    proc = nh.SampleProcessor(base, float(g[pre + 'cfg_discount']), float(g[pre + 'cfg_gae_lambda']),
+                              bool(g[pre + 'cfg_normalize_adv']), bool(g[pre + 'cfg_positive_adv']))
+    coeffs = []
+    fit = base.fit
+    base.fit = lambda p, target_key='returns': (fit(p, target_key), coeffs.append(base._coeffs.copy()))
+    data = proc.process_samples(paths)
+    assert np.array_equal(np.concatenate([d['returns'] for d in data]), g[pre + 'returns'])
+    np.testing.assert_allclose(np.stack(coeffs), g[pre + 'coeffs'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.concatenate([d['advantages'] for d in data]), g[pre + 'advantages'], rtol=1e-9, atol=1e-10)
+    np.testing.assert_array_equal(np.concatenate([d['observations'] for d in data]).astype(np.float32),
+                                  g[pre + 'observations_stacked'])
+
+
 def test_sampler_rollout_matches_reference(golden_dir):
     """Oracle sampler + envs reproduce the reference MetaSampler draw-for-draw (seed 1, configs[0])."""
     g = _load(golden_dir, 'sampler_rollout.npz')
