@@ -919,6 +919,14 @@ __global__ void adam_step_inc_kernel(int32_t* step) { *step += 1; }
 // -------------------------------------------------------------------------------------------------
 static int g_use_tc = 1;     // promp_set_option("tensor_cores", 0|1): HID = 64 policy kernels on tcgen05 (default) or CUDA cores
 
+static int g_tc_threads = 0;  // promp_set_option("tc_threads", 0|256|512): 0 = per-shape default
+// column groups of the TC kernels' thread mapping: 2 -> 256 threads (32 hidden units per thread), 4 -> 512 threads (16)
+static int tc_column_groups(int obs_dim) {
+    if (g_tc_threads == 256) return 2;
+    if (g_tc_threads == 512) return 4;
+    return obs_dim <= 4 ? 4 : 2;
+}
+
 struct TilePlan {
     int grid, q, kmax;
     int64_t partial_floats;
@@ -950,11 +958,11 @@ static int64_t counters_bytes(int M) { return (((int64_t)M * sizeof(int) + 15) /
 
 template <typename Kernel>
 static int launch_policy(Kernel kernel, int smem, int& occ_cache, PolicyArgs& A, int P, void* ws, int64_t ws_bytes,
-                         cudaStream_t st, const char* name, int tb = TB) {
+                         cudaStream_t st, const char* name, int tb = TB, int threads = PT_THREADS) {
     if (occ_cache == 0) {
         PROMP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
-        PROMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PT_THREADS, smem));
+        PROMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
         occ_cache = occ < 1 ? 1 : occ;
     }
     const TilePlan p = plan_tiles(A.M, A.N, sm_count() * occ_cache, P, tb);
@@ -967,7 +975,7 @@ static int launch_policy(Kernel kernel, int smem, int& occ_cache, PolicyArgs& A,
     A.partial = (float*)((char*)ws + counters_bytes(A.M));
     A.q = p.q;
     A.kmax = p.kmax;
-    kernel<<<p.grid, PT_THREADS, smem, st>>>(A);
+    kernel<<<p.grid, threads, smem, st>>>(A);
     PROMP_LAUNCH_CHECK(name);
     return PROMP_OK;
 }
@@ -983,9 +991,12 @@ template <int DO, int DA, int HID>
 static int launch_grad_any(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
     if constexpr (HID == TC_HID) {
         if (g_use_tc) {
-            static int occ = 0;
-            return launch_policy(policy_grad_tc_kernel<DO, DA>, (int)sizeof(GradTcSmem<DO, DA>), occ, A,
-                                 PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_tc_kernel", TBT);
+            static int occ2 = 0, occ4 = 0;
+            if (tc_column_groups(DO) == 4)
+                return launch_policy(policy_grad_tc_kernel<DO, DA, 4>, (int)sizeof(GradTcSmem<DO, DA, 4>), occ4, A,
+                                     PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_tc_kernel", TBT, 512);
+            return launch_policy(policy_grad_tc_kernel<DO, DA, 2>, (int)sizeof(GradTcSmem<DO, DA, 2>), occ2, A,
+                                 PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_grad_tc_kernel", TBT, 256);
         }
     }
     return launch_grad<DO, DA, HID>(A, ws, ws_bytes, st);
@@ -993,11 +1004,14 @@ static int launch_grad_any(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream
 
 template <int DO, int DA, int HID>
 static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st) {
-    if constexpr (HID == TC_HID && sizeof(HvpTcSmem<DO, DA>) <= 227 * 1024) {     // fits the 227 KB of one SM
+    if constexpr (HID == TC_HID && sizeof(HvpTcSmem<DO, DA, 2>) <= 227 * 1024) {     // fits the 227 KB of one SM
         if (g_use_tc) {
-            static int occ_tc = 0;
-            return launch_policy(policy_hvp_tc_kernel<DO, DA>, (int)sizeof(HvpTcSmem<DO, DA>), occ_tc, A,
-                                 PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_tc_kernel", TBT);
+            static int occ2 = 0, occ4 = 0;
+            if (tc_column_groups(DO) == 4)
+                return launch_policy(policy_hvp_tc_kernel<DO, DA, 4>, (int)sizeof(HvpTcSmem<DO, DA, 4>), occ4, A,
+                                     PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_tc_kernel", TBT, 512);
+            return launch_policy(policy_hvp_tc_kernel<DO, DA, 2>, (int)sizeof(HvpTcSmem<DO, DA, 2>), occ2, A,
+                                 PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_tc_kernel", TBT, 256);
         }
     }
     static int occ = 0;
@@ -1095,6 +1109,11 @@ extern "C" int promp_set_option(const char* name, int value) {
     PROMP_REQUIRE(name != nullptr, "promp_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) {
         g_use_tc = value ? 1 : 0;
+        return PROMP_OK;
+    }
+    if (strcmp(name, "tc_threads") == 0) {
+        PROMP_REQUIRE(value == 0 || value == 256 || value == 512, "promp_set_option: tc_threads must be 0, 256 or 512");
+        g_tc_threads = value;
         return PROMP_OK;
     }
     set_error("promp_set_option: unknown option '%s'", name);

@@ -80,6 +80,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_stw(uint32_t taddr, const float (&v)[32]) { tmem_st32(taddr, v); }
+__device__ __forceinline__ void tmem_stw(uint32_t taddr, const float (&v)[16]) { tmem_st16(taddr, v); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
@@ -113,7 +147,7 @@ struct SmallLayout {      // the parameters other than W1, compact
     static constexpr int SIZE = (LS + DA + 3) / 4 * 4;
 };
 
-template <int DO, int DA>
+template <int DO, int DA, int NQ>
 struct GradTcSmem {
     static constexpr int DOP = DOPad<DO>::V;
     alignas(16) unsigned char W1T_hi[TILE_W_BYTES];   // B of the forward GEMM: rows n = output unit, K = k
@@ -125,9 +159,9 @@ struct GradTcSmem {
     alignas(16) unsigned char LO[TILE_A_BYTES];       // H1_lo -> D2_lo ; flush scratch
     alignas(16) float Ps[SmallLayout<DO, DA>::SIZE];
     alignas(16) float X[TBT * DOP];
-    float MUP[2 * TBT * DA];
+    float MUP[NQ * TBT * DA];
     float DMU[TBT * DA];
-    float red[3 * (PT_THREADS / 32)];
+    float red[3 * 4 * NQ];
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
     int last;
@@ -141,7 +175,8 @@ struct GradTcSmem {
 // 128B_BASE32B layout - incompatible with the K-major use of the same tiles by the layer MMAs.  The CUDA-core version
 // was bound by shared-memory wavefronts (every LDS.128 costs 4, 8 per sample row per warp for 16 FFMA); the fragment
 // loads below are 12 conflict-free LDS.32 per 8 sample rows and the math leaves the FP32 pipe.
-//   warp w owns the 16 x 32 block  k in [16 (w&3), +16), j in [32 (w>>2), +32)  as 4 n-tiles of m16n8.
+//   warp w owns the 16 x 8NT block  k in [16 (w&3), +16), j in [8NT (w>>2), +8NT)  as NT n-tiles of m16n8
+//   (NT = 4 with 8 warps, 2 with 16 warps).
 //   fragment column t (t+4) <-> sample 8s+2t (8s+2t+1): with the 16-byte chunk padding this makes every fragment
 //   load hit 32 distinct banks (bank = 4 (g>>2) + (g&3) + 8 t).
 __device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -155,22 +190,22 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 // COLSUM: also accumulate the column sums of D (unscaled) from the B fragments: csum[nt] holds, per lane, the partial
 // over this lane's sample rows for column 32 (warp>>2) + 8 nt + (lane>>2); reduce over lane&3 at flush time.
-template <bool COLSUM>
+template <bool COLSUM, int NT>
 __device__ __forceinline__ void wgrad_mma_tile(const unsigned char* __restrict__ At, const unsigned char* __restrict__ Dt,
-                                               float scale, int warp, int lane, float (&acc)[4][4], float (&csum)[4]) {
+                                               float scale, int warp, int lane, float (&acc)[NT][4], float (&csum)[NT]) {
     const int g = lane >> 2, t = lane & 3;
-    const int k0 = 16 * (warp & 3) + g, j0 = 32 * (warp >> 2) + g;
+    const int k0 = 16 * (warp & 3) + g, j0 = 8 * NT * (warp >> 2) + g;
     const unsigned char* ap = At + (k0 >> 2) * SCA + (k0 & 3) * 4 + t * 32;     // rows k0 (and k0+8: two chunks further)
     const unsigned char* dp = Dt + (j0 >> 2) * SCA + (j0 & 3) * 4 + t * 32;     // n-tile nt: two chunks further each
 #pragma unroll 2
     for (int s = 0; s < TBT / 8; ++s) {
-        uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+        uint32_t ah[4], al[4], bh[NT][2], bl[NT][2];
         split_tf32(*reinterpret_cast<const float*>(ap + s * 128), ah[0], al[0]);
         split_tf32(*reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA), ah[1], al[1]);
         split_tf32(*reinterpret_cast<const float*>(ap + s * 128 + 16), ah[2], al[2]);
         split_tf32(*reinterpret_cast<const float*>(ap + s * 128 + 2 * SCA + 16), ah[3], al[3]);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             const float d0 = *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128);
             const float d1 = *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128 + 16);
             if (COLSUM) csum[nt] += d0 + d1;
@@ -179,17 +214,18 @@ __device__ __forceinline__ void wgrad_mma_tile(const unsigned char* __restrict__
         }
         // term-major order: consecutive MMAs hit different accumulators (no back-to-back dependent issue)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_16n8k8(acc[nt], al, bh[nt]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32_16n8k8(acc[nt], al, bh[nt]);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_16n8k8(acc[nt], ah, bl[nt]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32_16n8k8(acc[nt], ah, bl[nt]);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_16n8k8(acc[nt], ah, bh[nt]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32_16n8k8(acc[nt], ah, bh[nt]);
     }
 }
 // accumulator element (nt, i) of wgrad_mma_tile -> flat index into the [HID, HID] weight (row k, column j)
+template <int NT>
 __device__ __forceinline__ int wgrad_mma_index(int warp, int lane, int nt, int i) {
     const int g = lane >> 2, t = lane & 3;
-    return (16 * (warp & 3) + g + 8 * (i >> 1)) * TC_HID + 32 * (warp >> 2) + 8 * nt + 2 * t + (i & 1);
+    return (16 * (warp & 3) + g + 8 * (i >> 1)) * TC_HID + 8 * NT * (warp >> 2) + 8 * nt + 2 * t + (i & 1);
 }
 
 #ifdef PROMP_EXP_CLOCKS
@@ -206,15 +242,16 @@ __device__ unsigned long long g_phase_clk[16];
 #else
 #define PCLK(i)
 #endif
-template <int DO, int DA>
-__global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArgs A) {
+template <int DO, int DA, int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs A) {
     constexpr int HID = TC_HID;
     using L = PLayout<DO, DA, HID>;
     using SL = SmallLayout<DO, DA>;
-    using SM = GradTcSmem<DO, DA>;
+    using SM = GradTcSmem<DO, DA, NQ>;
+    constexpr int TCT = 128 * NQ, CW = TC_HID / NQ, NW = TCT / 32, NT = 8 / NQ;   // threads, columns per thread, warps, wgrad n-tiles per warp
     constexpr int DOP = SM::DOP;
     constexpr int PSTRIDE = L::P + PSTAT;
-    constexpr int NPART = PT_THREADS / HID, BPP = TBT / NPART;     // column role: 4 slices of 32 rows
+    constexpr int NPART = TCT / HID, BPP = TBT / NPART;     // column role: 4 slices of 32 rows
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
@@ -229,8 +266,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform copy for the MMA-issue branch
-    const int qd = warp & 3, half = warp >> 2;
-    const int r = qd * 32 + lane, c0 = 32 * half;          // row-half role: sample row r, hidden units [c0, c0+32)
+    const int qd = warp & 3, cq = warp >> 2;               // TMEM lane quadrant, column group
+    const int r = qd * 32 + lane, c0 = CW * cq;          // row / column-group role: sample row r, hidden units [c0, c0+32)
     const int cj = tid & (HID - 1), cp = tid / HID;        // column role
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
@@ -253,28 +290,28 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
 
-    float gW1[4][4], gB1f[4], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
+    float gW1[NT][4], gB1f[NT], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) gW1[a][0] = gW1[a][1] = gW1[a][2] = gW1[a][3] = 0.f;
+        for (int a = 0; a < NT; ++a) gW1[a][0] = gW1[a][1] = gW1[a][2] = gW1[a][3] = gB1f[a] = 0.f;
 #pragma unroll
         for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gB2w[d] = gLSw[d] = 0.f;
-        gB1f[0] = gB1f[1] = gB1f[2] = gB1f[3] = gB0c = 0.f;
+        gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
         th = A.params + (int64_t)m * A.param_stride;
         if (!first && A.param_stride == 0) return;
         __syncthreads();
-        for (int i = tid; i < DO * HID + HID; i += PT_THREADS) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);          // W0, b0
-        for (int i = tid; i < HID; i += PT_THREADS) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
-        for (int i = tid; i < HID * DA + 2 * DA; i += PT_THREADS) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);       // W2, b2, ls
-        for (int i = tid; i < HID * HID; i += PT_THREADS) {
+        for (int i = tid; i < DO * HID + HID; i += TCT) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);          // W0, b0
+        for (int i = tid; i < HID; i += TCT) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
+        for (int i = tid; i < HID * DA + 2 * DA; i += TCT) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);       // W2, b2, ls
+        for (int i = tid; i < HID * HID; i += TCT) {
             const int k = i / HID, j = i % HID;
             const float w = __ldg(th + L::W1 + i), wl = w - tf32_trunc(w);
             *reinterpret_cast<float*>(S.W1_hi + core_off(k, j, SCW)) = w;
@@ -294,19 +331,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
     };
     auto flush = [&](int m) {
         float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
-        float* scr = reinterpret_cast<float*>(S.LO);      // free between tiles (all MMAs have completed)
+        float* scr = reinterpret_cast<float*>(S.A1);      // A1 + LO (contiguous, 2 tiles): free between tiles (all MMAs have completed)
+        static_assert(NPART * DO * HID * 4 <= 2 * TILE_A_BYTES && NPART * HID * DA * 4 <= 2 * TILE_A_BYTES, "flush scratch");
         __syncthreads();
         if (want_grad) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index(warp, lane, nt, i)] = gW1[nt][i];
+                for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index<NT>(warp, lane, nt, i)] = gW1[nt][i];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {            // b1 gradient: fragment column sums, reduced over the 4 lanes of a column
+            for (int nt = 0; nt < NT; ++nt) {            // b1 gradient: fragment column sums, reduced over the 4 lanes of a column
                 float c = gB1f[nt];
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
                 c += __shfl_xor_sync(0xffffffffu, c, 2);
-                if ((lane & 3) == 0 && (warp & 3) == 0) part[L::B1 + 32 * (warp >> 2) + 8 * nt + (lane >> 2)] = c;
+                if ((lane & 3) == 0 && (warp & 3) == 0) part[L::B1 + 8 * NT * (warp >> 2) + 8 * nt + (lane >> 2)] = c;
             }
             scr[cp * HID + cj] = gB0c;
             __syncthreads();
@@ -319,7 +357,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 #pragma unroll
             for (int i = 0; i < DO; ++i) scr[(cp * DO + i) * HID + cj] = gW0p[i];
             __syncthreads();
-            for (int idx = tid; idx < DO * HID; idx += PT_THREADS) {
+            for (int idx = tid; idx < DO * HID; idx += TCT) {
                 float s = 0.f;
                 for (int p = 0; p < NPART; ++p) s += scr[p * DO * HID + idx];
                 part[L::W0 + idx] = s;
@@ -328,26 +366,26 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 #pragma unroll
             for (int d = 0; d < DA; ++d) scr[(cp * HID + cj) * DA + d] = gW2p[d];
             __syncthreads();
-            for (int idx = tid; idx < HID * DA; idx += PT_THREADS) {
+            for (int idx = tid; idx < HID * DA; idx += TCT) {
                 float s = 0.f;
                 for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
                 part[L::W2 + idx] = s;
             }
             __syncthreads();
-            if (half == 0 && lane == 0) {
+            if (cq == 0 && lane == 0) {
 #pragma unroll
                 for (int d = 0; d < DA; ++d) scr[qd * 2 * DA + d] = gB2w[d], scr[qd * 2 * DA + DA + d] = gLSw[d];
             }
             __syncthreads();
             if (tid < 2 * DA) part[L::B2 + tid] = scr[tid] + scr[2 * DA + tid] + scr[4 * DA + tid] + scr[6 * DA + tid];   // b2 then log_std
         }
-        const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);   // held by half == 0 threads, 0 elsewhere
+        const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);   // held by cq == 0 threads, 0 elsewhere
         __syncthreads();
-        if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
+        if (lane == 0) S.red[warp] = v0, S.red[NW + warp] = v1, S.red[2 * NW + warp] = v2;
         __syncthreads();
         if (tid < 3) {
             float s = 0.f;
-            for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+            for (int w = 0; w < NW; ++w) s += S.red[tid * NW + w];
             part[L::P + tid] = s;
         }
         __threadfence();
@@ -360,7 +398,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         if (S.last) {
             __threadfence();
             if (want_grad) {
-                for (int p = 4 * tid; p < L::P; p += 4 * PT_THREADS) {
+                for (int p = 4 * tid; p < L::P; p += 4 * TCT) {
                     const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
                     *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
                     if (A.out_params) {
@@ -396,19 +434,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         const int n0 = tile * TBT, nb = min(TBT, N - n0);
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
-        for (int i = tid; i < TBT * DOP; i += PT_THREADS) {
+        for (int i = tid; i < TBT * DOP; i += TCT) {
             const int b = i / DOP, c = i % DOP;
             S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
         }
         __syncthreads();
         PCLK(0);
-        // ---- layer 0 (CUDA cores, row-half role): H1 = tanh(X W0 + b0) -> A0 (fp32 = TF32 "hi" operand) and LO
+        // ---- layer 0 (CUDA cores, row / column-group role): H1 = tanh(X W0 + b0) -> A0 (fp32 = TF32 "hi" operand) and LO
         {
             float x[DO];
 #pragma unroll
             for (int i = 0; i < DO; ++i) x[i] = S.X[r * DOP + i];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
                 float h[4], hl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -439,13 +477,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         phase ^= 1;
         tc_fence_after();
         PCLK(2);
-        float h2[32];
-        tmem_ld32(tmem_row + c0, h2);
+        float h2[CW];
+        tmem_ldw(tmem_row + c0, h2);
         float mup[DA];
 #pragma unroll
         for (int d = 0; d < DA; ++d) mup[d] = 0.f;
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
+        for (int c4 = 0; c4 < CW / 4; ++c4) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int c = 4 * c4 + e;
@@ -457,19 +495,22 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
                 make_float4(h2[4 * c4], h2[4 * c4 + 1], h2[4 * c4 + 2], h2[4 * c4 + 3]);
         }
 #pragma unroll
-        for (int d = 0; d < DA; ++d) S.MUP[(half * TBT + r) * DA + d] = mup[d];
+        for (int d = 0; d < DA; ++d) S.MUP[(cq * TBT + r) * DA + d] = mup[d];
         tc_fence_before();
         __syncthreads();
         PCLK(3);
-        // ---- Gaussian head: one thread per sample row (half == 0)
-        if (half == 0) {
+        // ---- Gaussian head: one thread per sample row (cq == 0)
+        if (cq == 0) {
             float dmu[DA], dls[DA];
             if (r < nb) {
                 const int64_t n = g0 + r;
                 float mu[DA], a[DA], mo[DA], lso[DA];
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
-                    mu[d] = S.MUP[r * DA + d] + S.MUP[(TBT + r) * DA + d] + S.Ps[SL::B2 + d];
+                    float sm = S.Ps[SL::B2 + d];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) sm += S.MUP[(q * TBT + r) * DA + d];
+                    mu[d] = sm;
                     a[d] = __ldg(A.act + n * DA + d);
                     mo[d] = __ldg(A.old_mean + n * DA + d);
                     lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
@@ -521,7 +562,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 #pragma unroll
             for (int d = 0; d < DA; ++d) dm[d] = S.DMU[r * DA + d];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
                 float v[4], vl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -549,20 +590,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
         PCLK(6);
         // ---- ... while the warps do the weight gradient gW1 += H1^T D2 (mma.sync 3xTF32) and the bias column sums
         {
-            wgrad_mma_tile<true>(S.A0, S.A1, 1.f, warp, lane, gW1, gB1f);
+            wgrad_mma_tile<true, NT>(S.A0, S.A1, 1.f, warp, lane, gW1, gB1f);
         }
         PCLK(7);
         mbar_wait(&S.bar, phase);
         phase ^= 1;
         tc_fence_after();
-        float dh1[32];
-        tmem_ld32(tmem_row + 64 + c0, dh1);
+        float dh1[CW];
+        tmem_ldw(tmem_row + 64 + c0, dh1);
         tc_fence_before();
         __syncthreads();       // every CUDA-core read of H1 (weight gradient) is done before A0 is overwritten
         PCLK(8);
         // ---- D1 = dH1 * (1 - H1^2) -> A0 in place
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
+        for (int c4 = 0; c4 < CW / 4; ++c4) {
             float4* p = reinterpret_cast<float4*>(S.A0 + core_off(r, c0 + 4 * c4, SCA));
             const float4 h = *p;
             *p = make_float4(dh1[4 * c4] * (1.f - h.x * h.x), dh1[4 * c4 + 1] * (1.f - h.y * h.y),
@@ -608,7 +649,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_grad_tc_kernel(PolicyArg
 // The two weight-gradient GEMMs (H1^T C2, R1^T D2) contract over samples (MN-major operands) and stay on the CUDA
 // cores, overlapped with the backward MMAs.  TMEM map (512 columns allocated): Z2 0-63, RZ2 64-127, dH1 128-191,
 // CdH1 192-255, lo-A 256-319, lo-B 320-383.
-template <int DO, int DA>
+template <int DO, int DA, int NQ>
 struct HvpTcSmem {
     static constexpr int DOP = DOPad<DO>::V;
     alignas(16) unsigned char WB[4][TILE_W_BYTES];    // fwd: W1T_hi, W1T_lo, V1T_hi, V1T_lo ; bwd: W1_hi, W1_lo, aV1_hi, aV1_lo
@@ -619,26 +660,15 @@ struct HvpTcSmem {
     alignas(16) float Ps[SmallLayout<DO, DA>::SIZE];
     alignas(16) float Vs[SmallLayout<DO, DA>::SIZE];
     // X (observations) aliases T2a (needed only before H2 is written and, re-read from L2, after D2 is dead);
-    // MUP (per-half partial means) aliases WB[0] between the forward MMAs and the backward weight re-fill.
+    // MUP (per-column-group partial means) aliases WB[0..1] between the forward MMAs and the backward weight re-fill.
     float DMU[TBT * DA];
     float CMU[TBT * DA];
-    float red[3 * (PT_THREADS / 32)];
+    float red[3 * 4 * NQ];
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
     int last;
 };
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -664,26 +694,27 @@ __device__ __forceinline__ void issue_gemm_3xtf32_ts(uint32_t d_tmem, const unsi
         umma_tf32(d_tmem, umma_desc(a0 + 2 * s * SCA, SCA, 128), umma_desc(bh + 2 * s * SCW, SCW, 128), idesc, 1);
 }
 
-template <int DO, int DA>
-__global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs A) {
+template <int DO, int DA, int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A) {
     constexpr int HID = TC_HID;
     using L = PLayout<DO, DA, HID>;
     using SL = SmallLayout<DO, DA>;
-    using SM = HvpTcSmem<DO, DA>;
+    using SM = HvpTcSmem<DO, DA, NQ>;
+    constexpr int TCT = 128 * NQ, CW = TC_HID / NQ, NW = TCT / 32, NT = 8 / NQ;
     constexpr int DOP = SM::DOP;
     constexpr int PSTRIDE = L::P + PSTAT;
-    constexpr int NPART = PT_THREADS / HID, BPP = TBT / NPART;
+    constexpr int NPART = TCT / HID, BPP = TBT / NPART;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     float* const sX = reinterpret_cast<float*>(S.T2a);
     float* const sMUP = reinterpret_cast<float*>(S.WB[0]);
-    static_assert(TBT * DOP * 4 <= TILE_A_BYTES && 2 * TBT * 2 * DA * 4 <= TILE_W_BYTES, "aliased buffers must fit");
+    static_assert(TBT * DOP * 4 <= TILE_A_BYTES && NQ * TBT * 2 * DA * 4 <= 2 * TILE_W_BYTES, "aliased buffers must fit");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform copy for the MMA-issue branch
-    const int qd = warp & 3, half = warp >> 2;
-    const int r = qd * 32 + lane, c0 = 32 * half;
+    const int qd = warp & 3, cq = warp >> 2;               // TMEM lane quadrant, column group
+    const int r = qd * 32 + lane, c0 = CW * cq;
     const int cj = tid & (HID - 1), cp = tid / HID;
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
@@ -708,20 +739,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     constexpr uint32_t C_Z2 = 0, C_RZ2 = 64, C_DH1 = 128, C_CH1 = 192, C_LOA = 256, C_LOB = 320;
 
-    float gW1[4][4], gB1f[4], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];
+    float gW1[NT][4], gB1f[NT], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) gW1[a][c] = 0.f;
+        for (int a = 0; a < NT; ++a) gW1[a][0] = gW1[a][1] = gW1[a][2] = gW1[a][3] = gB1f[a] = 0.f;
 #pragma unroll
         for (int i = 0; i < DO; ++i) gW0p[i] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gW2p[d] = 0.f;
 #pragma unroll
         for (int d = 0; d < DA; ++d) gB2w[d] = gLSw[d] = 0.f;
-        gB1f[0] = gB1f[1] = gB1f[2] = gB1f[3] = gB0c = 0.f;
+        gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
@@ -729,15 +758,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         vg = A.vec + (int64_t)m * L::P;
         __syncthreads();
         const bool reload_p = first || A.param_stride != 0;
-        for (int i = tid; i < DO * HID + HID; i += PT_THREADS) {
+        for (int i = tid; i < DO * HID + HID; i += TCT) {
             if (reload_p) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);
             S.Vs[SL::W0 + i] = __ldcg(vg + L::W0 + i);
         }
-        for (int i = tid; i < HID; i += PT_THREADS) {
+        for (int i = tid; i < HID; i += TCT) {
             if (reload_p) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
             S.Vs[SL::B1 + i] = __ldcg(vg + L::B1 + i);
         }
-        for (int i = tid; i < HID * DA + 2 * DA; i += PT_THREADS) {
+        for (int i = tid; i < HID * DA + 2 * DA; i += TCT) {
             if (reload_p) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);
             S.Vs[SL::W2 + i] = __ldcg(vg + L::W2 + i);
         }
@@ -754,7 +783,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
     };
     // (re)fill the weight buffer from L2: forward = [W1^T, V1^T], backward = [W1, ac*V1], each as hi (fp32) + lo
     auto load_weights = [&](bool fwd) {
-        for (int i = tid; i < HID * HID; i += PT_THREADS) {
+        for (int i = tid; i < HID * HID; i += TCT) {
             const int k = i / HID, j = i % HID;
             const float w = __ldg(th + L::W1 + i);
             const float v = (fwd ? 1.f : ac) * __ldcg(vg + L::W1 + i);
@@ -767,18 +796,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
     };
     auto flush = [&](int m) {
         float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
-        float* scr = reinterpret_cast<float*>(S.T2b);
+        float* scr = reinterpret_cast<float*>(S.T2a);     // T2a + T2b (contiguous, 2 tiles)
+        static_assert(NPART * DO * HID * 4 <= 2 * TILE_A_BYTES && NPART * HID * DA * 4 <= 2 * TILE_A_BYTES, "flush scratch");
         __syncthreads();
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index(warp, lane, nt, i)] = gW1[nt][i];
+            for (int i = 0; i < 4; ++i) part[L::W1 + wgrad_mma_index<NT>(warp, lane, nt, i)] = gW1[nt][i];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             float c = gB1f[nt];
             c += __shfl_xor_sync(0xffffffffu, c, 1);
             c += __shfl_xor_sync(0xffffffffu, c, 2);
-            if ((lane & 3) == 0 && (warp & 3) == 0) part[L::B1 + 32 * (warp >> 2) + 8 * nt + (lane >> 2)] = c;
+            if ((lane & 3) == 0 && (warp & 3) == 0) part[L::B1 + 8 * NT * (warp >> 2) + 8 * nt + (lane >> 2)] = c;
         }
         scr[cp * HID + cj] = gB0c;
         __syncthreads();
@@ -791,7 +821,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
 #pragma unroll
         for (int i = 0; i < DO; ++i) scr[(cp * DO + i) * HID + cj] = gW0p[i];
         __syncthreads();
-        for (int idx = tid; idx < DO * HID; idx += PT_THREADS) {
+        for (int idx = tid; idx < DO * HID; idx += TCT) {
             float s = 0.f;
             for (int p = 0; p < NPART; ++p) s += scr[p * DO * HID + idx];
             part[L::W0 + idx] = s;
@@ -800,13 +830,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
 #pragma unroll
         for (int d = 0; d < DA; ++d) scr[(cp * HID + cj) * DA + d] = gW2p[d];
         __syncthreads();
-        for (int idx = tid; idx < HID * DA; idx += PT_THREADS) {
+        for (int idx = tid; idx < HID * DA; idx += TCT) {
             float s = 0.f;
             for (int p = 0; p < NPART; ++p) s += scr[p * HID * DA + idx];
             part[L::W2 + idx] = s;
         }
         __syncthreads();
-        if (half == 0 && lane == 0) {
+        if (cq == 0 && lane == 0) {
 #pragma unroll
             for (int d = 0; d < DA; ++d) scr[qd * 2 * DA + d] = gB2w[d], scr[qd * 2 * DA + DA + d] = gLSw[d];
         }
@@ -814,11 +844,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         if (tid < 2 * DA) part[L::B2 + tid] = scr[tid] + scr[2 * DA + tid] + scr[4 * DA + tid] + scr[6 * DA + tid];
         const float v0 = warp_sum(s_obj), v1 = warp_sum(s_kl), v2 = warp_sum(s_ratio);
         __syncthreads();
-        if (lane == 0) S.red[warp] = v0, S.red[8 + warp] = v1, S.red[16 + warp] = v2;
+        if (lane == 0) S.red[warp] = v0, S.red[NW + warp] = v1, S.red[2 * NW + warp] = v2;
         __syncthreads();
         if (tid < 3) {
             float s = 0.f;
-            for (int w = 0; w < PT_THREADS / 32; ++w) s += S.red[tid * 8 + w];
+            for (int w = 0; w < NW; ++w) s += S.red[tid * NW + w];
             part[L::P + tid] = s;
         }
         __threadfence();
@@ -828,7 +858,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         __syncthreads();
         if (S.last) {
             __threadfence();
-            for (int p = 4 * tid; p < L::P; p += 4 * PT_THREADS) {
+            for (int p = 4 * tid; p < L::P; p += 4 * TCT) {
                 const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
                 const float4 v4 = __ldcg(reinterpret_cast<const float4*>(vg + p));
                 *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) = make_float4(v4.x + s.x, v4.y + s.y, v4.z + s.z, v4.w + s.w);
@@ -857,7 +887,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
         auto load_x = [&]() {
-            for (int i = tid; i < TBT * DOP; i += PT_THREADS) {
+            for (int i = tid; i < TBT * DOP; i += TCT) {
                 const int b = i / DOP, c = i % DOP;
                 sX[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
             }
@@ -865,13 +895,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         load_x();
         load_weights(true);
         __syncthreads();
-        // ---- layer 0 and its tangent (CUDA cores, row-half role); lo parts of H1 / R1 -> TMEM
+        // ---- layer 0 and its tangent (CUDA cores, row / column-group role); lo parts of H1 / R1 -> TMEM
         {
-            float x[DO], hl[32], rl[32];
+            float x[DO], hl[CW], rl[CW];
 #pragma unroll
             for (int i = 0; i < DO; ++i) x[i] = sX[r * DOP + i];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
                 float h[4], r1[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -891,8 +921,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 *reinterpret_cast<float4*>(S.H1 + off) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(S.R1 + off) = make_float4(r1[0], r1[1], r1[2], r1[3]);
             }
-            tmem_st32(tmem_row + C_LOA + c0, hl);
-            tmem_st32(tmem_row + C_LOB + c0, rl);
+            tmem_stw(tmem_row + C_LOA + c0, hl);
+            tmem_stw(tmem_row + C_LOB + c0, rl);
         }
         // ---- forward MMAs: Z2 = H1 W1 ; RZ2 = R1 W1 + H1 V1
         proxy_fence_async();
@@ -908,15 +938,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         mbar_wait(&S.bar, phase);
         phase ^= 1;
         tc_fence_after();
-        float h2[32], r2[32];
-        tmem_ld32(tmem_row + C_Z2 + c0, h2);
-        tmem_ld32(tmem_row + C_RZ2 + c0, r2);
+        float h2[CW], r2[CW];
+        tmem_ldw(tmem_row + C_Z2 + c0, h2);
+        tmem_ldw(tmem_row + C_RZ2 + c0, r2);
         {
             float mup[DA], rmup[DA];
 #pragma unroll
             for (int d = 0; d < DA; ++d) mup[d] = rmup[d] = 0.f;
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int c = 4 * c4 + e;
@@ -935,22 +965,25 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
             }
 #pragma unroll
             for (int d = 0; d < DA; ++d) {
-                sMUP[((half * TBT + r) * 2 + 0) * DA + d] = mup[d];
-                sMUP[((half * TBT + r) * 2 + 1) * DA + d] = rmup[d];
+                sMUP[((cq * TBT + r) * 2 + 0) * DA + d] = mup[d];
+                sMUP[((cq * TBT + r) * 2 + 1) * DA + d] = rmup[d];
             }
         }
         tc_fence_before();
         __syncthreads();
-        // ---- Gaussian head and its tangent: one thread per sample row (half == 0)
-        if (half == 0) {
+        // ---- Gaussian head and its tangent: one thread per sample row (cq == 0)
+        if (cq == 0) {
             float dmu[DA], cmu[DA], cls[DA];
             if (r < nb) {
                 const int64_t n = g0 + r;
                 float mu[DA], rmu[DA], a[DA], mo[DA], lso[DA];
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
-                    mu[d] = sMUP[(r * 2 + 0) * DA + d] + sMUP[((TBT + r) * 2 + 0) * DA + d] + S.Ps[SL::B2 + d];
-                    rmu[d] = sMUP[(r * 2 + 1) * DA + d] + sMUP[((TBT + r) * 2 + 1) * DA + d] + S.Vs[SL::B2 + d];
+float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) sm += sMUP[((q * TBT + r) * 2 + 0) * DA + d], sr += sMUP[((q * TBT + r) * 2 + 1) * DA + d];
+                    mu[d] = sm;
+                    rmu[d] = sr;
                     a[d] = __ldg(A.act + n * DA + d);
                     mo[d] = __ldg(A.old_mean + n * DA + d);
                     lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
@@ -1007,11 +1040,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         __syncthreads();
         // ---- D2 = dH2 g2 -> T2a ; C2 = CdH2 g2 + ac dH2 (-2 H2 R2) -> T2b ; lo parts -> TMEM
         {
-            float dm[DA], cm[DA], dl[32], cl[32];
+            float dm[DA], cm[DA], dl[CW], cl[CW];
 #pragma unroll
             for (int d = 0; d < DA; ++d) dm[d] = S.DMU[r * DA + d], cm[d] = S.CMU[r * DA + d];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < CW / 4; ++c4) {
                 float d2[4], c2[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1033,8 +1066,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
                 *reinterpret_cast<float4*>(S.T2a + off) = make_float4(d2[0], d2[1], d2[2], d2[3]);
                 *reinterpret_cast<float4*>(S.T2b + off) = make_float4(c2[0], c2[1], c2[2], c2[3]);
             }
-            tmem_st32(tmem_row + C_LOA + c0, dl);
-            tmem_st32(tmem_row + C_LOB + c0, cl);
+            tmem_stw(tmem_row + C_LOA + c0, dl);
+            tmem_stw(tmem_row + C_LOB + c0, cl);
         }
         // ---- backward MMAs: dH1 = D2 W1^T ; CdH1 = C2 W1^T + D2 (ac V1)^T ...
         proxy_fence_async();
@@ -1049,21 +1082,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_hvp_tc_kernel(PolicyArgs
         }
         // ---- ... overlapped with the weight gradients out_W1 += H1^T C2 + R1^T (ac D2) (mma.sync 3xTF32) and colsum(C2)
         {
-            float unused[4] = {0.f, 0.f, 0.f, 0.f};
-            wgrad_mma_tile<true>(S.H1, S.T2b, 1.f, warp, lane, gW1, gB1f);
-            wgrad_mma_tile<false>(S.R1, S.T2a, ac, warp, lane, gW1, unused);
+            float unused[NT] = {};
+            wgrad_mma_tile<true, NT>(S.H1, S.T2b, 1.f, warp, lane, gW1, gB1f);
+            wgrad_mma_tile<false, NT>(S.R1, S.T2a, ac, warp, lane, gW1, unused);
         }
         mbar_wait(&S.bar, phase);
         phase ^= 1;
         tc_fence_after();
-        float dh1[32], ch1[32];
-        tmem_ld32(tmem_row + C_DH1 + c0, dh1);
-        tmem_ld32(tmem_row + C_CH1 + c0, ch1);
+        float dh1[CW], ch1[CW];
+        tmem_ldw(tmem_row + C_DH1 + c0, dh1);
+        tmem_ldw(tmem_row + C_CH1 + c0, ch1);
         tc_fence_before();
         __syncthreads();       // all CUDA-core reads of H1 / R1 are done before H1 is overwritten
         // ---- C1 = CdH1 g1 + ac dH1 (-2 H1 R1) -> H1 in place
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
+        for (int c4 = 0; c4 < CW / 4; ++c4) {
             const int off = core_off(r, c0 + 4 * c4, SCA);
             float4* p = reinterpret_cast<float4*>(S.H1 + off);
             const float4 h = *p;

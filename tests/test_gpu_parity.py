@@ -821,8 +821,9 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
     theta_t = (policy.theta.view(1, -1) + 0.05 * torch.randn(M, P, generator=torch.Generator().manual_seed(3)).cuda()).contiguous()
     res = {}
     try:
-        for tc in (0, 1):
-            _lib.set_option('tensor_cores', tc)
+        for tc in (0, 1, 2):          # 0: CUDA cores; 1 / 2: tcgen05 path with 256 / 512 threads per CTA
+            _lib.set_option('tensor_cores', 1 if tc else 0)
+            _lib.set_option('tc_threads', {0: 0, 1: 256, 2: 512}[tc])
             out = []
             for params, stride in ((policy.theta, 0), (theta_t, P)):
                 for obj in (0, 1, 2):
@@ -835,11 +836,13 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
             res[tc] = out
     finally:
         _lib.set_option('tensor_cores', 1)
-    for a, b in zip(res[0], res[1]):
-        assert rel_err(b[0], a[0]) < 2e-5, rel_err(b[0], a[0])
-        np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6)
-        np.testing.assert_allclose(b[2][:, :3], a[2][:, :3], rtol=1e-5, atol=1e-6)
-        np.testing.assert_allclose(b[3][:, :3], a[2][:, :3], rtol=1e-5, atol=1e-6)
+        _lib.set_option('tc_threads', 0)
+    for tc in (1, 2):
+        for a, b in zip(res[0], res[tc]):
+            assert rel_err(b[0], a[0]) < 2e-5, rel_err(b[0], a[0])
+            np.testing.assert_allclose(b[1], a[1], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(b[2][:, :3], a[2][:, :3], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(b[3][:, :3], a[2][:, :3], rtol=1e-5, atol=1e-6)
     # and against the fp64 oracle: the inner adapt step with shared theta, likelihood-ratio objective, no KL term
     try:
         _lib.set_option('tensor_cores', 1)
@@ -873,8 +876,9 @@ def test_tensor_core_policy_hvp_matches_simt(Do, Da, N, stride_mode):
         vec = torch.randn(M, P, generator=gen).cuda().contiguous()
         params, stride = (policy.theta, 0) if stride_mode == 'shared' else (theta_t, P)
         try:
-            for tc in (0, 1):
-                _lib.set_option('tensor_cores', tc)
+            for tc in (0, 1, 2):      # 0: CUDA cores; 1 / 2: tcgen05 path with 256 / 512 threads per CTA
+                _lib.set_option('tensor_cores', 1 if tc else 0)
+                _lib.set_option('tc_threads', {0: 0, 1: 256, 2: 512}[tc])
                 out = []
                 for klc, clip in ((0.0, 0), (5e-3, 0), (5e-3, 1)):
                     hv = torch.empty(M, P, device='cuda'); st = torch.zeros(M, 4, device='cuda')
@@ -883,7 +887,9 @@ def test_tensor_core_policy_hvp_matches_simt(Do, Da, N, stride_mode):
                 res[(inner, tc)] = out
         finally:
             _lib.set_option('tensor_cores', 1)
-        for a, b in zip(res[(inner, 0)], res[(inner, 1)]):
-            d = rel_err(b[0] - vec.cpu().numpy(), a[0] - vec.cpu().numpy())      # compare the H v part, not v + ...
-            assert d < 5e-5, d
-            np.testing.assert_allclose(b[1][:, :3], a[1][:, :3], rtol=1e-5, atol=1e-6)
+            _lib.set_option('tc_threads', 0)
+        for tc in (1, 2):
+            for a, b in zip(res[(inner, 0)], res[(inner, tc)]):
+                d = rel_err(b[0] - vec.cpu().numpy(), a[0] - vec.cpu().numpy())      # compare the H v part, not v + ...
+                assert d < 5e-5, d
+                np.testing.assert_allclose(b[1][:, :3], a[1][:, :3], rtol=1e-5, atol=1e-6)

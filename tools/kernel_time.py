@@ -14,6 +14,8 @@ def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else 'point'
     if os.environ.get('PROMP_TC'):
         _lib.set_option('tensor_cores', int(os.environ['PROMP_TC']))
+    if os.environ.get('PROMP_TC_THREADS'):
+        _lib.set_option('tc_threads', int(os.environ['PROMP_TC_THREADS']))
     Do, Da, M, N = (2, 2, 40, 2000) if wl == 'point' else (17, 6, 40, 4000)
     P = _lib.load().promp_num_params(Do, Da, 64)
     dev = torch.device('cuda')
