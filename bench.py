@@ -255,31 +255,50 @@ def run_gpu(args):
                       for n, v in kms.items()}
         peaks, peak_src = measured_peaks()
         N = E * H
-        # dominant kernel: policy_hvp_kernel.  Algorithmic bytes per launch (SURVEY.md section 8d "inner adapt /
-        # outer epoch" rows): obs + act + adv + old_mean per sample, once, + per-task params, direction and output.
+        # dominant kernels: promp_policy_grad (13 launches / iteration) and promp_policy_hvp (5).  Algorithmic bytes per
+        # launch (SURVEY.md section 8d "inner adapt / outer epoch" rows): obs + act + adv + old_mean per sample, once,
+        # + per-task params (+ direction) and output.  Algorithmic FLOPs: the dense MLP chain (fwd + bwd [+ tangents]).
         P = _lib.load().promp_num_params(wl['Do'], wl['Da'], 64)
-        hvp_bytes = M * N * 4 * (wl['Do'] + 2 * wl['Da'] + 1) + M * 4 * (wl['Da'] + 3 * P)
-        fwd_flops = 2 * (wl['Do'] * 64 + 64 * 64 + 64 * wl['Da'])
-        hvp_flops = M * N * (8 * 2 * 64 * 64 + 6 * 2 * wl['Do'] * 64 + 8 * 2 * 64 * wl['Da'])
-        hvp_ms = per_kernel.get('promp_policy_hvp', {}).get('avg_ms', float('nan'))
-        achieved = hvp_bytes / (hvp_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        Do_, Da_ = wl['Do'], wl['Da']
+        alg = {
+            'promp_policy_grad': dict(
+                bytes=M * N * 4 * (Do_ + 2 * Da_ + 1) + M * 4 * (Da_ + 3 * P),
+                flops=M * N * (3 * 2 * 64 * 64 + 2 * 2 * Do_ * 64 + 3 * 2 * 64 * Da_),
+                gemm_flops=M * N * 3 * 2 * 64 * 64, ncu='policy_grad'),
+            'promp_policy_hvp': dict(
+                bytes=M * N * 4 * (Do_ + 2 * Da_ + 1) + M * 4 * (Da_ + 3 * P),
+                flops=M * N * (8 * 2 * 64 * 64 + 6 * 2 * Do_ * 64 + 8 * 2 * 64 * Da_),
+                gemm_flops=M * N * 8 * 2 * 64 * 64, ncu='policy_hvp'),
+        }
         try:    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/profile_all.sh)
             km = json.load(open(os.path.join(ROOT, 'profiles', 'r01_kernel_metrics.json')))[args.workload]
-            kk = [k for k in km if k.startswith('policy_hvp_kernel')][0]
-            traffic = km[kk].get('dram_read_bytes', 0.0) + km[kk].get('dram_write_bytes', 0.0)
-            traffic_src = 'profiles/r01_kernel_metrics.json (cold-cache ncu replay; in the live loop the inputs are L2 hits)'
         except Exception:
-            pass
-        roof = dict(kernel='policy_hvp_kernel', bound='hbm', achieved=achieved, peak=peaks['hbm_gbs'], unit='GB/s',
-                    frac=achieved / peaks['hbm_gbs'], traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=hvp_bytes, avg_launch_ms=hvp_ms,
-                    fp32_tflops=hvp_flops / (hvp_ms * 1e-3) / 1e12,
-                    fp32_peak_tflops=148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12,
-                    note='kernel is fp32-FMA bound (AI ~ %d FLOP/B): the HBM fraction is small by construction; '
-                         'share of the iteration = %.0f%%' % (hvp_flops / hvp_bytes,
-                                                              100 * per_kernel.get('promp_policy_hvp', {}).get('total_ms_per_iter', 0)
-                                                              / max(sum(k['total_ms_per_iter'] for k in per_kernel.values()), 1e-9)))
+            km = {}
+        iter_ms = max(sum(k['total_ms_per_iter'] for k in per_kernel.values()), 1e-9)
+        fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+
+        def kernel_roof(name):
+            a_, pk = alg[name], per_kernel.get(name, {})
+            ms = pk.get('avg_ms', float('nan'))
+            ach = a_['bytes'] / (ms * 1e-3) / 1e9
+            kk = [k for k in km if k.startswith(a_['ncu'])]
+            traffic = (km[kk[0]].get('dram_read_bytes', 0.0) + km[kk[0]].get('dram_write_bytes', 0.0)) if kk else None
+            return dict(kernel=(kk[0] if kk else a_['ncu'] + '_kernel'), bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
+                        frac=ach / peaks['hbm_gbs'], traffic=traffic,
+                        traffic_source='profiles/r01_kernel_metrics.json (cold-cache ncu replay; in the live loop the inputs are L2 hits)' if kk else None,
+                        peak_source=peak_src, algorithmic_bytes_per_launch=a_['bytes'], avg_launch_ms=ms,
+                        launches_per_iter=pk.get('launches_per_iter'), share_of_iteration=pk.get('total_ms_per_iter', 0.0) / iter_ms,
+                        algorithmic_tflops=a_['flops'] / (ms * 1e-3) / 1e12, fp32_simt_peak_tflops=fp32_peak,
+                        tensor={'executed_tf32_tflops': 3 * a_['gemm_flops'] / (ms * 1e-3) / 1e12,
+                                'peak_bf16_tflops': peaks.get('bf16_tflops'),
+                                'note': 'layer GEMMs run as 3xTF32 tcgen05.mma (weight gradients: mma.sync); 3 MMAs per algorithmic GEMM'})
+        dom = max(alg, key=lambda n: per_kernel.get(n, {}).get('total_ms_per_iter', 0.0))
+        roof = kernel_roof(dom)
+        roof['note'] = ('arithmetic intensity ~ %d FLOP/B with everything L2/smem resident: neither HBM- nor tensor-peak-bound; the kernel is '
+                        'issue/latency-bound at 1 CTA/SM (see DESIGN.md section 3 phase table); the HBM fraction is small by construction'
+                        % (alg[dom]['flops'] / alg[dom]['bytes']))
+        other = [n for n in alg if n != dom][0]
+        roof['other_policy_kernel'] = kernel_roof(other)
         # HBM-bound scan kernel for reference: promp_process_samples reads obs twice + rew twice, writes ret + adv
         proc_bytes = M * N * (4 * 2 * wl['Do'] + 8 + 8)
         proc_ms = per_kernel.get('promp_process_samples', {}).get('avg_ms', float('nan'))
