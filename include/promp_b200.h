@@ -139,6 +139,23 @@ int promp_process_samples(int M, int E, int H, int obs_dim, const float* obs, co
                           float* returns, float* adv, double* coeffs, double* stats,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Variable-length paths (early termination: samplers/meta_sampler.py:116-125 appends a path whenever an env reports
+ * `done`, envs/point_envs/point_env_2d.py:49-53): the same computation over a per-task PATH TABLE instead of E x H.
+ * Task m owns n_paths[m] <= max_paths paths stored back to back; path e covers samples
+ * [path_off[m][e], path_off[m][e+1]) of the task's row (path_off [M, max_paths+1] int32 prefix sums, path_off[m][0] = 0);
+ * the baseline's time feature restarts at 0 in every path (baselines/linear_baseline.py:101-106).
+ *   obs [M,max_samples,Do]  rew [M,max_samples]   (rows past path_off[m][n_paths[m]] are padding)
+ *   returns / adv [M,max_samples]: padding rows of adv are written as 0
+ *   stats as above (per-path sums run over n_paths[m] paths)
+ */
+int64_t promp_process_workspace_bytes_ragged(int M, int max_paths, int max_samples, int obs_dim);
+int promp_process_samples_ragged(int M, int max_paths, int max_samples, int obs_dim, const float* obs, const float* rew,
+                                 const int32_t* path_off, const int32_t* n_paths, double discount, double gae_lambda,
+                                 double reg_coeff, int baseline_kind, int normalize_adv, int positive_adv,
+                                 float* returns, float* adv, double* coeffs, double* stats,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
+
 /* adj_avg_rewards = (r - mean_all)/(std_all + 1e-8) (samplers/meta_sample_processor.py:40-44);
  * mean/std are passed by the caller (reduced over all tasks / ranks from `stats`). */
 int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, double std, float* out, void* stream);
@@ -194,6 +211,29 @@ int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int N,
                      const float* vec, float* out, float* stats,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Variable-length paths: the same two kernels with a per-task valid-sample count.  Task m's rows [n_valid[m], N) of
+ * obs / act / adv / old_mean are padding and contribute nothing; every per-task mean (objective, KL, gradients) is
+ * taken over n_valid[m] samples, as tf.reduce_mean over the task's concatenated paths does in the reference
+ * (meta_algos/pro_mp.py:59-65, 135-147; samplers/meta_sample_processor.py:36-47).  n_valid [M] int32, device memory.
+ */
+int promp_policy_grad_ragged(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid,
+                             const float* params, int64_t param_stride,
+                             const float* obs, const float* act, const float* adv,
+                             const float* old_mean, const float* old_log_std, int ls_per_sample,
+                             int obj_kind, float obj_scale, float clip_eps, float kl_coeff,
+                             int clip_log_std, float min_log_std,
+                             float* grad, float* out_params, float sgd_lr, float* stats,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+int promp_policy_hvp_ragged(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid,
+                            const float* params, int64_t param_stride,
+                            const float* obs, const float* act, const float* adv,
+                            const float* old_mean, const float* old_log_std, int ls_per_sample,
+                            int obj_kind, float inner_lr, float kl_coeff,
+                            int clip_log_std, float min_log_std,
+                            const float* vec, float* out, float* stats,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* out[P] = scale * sum_m in[m,P]   (mean over tasks of the meta objective, pro_mp.py:151-155). */
 int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, void* stream);
 
@@ -224,8 +264,10 @@ int promp_ipc_close_handle(void* dev_ptr);
 int promp_allreduce_p2p(int world, int rank, int n, int capacity_floats, const float* in, float* out, float scale,
                         void* const* peers_dev, uint32_t* epoch_dev, uint32_t* error_flag_dev, void* stream);
 
-/* Runtime options.  "tensor_cores" = 1 (default) runs the hidden-64 promp_policy_grad on the tcgen05 / TMEM path (3xTF32
- * layer GEMMs, same results to fp32 round-off); 0 = CUDA-core fp32 path. */
+/* Runtime options.
+ *   "tensor_cores" = 1 (default): hidden-64 promp_policy_grad / promp_policy_hvp run their layer GEMMs on tcgen05 with TMEM
+ *                    accumulators (3xTF32 split; weight gradients on mma.sync), same results to fp32 round-off; 0 = CUDA cores.
+ *   "tc_threads"   = 0 (default: 512 threads per CTA for obs_dim <= 4, else 256), or force 256 / 512. */
 int promp_set_option(const char* name, int value);
 
 /* Policy forward only (MetaGaussianMLPPolicy.get_actions without sampling / distribution_info_sym):

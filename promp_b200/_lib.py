@@ -32,12 +32,19 @@ _SIGNATURES = {
     'promp_process_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int]),
     'promp_process_samples': (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_double, c_double, c_double, c_int, c_int,
                                       c_int, _P, _P, _P, _P, _P, c_int64, _P]),
+    'promp_process_workspace_bytes_ragged': (c_int64, [c_int, c_int, c_int, c_int]),
+    'promp_process_samples_ragged': (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_double, c_double, c_double, c_int,
+                                             c_int, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     'promp_adj_avg_rewards': (c_int, [c_int64, _P, c_double, c_double, _P, _P]),
     'promp_policy_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     'promp_policy_grad': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                   c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, c_int64, _P]),
     'promp_policy_hvp': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                  c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
+    'promp_policy_grad_ragged': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
+                                         c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, c_int64, _P]),
+    'promp_policy_hvp_ragged': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
+                                        c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
     'promp_reduce_tasks': (c_int, [c_int, c_int, _P, c_float, _P, _P]),
     'promp_adam_tf1': (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
     'promp_policy_forward': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P]),

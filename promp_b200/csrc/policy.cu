@@ -44,6 +44,7 @@ struct PolicyArgs {
     int* counters;       // [M], zero on entry, left zero on exit
     int q;               // tiles per CTA
     int kmax;            // max task segments per CTA
+    const int32_t* n_valid;   // [M] valid samples per task (rows >= n_valid[m] are padding) or nullptr = N everywhere
 };
 
 // Tile-range bookkeeping shared by both kernels.
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A
     const int cj = tid % HID, cp = tid / HID;        // column role
     const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
-    const float invN = 1.0f / (float)N;
+    float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
+    int Nm = N;
     const bool want_grad = A.grad != nullptr;
     const float* th = nullptr;
     HeadIn<DA> hin;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
+        if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
         th = A.params + (int64_t)m * A.param_stride;
         if (!first && A.param_stride == 0) return;       // shared theta: weights already resident
         __syncthreads();
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A
             zero_acc();
             cur_m = m;
         }
-        const int n0 = tile * TB, nb = min(TB, N - n0);
+        const int n0 = tile * TB, nb = max(0, min(TB, Nm - n0));
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
         for (int i = tid; i < TB * DOP; i += PT_THREADS) {
@@ -488,7 +491,8 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     const int cj = tid % HID, cp = tid / HID;
     const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
-    const float invN = 1.0f / (float)N;
+    float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
+    int Nm = N;
     const float ac = -A.inner_lr;                 // coefficient of H vec in `out`
     const float* th = nullptr;
     HeadIn<DA> hin;
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
+        if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
         th = A.params + (int64_t)m * A.param_stride;
         const float* vg = A.vec + (int64_t)m * L::P;
         const bool reload_p = first || A.param_stride != 0;      // shared theta stays resident across tasks
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
             zero_acc();
             cur_m = m;
         }
-        const int n0 = tile * TB, nb = min(TB, N - n0);
+        const int n0 = tile * TB, nb = max(0, min(TB, Nm - n0));
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
         for (int i = tid; i < TB * DOP; i += PT_THREADS) {
@@ -1065,13 +1070,13 @@ static int check_policy_args(const char* who, int M, int N, const void* params, 
     return PROMP_OK;
 }
 
-extern "C" int promp_policy_grad(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
-                                 int64_t param_stride, const float* obs, const float* act, const float* adv,
-                                 const float* old_mean, const float* old_log_std, int ls_per_sample, int obj_kind,
-                                 float obj_scale, float clip_eps, float kl_coeff, int clip_log_std, float min_log_std,
-                                 float* grad, float* out_params, float sgd_lr, float* stats, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
-    int st = check_policy_args("promp_policy_grad", M, N, params, obs, act, adv, old_mean, old_log_std, workspace);
+extern "C" int promp_policy_grad_ragged(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid,
+                                        const float* params, int64_t param_stride, const float* obs, const float* act,
+                                        const float* adv, const float* old_mean, const float* old_log_std, int ls_per_sample,
+                                        int obj_kind, float obj_scale, float clip_eps, float kl_coeff, int clip_log_std,
+                                        float min_log_std, float* grad, float* out_params, float sgd_lr, float* stats,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_policy_args(n_valid ? "promp_policy_grad_ragged" : "promp_policy_grad", M, N, params, obs, act, adv, old_mean, old_log_std, workspace);
     if (st != PROMP_OK) return st;
     PROMP_REQUIRE(obj_kind >= 0 && obj_kind <= 3, "promp_policy_grad: bad obj_kind %d", obj_kind);
     PROMP_REQUIRE(!(out_params && !grad), "promp_policy_grad: out_params needs grad");
@@ -1080,17 +1085,29 @@ extern "C" int promp_policy_grad(int obs_dim, int act_dim, int hidden, int M, in
     A.obs = obs; A.act = act; A.adv = adv; A.old_mean = old_mean; A.old_ls = old_log_std;
     A.ls_per_sample = ls_per_sample; A.obj_kind = obj_kind; A.obj_scale = obj_scale; A.clip_eps = clip_eps;
     A.kl_coeff = kl_coeff; A.clip_log_std = clip_log_std; A.min_log_std = min_log_std;
-    A.grad = grad; A.out_params = out_params; A.sgd_lr = sgd_lr; A.stats = stats;
+    A.grad = grad; A.out_params = out_params; A.sgd_lr = sgd_lr; A.stats = stats; A.n_valid = n_valid;
     cudaStream_t s = (cudaStream_t)stream;
     PROMP_DISPATCH_DIMS(launch_grad_any, A, workspace, workspace_bytes, s)
 }
 
-extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
-                                int64_t param_stride, const float* obs, const float* act, const float* adv,
-                                const float* old_mean, const float* old_log_std, int ls_per_sample, int obj_kind,
-                                float inner_lr, float kl_coeff, int clip_log_std, float min_log_std, const float* vec,
-                                float* out, float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
-    int st = check_policy_args("promp_policy_hvp", M, N, params, obs, act, adv, old_mean, old_log_std, workspace);
+extern "C" int promp_policy_grad(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
+                                 int64_t param_stride, const float* obs, const float* act, const float* adv,
+                                 const float* old_mean, const float* old_log_std, int ls_per_sample, int obj_kind,
+                                 float obj_scale, float clip_eps, float kl_coeff, int clip_log_std, float min_log_std,
+                                 float* grad, float* out_params, float sgd_lr, float* stats, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+    return promp_policy_grad_ragged(obs_dim, act_dim, hidden, M, N, nullptr, params, param_stride, obs, act, adv, old_mean,
+                                    old_log_std, ls_per_sample, obj_kind, obj_scale, clip_eps, kl_coeff, clip_log_std, min_log_std,
+                                    grad, out_params, sgd_lr, stats, workspace, workspace_bytes, stream);
+}
+
+extern "C" int promp_policy_hvp_ragged(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid,
+                                       const float* params, int64_t param_stride, const float* obs, const float* act,
+                                       const float* adv, const float* old_mean, const float* old_log_std, int ls_per_sample,
+                                       int obj_kind, float inner_lr, float kl_coeff, int clip_log_std, float min_log_std,
+                                       const float* vec, float* out, float* stats, void* workspace, int64_t workspace_bytes,
+                                       void* stream) {
+    int st = check_policy_args(n_valid ? "promp_policy_hvp_ragged" : "promp_policy_hvp", M, N, params, obs, act, adv, old_mean, old_log_std, workspace);
     if (st != PROMP_OK) return st;
     PROMP_REQUIRE(obj_kind == PROMP_OBJ_RATIO || obj_kind == PROMP_OBJ_LOGLIK,
                   "promp_policy_hvp: inner objective must be RATIO or LOGLIK (got %d)", obj_kind);
@@ -1100,9 +1117,19 @@ extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int
     A.obs = obs; A.act = act; A.adv = adv; A.old_mean = old_mean; A.old_ls = old_log_std;
     A.ls_per_sample = ls_per_sample; A.obj_kind = obj_kind; A.obj_scale = 1.f; A.clip_eps = 0.f;
     A.kl_coeff = kl_coeff; A.clip_log_std = clip_log_std; A.min_log_std = min_log_std;
-    A.vec = vec; A.out = out; A.inner_lr = inner_lr; A.stats = stats;
+    A.vec = vec; A.out = out; A.inner_lr = inner_lr; A.stats = stats; A.n_valid = n_valid;
     cudaStream_t s = (cudaStream_t)stream;
     PROMP_DISPATCH_DIMS(launch_hvp, A, workspace, workspace_bytes, s)
+}
+
+extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int N, const float* params,
+                                int64_t param_stride, const float* obs, const float* act, const float* adv,
+                                const float* old_mean, const float* old_log_std, int ls_per_sample, int obj_kind,
+                                float inner_lr, float kl_coeff, int clip_log_std, float min_log_std, const float* vec,
+                                float* out, float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
+    return promp_policy_hvp_ragged(obs_dim, act_dim, hidden, M, N, nullptr, params, param_stride, obs, act, adv, old_mean,
+                                   old_log_std, ls_per_sample, obj_kind, inner_lr, kl_coeff, clip_log_std, min_log_std, vec, out,
+                                   stats, workspace, workspace_bytes, stream);
 }
 
 extern "C" int promp_set_option(const char* name, int value) {

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
     const int cj = tid & (HID - 1), cp = tid / HID;        // column role
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
-    const float invN = 1.0f / (float)N;
+    float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
+    int Nm = N;
     const bool want_grad = A.grad != nullptr;
     const float* th = nullptr;
     HeadIn<DA> hin;
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
+        if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
         th = A.params + (int64_t)m * A.param_stride;
         if (!first && A.param_stride == 0) return;
         __syncthreads();
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
             cur_m = m;
             PCLK(12);
         }
-        const int n0 = tile * TBT, nb = min(TBT, N - n0);
+        const int n0 = tile * TBT, nb = max(0, min(TBT, Nm - n0));
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
         for (int i = tid; i < TBT * DOP; i += TCT) {
@@ -718,7 +720,8 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
     const int cj = tid & (HID - 1), cp = tid / HID;
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
-    const float invN = 1.0f / (float)N;
+    float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
+    int Nm = N;
     const float ac = -A.inner_lr;
     const float* th = nullptr;
     const float* vg = nullptr;
@@ -754,6 +757,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
         s_obj = s_kl = s_ratio = 0.f;
     };
     auto load_task = [&](int m, bool first) {
+        if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
         th = A.params + (int64_t)m * A.param_stride;
         vg = A.vec + (int64_t)m * L::P;
         __syncthreads();
@@ -883,7 +887,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
             zero_acc();
             cur_m = m;
         }
-        const int n0 = tile * TBT, nb = min(TBT, N - n0);
+        const int n0 = tile * TBT, nb = max(0, min(TBT, Nm - n0));
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
         auto load_x = [&]() {

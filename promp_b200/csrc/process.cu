@@ -64,7 +64,17 @@ struct ProcArgs {
     double* gram_p;  // [M][C][PS_MAXPAIR] partial Gram matrices
     double* stat_p;  // [M][C][8] partial path statistics
     int C, EPC;      // trajectory chunks per task, trajectories per chunk
+    // variable-length paths (early termination, meta_sampler.py:116-125); path_off == nullptr: E paths of H steps each
+    const int32_t* path_off;   // [M][Pmax+1] sample offset of every path inside its task (prefix sums), E := Pmax
+    const int32_t* n_paths;    // [M] number of paths of each task (<= Pmax)
+    int NS;                    // sample stride between tasks (E*H, or Nmax for variable-length paths)
+    int32_t* tpos;             // [M][NS] workspace: time index of every sample inside its path (variable-length only)
 };
+// path table helpers: number of paths of task m, offset of path e
+__device__ __forceinline__ int n_paths_of(const ProcArgs& A, int m) { return A.path_off ? __ldg(A.n_paths + m) : A.E; }
+__device__ __forceinline__ int path_begin(const ProcArgs& A, int m, int e) {
+    return A.path_off ? __ldg(A.path_off + (int64_t)m * (A.E + 1) + e) : e * A.H;
+}
 
 // LinearFeatureBaseline._features (baselines/linear_baseline.py:101-106) for one sample, float64:
 //   [clip(o,-10,10), clip(o)^2, t, t^2, t^3, 1] with t = step/100
@@ -95,13 +105,14 @@ __device__ __forceinline__ void pair_tables(int NC, int n_pairs, unsigned char* 
 // ~2 CTAs on every SM (a task-per-CTA launch uses only M of the 148 SMs and is fp64-FMA bound for F = 38).
 __global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
     const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x;
-    const int E = A.E, H = A.H, Do = A.Do, N = E * H;
+    const int E = n_paths_of(A, m), H = A.H, Do = A.Do, NS = A.NS;
     const int F = 2 * Do + 4, NC = F + 1;
     const int n_pairs = NC * (NC + 1) / 2;
-    const int e_lo = c * A.EPC, e_hi = min(E, e_lo + A.EPC);
-    const float* obs = A.obs + (int64_t)m * N * Do;
-    const float* rew = A.rew + (int64_t)m * N;
-    double* ret64 = A.ws + (int64_t)m * 2 * N;
+    const int e_lo = min(E, c * A.EPC), e_hi = min(E, e_lo + A.EPC);
+    const float* obs = A.obs + (int64_t)m * NS * Do;
+    const float* rew = A.rew + (int64_t)m * NS;
+    double* ret64 = A.ws + (int64_t)m * 2 * NS;
+    int32_t* tpos = A.tpos ? A.tpos + (int64_t)m * NS : nullptr;
 
     __shared__ double red[PS_THREADS / 32];
     __shared__ double tile[PS_TS * PS_MAXCOL];
@@ -112,13 +123,15 @@ __global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
     double sR0 = 0, sG = 0, sG2 = 0, mxG = -1e300, mnG = 1e300, sr = 0, sr2 = 0;
     for (int e = e_lo + tid; e < e_hi; e += PS_THREADS) {
         double R = 0.0, G = 0.0;
-        for (int t = H - 1; t >= 0; --t) {
-            const double r = (double)rew[e * H + t];
+        const int o = path_begin(A, m, e), L = path_begin(A, m, e + 1) - o;
+        for (int t = L - 1; t >= 0; --t) {
+            const double r = (double)rew[o + t];
             R = r + A.discount * R;
             G += r;
             sr += r;
             sr2 += r * r;
-            ret64[e * H + t] = R;
+            ret64[o + t] = R;
+            if (tpos) tpos[o + t] = t;
         }
         sR0 += R;
         sG += G;
@@ -134,8 +147,8 @@ __global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
         sp[0] = sR0; sp[1] = sG; sp[2] = sG2; sp[3] = mxG; sp[4] = mnG; sp[5] = sr; sp[6] = sr2; sp[7] = 0.0;
     }
     __syncthreads();   // ret64 of this CTA's trajectories visible to the whole CTA
-    const int n_lo = e_lo * H, n_hi = e_hi * H;
-    for (int n = n_lo + tid; n < n_hi; n += PS_THREADS) A.returns[(int64_t)m * N + n] = (float)ret64[n];
+    const int n_lo = path_begin(A, m, e_lo), n_hi = path_begin(A, m, e_hi);
+    for (int n = n_lo + tid; n < n_hi; n += PS_THREADS) A.returns[(int64_t)m * NS + n] = (float)ret64[n];
     if (A.baseline_kind != PROMP_BASELINE_LINEAR_FEATURE) return;
 
     // ---- partial Gram matrix over this CTA's samples (baselines/linear_baseline.py:66-73)
@@ -148,7 +161,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
         __syncthreads();
         for (int s = tid; s < ns; s += PS_THREADS) {     // one thread builds one sample's feature row
             const int n = n0 + s;
-            features(obs + (int64_t)n * Do, Do, n % H, &tile[s * NC]);
+            features(obs + (int64_t)n * Do, Do, tpos ? tpos[n] : n % H, &tile[s * NC]);
             tile[s * NC + F] = ret64[n];
         }
         __syncthreads();
@@ -183,12 +196,14 @@ __global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
 // ridge / NaN-retry rule, predict, GAE scan, per-task moments, advantages.
 __global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) {
     const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int E = A.E, H = A.H, Do = A.Do, N = E * H;
+    const int E = n_paths_of(A, m), H = A.H, Do = A.Do, NS = A.NS;
+    const int N = path_begin(A, m, E);                 // valid samples of this task
     const int F = 2 * Do + 4, NC = F + 1;
     const int n_pairs = NC * (NC + 1) / 2;
-    const float* obs = A.obs + (int64_t)m * N * Do;
-    const float* rew = A.rew + (int64_t)m * N;
-    double* adv64 = A.ws + (int64_t)m * 2 * N + N;
+    const float* obs = A.obs + (int64_t)m * NS * Do;
+    const float* rew = A.rew + (int64_t)m * NS;
+    double* adv64 = A.ws + (int64_t)m * 2 * NS + NS;
+    const int32_t* tpos = A.tpos ? A.tpos + (int64_t)m * NS : nullptr;
 
     __shared__ double red[PS_THREADS / 32];
     __shared__ double gram[PS_MAXPAIR];                 // packed upper triangle over NC columns
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) 
         // ---- predict b_n = phi_n . w (baselines/linear_baseline.py:17-33)
         for (int n = tid; n < N; n += PS_THREADS) {
             double f[PS_MAXCOL];
-            features(obs + (int64_t)n * Do, Do, n % H, f);
+            features(obs + (int64_t)n * Do, Do, tpos ? tpos[n] : n % H, f);
             double b = 0.0;
             for (int i = 0; i < F; ++i) b = fma(f[i], wv[i], b);
             adv64[n] = b;
@@ -294,11 +309,12 @@ __global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) 
     double s1 = 0.0;
     for (int e = tid; e < E; e += PS_THREADS) {
         double b_next = 0.0, a_next = 0.0;
-        for (int t = H - 1; t >= 0; --t) {
-            const double b = adv64[e * H + t];
-            const double delta = (double)rew[e * H + t] + A.discount * b_next - b;
+        const int o = path_begin(A, m, e), L = path_begin(A, m, e + 1) - o;
+        for (int t = L - 1; t >= 0; --t) {
+            const double b = adv64[o + t];
+            const double delta = (double)rew[o + t] + A.discount * b_next - b;
             const double a = delta + gl * a_next;
-            adv64[e * H + t] = a;
+            adv64[o + t] = a;
             s1 += a;
             a_next = a;
             b_next = b;
@@ -327,8 +343,9 @@ __global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) 
     for (int n = tid; n < N; n += PS_THREADS) {
         double a = (adv64[n] - mean) * inv;
         if (A.positive_adv) a = (a - mn) + 1e-8;
-        A.adv[(int64_t)m * N + n] = (float)a;
+        A.adv[(int64_t)m * NS + n] = (float)a;
     }
+    for (int n = N + tid; n < NS; n += PS_THREADS) A.adv[(int64_t)m * NS + n] = 0.f;      // padding rows (variable-length paths)
     if (A.stats && tid == 0) A.stats[(int64_t)m * 8 + 7] = reg_used;
 }
 
@@ -380,7 +397,7 @@ extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const flo
     double* gram_p = ws + (int64_t)M * 2 * E * H;
     double* stat_p = gram_p + (int64_t)M * C * PS_MAXPAIR;
     ProcArgs A{M, E, H, obs_dim, obs, rew, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv,
-               returns, adv, coeffs, stats, ws, gram_p, stat_p, C, EPC};
+               returns, adv, coeffs, stats, ws, gram_p, stat_p, C, EPC, nullptr, nullptr, E * H, nullptr};
     process_gram_kernel<<<dim3(C, M), PS_THREADS, 0, (cudaStream_t)stream>>>(A);
     PROMP_LAUNCH_CHECK("process_gram_kernel");
     process_finish_kernel<<<M, PS_THREADS, 0, (cudaStream_t)stream>>>(A);
@@ -394,5 +411,48 @@ extern "C" int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, d
     adj_avg_rewards_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(n, rew, mean,
                                                                                          1.0 / (std + 1e-8), out);
     PROMP_LAUNCH_CHECK("adj_avg_rewards_kernel");
+    return PROMP_OK;
+}
+
+// ---- variable-length paths: same kernels driven by a per-task path table ------------------------------------------
+extern "C" int64_t promp_process_workspace_bytes_ragged(int M, int max_paths, int max_samples, int obs_dim) {
+    (void)obs_dim;
+    int C, EPC;
+    proc_chunks(M, max_paths, &C, &EPC);
+    return ((int64_t)M * 2 * max_samples + (int64_t)M * C * (PS_MAXPAIR + 8)) * (int64_t)sizeof(double) +
+           (int64_t)M * max_samples * (int64_t)sizeof(int32_t);
+}
+
+extern "C" int promp_process_samples_ragged(int M, int max_paths, int max_samples, int obs_dim, const float* obs,
+                                            const float* rew, const int32_t* path_off, const int32_t* n_paths, double discount,
+                                            double gae_lambda, double reg_coeff, int baseline_kind, int normalize_adv,
+                                            int positive_adv, float* returns, float* adv, double* coeffs, double* stats,
+                                            void* workspace, int64_t workspace_bytes, void* stream) {
+    PROMP_REQUIRE(M > 0 && max_paths > 0 && max_samples > 0 && obs_dim > 0, "promp_process_samples_ragged: dimensions must be positive");
+    PROMP_REQUIRE(M <= 65535, "promp_process_samples_ragged: M=%d exceeds the grid.y limit", M);
+    PROMP_REQUIRE(2 * obs_dim + 5 <= PS_MAXCOL, "promp_process_samples_ragged: obs_dim %d too large (max %d)", obs_dim,
+                  (PS_MAXCOL - 5) / 2);
+    PROMP_REQUIRE(obs && rew && returns && adv && workspace && path_off && n_paths, "promp_process_samples_ragged: null pointer argument");
+    PROMP_REQUIRE(baseline_kind == PROMP_BASELINE_ZERO || baseline_kind == PROMP_BASELINE_LINEAR_FEATURE,
+                  "promp_process_samples_ragged: unknown baseline kind %d", baseline_kind);
+    PROMP_REQUIRE(discount >= 0.0 && discount <= 1.0 && gae_lambda >= 0.0 && gae_lambda <= 1.0,
+                  "promp_process_samples_ragged: discount and gae_lambda must be in [0,1]");
+    const int64_t need = promp_process_workspace_bytes_ragged(M, max_paths, max_samples, obs_dim);
+    if (workspace_bytes < need) {
+        set_error("promp_process_samples_ragged: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need);
+        return PROMP_ERR_WORKSPACE;
+    }
+    int C, EPC;
+    proc_chunks(M, max_paths, &C, &EPC);
+    double* ws = (double*)workspace;
+    double* gram_p = ws + (int64_t)M * 2 * max_samples;
+    double* stat_p = gram_p + (int64_t)M * C * PS_MAXPAIR;
+    int32_t* tpos = (int32_t*)(stat_p + (int64_t)M * C * 8);
+    ProcArgs A{M, max_paths, 0, obs_dim, obs, rew, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv,
+               returns, adv, coeffs, stats, ws, gram_p, stat_p, C, EPC, path_off, n_paths, max_samples, tpos};
+    process_gram_kernel<<<dim3(C, M), PS_THREADS, 0, (cudaStream_t)stream>>>(A);
+    PROMP_LAUNCH_CHECK("process_gram_kernel");
+    process_finish_kernel<<<M, PS_THREADS, 0, (cudaStream_t)stream>>>(A);
+    PROMP_LAUNCH_CHECK("process_finish_kernel");
     return PROMP_OK;
 }

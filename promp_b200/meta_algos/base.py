@@ -14,7 +14,7 @@ is the transpose of d theta_{s+1} / d theta_s = I - alpha H_s).
 import numpy as np
 
 from promp_b200 import _lib
-from promp_b200.samplers.device_data import SamplesData, PhaseData
+from promp_b200.samplers.device_data import SamplesData, PhaseData, RaggedSamplesData
 from promp_b200.utils.dist import allreduce_sum_, world_size  # noqa: F401
 
 
@@ -56,7 +56,8 @@ class MAMLAlgo(object):
         import torch
         assert len(samples) == self.meta_batch_size
         first = samples[0]
-        if isinstance(first, SamplesData) and all(isinstance(s, SamplesData) and s.phase is first.phase for s in samples):
+        if isinstance(first, (SamplesData, RaggedSamplesData)) and \
+                all(isinstance(s, (SamplesData, RaggedSamplesData)) and s.phase is first.phase for s in samples):
             return first.phase
         # reference-style numpy dicts: upload (ref _extract_input_dict, base.py:245-280)
         p = self.policy
@@ -80,7 +81,9 @@ class MAMLAlgo(object):
         ws = self._workspace(phase.N)
         full = getattr(phase, 'log_std_full', None)
         old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
-        _lib.call('promp_policy_grad', p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N,
+        n_valid = getattr(phase, 'n_valid', None)           # variable-length paths: per-task sample counts
+        entry, extra = ('promp_policy_grad', ()) if n_valid is None else ('promp_policy_grad_ragged', (_lib.ptr(n_valid),))
+        _lib.call(entry, p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N, *extra,
                   _lib.ptr(params), stride, _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.adv),
                   _lib.ptr(phase.mean), _lib.ptr(old_ls), per_sample, obj_kind, float(obj_scale), float(clip_eps),
                   float(kl_coeff), int(clip_log_std), float(p.min_log_std), _lib.ptr(grad), _lib.ptr(out_params),
@@ -91,7 +94,9 @@ class MAMLAlgo(object):
         ws = self._workspace(phase.N)
         full = getattr(phase, 'log_std_full', None)
         old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
-        _lib.call('promp_policy_hvp', p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N,
+        n_valid = getattr(phase, 'n_valid', None)
+        entry, extra = ('promp_policy_hvp', ()) if n_valid is None else ('promp_policy_hvp_ragged', (_lib.ptr(n_valid),))
+        _lib.call(entry, p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N, *extra,
                   _lib.ptr(params), stride, _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.adv),
                   _lib.ptr(phase.mean), _lib.ptr(old_ls), per_sample, self.inner_obj_kind, float(self.inner_lr),
                   float(kl_coeff), int(clip_log_std), float(p.min_log_std), _lib.ptr(vec), _lib.ptr(out),

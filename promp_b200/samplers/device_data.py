@@ -50,6 +50,83 @@ class PhaseData(object):
         return 4 * (self.obs_dim + 2 * self.act_dim + 1) + 1 + 8 * len(self.info_keys)
 
 
+class RaggedPhaseData(PhaseData):
+    """Variable-length paths (early termination, meta_sampler.py:116-125): task m owns n_paths[m] paths stored back to
+    back in its row of the [M, Nmax] tensors; rows past n_valid[m] are padding.  `N` (= Nmax) is the row stride the
+    policy kernels see; per-task means run over n_valid[m] (promp_policy_*_ragged)."""
+
+    def __init__(self, path_lens, obs_dim, act_dim, device):
+        import torch
+        self.path_lens = [list(map(int, l)) for l in path_lens]
+        M = len(self.path_lens)
+        n_valid = [sum(l) for l in self.path_lens]
+        n_paths = [len(l) for l in self.path_lens]
+        Pmax = max(n_paths)
+        Nmax = (max(n_valid) + 3) // 4 * 4
+        PhaseData.__init__(self, M, 1, Nmax, obs_dim, act_dim, device)
+        self.E, self.H = Pmax, None
+        for t in (self.obs, self.act, self.mean, self.rew):
+            t.zero_()
+        self.done.zero_()
+        off = np.zeros((M, Pmax + 1), dtype=np.int32)
+        for m, lens in enumerate(self.path_lens):
+            off[m, 1:len(lens) + 1] = np.cumsum(lens)
+            off[m, len(lens) + 1:] = off[m, len(lens)]
+        self.path_off_host = off
+        self.n_valid_host = np.asarray(n_valid, dtype=np.int32)
+        self.n_paths_host = np.asarray(n_paths, dtype=np.int32)
+        self.path_off = torch.from_numpy(off).to(device)
+        self.n_valid = torch.from_numpy(self.n_valid_host).to(device)
+        self.n_paths = torch.from_numpy(self.n_paths_host).to(device)
+
+    @property
+    def total_paths(self):
+        return int(self.n_paths_host.sum())
+
+
+class RaggedSamplesData(dict):
+    """SamplesData for a RaggedPhaseData: the 8 keys trimmed to the task's n_valid samples."""
+
+    def __init__(self, phase, m, processor=None):
+        super(RaggedSamplesData, self).__init__()
+        self.phase, self.m, self._processor = phase, m, processor
+
+    def __missing__(self, key):
+        p, m = self.phase, self.m
+        n = int(p.n_valid_host[m])
+        if key == 'observations':
+            v = p.host('obs')[m, :n]
+        elif key == 'actions':
+            v = p.host('act')[m, :n]
+        elif key == 'rewards':
+            v = p.host('rew')[m, :n]
+        elif key == 'returns':
+            v = p.host('returns')[m, :n]
+        elif key == 'advantages':
+            v = p.host('adv')[m, :n]
+        elif key == 'agent_infos':
+            v = dict(mean=p.host('mean')[m, :n], log_std=np.broadcast_to(p.host('log_std')[m], (n, p.act_dim)))
+        elif key == 'env_infos':
+            v = {}
+        elif key == 'adj_avg_rewards':
+            if p.adj_avg_rewards is None and self._processor is not None:
+                self._processor.compute_adj_avg_rewards(p)
+            v = p.host('adj_avg_rewards')[m, :n]
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def keys(self):
+        return list(SamplesData.KEYS)
+
+    def __len__(self):
+        return len(SamplesData.KEYS)
+
+    def __iter__(self):
+        return iter(SamplesData.KEYS)
+
+
 class LazyPath(dict):
     """One trajectory (task m, env e) as the dict the reference builds at meta_sampler.py:116-123."""
 

@@ -7,7 +7,7 @@ dicts with the 8 keys).  All numerics run in promp_process_samples (one CTA per 
 import numpy as np
 
 from promp_b200 import _lib
-from promp_b200.samplers.device_data import PhaseData, PathsMetaBatch, SamplesData
+from promp_b200.samplers.device_data import PhaseData, PathsMetaBatch, SamplesData, RaggedPhaseData, RaggedSamplesData
 from promp_b200.utils import logger
 
 
@@ -26,10 +26,8 @@ def _phase_from_host_paths(paths_meta_batch, device):
     tasks = list(paths_meta_batch.values())
     E = len(tasks[0])
     H = len(tasks[0][0]["rewards"])
-    for paths in tasks:
-        if len(paths) != E or any(len(p["rewards"]) != H for p in paths):
-            raise NotImplementedError("promp_b200: variable-length / ragged paths are not supported by the device "
-                                      "sample processor yet (SURVEY.md section 8f item 2)")
+    if any(len(paths) != E or any(len(p["rewards"]) != H for p in paths) for paths in tasks):
+        return _ragged_phase_from_host_paths(tasks, device)
     obs0 = np.asarray(tasks[0][0]["observations"])
     act0 = np.asarray(tasks[0][0]["actions"])
     Do = obs0.shape[1] if obs0.ndim > 1 else 1
@@ -56,8 +54,46 @@ def _phase_from_host_paths(paths_meta_batch, device):
     return phase
 
 
+def _ragged_phase_from_host_paths(tasks, device):
+    """Variable-length paths (early-terminating envs through the stepwise sampler): padded [M, Nmax] layout + path table."""
+    import torch
+    if any(len(paths) == 0 for paths in tasks):
+        raise ValueError("promp_b200: every task needs at least one completed path")
+    obs0 = np.asarray(tasks[0][0]["observations"])
+    act0 = np.asarray(tasks[0][0]["actions"])
+    Do = obs0.shape[1] if obs0.ndim > 1 else 1
+    Da = act0.shape[1] if act0.ndim > 1 else 1
+    phase = RaggedPhaseData([[len(p["rewards"]) for p in paths] for paths in tasks], Do, Da, device)
+    M, N = phase.M, phase.N
+
+    def stack(key, d, sub=None):
+        out = np.zeros((M, N, d), dtype=np.float32)
+        for m, paths in enumerate(tasks):
+            n = int(phase.n_valid_host[m])
+            src = [np.asarray((p[key] if sub is None else p[key][sub]), dtype=np.float32).reshape(-1, d) for p in paths]
+            out[m, :n] = np.concatenate(src)
+        return out
+    phase.obs.copy_(torch.from_numpy(stack("observations", Do)))
+    phase.act.copy_(torch.from_numpy(stack("actions", Da)))
+    phase.rew.copy_(torch.from_numpy(stack("rewards", 1)[..., 0]))
+    done = np.zeros((M, N), dtype=np.uint8)
+    for m in range(M):
+        done[m, phase.path_off_host[m, 1:phase.n_paths_host[m] + 1] - 1] = 1
+    phase.done.copy_(torch.from_numpy(done))
+    ai = tasks[0][0].get("agent_infos") or {}
+    if "mean" in ai:
+        phase.mean.copy_(torch.from_numpy(stack("agent_infos", Da, "mean")))
+        phase.log_std.copy_(torch.from_numpy(np.stack(
+            [np.asarray(paths[0]["agent_infos"]["log_std"], dtype=np.float32).reshape(-1, Da)[0] for paths in tasks])))
+    else:
+        phase.log_std.zero_()
+    return phase
+
+
 def run_process_kernel(phase, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv):
     import torch
+    if isinstance(phase, RaggedPhaseData):
+        return _run_process_kernel_ragged(phase, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv)
     M, E, H, Do = phase.M, phase.E, phase.H, phase.obs_dim
     dev = phase.obs.device
     if phase.returns is None:
@@ -74,6 +110,28 @@ def run_process_kernel(phase, discount, gae_lambda, reg_coeff, baseline_kind, no
               float(gae_lambda), float(reg_coeff), int(baseline_kind), int(bool(normalize_adv)), int(bool(positive_adv)),
               _lib.ptr(phase.returns), _lib.ptr(phase.adv), _lib.ptr(phase.coeffs), _lib.ptr(phase.stats),
               _lib.ptr(ws), ws.numel() * 8, _lib.stream())
+    phase.adj_avg_rewards = None
+    phase.invalidate_host()
+
+
+def _run_process_kernel_ragged(phase, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv):
+    import torch
+    M, Pmax, N, Do = phase.M, phase.E, phase.N, phase.obs_dim
+    dev = phase.obs.device
+    if phase.returns is None:
+        phase.returns = torch.zeros(M, N, dtype=torch.float32, device=dev)
+        phase.adv = torch.zeros(M, N, dtype=torch.float32, device=dev)
+        phase.coeffs = torch.zeros(M, 2 * Do + 4, dtype=torch.float64, device=dev)
+        phase.stats = torch.zeros(M, 8, dtype=torch.float64, device=dev)
+    nbytes = _lib.load().promp_process_workspace_bytes_ragged(M, Pmax, N, Do)
+    ws = getattr(phase, '_proc_ws', None)
+    if ws is None or ws.numel() * 8 < nbytes:
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        phase._proc_ws = ws
+    _lib.call('promp_process_samples_ragged', M, Pmax, N, Do, _lib.ptr(phase.obs), _lib.ptr(phase.rew), _lib.ptr(phase.path_off),
+              _lib.ptr(phase.n_paths), float(discount), float(gae_lambda), float(reg_coeff), int(baseline_kind),
+              int(bool(normalize_adv)), int(bool(positive_adv)), _lib.ptr(phase.returns), _lib.ptr(phase.adv),
+              _lib.ptr(phase.coeffs), _lib.ptr(phase.stats), _lib.ptr(ws), ws.numel() * 8, _lib.stream())
     phase.adj_avg_rewards = None
     phase.invalidate_host()
 
@@ -110,7 +168,8 @@ class MetaSampleProcessor(object):
         """samples_data['adj_avg_rewards'] (meta_sample_processor.py:40-44), computed on first access."""
         import torch
         st = phase.stats[:, 5:7].sum(0)
-        cnt = torch.tensor([float(phase.M * phase.N)], dtype=torch.float64, device=st.device)
+        n_total = float(phase.n_valid_host.sum()) if isinstance(phase, RaggedPhaseData) else float(phase.M * phase.N)
+        cnt = torch.tensor([n_total], dtype=torch.float64, device=st.device)
         vec = torch.cat([st, cnt])
         if allreduce is not None:
             allreduce(vec)
@@ -135,7 +194,8 @@ class MetaSampleProcessor(object):
         if hasattr(self.baseline, '_coeffs') and _baseline_kind(self.baseline) == 1:
             self.baseline._lazy_coeffs = (phase, phase.M - 1)
             self.baseline._coeffs = _LazyCoeffs(phase)      # last task's fit, fetched on demand
-        samples = [SamplesData(phase, m, self) for m in range(phase.M)]
+        cls = RaggedSamplesData if isinstance(phase, RaggedPhaseData) else SamplesData
+        samples = [cls(phase, m, self) for m in range(phase.M)]
         self._log_path_stats(phase, log, log_prefix)
         return samples
 
@@ -146,7 +206,7 @@ class MetaSampleProcessor(object):
         used by the CUDA-graph Trainer, which reads all logged scalars back with a single D2H copy."""
         import torch
         st = phase.stats
-        n = float(phase.M * phase.E)
+        n = float(phase.total_paths) if isinstance(phase, RaggedPhaseData) else float(phase.M * phase.E)
         s = st[:, :3].sum(0)
         mean_g = s[1] / n
         std = torch.sqrt(torch.clamp(s[2] / n - mean_g * mean_g, min=0.0))
@@ -157,7 +217,7 @@ class MetaSampleProcessor(object):
         if not log:
             return
         st = phase.host('stats')
-        n = phase.M * phase.E
+        n = phase.total_paths if isinstance(phase, RaggedPhaseData) else phase.M * phase.E
         sR0, sG, sG2 = st[:, 0].sum(), st[:, 1].sum(), st[:, 2].sum()
         mean_g = sG / n
         if log == 'reward':

@@ -750,18 +750,57 @@ def test_policy_kernels_deterministic_and_batch_independent():
         assert rel_err(hv.cpu().numpy(), outs[0][2][sl].cpu().numpy()) < 5e-6
 
 
-def test_ragged_paths_are_rejected_loudly():
-    """Variable-length paths are a 'next' row: the device processor must refuse them, not silently mis-process."""
+def test_processor_argument_contract():
+    """process_samples keeps the reference's argument contract (meta_sample_processor.py:25); variable-length paths are
+    accepted (see the ragged tests below)."""
     _cuda()
     from promp_b200.samplers import MetaSampleProcessor
     from promp_b200.baselines import LinearFeatureBaseline, ZeroBaseline
     rng = np.random.RandomState(0)
     paths = {0: [dict(observations=rng.randn(L, 2), actions=rng.randn(L, 2), rewards=rng.randn(L), env_infos={}, agent_infos={})
                  for L in (5, 7)]}
-    with pytest.raises(NotImplementedError):
-        MetaSampleProcessor(LinearFeatureBaseline()).process_samples(paths)
+    data = MetaSampleProcessor(LinearFeatureBaseline()).process_samples(paths)
+    assert len(data) == 1 and data[0]['advantages'].shape == (12,)
     with pytest.raises(AssertionError):
         MetaSampleProcessor(ZeroBaseline()).process_samples([paths[0]])       # must be a dict (meta_sample_processor.py:25)
+    with pytest.raises(ValueError):
+        MetaSampleProcessor(ZeroBaseline()).process_samples({0: paths[0], 1: []})   # a task without a completed path
+
+
+def test_early_terminating_env_end_to_end():
+    """MetaPointEnv (done near the origin, point_env_2d.py:49-53) through the stepwise sampler's "collect until
+    >= M*E*H samples in completed paths" loop (meta_sampler.py:87-137), the ragged processor, adapt and one ProMP
+    optimisation: variable-length paths all the way down, finite results, per-task sample counts as sampled."""
+    torch = _cuda()
+    from promp_b200.envs import MetaPointEnv, normalize
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.baselines import LinearFeatureBaseline
+    from promp_b200.samplers import MetaSampler, MetaSampleProcessor
+    from promp_b200.meta_algos import ProMP
+    np.random.seed(3)
+    M, E, H = 4, 5, 12
+    env = normalize(MetaPointEnv())
+    policy = MetaGaussianMLPPolicy(name="p", obs_dim=2, action_dim=2, meta_batch_size=M, hidden_sizes=(64, 64))
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H)
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1.0, normalize_adv=True)
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3, num_ppo_steps=2)
+    sampler.update_tasks()
+    policy.switch_to_pre_update()
+    all_samples = []
+    theta0 = policy.theta.clone()
+    for step in range(2):
+        paths = sampler.obtain_samples()
+        lens = [[len(p['rewards']) for p in paths[m]] for m in range(M)]
+        assert sum(map(sum, lens)) >= M * E * H and all(max(l) <= H for l in lens)
+        data = proc.process_samples(paths)
+        assert [len(d['advantages']) for d in data] == [sum(l) for l in lens]
+        assert all(np.isfinite(d['advantages']).all() for d in data)
+        all_samples.append(data)
+        if step == 0:
+            algo._adapt(data)
+    algo.optimize_policy(all_samples, log=False)
+    th1 = policy.theta
+    assert torch.isfinite(th1).all() and not torch.equal(th1, theta0)
 
 
 @pytest.mark.parametrize('exploration', [False, True])
@@ -893,3 +932,101 @@ def test_tensor_core_policy_hvp_matches_simt(Do, Da, N, stride_mode):
                 d = rel_err(b[0] - vec.cpu().numpy(), a[0] - vec.cpu().numpy())      # compare the H v part, not v + ...
                 assert d < 5e-5, d
                 np.testing.assert_allclose(b[1][:, :3], a[1][:, :3], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# variable-length paths (early termination, meta_sampler.py:116-125)
+@pytest.mark.parametrize('case', ['r1', 'r2', 'r3'])
+def test_process_samples_ragged_matches_reference_golden(golden_dir, case):
+    """MetaSampleProcessor on variable-length host paths -> promp_process_samples_ragged, against the unmodified
+    reference's outputs (tests/golden/process_samples_ragged.npz): returns, baseline coefficients, advantages."""
+    torch = _cuda()
+    from test_oracle_golden import ragged_paths_from_golden
+    from promp_b200.samplers import MetaSampleProcessor
+    from promp_b200.baselines import LinearFeatureBaseline
+    g = np.load(os.path.join(golden_dir, 'process_samples_ragged.npz'))
+    pre = 'case_%s_' % case
+    paths = ragged_paths_from_golden(g, pre)
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=float(g[pre + 'cfg_discount']),
+                               gae_lambda=float(g[pre + 'cfg_gae_lambda']), normalize_adv=bool(g[pre + 'cfg_normalize_adv']),
+                               positive_adv=bool(g[pre + 'cfg_positive_adv']))
+    data = proc.process_samples(paths, log=False)
+    assert len(data) == len(paths) and len(data[0].keys()) == 8
+    got_ret = np.concatenate([d['returns'] for d in data])
+    got_adv = np.concatenate([d['advantages'] for d in data])
+    np.testing.assert_allclose(got_ret, g[pre + 'returns'], rtol=2e-7, atol=1e-6)
+    assert rel_err(got_adv, g[pre + 'advantages']) < 1e-5
+    np.testing.assert_allclose(data[0].phase.host('coeffs'), g[pre + 'coeffs'], rtol=1e-6, atol=1e-8)
+    np.testing.assert_array_equal(np.concatenate([d['observations'] for d in data]), g[pre + 'observations_stacked'])
+    # sample counts per task follow the path table
+    lens = np.split(g[pre + 'path_len'], np.cumsum(g[pre + 'n_paths'])[:-1])
+    assert [len(d['rewards']) for d in data] == [int(l.sum()) for l in lens]
+
+
+def _ragged_phase(torch, n_valid, Do, Da, theta, seed, paths_per_task=3):
+    """Synthetic variable-length phase: task m has n_valid[m] samples split into a few paths; padding rows hold garbage
+    on purpose (they must not contribute)."""
+    from promp_b200.samplers.device_data import RaggedPhaseData
+    from oracle import tf_half as th
+    M = len(n_valid)
+    g = torch.Generator().manual_seed(seed)
+    lens = []
+    for n in n_valid:
+        cuts = sorted(set(int(x) for x in torch.randint(1, n, (paths_per_task - 1,), generator=g))) if n > paths_per_task else []
+        edges = [0] + cuts + [n]
+        lens.append([b - a for a, b in zip(edges[:-1], edges[1:])])
+    ph = RaggedPhaseData(lens, Do, Da, torch.device('cuda'))
+    N = ph.N
+    obs = torch.randn(M, N, Do, generator=g)
+    th_t = torch.as_tensor(theta).view(1, -1).expand(M, -1)
+    mean, ls = th.dist_info(th_t, obs, (Do, Da, (64, 64)))
+    old_mean = mean + 0.1 * torch.randn(M, N, Da, generator=g)
+    old_ls = (ls + 0.05 * torch.randn(M, 1, Da, generator=g)).expand(M, N, Da).contiguous()
+    act = old_mean + torch.exp(old_ls) * torch.randn(M, N, Da, generator=g)
+    adv = torch.randn(M, N, generator=g)
+    cpu = []
+    for m, n in enumerate(n_valid):
+        cpu.append(dict(obs=obs[m:m + 1, :n], act=act[m:m + 1, :n], adv=adv[m:m + 1, :n], mean=old_mean[m:m + 1, :n],
+                        log_std=old_ls[m:m + 1, :n]))
+        obs[m, n:] = 1e3; act[m, n:] = -50.0; adv[m, n:] = 1e4; old_mean[m, n:] = 7.0          # poison the padding
+    ph.obs.copy_(obs); ph.act.copy_(act); ph.mean.copy_(old_mean); ph.log_std.copy_(old_ls[:, 0])
+    ph.adv = adv.cuda()
+    return cpu, ph
+
+
+@pytest.mark.parametrize('Do,Da', [(2, 2), (17, 6)])
+@pytest.mark.parametrize('tc', [0, 1])
+def test_ragged_meta_gradient_matches_oracle(Do, Da, tc):
+    """ProMP meta-gradient with a different number of valid samples per task and per phase (promp_policy_*_ragged):
+    per-task means run over n_valid[m], padding rows are ignored.  Oracle: fp64 autograd per task on the trimmed data."""
+    torch = _cuda()
+    from promp_b200 import _lib
+    from oracle import tf_half as th
+    M = 5
+    policy, algo = _algo(torch, 'promp', M, Do, Da)
+    dims = (Do, Da, (64, 64))
+    theta = policy.theta.cpu().numpy()
+    nv = [[130, 517, 64, 1000, 333], [257, 90, 700, 128, 411]]
+    cpus, phases = [], []
+    for s in range(2):
+        c, p = _ragged_phase(torch, nv[s], Do, Da, theta, 20 + s)
+        cpus.append(c); phases.append(p)
+    coeff = list(algo.inner_kl_coeff)
+    g_want, obj_want = 0.0, 0.0
+    for m in range(M):
+        t64 = torch.tensor(theta, dtype=torch.float64, requires_grad=True)
+        data_m = [{k: v.double() for k, v in cpus[s][m].items()} for s in range(2)]
+        obj, _, _ = th.meta_objective(t64, data_m, dims, 0.1, 'promp', 0.3, coeff)
+        (gm,) = torch.autograd.grad(obj, t64)
+        g_want = g_want + gm.numpy() / M
+        obj_want += float(obj) / M
+    try:
+        _lib.set_option('tensor_cores', tc)
+        res = algo._objective_pass(phases, want_grad=True)
+        terms = algo.loss_terms(res).cpu().numpy()
+        g_got = res['grad'].cpu().numpy()
+    finally:
+        _lib.set_option('tensor_cores', 1)
+    assert abs(terms[0] - obj_want) < 1e-4 * max(1.0, abs(obj_want))
+    err = rel_err(g_got, g_want)
+    assert err < 1e-4, err
