@@ -43,7 +43,9 @@ class LinearFeatureBaseline(object):
         pass
 
     def __getstate__(self):
-        return dict(reg_coeff=self._reg_coeff, coeffs=self._coeffs)
+        import numpy as np
+        coeffs = None if self._coeffs is None else np.asarray(self._coeffs, dtype=np.float64)   # a lazy device view -> numbers
+        return dict(reg_coeff=self._reg_coeff, coeffs=coeffs)
 
     def __setstate__(self, d):
         self._reg_coeff, self._coeffs = d['reg_coeff'], d['coeffs']

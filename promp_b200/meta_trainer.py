@@ -168,7 +168,38 @@ class Trainer(object):
         logger.log("Training finished")
 
     def get_itr_snapshot(self, itr):
-        return dict(itr=itr, policy=self.policy, env=self.env, baseline=self.baseline)
+        """meta_trainer.py:153-158: {itr, policy, env, baseline} (picklable: the policy pickles its init arguments and a
+        host copy of the parameters, policies/base.py:205-215), plus what a bit-identical resume needs and the reference
+        drops: optimizer slots, adaptive KL coefficients, the sampled-timesteps counter."""
+        snap = dict(itr=itr, policy=self.policy, env=self.env, baseline=self.baseline)
+        extra = dict(total_timesteps_sampled=self.sampler.total_timesteps_sampled)
+        opt = getattr(self.algo, 'optimizer', None)
+        if hasattr(opt, 'get_state') and getattr(opt, '_target', None) is not None:
+            extra['optimizer'] = opt.get_state()
+        if hasattr(self.algo, 'inner_kl_coeff'):
+            extra['inner_kl_coeff'] = np.asarray(self.algo.inner_kl_coeff, dtype=np.float64).copy()
+        snap['promp_b200_state'] = extra
+        return snap
+
+    def restore(self, snapshot):
+        """Resume from a snapshot dict or file written by logger.save_itr_params: parameters, optimizer slots, KL
+        coefficients and counters are restored into the live objects; training continues at itr + 1."""
+        if isinstance(snapshot, str):
+            snapshot = logger.load_snapshot(snapshot)
+        src = snapshot['policy']
+        self.policy.set_params(src.get_param_values() if hasattr(src, 'get_param_values') else src)
+        if snapshot.get('baseline') is not None and hasattr(self.baseline, '__setstate__') and hasattr(snapshot['baseline'], '__getstate__'):
+            self.baseline.__setstate__(snapshot['baseline'].__getstate__())
+        extra = snapshot.get('promp_b200_state', {})
+        opt = getattr(self.algo, 'optimizer', None)
+        if 'optimizer' in extra and hasattr(opt, 'set_state'):
+            opt.set_state(extra['optimizer'])
+        if 'inner_kl_coeff' in extra and hasattr(self.algo, 'inner_kl_coeff'):
+            self.algo.inner_kl_coeff = np.asarray(extra['inner_kl_coeff'], dtype=np.float64).copy()
+        self.sampler.total_timesteps_sampled = int(extra.get('total_timesteps_sampled', self.sampler.total_timesteps_sampled))
+        self.start_itr = int(snapshot['itr']) + 1
+        self._graph_step = None
+        return self.start_itr
 
     def log_diagnostics(self, paths, prefix):
         self.env.log_diagnostics(paths, prefix)

@@ -22,6 +22,17 @@ class MAMLPPOOptimizer(object):
         self.v = torch.zeros(P, dtype=torch.float32, device=policy.device)
         self.step = torch.zeros(1, dtype=torch.int32, device=policy.device)
 
+    def get_state(self):
+        """Adam slots as numpy (snapshots; the reference's tf.train.Saver-less snapshot drops them, we keep them so that a
+        resumed run continues bit-identically)."""
+        return dict(m=self.m.cpu().numpy(), v=self.v.cpu().numpy(), step=int(self.step.item()))
+
+    def set_state(self, st):
+        import torch
+        self.m.copy_(torch.from_numpy(st['m']))
+        self.v.copy_(torch.from_numpy(st['v']))
+        self.step.fill_(int(st['step']))
+
     def apply_gradient(self, grad):
         p = self._target
         _lib.call('promp_adam_tf1', p.num_params, _lib.ptr(p.theta), _lib.ptr(grad), _lib.ptr(self.m), _lib.ptr(self.v),

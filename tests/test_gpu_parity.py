@@ -1030,3 +1030,51 @@ def test_ragged_meta_gradient_matches_oracle(Do, Da, tc):
     assert abs(terms[0] - obj_want) < 1e-4 * max(1.0, abs(obj_want))
     err = rel_err(g_got, g_want)
     assert err < 1e-4, err
+
+
+def test_snapshot_and_resume(tmp_path):
+    """meta_trainer.py:144-158 + utils/logger.py:376-396: Trainer.train() writes a joblib snapshot {itr, policy, env,
+    baseline} from device state plus progress.csv with the reference's keys; Trainer.restore() on a fresh stack brings
+    back parameters, Adam slots, KL coefficients and counters, and training continues at itr + 1."""
+    torch = _cuda()
+    import csv
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    from promp_b200.utils import logger
+    M, E, H = 4, 3, 30
+
+    def make(n_itr):
+        env, policy, sampler, proc = _make_stack('point', M, E, H)
+        algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3,
+                     num_ppo_steps=2, clip_eps=0.3, init_inner_kl_penalty=5e-4, adaptive_inner_kl_penalty=True)
+        return policy, algo, Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=n_itr,
+                                     num_inner_grad_steps=1)
+    d = str(tmp_path / 'run')
+    try:
+        logger.configure(dir=d, format_strs=['csv', 'json'], snapshot_mode='last')
+        policy, algo, trainer = make(2)
+        trainer.train()
+        snap_path = os.path.join(d, 'params.pkl')
+        assert os.path.exists(snap_path)
+        rows = list(csv.DictReader(open(os.path.join(d, 'progress.csv'))))
+        assert len(rows) == 2 and rows[1]['Itr'] == '1' and 'Step_1-AverageReturn' in rows[0] and 'LossAfter' in rows[0]
+        snap = logger.load_snapshot(snap_path)
+        assert set(('itr', 'policy', 'env', 'baseline')) <= set(snap) and snap['itr'] == 1
+        assert torch.equal(snap['policy'].theta.cpu(), policy.theta.cpu())
+        assert snap['baseline']._coeffs is not None and np.isfinite(np.asarray(snap['baseline']._coeffs)).all()
+        # resume on a fresh stack
+        logger.configure(dir=str(tmp_path / 'run2'), format_strs=['json'], snapshot_mode='none')
+        np.random.seed(77)
+        policy2, algo2, trainer2 = make(3)
+        assert not torch.equal(policy2.theta, policy.theta)
+        assert trainer2.restore(snap_path) == 2
+        assert torch.equal(policy2.theta, policy.theta)
+        assert torch.equal(algo2.optimizer.m, algo.optimizer.m) and torch.equal(algo2.optimizer.v, algo.optimizer.v)
+        assert int(algo2.optimizer.step.item()) == int(algo.optimizer.step.item()) == 4
+        np.testing.assert_array_equal(algo2.inner_kl_coeff, algo.inner_kl_coeff)
+        assert trainer2.sampler.total_timesteps_sampled == 2 * 2 * M * E * H
+        trainer2.train()                                            # runs exactly iteration 2
+        kv = logger.last_dump()
+        assert kv['Itr'] == 2 and kv['n_timesteps'] == 3 * 2 * M * E * H and np.isfinite(kv['LossAfter'])
+    finally:
+        logger.reset()

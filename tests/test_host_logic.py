@@ -225,3 +225,36 @@ print('reference trainer ok')
 ''' % ROOT
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and 'reference trainer ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_logger_file_formats_and_snapshot_modes(tmp_path):
+    """utils/logger.py:37-146, 376-427 behaviours: progress.csv grows its header and pads earlier rows when new keys
+    appear, progress.json holds one object per dump, log.txt the printed table; snapshot_mode all / last / gap /
+    last_gap / none choose the file names the reference uses."""
+    import csv
+    import json
+    from promp_b200.utils import logger
+    d = str(tmp_path / 'run')
+    try:
+        logger.configure(dir=d, format_strs=['log', 'csv', 'json'], snapshot_mode='gap', snapshot_gap=2)
+        logger.logkv('Itr', 0); logger.logkv('Step_0-AverageReturn', np.float32(-1.5)); logger.dumpkvs()
+        logger.logkv('Itr', 1); logger.logkv('Step_0-AverageReturn', -1.25); logger.logkv('KLCoeffInner', 5e-4); logger.dumpkvs()
+        logger.log('hello', ' world')
+        assert logger.save_itr_params(1, dict(itr=1)) is None
+        p = logger.save_itr_params(2, dict(itr=2, x=np.arange(3)))
+        assert os.path.basename(p) == 'itr_2.pkl' and logger.load_snapshot(p)['itr'] == 2
+        rows = list(csv.reader(open(os.path.join(d, 'progress.csv'))))
+        assert rows[0] == ['Itr', 'Step_0-AverageReturn', 'KLCoeffInner']
+        assert rows[1] == ['0', '-1.5', ''] and rows[2] == ['1', '-1.25', '0.0005']
+        js = [json.loads(l) for l in open(os.path.join(d, 'progress.json'))]
+        assert js[0] == {'Itr': 0, 'Step_0-AverageReturn': -1.5} and js[1]['KLCoeffInner'] == 5e-4
+        txt = open(os.path.join(d, 'log.txt')).read()
+        assert '| Itr ' in txt and 'hello world' in txt and txt.count('-1.5') == 1
+        for mode, itr, want in (('all', 3, 'itr_3.pkl'), ('last', 3, 'params.pkl'), ('last_gap', 4, 'params.pkl'), ('none', 4, None)):
+            logger.configure(dir=d, format_strs=['json'], snapshot_mode=mode, snapshot_gap=2)
+            got = logger.save_itr_params(itr, dict(itr=itr))
+            assert (got and os.path.basename(got)) == want
+        with pytest.raises(ValueError):
+            logger.configure(dir=d, format_strs=['tensorboard'])
+    finally:
+        logger.reset()
