@@ -64,9 +64,10 @@ def get_obs(qpos, qvel):
     return np.concatenate([qpos[..., 1:], qvel], axis=-1)
 
 
-def step(qpos, qvel, u, direction):
+def step(qpos, qvel, u, direction, goal_velocity=None):
     """One env step on (..., 9) state arrays; `u` is the already-rescaled/clipped action (..., 6).
-    Returns (qpos', qvel', reward, reward_run, reward_ctrl)."""
+    Returns (qpos', qvel', reward, reward_run, reward_ctrl).  goal_velocity given: HalfCheetahRandVel reward
+    reward_run = -|forward_vel - goal_velocity| (half_cheetah_rand_vel.py:30-40) instead of direction * forward_vel."""
     dt_ = qpos.dtype.type
     qpos = qpos.copy()
     qvel = qvel.copy()
@@ -100,7 +101,11 @@ def step(qpos, qvel, u, direction):
         qvel[..., 2] = pd
         qpos[..., 2] = qpos[..., 2] + h * pd
     reward_ctrl = -dt_(0.05) * np.sum(np.square(u), axis=-1)
-    reward_run = np.asarray(direction, dtype=qpos.dtype) * (qpos[..., 0] - x_before) / dt_(DT)
+    forward_vel = (qpos[..., 0] - x_before) / dt_(DT)
+    if goal_velocity is None:
+        reward_run = np.asarray(direction, dtype=qpos.dtype) * forward_vel
+    else:
+        reward_run = -np.abs(forward_vel - np.asarray(goal_velocity, dtype=qpos.dtype))
     return qpos, qvel, reward_ctrl + reward_run, reward_run, reward_ctrl
 
 

@@ -115,7 +115,10 @@ __device__ __forceinline__ JointConst joint_const(int j) {
 
 // root: x, z, pitch, xd, zd, pd
 // Serial version (one thread per env): state = qpos[9] ++ qvel[9]; u[6] already rescaled+clipped.
-__device__ inline void step_serial(float* st, const float* u, float dir, float& reward, float& r_run, float& r_ctrl) {
+// mode 0: HalfCheetahRandDirec, r_run = task * v (task = direction);  mode 1: HalfCheetahRandVel, r_run = -|v - task| (task = goal
+// velocity; half_cheetah_rand_vel.py:30-40).  fwd_vel = (x_after - x_before) / dt.
+__device__ inline void step_serial(float* st, const float* u, float task, int mode, float& reward, float& r_run, float& r_ctrl,
+                                   float& fwd_vel) {
     float x0 = st[0];
     for (int s = 0; s < FRAME_SKIP; ++s) {
         float thrust = 0.f, lift = 0.f, twist = 0.f;
@@ -146,7 +149,8 @@ __device__ inline void step_serial(float* st, const float* u, float dir, float& 
     float su = 0.f;
     for (int j = 0; j < NJ; ++j) su += u[j] * u[j];
     r_ctrl = -0.05f * su;
-    r_run = dir * (st[0] - x0) / DT;
+    fwd_vel = (st[0] - x0) / DT;
+    r_run = mode ? -fabsf(fwd_vel - task) : task * fwd_vel;
     reward = r_ctrl + r_run;
 }
 
@@ -158,8 +162,8 @@ __device__ __forceinline__ float sum8(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
 }
-__device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& q, float& qd, float (&root)[6], float dir,
-                                          float& reward, float& r_run, float& r_ctrl) {
+__device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& q, float& qd, float (&root)[6], float task, int mode,
+                                          float& reward, float& r_run, float& r_ctrl, float& fwd_vel) {
     float x0 = root[0];
 #pragma unroll 1
     for (int s = 0; s < FRAME_SKIP; ++s) {
@@ -182,7 +186,8 @@ __device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& 
         root[2] = root[2] + HS * pd;
     }
     r_ctrl = -0.05f * sum8(u * u);
-    r_run = dir * (root[0] - x0) / DT;
+    fwd_vel = (root[0] - x0) / DT;
+    r_run = mode ? -fabsf(fwd_vel - task) : task * fwd_vel;
     reward = r_ctrl + r_run;
 }
 }  // namespace cheetah

@@ -48,7 +48,7 @@ struct RolloutSmem {
     float st_act[T_CH * T::DA];
     float st_mean[T_CH * T::DA];
     float st_rew[T_CH];
-    float st_info[2 * T_CH];
+    float st_info[3 * T_CH];
 };
 
 template <int KIND, int HID>
@@ -263,11 +263,12 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                     if (jl == d) al = a[d];
                 // raw MuJoCo env: ctrlrange clips the torque to [-1, 1] inside the simulator
                 const float u_l = jl < 6 ? (A.normalized ? normalized_action(al, -1.f, 1.f) : fminf(fmaxf(al, -1.f), 1.f)) : 0.f;
-                float r_run, r_ctrl;
-                cheetah::step_warp(jc, u_l, q, qd, root, task[0], r, r_run, r_ctrl);
+                float r_run, r_ctrl, fwd_vel;
+                cheetah::step_warp(jc, u_l, q, qd, root, task[0], A.reward_type, r, r_run, r_ctrl, fwd_vel);
                 if (lane == 0) {
                     S.st_info[tt] = r_run;
                     S.st_info[T_CH + tt] = r_ctrl;
+                    S.st_info[2 * T_CH + tt] = fwd_vel;
                 }
             }
             if (lane == 0) S.st_rew[tt] = r;
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                     const int64_t tot = (int64_t)A.M * A.E * A.H;
                     A.info[base + t0 + lane] = S.st_info[lane];
                     A.info[tot + base + t0 + lane] = S.st_info[T_CH + lane];
+                    if (A.reward_type == 1) A.info[2 * tot + base + t0 + lane] = S.st_info[2 * T_CH + lane];   // RandVel: forward_vel
                 }
             }
         }
@@ -338,13 +340,14 @@ __global__ void env_step_kernel(int reward_type, float radius, int normalized, i
     } else if (KIND == PROMP_ENV_POINT) {
         r = point_step(st[0], st[1], a[0], a[1], dn, normalized != 0);
     } else {
-        float u[DA], rr, rc;
+        float u[DA], rr, rc, fv;
 #pragma unroll
         for (int k = 0; k < DA; ++k) u[k] = normalized ? normalized_action(a[k], -1.f, 1.f) : fminf(fmaxf(a[k], -1.f), 1.f);
-        cheetah::step_serial(st, u, task_params[(int64_t)i * TD], r, rr, rc);
+        cheetah::step_serial(st, u, task_params[(int64_t)i * TD], reward_type, r, rr, rc, fv);
         if (info) {
             info[i] = rr;
             info[n_env + i] = rc;
+            if (reward_type == 1) info[2 * n_env + i] = fv;
         }
     }
     int t = ts[i] + 1;
@@ -435,7 +438,8 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
             return hidden == 64 ? launch_rollout<PROMP_ENV_POINT_CORNER, 64>(A, st)
                                 : launch_rollout<PROMP_ENV_POINT_CORNER, 32>(A, st);
         case PROMP_ENV_CHEETAH_DIR:
-            PROMP_REQUIRE(info != nullptr, "promp_rollout: cheetah needs the info buffer [2,M,E,H]");
+            PROMP_REQUIRE(info != nullptr, "promp_rollout: cheetah needs the info buffer [2,M,E,H] ([3,M,E,H] for reward_type 1)");
+            PROMP_REQUIRE(reward_type == 0 || reward_type == 1, "promp_rollout: cheetah reward_type must be 0 (RandDirec) or 1 (RandVel)");
             return hidden == 64 ? launch_rollout<PROMP_ENV_CHEETAH_DIR, 64>(A, st)
                                 : launch_rollout<PROMP_ENV_CHEETAH_DIR, 32>(A, st);
         case PROMP_ENV_POINT:

@@ -15,6 +15,8 @@ from promp_b200.utils import logger
 
 class HalfCheetahRandDirecEnv(MetaEnv):
     env_kind = _lib.ENV_CHEETAH_DIR
+    reward_type = 0                      # device reward mode: direction * forward_vel
+    info_keys = ('reward_run', 'reward_ctrl')
     obs_dim = 17
     act_dim = 6
 

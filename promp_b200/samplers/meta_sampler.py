@@ -97,8 +97,9 @@ class MetaSampler(object):
         M, E, H = self.meta_batch_size, self.envs_per_task, self.max_path_length
         params, stride, clip = self.policy.sampling_params()
         if s['env_kind'] == _lib.ENV_CHEETAH_DIR and phase.info is None:
-            phase.info = torch.empty(2, M, E * H, dtype=torch.float32, device=self.device)
-            phase.info_keys = ('reward_run', 'reward_ctrl')
+            keys = tuple(getattr(getattr(self.env, '_wrapped_env', self.env), 'info_keys', ('reward_run', 'reward_ctrl')))
+            phase.info = torch.empty(len(keys), M, E * H, dtype=torch.float32, device=self.device)
+            phase.info_keys = keys
         self._phase_counter += 1
         _lib.call('promp_rollout', s['env_kind'], s['reward_type'], s['radius'], int(s.get('normalized', False)), M, E, H,
                   self.policy.hidden,

@@ -33,9 +33,10 @@ class MetaDeviceEnvExecutor(object):
         self._obs = torch.zeros(self.n_envs, self.spec['obs_dim'], **f32)
         self._rew = torch.zeros(self.n_envs, **f32)
         self._done = torch.zeros(self.n_envs, dtype=torch.uint8, device=self.device)
-        self._info = torch.zeros(2, self.n_envs, **f32)
+        inner_env = getattr(env, '_wrapped_env', env)
+        self.info_keys = tuple(getattr(inner_env, 'info_keys', ())) if self.spec['env_kind'] == _lib.ENV_CHEETAH_DIR else ()
+        self._info = torch.zeros(max(len(self.info_keys), 2), self.n_envs, **f32)
         self._dummy_reset = torch.zeros(self.n_envs, sd, **f32)
-        self.info_keys = ('reward_run', 'reward_ctrl') if self.spec['env_kind'] == _lib.ENV_CHEETAH_DIR else ()
 
     @property
     def num_envs(self):

@@ -1078,3 +1078,72 @@ def test_snapshot_and_resume(tmp_path):
         assert kv['Itr'] == 2 and kv['n_timesteps'] == 3 * 2 * M * E * H and np.isfinite(kv['LossAfter'])
     finally:
         logger.reset()
+
+
+def test_half_cheetah_rand_vel_surrogate():
+    """HalfCheetahRandVelEnv (half_cheetah_rand_vel.py:13-40): tasks ~ U(0,3) from the numpy RNG, reward_run =
+    -|forward_vel - goal|, env_infos {forward_vel, reward_run, reward_ctrl}; fused rollout and the vec-env step kernel
+    against the surrogate's spec (oracle/cheetah_surrogate.py) replayed with the kernel's own actions; one full ProMP
+    iteration through the Trainer with the reference's log keys."""
+    torch = _cuda()
+    from oracle import cheetah_surrogate as cs
+    from promp_b200.envs import normalize, HalfCheetahRandVelEnv
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.samplers import MetaSampler, MetaSampleProcessor
+    from promp_b200.samplers.vectorized_env_executor import MetaDeviceEnvExecutor
+    from promp_b200.baselines import LinearFeatureBaseline
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    from promp_b200.utils import logger
+    M, E, H = 3, 4, 40
+    np.random.seed(11)
+    env = normalize(HalfCheetahRandVelEnv())
+    policy = MetaGaussianMLPPolicy(name="p", obs_dim=17, action_dim=6, meta_batch_size=M, hidden_sizes=(64, 64))
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H)
+    np.random.seed(5)
+    want_tasks = np.random.uniform(0.0, 3.0, (M,))
+    np.random.seed(5)
+    sampler.update_tasks()
+    goals = sampler.vec_env.task_params_per_task.cpu().numpy()[:, 0]
+    np.testing.assert_allclose(goals, want_tasks.astype(np.float32), rtol=0, atol=0)
+    rng = np.random.RandomState(2)
+    noise = rng.randn(M, E, H, 6).astype(np.float32)
+    init = np.zeros((M, E, 18), dtype=np.float32)
+    init[..., :9] = rng.uniform(-.1, .1, size=(M, E, 9))
+    init[..., 9:] = 0.1 * rng.randn(M, E, 9)
+    policy.switch_to_pre_update()
+    sampler.inject(noise=noise, init_state=init)
+    ph = sampler.obtain_samples().phase
+    assert ph.info.shape[0] == 3 and ph.info_keys == ('reward_run', 'reward_ctrl', 'forward_vel')
+    obs = ph.obs.cpu().numpy().reshape(M, E, H, 17)
+    act = ph.act.cpu().numpy().reshape(M, E, H, 6)
+    rew = ph.rew.cpu().numpy().reshape(M, E, H)
+    info = ph.info.cpu().numpy().reshape(3, M, E, H)
+    qpos, qvel = init[..., :9].copy(), init[..., 9:].copy()
+    for t in range(H):
+        u = np.clip(np.float32(-1.0) + (act[:, :, t] + np.float32(10.0)) * np.float32(2.0) / np.float32(20.0), -1, 1)
+        x0 = qpos[..., 0].copy()
+        qpos, qvel, r, rr, rc = cs.step(qpos, qvel, u.astype(np.float32), None, goal_velocity=goals[:, None].astype(np.float32))
+        np.testing.assert_allclose(info[2, :, :, t], (qpos[..., 0] - x0) / np.float32(0.05), rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(info[0, :, :, t], rr, rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(info[0, :, :, t], -np.abs(info[2, :, :, t] - goals[:, None]), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rew[:, :, t], r, rtol=1e-3, atol=2e-4)
+        if t + 1 < H:
+            qpos[..., 1:] = obs[:, :, t + 1, :8]
+            qvel[...] = obs[:, :, t + 1, 8:]
+    # vec-env step kernel: same reward mode, three env_infos keys
+    ex = MetaDeviceEnvExecutor(env, 2, 1, max_path_length=10)
+    ex.set_tasks([0.5, 2.5])
+    ex.reset()
+    _, r, d, infos = ex.step([np.ones(6), -np.ones(6)])
+    assert set(infos[0]) == {'reward_run', 'reward_ctrl', 'forward_vel'}
+    for i, goal in enumerate((0.5, 2.5)):
+        assert abs(infos[i]['reward_run'] + abs(infos[i]['forward_vel'] - goal)) < 1e-5
+        assert abs(r[i] - (infos[i]['reward_run'] + infos[i]['reward_ctrl'])) < 1e-5
+    # one full iteration through the trainer
+    logger.set_quiet(True)
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3, num_ppo_steps=2)
+    Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1, num_inner_grad_steps=1).train()
+    kv = logger.last_dump()
+    assert np.isfinite(kv['LossAfter']) and 'Step_1-AvgForwardVel' in kv and np.isfinite(kv['Step_0-AverageReturn'])
