@@ -59,7 +59,7 @@ int promp_version(void);
 int promp_num_params(int obs_dim, int act_dim, int hidden);
 /* State floats per env for init_state / final_state: 2 (point envs), 18 (cheetah: qpos[9] qvel[9]). */
 int promp_env_state_dim(int env_kind);
-/* Floats per task in task_params: 2 (point corner goal), 0 -> pass 1 dummy (point), 1 (cheetah dir). */
+/* Floats per task in task_params: 2 (point corner goal), 0 -> pass 1 dummy (point), 1 (cheetah: direction or goal velocity). */
 int promp_env_task_dim(int env_kind);
 
 /*
@@ -84,6 +84,9 @@ int promp_env_task_dim(int env_kind);
  * outputs (all written):
  *   obs [M,E,H,Do]  act [M,E,H,Da]  mean [M,E,H,Da]  rew [M,E,H]  done [M,E,H] (uint8)
  *   info [2,M,E,H]  (cheetah: reward_run, reward_ctrl; others: untouched, may be NULL)
+ *        [3,M,E,H]  for the cheetah with reward_type 1 = HalfCheetahRandVel (mujoco_envs/half_cheetah_rand_vel.py:30-40:
+ *                   reward_run = -|forward_vel - task|, task = goal velocity): third channel = forward_vel;
+ *                   reward_type 0 = HalfCheetahRandDirec (reward_run = task * forward_vel, task = direction)
  *   log_std_out [M,Da]  the per-task reported log_std (constant over the phase)
  *   final_state [M,E,state_dim] or NULL
  */
