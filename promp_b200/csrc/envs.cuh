@@ -41,9 +41,17 @@ struct PointCornerCfg {
     bool normalized;
 };
 
+// sqrt.approx (MUFU.RSQ-based, max relative error 2^-23 per the PTX ISA, i.e. within 1 ulp of sqrtf) without sqrtf's
+// fix-up sequence and slow-path branch: the sparse reward needs five to six distances per env step and the branches
+// serialised them (617 clk of a 1644 clk env step went here; tools/rollout_time.py).
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float dist2d(float x, float y, float gx, float gy) {
     float dx = x - gx, dy = y - gy;
-    return sqrtf(dx * dx + dy * dy);
+    return sqrt_fast(dx * dx + dy * dy);
 }
 
 // s (in/out): state; (ax, ay): policy-space action.  Returns reward.
@@ -89,7 +97,7 @@ __device__ __forceinline__ float point_step(float& sx, float& sy, float ax, floa
     sx += ex;
     sy += ey;
     done = (fabsf(sx) < 0.01f) && (fabsf(sy) < 0.01f);
-    return -sqrtf(sx * sx + sy * sy);
+    return -sqrt_fast(sx * sx + sy * sy);
 }
 
 // ------------------------------------------------------------------ cheetah surrogate
@@ -165,6 +173,7 @@ __device__ __forceinline__ float sum8(float v) {
 __device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& q, float& qd, float (&root)[6], float task, int mode,
                                           float& reward, float& r_run, float& r_ctrl, float& fwd_vel) {
     float x0 = root[0];
+    const float twist = sum8(jc.p * u);          // the torques are constant over the sub-steps: one reduction, not five
 #pragma unroll 1
     for (int s = 0; s < FRAME_SKIP; ++s) {
         float acc = jc.g * u - jc.k * q - jc.d * qd;
@@ -174,7 +183,6 @@ __device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& 
         __sincosf(q + root[2] + jc.ph, &sn, &cs);   // |angle| stays O(1): fast path error ~5e-7
         float thrust = sum8(jc.c * qd * sn);
         float lift = sum8(jc.c * qd * cs);
-        float twist = sum8(jc.p * u);
         float xd = root[3] + HS * (thrust - BX * root[3]);
         root[3] = xd;
         root[0] = root[0] + HS * xd;

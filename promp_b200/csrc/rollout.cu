@@ -51,6 +51,21 @@ struct RolloutSmem {
     float st_info[3 * T_CH];
 };
 
+#ifdef PROMP_EXP_CLOCKS
+// experiment build only: per-phase clock64 totals of warp 0 of CTA (0,0) (tools/rollout_time.py)
+__device__ unsigned long long g_ro_clk[16];
+#define RCLK(i)                                                           \
+    do {                                                                  \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {     \
+            const long long t_ = clock64();                               \
+            ro_clk[i] += (unsigned long long)(t_ - ro_last);              \
+            ro_last = t_;                                                 \
+        }                                                                 \
+    } while (0)
+#else
+#define RCLK(i)
+#endif
+
 template <int KIND, int HID>
 __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
     using T = EnvTraits<KIND>;
@@ -66,6 +81,10 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
     __shared__ __align__(16) RolloutSmem<KIND, HID> smem_all[RO_WARPS];
     RolloutSmem<KIND, HID>& S = smem_all[w];
 
+#ifdef PROMP_EXP_CLOCKS
+    unsigned long long ro_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ro_last = clock64();
+#endif
     const float* th = A.params + (int64_t)m * A.param_stride;
     if (A.stream_id_dev) A.stream_id += *A.stream_id_dev;   // device-side phase counter (CUDA-graph replays)
     const int64_t env_id = (int64_t)m * A.E + e;     // global env index
@@ -169,6 +188,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
 
     const PointCornerCfg pcfg{A.reward_type, A.radius, A.normalized != 0};
 
+    RCLK(0);
     for (int t0 = 0; t0 < A.H; t0 += T_CH) {
         const int nt = min(T_CH, A.H - t0);
         // ---- action noise for this chunk -> shared memory
@@ -191,6 +211,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
             }
         }
         __syncwarp();
+        RCLK(1);
 
         for (int tt = 0; tt < nt; ++tt) {
             // ---- layer 0: h1 = tanh(obs W0 + b0)           (policies/networks/mlp.py:96-117)
@@ -207,34 +228,42 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
             // stage obs_t (the observation the action is computed from)
             if (lane < DO) S.st_obs[tt * DO + lane] = S.obs[lane];
             __syncwarp();
-            // ---- layer 1: h2 = tanh(h1 W1 + b1); two accumulators per output for ILP
-            float acc[NU][2];
+            RCLK(2);
+            // ---- layer 1: h2 = tanh(h1 W1 + b1); NACC accumulators per output for ILP (4 where the registers allow it)
+            constexpr int NACC = (KIND == PROMP_ENV_CHEETAH_DIR) ? 2 : 4;
+            float acc[NU][NACC];
 #pragma unroll
-            for (int u = 0; u < NU; ++u) acc[u][0] = b1[u], acc[u][1] = 0.f;
+            for (int u = 0; u < NU; ++u) {
+                acc[u][0] = b1[u];
+#pragma unroll
+                for (int a = 1; a < NACC; ++a) acc[u][a] = 0.f;
+            }
 #pragma unroll
             for (int k4 = 0; k4 < HID / 4; ++k4) {
                 const float4 h = *reinterpret_cast<const float4*>(&S.h1[4 * k4]);   // warp-broadcast LDS.128
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
-                    acc[u][0] = fmaf(h.x, w1[4 * k4 + 0][u], acc[u][0]);
-                    acc[u][1] = fmaf(h.y, w1[4 * k4 + 1][u], acc[u][1]);
-                    acc[u][0] = fmaf(h.z, w1[4 * k4 + 2][u], acc[u][0]);
-                    acc[u][1] = fmaf(h.w, w1[4 * k4 + 3][u], acc[u][1]);
+                    acc[u][0 % NACC] = fmaf(h.x, w1[4 * k4 + 0][u], acc[u][0 % NACC]);
+                    acc[u][1 % NACC] = fmaf(h.y, w1[4 * k4 + 1][u], acc[u][1 % NACC]);
+                    acc[u][2 % NACC] = fmaf(h.z, w1[4 * k4 + 2][u], acc[u][2 % NACC]);
+                    acc[u][3 % NACC] = fmaf(h.w, w1[4 * k4 + 3][u], acc[u][3 % NACC]);
                 }
             }
+            RCLK(3);
             // ---- layer 2: mean = h2 W2 + b2 (warp shuffle reduction over the hidden units)
             float mu[DA];
 #pragma unroll
             for (int d = 0; d < DA; ++d) mu[d] = 0.f;
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
-                const float h2 = tanh_fast(acc[u][0] + acc[u][1]);
+                const float h2 = tanh_fast(NACC == 4 ? (acc[u][0] + acc[u][1]) + (acc[u][2 % NACC] + acc[u][3 % NACC]) : acc[u][0] + acc[u][1]);
 #pragma unroll
                 for (int d = 0; d < DA; ++d) mu[d] = fmaf(h2, w2[u][d], mu[d]);
             }
 #pragma unroll
             for (int d = 0; d < DA; ++d) mu[d] = warp_sum(mu[d]) + b2[d];
 
+            RCLK(4);
             // ---- sample: a = mean + eps * exp(log_std)      (gaussian_mlp_policy.py:74)
             float a[DA];
 #pragma unroll
@@ -248,6 +277,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                 S.st_mean[tt * DA + lane] = ml;
             }
 
+            RCLK(5);
             // ---- env step (NormalizedEnv rescale + env dynamics + reward)
             float r;
             if (KIND == PROMP_ENV_POINT_CORNER) {
@@ -272,9 +302,11 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                 }
             }
             if (lane == 0) S.st_rew[tt] = r;
+            RCLK(6);
             __syncwarp();      // all lanes are done reading S.obs / S.h1 of this step
             write_obs();
             __syncwarp();
+            RCLK(7);
         }
 
         // ---- coalesced flush of the staged chunk: consecutive lanes -> consecutive floats
@@ -300,6 +332,11 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
         __syncwarp();
     }
 
+#ifdef PROMP_EXP_CLOCKS
+    RCLK(1);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) g_ro_clk[i] += ro_clk[i];
+#endif
     if (A.final_state) {
         float* fs = A.final_state + env_id * SD;
         if (KIND == PROMP_ENV_CHEETAH_DIR) {
@@ -507,3 +544,15 @@ extern "C" int promp_env_observe(int env_kind, int n_env, const float* state, fl
     PROMP_LAUNCH_CHECK("env_observe_kernel");
     return PROMP_OK;
 }
+
+#ifdef PROMP_EXP_CLOCKS
+extern "C" int promp_debug_rollout_clocks(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, promp::g_ro_clk, 16 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(promp::g_ro_clk, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
