@@ -237,6 +237,16 @@ int promp_policy_hvp_ragged(int obs_dim, int act_dim, int hidden, int M, int N, 
                             const float* vec, float* out, float* stats,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Scalars of one meta-objective evaluation (optimizers/maml_first_order_optimizer.py:146-163 compute_stats; the
+ * objective of meta_algos/pro_mp.py:151-155) from the stats rows the policy kernels wrote:
+ *   stats_all [S, M, 4]: row s < S-1 = inner step s (surr, KL, ...), row S-1 = outer objective (surr, KL, ...)
+ *   out[0] = mean_m surr_{S-1,m} (+ mean_s coeff[s] * inner_kl_s if coeff != NULL), out[1..S-1] = mean inner KLs,
+ *   out[S] = mean outer KL; means use inv_m_global = 1 / (M * world size); only the first n_out values are stored.
+ */
+int promp_meta_loss_terms(int S, int M, const float* stats_all, float inv_m_global, const float* coeff, int n_out,
+                          float* out, void* stream);
+
 /* out[P] = scale * sum_m in[m,P]   (mean over tasks of the meta objective, pro_mp.py:151-155). */
 int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, void* stream);
 

@@ -921,6 +921,35 @@ __global__ void adam_tf1_kernel(int P, float* theta, const float* grad, float* m
 }
 __global__ void adam_step_inc_kernel(int32_t* step) { *step += 1; }
 
+// [loss, inner_kl_0 .. inner_kl_{S-2}, outer_kl] of one meta-objective evaluation from the per-launch stats rows
+// stats_all [S, M, 4] (row s < S-1: inner step s -> (surr, KL); row S-1: outer objective -> (surr, KL)):
+//   loss = mean_m surr_{S-1,m} (+ mean_s coeff_s * inner_kl_s when coeff != NULL: pro_mp.py:151-155), means over M_global.
+// One block, warp w reduces term w in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) meta_loss_terms_kernel(int S, int M, const float* __restrict__ stats_all, float inv_mg,
+                                                               const float* __restrict__ coeff, int n_out, float* __restrict__ out) {
+    __shared__ float terms[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < S + 1) {
+        const int row = (w == 0 || w == S) ? S - 1 : w - 1;       // term 0: outer surr; 1..S-1: inner KLs; S: outer KL
+        const int col = (w == 0) ? 0 : 1;
+        float a = 0.f;
+        for (int m = lane; m < M; m += 32) a += stats_all[((int64_t)row * M + m) * 4 + col];
+        a = warp_sum(a) * inv_mg;
+        if (lane == 0) terms[w] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float loss = terms[0];
+        if (coeff && S > 1) {
+            float pen = 0.f;
+            for (int s = 0; s < S - 1; ++s) pen += coeff[s] * terms[1 + s];
+            loss += pen / (float)(S - 1);
+        }
+        out[0] = loss;
+        for (int i = 1; i < n_out && i < S + 1; ++i) out[i] = terms[i];
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 static int g_use_tc = 1;     // promp_set_option("tensor_cores", 0|1): HID = 64 policy kernels on tcgen05 (default) or CUDA cores
 
@@ -1159,6 +1188,15 @@ extern "C" int promp_reduce_tasks(int M, int P, const float* in, float scale, fl
     PROMP_REQUIRE(M > 0 && P > 0 && in && out, "promp_reduce_tasks: bad arguments");
     reduce_tasks_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(M, P, in, scale, out);
     PROMP_LAUNCH_CHECK("reduce_tasks_kernel");
+    return PROMP_OK;
+}
+
+extern "C" int promp_meta_loss_terms(int S, int M, const float* stats_all, float inv_m_global, const float* coeff, int n_out,
+                                     float* out, void* stream) {
+    PROMP_REQUIRE(S >= 1 && S <= 7 && M > 0 && stats_all && out && n_out >= 1 && n_out <= S + 1,
+                  "promp_meta_loss_terms: bad arguments (1 <= S <= 7 sampling phases, 1 <= n_out <= S+1)");
+    meta_loss_terms_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(S, M, stats_all, inv_m_global, coeff, n_out, out);
+    PROMP_LAUNCH_CHECK("meta_loss_terms_kernel");
     return PROMP_OK;
 }
 

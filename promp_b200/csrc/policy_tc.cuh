@@ -399,9 +399,21 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         PCLK(15);
         if (S.last) {
             __threadfence();
+            // the trailing float4 of every partial slot holds the objective / KL / ratio sums: reduced by the same loop
+            static_assert(L::P % 4 == 0 && PSTAT == 4, "stats ride on the float4 reduction");
+            if (!want_grad && tid == 0 && A.stats) {
+                const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, L::P);
+                A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN, A.stats[(int64_t)m * 4 + 2] = s.z * invN;
+            }
             if (want_grad) {
-                for (int p = 4 * tid; p < L::P; p += 4 * TCT) {
+                for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
                     const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                    if (p == L::P) {
+                        if (A.stats)
+                            A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN,
+                                                    A.stats[(int64_t)m * 4 + 2] = s.z * invN;
+                        continue;
+                    }
                     *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
                     if (A.out_params) {
                         const float4 t4 = __ldg(reinterpret_cast<const float4*>(th + p));
@@ -409,12 +421,6 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
                             make_float4(t4.x - A.sgd_lr * s.x, t4.y - A.sgd_lr * s.y, t4.z - A.sgd_lr * s.z, t4.w - A.sgd_lr * s.w);
                     }
                 }
-            }
-            if (A.stats && tid < 3) {
-                float s = 0.f;
-                for (int c = c_lo; c <= c_hi; ++c)
-                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + L::P + tid);
-                A.stats[(int64_t)m * 4 + tid] = s * invN;
             }
             if (tid == 0) A.counters[m] = 0;
         }
@@ -862,16 +868,16 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
         __syncthreads();
         if (S.last) {
             __threadfence();
-            for (int p = 4 * tid; p < L::P; p += 4 * TCT) {
+            for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
                 const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                if (p == L::P) {                  // trailing float4 of the slot: objective / KL / ratio sums
+                    if (A.stats)
+                        A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN,
+                                                A.stats[(int64_t)m * 4 + 2] = s.z * invN;
+                    continue;
+                }
                 const float4 v4 = __ldcg(reinterpret_cast<const float4*>(vg + p));
                 *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) = make_float4(v4.x + s.x, v4.y + s.y, v4.z + s.z, v4.w + s.w);
-            }
-            if (A.stats && tid < 3) {
-                float s = 0.f;
-                for (int c = c_lo; c <= c_hi; ++c)
-                    s += __ldcg(A.partial + ((int64_t)c * A.kmax + (m - ts.first_task(c))) * PSTRIDE + L::P + tid);
-                A.stats[(int64_t)m * 4 + tid] = s * invN;
             }
             if (tid == 0) A.counters[m] = 0;
         }

@@ -144,21 +144,20 @@ class MAMLAlgo(object):
         dev = p.device
         cur, stride, clip = theta, 0, 1              # step 0 = distribution_info_sym(params=None): clipped log_std
         chain = []
-        inner_kl = torch.zeros(max(S - 1, 0), M, dtype=torch.float32, device=dev)
+        # one stats buffer per evaluation, fully written by the kernels (no fills, no copies): row s = launch s
+        stats_all = torch.empty(S, M, 4, dtype=torch.float32, device=dev)
         for s in range(S - 1):
             g = torch.empty(M, P, dtype=torch.float32, device=dev)
             nxt = torch.empty(M, P, dtype=torch.float32, device=dev)
-            st = torch.zeros(M, 4, dtype=torch.float32, device=dev)
             self._grad(phases[s], cur, stride, self.inner_obj_kind, clip_log_std=clip, grad=g, out_params=nxt,
-                       sgd_lr=self.inner_lr, stats=st)
-            inner_kl[s] = st[:, 1]
+                       sgd_lr=self.inner_lr, stats=stats_all[s])
             chain.append((cur, stride, clip))
             cur, stride, clip = nxt, P, 0
-        st = torch.zeros(M, 4, dtype=torch.float32, device=dev)
         v = torch.empty(M, P, dtype=torch.float32, device=dev) if want_grad else None
         self._grad(phases[-1], cur, stride, outer_obj_kind, obj_scale=outer_obj_scale, clip_eps=clip_eps,
-                   kl_coeff=outer_kl_coeff, clip_log_std=clip, grad=v, stats=st)
-        out = dict(surr=st[:, 0], outer_kl=st[:, 1], inner_kl=inner_kl, grad=None)
+                   kl_coeff=outer_kl_coeff, clip_log_std=clip, grad=v, stats=stats_all[S - 1])
+        out = dict(surr=stats_all[S - 1, :, 0], outer_kl=stats_all[S - 1, :, 1], inner_kl=stats_all[:S - 1, :, 1],
+                   stats_all=stats_all, grad=None)
         if want_grad:
             for s in range(S - 2, -1, -1):
                 prm, strd, clp = chain[s]

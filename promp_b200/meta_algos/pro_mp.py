@@ -36,6 +36,7 @@ class ProMP(MAMLAlgo):
         return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, coeffs, want_grad)
 
     LOG_KEYS = ('LossBefore', 'LossAfter', 'KLInner')
+    FUSED_LOSS_TERMS = True      # loss_terms(res, out=, n_out=) is one promp_meta_loss_terms launch
 
     def optimize_phases(self, phases):
         """optimize_policy on PhaseData objects, everything left on the device.  Returns the float64 device vector
@@ -79,21 +80,30 @@ class ProMP(MAMLAlgo):
                                     outer_kl=host[2 + S1])
         return self._last_stats
 
-    def loss_terms(self, res):
+    def loss_terms(self, res, out=None, n_out=None):
         """Scalar meta objective + KLs (global means) from a _meta_pass result, as a device vector
-        [loss, inner_kl_0.., outer_kl]."""
+        [loss, inner_kl_0.., outer_kl] (one promp_meta_loss_terms launch; `out` / `n_out`: write the first n_out values
+        into a caller-provided buffer)."""
         import torch
         Mg = self.meta_batch_size * world_size()
         S1 = self.num_inner_grad_steps
-        vec = torch.cat([res['surr'].sum().view(1), res['inner_kl'].sum(1).view(-1), res['outer_kl'].sum().view(1)]) / Mg
-        allreduce_sum_(vec)
+        st = res['stats_all']
         key = tuple(float(c) for c in self.inner_kl_coeff)
         if getattr(self, '_coeff_key', None) != key:          # cached on the device (no H2D inside a graph capture)
-            self._coeff_dev = torch.tensor(key, dtype=torch.float32, device=vec.device)
+            self._coeff_dev = torch.tensor(key, dtype=torch.float32, device=st.device)
             self._coeff_key = key
-        coeff = self._coeff_dev
-        penalty = (coeff * vec[1:1 + S1]).mean() if S1 > 0 else vec.new_zeros(())
-        return torch.cat([(vec[0] + penalty).view(1), vec[1:]])
+        if out is None:
+            out = torch.empty(S1 + 2, dtype=torch.float32, device=st.device)
+        n_out = S1 + 2 if n_out is None else n_out
+        single = world_size() == 1
+        _lib.call('promp_meta_loss_terms', S1 + 1, self.meta_batch_size, _lib.ptr(st), 1.0 / Mg,
+                  _lib.ptr(self._coeff_dev) if (single and S1 > 0) else None, n_out if single else S1 + 2, _lib.ptr(out),
+                  _lib.stream())
+        if not single:                                        # sum the per-rank means, then add the penalty
+            allreduce_sum_(out)
+            if S1 > 0:
+                out[0] += (self._coeff_dev * out[1:1 + S1]).mean()
+        return out
 
     def adapt_kl_coeff(self, kl_coeff, kl_values, kl_target):
         """pro_mp.py:201-214."""

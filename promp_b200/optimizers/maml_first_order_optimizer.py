@@ -42,15 +42,23 @@ class MAMLPPOOptimizer(object):
         """optimize (:82-115) + compute_stats (:146-163).  Returns a device vector
         [loss_before, loss_after, inner_kl_0.., outer_kl] without synchronising the host."""
         import torch
+        S1 = algo.num_inner_grad_steps
+        fused = getattr(algo, 'FUSED_LOSS_TERMS', False)
+        if fused:
+            # [loss_before | loss_after, inner_kls, outer_kl] written in place by promp_meta_loss_terms: no cat / slicing kernels
+            final = torch.empty(S1 + 3, dtype=torch.float32, device=algo.policy.device)
         loss_before = None
         for epoch in range(self._max_epochs):
             res = algo._objective_pass(phases, want_grad=True)
             allreduce_sum_(res['grad'])                 # the ONE collective of the data path: [P] floats over NVLink
             if loss_before is None:
-                loss_before = algo.loss_terms(res)[0:1]
+                loss_before = algo.loss_terms(res, out=final[0:], n_out=1)[0:1] if fused else algo.loss_terms(res)[0:1]
             self.apply_gradient(res['grad'])
             self.last_grad = res['grad']
         res = algo._objective_pass(phases, want_grad=False)
+        if fused and loss_before is not None:
+            algo.loss_terms(res, out=final[1:])
+            return final
         terms = algo.loss_terms(res)
         if loss_before is None:
             loss_before = terms[0:1]

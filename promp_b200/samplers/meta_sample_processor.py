@@ -99,8 +99,9 @@ def run_process_kernel(phase, discount, gae_lambda, reg_coeff, baseline_kind, no
     if phase.returns is None:
         phase.returns = torch.empty(M, E * H, dtype=torch.float32, device=dev)
         phase.adv = torch.empty(M, E * H, dtype=torch.float32, device=dev)
-        phase.coeffs = torch.zeros(M, 2 * Do + 4, dtype=torch.float64, device=dev)
-        phase.stats = torch.zeros(M, 8, dtype=torch.float64, device=dev)
+        # both are fully written by the kernels (coeffs only by the linear-feature baseline): no fill launches
+        phase.coeffs = (torch.empty if baseline_kind == 1 else torch.zeros)(M, 2 * Do + 4, dtype=torch.float64, device=dev)
+        phase.stats = torch.empty(M, 8, dtype=torch.float64, device=dev)
     nbytes = _lib.load().promp_process_workspace_bytes(M, E, H, Do)
     ws = getattr(phase, '_proc_ws', None)
     if ws is None or ws.numel() * 8 < nbytes:
