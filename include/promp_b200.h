@@ -39,7 +39,13 @@ typedef enum {
 
 /* env kinds (envs/point_envs/point_env_2d_corner.py, envs/point_envs/point_env_2d.py,
  * envs/mujoco_envs/half_cheetah_rand_direc.py [analytic surrogate]) */
-enum { PROMP_ENV_POINT_CORNER = 0, PROMP_ENV_POINT = 1, PROMP_ENV_CHEETAH_DIR = 2 };
+enum {
+    PROMP_ENV_POINT_CORNER = 0,
+    PROMP_ENV_POINT = 1,
+    PROMP_ENV_CHEETAH_DIR = 2,
+    PROMP_ENV_POINT_WALLS = 3,     /* envs/point_envs/point_env_2d_walls.py: two circular walls with one gap each      */
+    PROMP_ENV_POINT_MOMENTUM = 4   /* envs/point_envs/point_env_2d_momentum.py: actions accelerate, obs = (pos, vel)   */
+};
 /* MetaPointEnvCorner.reward_type (point_env_2d_corner.py:13-16) */
 enum { PROMP_REWARD_SPARSE = 0, PROMP_REWARD_DENSE = 1, PROMP_REWARD_DENSE_SQUARED = 2 };
 /* objective kinds of promp_policy_grad */
@@ -57,9 +63,10 @@ int promp_version(void);
 
 /* Number of policy parameters P for (obs_dim, act_dim, hidden,hidden). */
 int promp_num_params(int obs_dim, int act_dim, int hidden);
-/* State floats per env for init_state / final_state: 2 (point envs), 18 (cheetah: qpos[9] qvel[9]). */
+/* State floats per env for init_state / final_state: 2 (point envs; 4 = pos, vel for the momentum env), 18 (cheetah: qpos[9] qvel[9]). */
 int promp_env_state_dim(int env_kind);
-/* Floats per task in task_params: 2 (point corner goal), 0 -> pass 1 dummy (point), 1 (cheetah: direction or goal velocity). */
+/* Floats per task in task_params: 2 (point corner / momentum goal), 0 -> pass 1 dummy (point), 1 (cheetah: direction or goal
+ * velocity), 6 (walls: goal, gap_1, gap_2). */
 int promp_env_task_dim(int env_kind);
 
 /*

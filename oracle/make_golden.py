@@ -138,6 +138,63 @@ def gen_process_samples():
     np.savez_compressed(os.path.join(OUT, 'process_samples.npz'), **out)
 
 
+def gen_point_variants_steps():
+    """MetaPointEnvWalls (dense / dense_squared) and MetaPointEnvMomentum (three reward types) under normalize:
+    seeded tasks (pins the RNG order of sample_tasks), resets and closed-loop steps under a random walk that is
+    strong enough to hit both walls."""
+    import copy
+    from meta_policy_search.envs.point_envs.point_env_2d_walls import MetaPointEnvWalls
+    from meta_policy_search.envs.point_envs.point_env_2d_momentum import MetaPointEnvMomentum
+    from meta_policy_search.envs.normalized_env import normalize
+    out = {}
+    T, n_env = 150, 12
+    rng = np.random.RandomState(21)
+    drift = rng.randn(1, n_env, 2) * 4.0                          # per-env outward drift so that the walls get crossed
+    actions = (drift + 6.0 * rng.randn(T, n_env, 2)).astype(np.float32).astype(np.float64)
+    out['walls_actions'] = actions
+    for rtype in ('dense', 'dense_squared'):
+        env = normalize(MetaPointEnvWalls(reward_type=rtype))
+        np.random.seed(17)
+        tasks = env.sample_tasks(n_env)
+        envs = [copy.deepcopy(env) for _ in range(n_env)]
+        obs0 = np.zeros((n_env, 2)); obs = np.zeros((T, n_env, 2)); rew = np.zeros((T, n_env))
+        for i, e in enumerate(envs):
+            e.set_task(tasks[i])
+            obs0[i] = e.reset()
+        for t in range(T):
+            for i, e in enumerate(envs):
+                o, r, d, info = e.step(actions[t, i])
+                assert d is False and info == {}
+                obs[t, i], rew[t, i] = o, r
+        out['walls_tasks'] = np.stack([np.concatenate([tk['goal'], tk['gap_1'], tk['gap_2']]) for tk in tasks]).astype(np.float64)
+        out['walls_obs0'] = obs0
+        out['walls_next_obs_' + rtype] = obs
+        out['walls_rewards_' + rtype] = rew
+    out['walls_rng_probe_after'] = np.random.uniform(size=3)
+    T2 = 60
+    actions = (3.0 * rng.randn(T2, n_env, 2)).astype(np.float32).astype(np.float64)
+    out['momentum_actions'] = actions
+    for rtype in ('sparse', 'dense', 'dense_squared'):
+        env = normalize(MetaPointEnvMomentum(reward_type=rtype))
+        np.random.seed(19)
+        tasks = env.sample_tasks(n_env)
+        envs = [copy.deepcopy(env) for _ in range(n_env)]
+        obs0 = np.zeros((n_env, 4)); obs = np.zeros((T2, n_env, 4)); rew = np.zeros((T2, n_env))
+        for i, e in enumerate(envs):
+            e.set_task(tasks[i])
+            obs0[i] = e.reset()
+        for t in range(T2):
+            for i, e in enumerate(envs):
+                o, r, d, info = e.step(actions[t, i])
+                assert d is False and info == {}
+                obs[t, i], rew[t, i] = o, r
+        out['momentum_goals'] = np.asarray(tasks, dtype=np.float64)
+        out['momentum_obs0'] = obs0
+        out['momentum_next_obs_' + rtype] = obs
+        out['momentum_rewards_' + rtype] = rew
+    np.savez_compressed(os.path.join(OUT, 'point_variants_steps.npz'), **out)
+
+
 def gen_process_samples_ragged():
     """MetaSampleProcessor + LinearFeatureBaseline on VARIABLE-LENGTH paths (early termination,
     meta_sampler.py:116-125): per task a different number of paths and samples.  Stored flat with offsets."""
@@ -251,5 +308,6 @@ if __name__ == '__main__':
     gen_sampler_rollout()
     gen_baseline_known()
     gen_process_samples_ragged()
+    gen_point_variants_steps()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -66,6 +66,82 @@ class PointEnvCorner(object):
         pass
 
 
+class PointEnvWalls(PointEnvCorner):
+    """ref: envs/point_envs/point_env_2d_walls.py:7-117 (MetaPointEnvWalls): two circular walls (radius 1 and 2), each
+    with one gap of radius 1 around gap_k; tasks = {goal corner, gap_1 on the unit circle, gap_2 on the radius-2 circle}."""
+
+    def __init__(self, reward_type='dense', sparse_reward_radius=2):
+        PointEnvCorner.__init__(self, reward_type, sparse_reward_radius)
+        self.gap_1 = self.gap_2 = None
+
+    def sample_tasks(self, n_tasks):                       # ref :102-108 (one choice draw, then two normal draws)
+        goals = [self.corners[i] for i in np.random.choice(range(4), size=n_tasks)]
+        g1 = np.random.normal(size=(n_tasks, 2))
+        g1 /= np.linalg.norm(g1, axis=1)[..., np.newaxis]
+        g2 = np.random.normal(size=(n_tasks, 2))
+        g2 /= (np.linalg.norm(g2, axis=1) / 2)[..., np.newaxis]
+        return [dict(goal=a, gap_1=b, gap_2=c) for a, b, c in zip(goals, g1, g2)]
+
+    def set_task(self, task):
+        self.goal, self.gap_1, self.gap_2 = task['goal'], task['gap_1'], task['gap_2']
+
+    def get_task(self):
+        return dict(goal=self.goal, gap_1=self.gap_1, gap_2=self.gap_2)
+
+    def reward(self, prev, nxt):                           # ref :75-90 (the 'sparse' branch yields None outside the radius)
+        g = np.sqrt(np.sum((nxt - self.goal) ** 2))
+        if self.reward_type == 'dense':
+            return -g
+        if self.reward_type == 'dense_squared':
+            return -g ** 2
+        return (np.sqrt(np.sum((prev - self.goal) ** 2)) - g) if g < self.sparse_reward_radius else None
+
+    def step(self, action):                                # ref :22-51: reward first, then the wall projection
+        prev = self._state
+        nxt = prev + np.clip(action, -0.2, 0.2)
+        r = self.reward(prev, nxt)
+        pn, nn = np.linalg.norm(prev), np.linalg.norm(nxt)
+        if pn < 1 and nn > 1:
+            if np.linalg.norm(nxt - self.gap_1) > 1:
+                nxt = nxt / (nn + 1e-6)
+        elif pn < 2 and nn > 2:
+            if np.linalg.norm(nxt - self.gap_2) > 1:
+                nxt = nxt / (nn * 0.5 + 1e-6)
+        self._state = nxt
+        return self._state.copy(), r, False, {}
+
+
+class PointEnvMomentum(PointEnvCorner):
+    """ref: envs/point_envs/point_env_2d_momentum.py:7-88 (MetaPointEnvMomentum): the action accelerates the point;
+    obs = (position, velocity); sparse reward = max(radius - goal distance, 0)."""
+    obs_dim = 4
+    action_low = np.full(2, -0.1, dtype=np.float32)
+    action_high = np.full(2, 0.1, dtype=np.float32)
+
+    def __init__(self, reward_type='sparse', sparse_reward_radius=2):
+        PointEnvCorner.__init__(self, reward_type, sparse_reward_radius)
+        self._velocity = None
+
+    def reset(self):                                       # ref :44-54: position draw, then velocity draw
+        self._state = np.random.uniform(-0.2, 0.2, size=(2,))
+        self._velocity = np.random.uniform(-0.1, 0.1, size=(2,))
+        return np.hstack((self._state, self._velocity))
+
+    def reward(self, prev, nxt):                           # ref :63-72
+        g = np.sqrt(np.sum((nxt - self.goal) ** 2))
+        if self.reward_type == 'dense':
+            return -g
+        if self.reward_type == 'dense_squared':
+            return -g ** 2
+        return np.maximum(self.sparse_reward_radius - g, 0)
+
+    def step(self, action):                                # ref :22-42
+        prev = self._state
+        self._velocity = self._velocity + np.clip(action, -0.1, 0.1)
+        self._state = prev + self._velocity
+        return np.hstack((self._state, self._velocity)), self.reward(prev, self._state), False, {}
+
+
 class PointEnv(object):
     """ref: envs/point_envs/point_env_2d.py:7-71 (MetaPointEnv; early `done`, no task)."""
     obs_dim = 2

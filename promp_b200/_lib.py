@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('PROMP_B200_LIB', os.path.join(_HERE, 'libpromp_b200.so'))   # override: kernel experiments
 
 # enums (mirror include/promp_b200.h)
-ENV_POINT_CORNER, ENV_POINT, ENV_CHEETAH_DIR = 0, 1, 2
+ENV_POINT_CORNER, ENV_POINT, ENV_CHEETAH_DIR, ENV_POINT_WALLS, ENV_POINT_MOMENTUM = 0, 1, 2, 3, 4
 REWARD_SPARSE, REWARD_DENSE, REWARD_DENSE_SQUARED = 0, 1, 2
 OBJ_RATIO, OBJ_LOGLIK, OBJ_CLIP, OBJ_NONE = 0, 1, 2, 3
 BASELINE_ZERO, BASELINE_LINEAR_FEATURE = 0, 1

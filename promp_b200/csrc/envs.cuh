@@ -21,6 +21,12 @@ template <> struct EnvTraits<PROMP_ENV_POINT> {
 template <> struct EnvTraits<PROMP_ENV_CHEETAH_DIR> {
     static constexpr int DO = 17, DA = 6, SD = 18, TD = 1, NINFO = 2;
 };
+template <> struct EnvTraits<PROMP_ENV_POINT_WALLS> {
+    static constexpr int DO = 2, DA = 2, SD = 2, TD = 6, NINFO = 0;       // task = goal, gap_1, gap_2
+};
+template <> struct EnvTraits<PROMP_ENV_POINT_MOMENTUM> {
+    static constexpr int DO = 4, DA = 2, SD = 4, TD = 2, NINFO = 0;       // state = obs = (pos, vel)
+};
 
 // NormalizedEnv.step action map, same evaluation order as the reference expression
 //   lb + (a + scale) * (ub - lb) / (2*scale), then clip to [lb, ub]       (normalization_scale = 10)
@@ -98,6 +104,53 @@ __device__ __forceinline__ float point_step(float& sx, float& sy, float ax, floa
     sy += ey;
     done = (fabsf(sx) < 0.01f) && (fabsf(sy) < 0.01f);
     return -sqrt_fast(sx * sx + sy * sy);
+}
+
+// ------------------------------------------------------------------ point walls (ref point_env_2d_walls.py:22-51)
+// s' = s + clip(a, +-0.2); the reward is taken at s' BEFORE the wall logic (:37-39); crossing the unit circle outside
+// gap_1 (distance > 1 from the gap centre) projects s' back to just inside radius 1, crossing the radius-2 circle
+// outside gap_2 to just inside radius 2 (:40-49).  reward_type dense / dense_squared (the reference's 'sparse' branch
+// returns None outside the radius and cannot be sampled).
+__device__ __forceinline__ float point_walls_step(float& sx, float& sy, float ax, float ay, const float* task, int reward_type,
+                                                  bool normalized) {
+    const float lim = 0.2f;
+    float ex = env_action(ax, -lim, lim, normalized), ey = env_action(ay, -lim, lim, normalized);
+    ex = fminf(fmaxf(ex, -lim), lim);
+    ey = fminf(fmaxf(ey, -lim), lim);
+    const float px = sx, py = sy;
+    float nx = px + ex, ny = py + ey;
+    const float g = dist2d(nx, ny, task[0], task[1]);
+    const float r = (reward_type == PROMP_REWARD_DENSE_SQUARED) ? -(g * g) : -g;
+    const float pn = sqrt_fast(px * px + py * py), nn = sqrt_fast(nx * nx + ny * ny);
+    if (pn < 1.f && nn > 1.f) {
+        if (dist2d(nx, ny, task[2], task[3]) > 1.f) {
+            const float inv = 1.f / (nn + 1e-6f);
+            nx *= inv, ny *= inv;
+        }
+    } else if (pn < 2.f && nn > 2.f) {
+        if (dist2d(nx, ny, task[4], task[5]) > 1.f) {
+            const float inv = 1.f / (nn * 0.5f + 1e-6f);
+            nx *= inv, ny *= inv;
+        }
+    }
+    sx = nx, sy = ny;
+    return r;
+}
+
+// ------------------------------------------------------------------ point momentum (ref point_env_2d_momentum.py:22-42, 58-68)
+// v' = v + clip(a, +-0.1); s' = s + v'; obs = (s', v'); reward at s': sparse (default) = max(radius - |s' - goal|, 0)
+__device__ __forceinline__ float point_momentum_step(float& sx, float& sy, float& vx, float& vy, float ax, float ay, float gx,
+                                                     float gy, const PointCornerCfg& cfg) {
+    const float lim = 0.1f;
+    float ex = env_action(ax, -lim, lim, cfg.normalized), ey = env_action(ay, -lim, lim, cfg.normalized);
+    ex = fminf(fmaxf(ex, -lim), lim);
+    ey = fminf(fmaxf(ey, -lim), lim);
+    vx += ex, vy += ey;
+    sx += vx, sy += vy;
+    const float g = dist2d(sx, sy, gx, gy);
+    if (cfg.reward_type == PROMP_REWARD_DENSE) return -g;
+    if (cfg.reward_type == PROMP_REWARD_DENSE_SQUARED) return -(g * g);
+    return fmaxf(cfg.radius - g, 0.f);
 }
 
 // ------------------------------------------------------------------ cheetah surrogate

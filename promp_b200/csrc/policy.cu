@@ -1071,7 +1071,9 @@ static int launch_forward(int M, int N, const float* params, int64_t stride, con
     if (obs_dim == 2 && act_dim == 2 && hidden == 32) return FN<2, 2, 32>(__VA_ARGS__);        \
     if (obs_dim == 17 && act_dim == 6 && hidden == 64) return FN<17, 6, 64>(__VA_ARGS__);      \
     if (obs_dim == 17 && act_dim == 6 && hidden == 32) return FN<17, 6, 32>(__VA_ARGS__);      \
-    set_error("unsupported (obs_dim, act_dim, hidden) = (%d, %d, %d); built: (2,2,{32,64}), (17,6,{32,64})", \
+    if (obs_dim == 4 && act_dim == 2 && hidden == 64) return FN<4, 2, 64>(__VA_ARGS__);        \
+    if (obs_dim == 4 && act_dim == 2 && hidden == 32) return FN<4, 2, 32>(__VA_ARGS__);        \
+    set_error("unsupported (obs_dim, act_dim, hidden) = (%d, %d, %d); built: (2,2,{32,64}), (4,2,{32,64}), (17,6,{32,64})", \
               obs_dim, act_dim, hidden);                                                       \
     return PROMP_ERR_INVALID_ARG;
 

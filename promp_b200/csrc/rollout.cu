@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
     for (int i = 0; i < TD; ++i) task[i] = __ldg(A.task_params + (int64_t)m * TD + i);
 
     // env state registers
-    float sx = 0.f, sy = 0.f;                    // point envs
+    float sx = 0.f, sy = 0.f, vx = 0.f, vy = 0.f;   // point envs (vx, vy: momentum env)
     float q = 0.f, qd = 0.f, root[6] = {0, 0, 0, 0, 0, 0};   // cheetah: lane's joint (lane&7) + replicated root
     cheetah::JointConst jc = cheetah::joint_const(lane & 7);
 
@@ -157,13 +157,15 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
         if (A.init_state) {
             sx = A.init_state[env_id * SD + 0];
             sy = A.init_state[env_id * SD + 1];
+            if (KIND == PROMP_ENV_POINT_MOMENTUM) vx = A.init_state[env_id * SD + 2], vy = A.init_state[env_id * SD + 3];
         } else {
             uint32_t r[4];
             Philox::gen((uint32_t)env_id, 0u, (uint32_t)A.stream_id,
                         0x52000000u | (uint32_t)((A.stream_id >> 32) & 0xffffffu), A.seed, r);
-            const float lim = (KIND == PROMP_ENV_POINT_CORNER) ? 0.2f : 2.0f;   // reset ranges (:50 / point_env_2d.py:34)
+            const float lim = (KIND == PROMP_ENV_POINT) ? 2.0f : 0.2f;   // reset ranges (point_env_2d_corner.py:50 / point_env_2d.py:34)
             sx = -lim + 2.f * lim * u01(r[0]);
             sy = -lim + 2.f * lim * u01(r[1]);
+            if (KIND == PROMP_ENV_POINT_MOMENTUM) vx = -0.1f + 0.2f * u01(r[2]), vy = -0.1f + 0.2f * u01(r[3]);   // (:52)
         }
     }
 
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
         } else if (lane == 0) {
             S.obs[0] = sx;
             S.obs[1] = sy;
+            if (KIND == PROMP_ENV_POINT_MOMENTUM) S.obs[2] = vx, S.obs[3] = vy;
         }
     };
     write_obs();
@@ -285,6 +288,10 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
             } else if (KIND == PROMP_ENV_POINT) {
                 bool dn;
                 r = point_step(sx, sy, a[0], a[1], dn, A.normalized != 0);   // early `done` is ignored by the fused kernel
+            } else if (KIND == PROMP_ENV_POINT_WALLS) {
+                r = point_walls_step(sx, sy, a[0], a[1], task, A.reward_type, A.normalized != 0);
+            } else if (KIND == PROMP_ENV_POINT_MOMENTUM) {
+                r = point_momentum_step(sx, sy, vx, vy, a[0], a[1], task[0], task[1], pcfg);
             } else {
                 float al = 0.f;
                 const int jl = lane & 7;
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
         } else if (lane == 0) {
             fs[0] = sx;
             fs[1] = sy;
+            if (KIND == PROMP_ENV_POINT_MOMENTUM) fs[2] = vx, fs[3] = vy;
         }
     }
 }
@@ -376,6 +384,12 @@ __global__ void env_step_kernel(int reward_type, float radius, int normalized, i
         r = point_corner_step(st[0], st[1], a[0], a[1], task_params[(int64_t)i * TD], task_params[(int64_t)i * TD + 1], cfg);
     } else if (KIND == PROMP_ENV_POINT) {
         r = point_step(st[0], st[1], a[0], a[1], dn, normalized != 0);
+    } else if (KIND == PROMP_ENV_POINT_WALLS) {
+        r = point_walls_step(st[0], st[1], a[0], a[1], task_params + (int64_t)i * TD, reward_type, normalized != 0);
+    } else if (KIND == PROMP_ENV_POINT_MOMENTUM) {
+        PointCornerCfg cfg{reward_type, radius, normalized != 0};
+        r = point_momentum_step(st[0], st[1], st[SD > 2 ? 2 : 0], st[SD > 3 ? 3 : 1], a[0], a[1], task_params[(int64_t)i * TD],
+                                task_params[(int64_t)i * TD + 1], cfg);
     } else {
         float u[DA], rr, rc, fv;
 #pragma unroll
@@ -405,8 +419,8 @@ __global__ void env_step_kernel(int reward_type, float radius, int normalized, i
 #pragma unroll
         for (int k = 0; k < 9; ++k) next_obs[(int64_t)i * DO + 8 + k] = st[9 + k];
     } else {
-        next_obs[(int64_t)i * DO] = st[0];
-        next_obs[(int64_t)i * DO + 1] = st[1];
+#pragma unroll
+        for (int k = 0; k < DO; ++k) next_obs[(int64_t)i * DO + k] = st[k];       // point envs: obs = state
     }
 }
 
@@ -419,8 +433,7 @@ __global__ void env_observe_kernel(int n_env, const float* state, float* obs) {
         for (int k = 0; k < 8; ++k) obs[(int64_t)i * T::DO + k] = state[(int64_t)i * T::SD + 1 + k];
         for (int k = 0; k < 9; ++k) obs[(int64_t)i * T::DO + 8 + k] = state[(int64_t)i * T::SD + 9 + k];
     } else {
-        obs[(int64_t)i * 2] = state[(int64_t)i * 2];
-        obs[(int64_t)i * 2 + 1] = state[(int64_t)i * 2 + 1];
+        for (int k = 0; k < T::DO; ++k) obs[(int64_t)i * T::DO + k] = state[(int64_t)i * T::SD + k];
     }
 }
 
@@ -441,6 +454,8 @@ extern "C" int promp_env_state_dim(int env_kind) {
         case PROMP_ENV_POINT_CORNER: return 2;
         case PROMP_ENV_POINT: return 2;
         case PROMP_ENV_CHEETAH_DIR: return 18;
+        case PROMP_ENV_POINT_WALLS: return 2;
+        case PROMP_ENV_POINT_MOMENTUM: return 4;
     }
     return -1;
 }
@@ -449,6 +464,8 @@ extern "C" int promp_env_task_dim(int env_kind) {
         case PROMP_ENV_POINT_CORNER: return 2;
         case PROMP_ENV_POINT: return 1;
         case PROMP_ENV_CHEETAH_DIR: return 1;
+        case PROMP_ENV_POINT_WALLS: return 6;
+        case PROMP_ENV_POINT_MOMENTUM: return 2;
     }
     return -1;
 }
@@ -479,6 +496,13 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
             PROMP_REQUIRE(reward_type == 0 || reward_type == 1, "promp_rollout: cheetah reward_type must be 0 (RandDirec) or 1 (RandVel)");
             return hidden == 64 ? launch_rollout<PROMP_ENV_CHEETAH_DIR, 64>(A, st)
                                 : launch_rollout<PROMP_ENV_CHEETAH_DIR, 32>(A, st);
+        case PROMP_ENV_POINT_WALLS:
+            PROMP_REQUIRE(reward_type == PROMP_REWARD_DENSE || reward_type == PROMP_REWARD_DENSE_SQUARED,
+                          "promp_rollout: the walls env supports reward_type dense / dense_squared");
+            return hidden == 64 ? launch_rollout<PROMP_ENV_POINT_WALLS, 64>(A, st) : launch_rollout<PROMP_ENV_POINT_WALLS, 32>(A, st);
+        case PROMP_ENV_POINT_MOMENTUM:
+            return hidden == 64 ? launch_rollout<PROMP_ENV_POINT_MOMENTUM, 64>(A, st)
+                                : launch_rollout<PROMP_ENV_POINT_MOMENTUM, 32>(A, st);
         case PROMP_ENV_POINT:
             set_error("promp_rollout: MetaPointEnv terminates early (variable-length paths); use the stepwise "
                       "sampler (promp_env_step) for it");
@@ -521,6 +545,14 @@ extern "C" int promp_env_step(int env_kind, int reward_type, float sparse_radius
                                                                       actions, task_params, reset_state, next_obs, rew,
                                                                       done, info);
             break;
+        case PROMP_ENV_POINT_WALLS:
+            env_step_kernel<PROMP_ENV_POINT_WALLS><<<gs, bs, 0, st>>>(reward_type, sparse_radius, normalize_actions, n_env, H, state, ts,
+                                                                      actions, task_params, reset_state, next_obs, rew, done, info);
+            break;
+        case PROMP_ENV_POINT_MOMENTUM:
+            env_step_kernel<PROMP_ENV_POINT_MOMENTUM><<<gs, bs, 0, st>>>(reward_type, sparse_radius, normalize_actions, n_env, H, state,
+                                                                         ts, actions, task_params, reset_state, next_obs, rew, done, info);
+            break;
         default:
             set_error("promp_env_step: unknown env_kind %d", env_kind);
             return PROMP_ERR_INVALID_ARG;
@@ -537,6 +569,8 @@ extern "C" int promp_env_observe(int env_kind, int n_env, const float* state, fl
         case PROMP_ENV_POINT_CORNER: env_observe_kernel<PROMP_ENV_POINT_CORNER><<<gs, bs, 0, st>>>(n_env, state, obs); break;
         case PROMP_ENV_POINT: env_observe_kernel<PROMP_ENV_POINT><<<gs, bs, 0, st>>>(n_env, state, obs); break;
         case PROMP_ENV_CHEETAH_DIR: env_observe_kernel<PROMP_ENV_CHEETAH_DIR><<<gs, bs, 0, st>>>(n_env, state, obs); break;
+        case PROMP_ENV_POINT_WALLS: env_observe_kernel<PROMP_ENV_POINT_WALLS><<<gs, bs, 0, st>>>(n_env, state, obs); break;
+        case PROMP_ENV_POINT_MOMENTUM: env_observe_kernel<PROMP_ENV_POINT_MOMENTUM><<<gs, bs, 0, st>>>(n_env, state, obs); break;
         default:
             set_error("promp_env_observe: unknown env_kind %d", env_kind);
             return PROMP_ERR_INVALID_ARG;

@@ -370,7 +370,7 @@ def test_likelihood_ratio_is_one_at_first_inner_step():
 
 
 @pytest.mark.parametrize('Do,Da,hidden,N,S1', [(2, 2, 64, 256, 1), (17, 6, 64, 150, 1), (2, 2, 64, 100, 2),
-                                               (17, 6, 32, 90, 1), (2, 2, 32, 70, 2)])
+                                               (17, 6, 32, 90, 1), (2, 2, 32, 70, 2), (4, 2, 64, 300, 1), (4, 2, 32, 130, 1)])
 @pytest.mark.parametrize('kind', ['promp', 'trpo'])
 def test_meta_gradient_matches_oracle(Do, Da, hidden, N, S1, kind):
     """Second-order meta-gradient (forward chain + exact HVP backward chain) vs torch double-backward.
@@ -844,7 +844,7 @@ def test_vpg_maml_matches_oracle(exploration):
     assert abs(algo.last_stats['loss_before'] - float(obj)) < 1e-4 * max(1.0, abs(float(obj)))
 
 
-@pytest.mark.parametrize('Do,Da,N', [(2, 2, 2000), (17, 6, 700), (2, 2, 130)])
+@pytest.mark.parametrize('Do,Da,N', [(2, 2, 2000), (17, 6, 700), (2, 2, 130), (4, 2, 391)])
 def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
     """promp_set_option("tensor_cores", 1): the tcgen05/TMEM 3xTF32 path of policy_grad (layer GEMMs on the tensor
     cores) gives the CUDA-core path's results to fp32 round-off, for shared and per-task parameters, grad and
@@ -896,7 +896,7 @@ def test_tensor_core_policy_grad_matches_simt_and_oracle(Do, Da, N):
 
 
 @pytest.mark.parametrize('Do,Da,N,stride_mode', [(2, 2, 2000, 'shared'), (2, 2, 2000, 'per_task'), (2, 2, 130, 'shared'),
-                                                  (17, 6, 700, 'per_task'), (17, 6, 129, 'shared')])
+                                                  (17, 6, 700, 'per_task'), (17, 6, 129, 'shared'), (4, 2, 391, 'per_task')])
 def test_tensor_core_policy_hvp_matches_simt(Do, Da, N, stride_mode):
     """The tcgen05 path of policy_hvp (forward and backward layer GEMMs as 3xTF32 MMAs with the "lo" A operands in
     tensor memory) gives the CUDA-core path's backward-chain vector to fp32 round-off, for both inner
@@ -1147,3 +1147,99 @@ def test_half_cheetah_rand_vel_surrogate():
     Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1, num_inner_grad_steps=1).train()
     kv = logger.last_dump()
     assert np.isfinite(kv['LossAfter']) and 'Step_1-AvgForwardVel' in kv and np.isfinite(kv['Step_0-AverageReturn'])
+
+
+def test_point_walls_and_momentum_envs(golden_dir):
+    """MetaPointEnvWalls / MetaPointEnvMomentum: the vec-env step kernel against the
+    unmodified reference (tests/golden/point_variants_steps.npz, trajectory glued to the reference each step so float32
+    drift cannot flip a wall decision later), task draws in the reference's RNG order, the fused rollout bit-identical to
+    the step kernel, and a full ProMP iteration on the momentum env (obs_dim 4 policy kernels)."""
+    torch = _cuda()
+    from promp_b200.envs import normalize, MetaPointEnvWalls, MetaPointEnvMomentum
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from promp_b200.samplers import MetaSampler, MetaSampleProcessor, MetaDeviceEnvExecutor
+    from promp_b200.baselines import LinearFeatureBaseline
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    from promp_b200.utils import logger
+    g = _load(golden_dir, 'point_variants_steps.npz')
+    # ---- walls: tasks (RNG order) + steps
+    T, n_env, _ = g['walls_actions'].shape
+    for rtype in ('dense', 'dense_squared'):
+        env = normalize(MetaPointEnvWalls(reward_type=rtype))
+        np.random.seed(17)
+        tasks = env.sample_tasks(n_env)
+        np.testing.assert_array_equal(np.stack([np.concatenate([t['goal'], t['gap_1'], t['gap_2']]) for t in tasks]), g['walls_tasks'])
+        ex = MetaDeviceEnvExecutor(env, n_env, 1, max_path_length=10 ** 6)
+        ex.set_tasks(tasks)
+        ex.state.copy_(torch.from_numpy(g['walls_obs0'].astype(np.float32)))
+        n_bad = 0
+        for t in range(T):
+            obs, rew, dones, infos = ex.step(g['walls_actions'][t])
+            want = g['walls_next_obs_' + rtype][t]
+            bad = np.abs(np.asarray(obs) - want).max(axis=1) > 5e-5          # a float32 norm within 1 ulp of a wall radius
+            n_bad += int(bad.sum())
+            np.testing.assert_allclose(np.asarray(rew), g['walls_rewards_' + rtype][t], rtol=1e-5, atol=1e-5)
+            assert not dones.any() and infos[0] == {}
+            ex.state.copy_(torch.from_numpy(want.astype(np.float32)))
+        assert n_bad <= 2, n_bad
+    with pytest.raises(NotImplementedError):
+        MetaPointEnvWalls(reward_type='sparse')
+    # ---- momentum: steps for the three reward types
+    T, n_env, _ = g['momentum_actions'].shape
+    for rtype in ('sparse', 'dense', 'dense_squared'):
+        env = normalize(MetaPointEnvMomentum(reward_type=rtype))
+        np.random.seed(19)
+        tasks = env.sample_tasks(n_env)
+        np.testing.assert_array_equal(np.asarray(tasks, dtype=np.float64), g['momentum_goals'])
+        ex = MetaDeviceEnvExecutor(env, n_env, 1, max_path_length=10 ** 6)
+        ex.set_tasks(tasks)
+        np.random.seed(19); env.sample_tasks(n_env)
+        np.testing.assert_allclose(np.asarray(ex.reset()), g['momentum_obs0'], rtol=0, atol=1e-7)   # reset draw order: pos, vel per env
+        for t in range(T):
+            obs, rew, dones, infos = ex.step(g['momentum_actions'][t])
+            np.testing.assert_allclose(np.asarray(obs), g['momentum_next_obs_' + rtype][t], rtol=0, atol=5e-5)
+            np.testing.assert_allclose(np.asarray(rew), g['momentum_rewards_' + rtype][t], rtol=1e-4, atol=2e-5)
+            ex.state.copy_(torch.from_numpy(g['momentum_next_obs_' + rtype][t].astype(np.float32)))
+    # ---- fused rollout == step kernel replayed with the rollout's own actions (same device functions -> bit-identical)
+    for make, sd in ((lambda: MetaPointEnvWalls(), 2), (lambda: MetaPointEnvMomentum(), 4)):
+        M, E, H = 3, 4, 50
+        np.random.seed(23)
+        env = normalize(make())
+        policy = MetaGaussianMLPPolicy(name="p", obs_dim=sd, action_dim=2, meta_batch_size=M, hidden_sizes=(64, 64))
+        policy.set_params(policy.get_param_values() if False else policy.theta.cpu().numpy() * 3.0)     # larger actions: reach the walls
+        sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H)
+        sampler.update_tasks()
+        policy.switch_to_pre_update()
+        rng = np.random.RandomState(4)
+        noise = (8.0 * rng.randn(M, E, H, 2)).astype(np.float32)
+        init = np.zeros((M, E, sd), dtype=np.float32)
+        init[..., :2] = rng.uniform(-0.2, 0.2, size=(M, E, 2))
+        if sd == 4:
+            init[..., 2:] = rng.uniform(-0.1, 0.1, size=(M, E, 2))
+        sampler.inject(noise=noise, init_state=init)
+        ph = sampler.obtain_samples().phase
+        obs = ph.obs.cpu().numpy().reshape(M * E, H, sd)
+        act = ph.act.cpu().numpy().reshape(M * E, H, 2)
+        rew = ph.rew.cpu().numpy().reshape(M * E, H)
+        assert np.isfinite(obs).all() and (sd == 4 or np.linalg.norm(obs, axis=-1).max() > 1.0)
+        ex = MetaDeviceEnvExecutor(env, M, E, max_path_length=10 ** 6)
+        ex.set_tasks(sampler.vec_env.tasks)
+        ex.state.copy_(torch.from_numpy(init.reshape(M * E, sd)))
+        for t in range(H):
+            np.testing.assert_array_equal(ex.state.cpu().numpy(), obs[:, t])
+            o, r, _, _ = ex.step(act[:, t])
+            np.testing.assert_array_equal(np.asarray(r, dtype=np.float32), rew[:, t])
+    # ---- a full ProMP iteration on the momentum env through the Trainer
+    logger.set_quiet(True)
+    np.random.seed(2)
+    M, E, H = 4, 5, 30
+    env = normalize(MetaPointEnvMomentum())
+    policy = MetaGaussianMLPPolicy(name="p", obs_dim=4, action_dim=2, meta_batch_size=M, hidden_sizes=(64, 64))
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H)
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3, num_ppo_steps=2)
+    th0 = policy.theta.clone()
+    Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1, num_inner_grad_steps=1).train()
+    kv = logger.last_dump()
+    assert np.isfinite(kv['LossAfter']) and np.isfinite(kv['Step_1-AverageReturn']) and not torch.equal(policy.theta, th0)

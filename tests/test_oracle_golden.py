@@ -93,6 +93,42 @@ def test_process_samples_matches_reference(golden_dir, case):
         np.testing.assert_array_equal(data[0]['observations'], obs[0].reshape(-1, cfg['Do']))
 
 
+def test_point_variants_match_reference(golden_dir):
+    """MetaPointEnvWalls / MetaPointEnvMomentum restatements vs the unmodified reference (point_variants_steps.npz):
+    task draws (RNG order), resets and 150 / 60 closed-loop steps, bit for bit."""
+    import copy
+    g = _load(golden_dir, 'point_variants_steps.npz')
+    T, n_env, _ = g['walls_actions'].shape
+    for rtype in ('dense', 'dense_squared'):
+        env = nh.NormalizedEnv(nh.PointEnvWalls(reward_type=rtype))
+        np.random.seed(17)
+        tasks = env.sample_tasks(n_env)
+        assert np.array_equal(np.stack([np.concatenate([t['goal'], t['gap_1'], t['gap_2']]) for t in tasks]), g['walls_tasks'])
+        envs = [copy.deepcopy(env) for _ in range(n_env)]
+        for i, e in enumerate(envs):
+            e.set_task(tasks[i])
+            assert np.array_equal(e.reset(), g['walls_obs0'][i])
+        for t in range(T):
+            for i, e in enumerate(envs):
+                o, r, d, info = e.step(g['walls_actions'][t, i])
+                assert np.array_equal(o, g['walls_next_obs_' + rtype][t, i]) and r == g['walls_rewards_' + rtype][t, i]
+    assert np.array_equal(np.random.uniform(size=3), g['walls_rng_probe_after'])
+    T, n_env, _ = g['momentum_actions'].shape
+    for rtype in ('sparse', 'dense', 'dense_squared'):
+        env = nh.NormalizedEnv(nh.PointEnvMomentum(reward_type=rtype))
+        np.random.seed(19)
+        tasks = env.sample_tasks(n_env)
+        assert np.array_equal(np.asarray(tasks, dtype=np.float64), g['momentum_goals'])
+        envs = [copy.deepcopy(env) for _ in range(n_env)]
+        for i, e in enumerate(envs):
+            e.set_task(tasks[i])
+            assert np.array_equal(e.reset(), g['momentum_obs0'][i])
+        for t in range(T):
+            for i, e in enumerate(envs):
+                o, r, d, info = e.step(g['momentum_actions'][t, i])
+                assert np.array_equal(o, g['momentum_next_obs_' + rtype][t, i]) and r == g['momentum_rewards_' + rtype][t, i]
+
+
 def ragged_paths_from_golden(g, pre):
     """Rebuild the per-task path lists of a process_samples_ragged.npz case (float64 like the reference's inputs)."""
     M = int(g[pre + 'cfg_M'])
