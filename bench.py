@@ -233,10 +233,12 @@ def run_gpu(args):
     if use_graph:
         # the public training entry point with use_cuda_graph=True: host numpy draws of tasks + reset states (reference
         # RNG order) -> pinned -> H2D, graph replay, one D2H of the packed logged scalars, logger keys emitted
-        e2e_step = tr_e2e.capture_graph(warmup=2, log=True)
+        e2e_step = tr_e2e.capture_graph(warmup=2, log=True, prefetch_host_inputs=True)
         ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps, e2e_step)
         h2d, d2h = tr_e2e.graph_h2d_bytes, tr_e2e.graph_d2h_bytes
-        e2e_api = 'promp_b200.meta_trainer.Trainer(use_cuda_graph=True).train() iteration, reset_mode=numpy, log=True'
+        e2e_api = ('promp_b200.meta_trainer.Trainer.capture_graph(log=True, prefetch_host_inputs=True) step: numpy-drawn tasks + reset states '
+                   '(reference RNG order, reset_mode=numpy; the NEXT iteration is drawn into a second pinned slot while the GPU runs), '
+                   'H2D from pinned memory, graph replay, one D2H of the logged scalars, logger keys emitted')
     else:
         ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps)
         h2d = 4 * (M * sd['task_dim'] + S * M * E * sd['state_dim'])

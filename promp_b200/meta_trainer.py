@@ -15,7 +15,7 @@ from promp_b200.utils import logger
 
 class Trainer(object):
     def __init__(self, algo, env, sampler, sample_processor, policy, n_itr, start_itr=0, num_inner_grad_steps=1,
-                 sess=None, use_cuda_graph=False):
+                 sess=None, use_cuda_graph=False, prefetch_host_inputs=False):
         self.algo, self.env, self.sampler, self.sample_processor = algo, env, sampler, sample_processor
         self.baseline = sample_processor.baseline
         self.policy = policy
@@ -23,6 +23,7 @@ class Trainer(object):
         self.num_inner_grad_steps = num_inner_grad_steps
         self.sess = sess
         self.use_cuda_graph = use_cuda_graph      # replay the device part of every iteration as one CUDA graph
+        self.prefetch_host_inputs = prefetch_host_inputs   # graph mode: draw iteration i+1's host inputs while the GPU runs i
         self._graph_step = None
 
     def train_iteration(self, itr, log=True):
@@ -59,13 +60,17 @@ class Trainer(object):
         return all_samples_data
 
     # ------------------------------------------------------------------ CUDA-graph replay of the device part
-    def capture_graph(self, warmup=3, log=False):
+    def capture_graph(self, warmup=3, log=False, prefetch_host_inputs=False):
         """Capture everything of a meta-iteration that runs on the device (S x [rollout + processing], inner adapt
         steps, K Adam epochs + stats pass: ~40 kernel launches) into ONE CUDA graph and return step().
 
         step() = host part of the reference iteration (numpy task draw; with reset_mode='numpy' also every phase's
         reset states, in the reference's RNG order) -> H2D into static buffers -> graph replay -> (log=True) one D2H
         copy of the packed vector of logged scalars, emitted under the reference's logger keys.
+        prefetch_host_inputs=True (reset_mode='numpy' only) software-pipelines the host half: iteration i+1's numpy draws
+        go into a second pinned staging slot while the GPU executes iteration i, so step() only starts the H2D copies and
+        the replay.  The draw ORDER is unchanged (same values for the same iteration), but the global numpy RNG is
+        consumed one iteration ahead - do not interleave other np.random users with step().
         Requirements: device policy + fixed-horizon device env, fixed KL coefficient.  With world_size > 1 the
         NCCL all-reduces of the meta-gradient are captured into the graph as well."""
         import torch
@@ -135,10 +140,22 @@ class Trainer(object):
         self.graph_d2h_bytes = 8 * len(keys) if log else 0
         n_steps = M * E * H * S
 
+        prefetch = bool(prefetch_host_inputs) and numpy_resets
+        state['slot'], state['drawn'] = 0, False
+
         def step(itr=0):
             t0 = time.time()
-            self.graph_h2d_bytes = host_part()
+            if prefetch:
+                if not state['drawn']:
+                    sampler.draw_host_inputs(S, state['slot'])
+                self.graph_h2d_bytes = sampler.upload_host_inputs(state['slot'])
+            else:
+                self.graph_h2d_bytes = host_part()
             graph.replay()
+            if prefetch:          # next iteration's host draws overlap the replay that was just enqueued
+                state['slot'] ^= 1
+                sampler.draw_host_inputs(S, state['slot'])
+                state['drawn'] = True
             sampler.total_timesteps_sampled += n_steps
             if log:
                 torch.cuda.current_stream().synchronize()
@@ -158,7 +175,7 @@ class Trainer(object):
             logger.log("\n ---------------- Iteration %d ----------------" % itr)
             if self.use_cuda_graph:
                 if self._graph_step is None:
-                    self._graph_step = self.capture_graph(log=True)
+                    self._graph_step = self.capture_graph(log=True, prefetch_host_inputs=self.prefetch_host_inputs)
                 self._graph_step(itr)
             else:
                 self.train_iteration(itr)

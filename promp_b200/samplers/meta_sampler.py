@@ -58,12 +58,7 @@ class MetaSampler(object):
     # ------------------------------------------------------------------------------------------
     def update_tasks(self):
         """meta_sampler.py:51-57."""
-        if self.task_shard is None:
-            tasks = self.env.sample_tasks(self.meta_batch_size)
-        else:
-            rank, world = self.task_shard
-            all_tasks = self.env.sample_tasks(self.meta_batch_size * world)
-            tasks = shard_tasks(all_tasks, rank, world)
+        tasks = self._draw_tasks()
         assert len(tasks) == self.meta_batch_size
         self.vec_env.set_tasks(tasks)
 
@@ -113,24 +108,53 @@ class MetaSampler(object):
         phase.invalidate_host()
         return phase
 
-    def stage_host_inputs(self, n_phases):
-        """Graph mode with reset_mode='numpy': draw this iteration's tasks and every phase's reset states from the
-        global numpy RNG in the reference's consumption order (sample_tasks; then per phase: M*E resets, and the M*E
-        end-of-horizon resets whose observations the reference discards) into pinned memory and start the H2D copies
-        into the static device buffers the captured rollouts read."""
+    def _draw_tasks(self):
+        """The reference's task draw (meta_sampler.py:51-57) for this rank's shard; host objects only."""
+        if self.task_shard is None:
+            return self.env.sample_tasks(self.meta_batch_size)
+        rank, world = self.task_shard
+        return shard_tasks(self.env.sample_tasks(self.meta_batch_size * world), rank, world)
+
+    def draw_host_inputs(self, n_phases, slot=0):
+        """Graph mode with reset_mode='numpy', host half: draw one iteration's tasks and every phase's reset states from
+        the global numpy RNG in the reference's consumption order (sample_tasks; then per phase: M*E resets, and the M*E
+        end-of-horizon resets whose observations the reference discards) into PINNED staging buffers (two slots, so the
+        next iteration can be drawn while the previous upload may still be in flight).  No device interaction."""
         import torch
         M, E = self.meta_batch_size, self.envs_per_task
         inner = getattr(self.env, '_wrapped_env', self.env)
-        sd = self.spec['state_dim']
-        if getattr(self, '_static_init', None) is None or len(self._static_init) != n_phases:
+        sd, td = self.spec['state_dim'], self.spec['task_dim']
+        if getattr(self, '_pinned_init', None) is None or len(self._pinned_init[0]) != n_phases:
             self._static_init = [torch.empty(M, E, sd, dtype=torch.float32, device=self.device) for _ in range(n_phases)]
-            self._pinned_init = [torch.empty(M, E, sd, dtype=torch.float32).pin_memory() for _ in range(n_phases)]
-        self.update_tasks()
+            self._pinned_init = [[torch.empty(M, E, sd, dtype=torch.float32).pin_memory() for _ in range(n_phases)] for _ in range(2)]
+            self._pinned_tasks = [torch.empty(M, td, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._staged_tasks = [None, None]
+        tasks = self._draw_tasks()
+        assert len(tasks) == self.meta_batch_size
+        self._staged_tasks[slot] = list(tasks)
+        self._pinned_tasks[slot].copy_(torch.from_numpy(np.stack([inner.task_vector(t) for t in tasks]).astype(np.float32)))
         for s in range(n_phases):
-            self._pinned_init[s].copy_(torch.from_numpy(inner.host_reset_states(M * E).astype(np.float32).reshape(M, E, sd)))
-            self._static_init[s].copy_(self._pinned_init[s], non_blocking=True)
+            self._pinned_init[slot][s].copy_(torch.from_numpy(inner.host_reset_states(M * E).astype(np.float32).reshape(M, E, sd)))
             inner.host_reset_states(M * E)     # discarded end-of-horizon resets (vectorized_env_executor.py:47-50)
-        return 4 * (M * self.spec['task_dim'] + n_phases * M * E * sd)
+
+    def upload_host_inputs(self, slot=0):
+        """Device half: start the H2D copies of a drawn slot into the static buffers the captured rollouts read."""
+        ve = self.vec_env
+        ve.tasks = self._staged_tasks[slot]
+        if len(ve.tasks):
+            self.env.set_task(ve.tasks[-1])
+        ve.task_params_per_task.copy_(self._pinned_tasks[slot], non_blocking=True)
+        ve._per_env_tasks_stale = True      # the per-env expansion (stepwise path only) is rebuilt on demand
+        n_phases = len(self._static_init)
+        for s in range(n_phases):
+            self._static_init[s].copy_(self._pinned_init[slot][s], non_blocking=True)
+        M, E = self.meta_batch_size, self.envs_per_task
+        return 4 * (M * self.spec['task_dim'] + n_phases * M * E * self.spec['state_dim'])
+
+    def stage_host_inputs(self, n_phases):
+        """draw_host_inputs + upload_host_inputs for the current iteration (no look-ahead)."""
+        self.draw_host_inputs(n_phases, 0)
+        return self.upload_host_inputs(0)
 
     def enable_device_phase_counter(self):
         """Keep the Philox phase counter in device memory so that a captured CUDA graph draws fresh

@@ -72,6 +72,9 @@ class MetaDeviceEnvExecutor(object):
         """vectorized_env_executor.py:25-52 -> (obs, rewards, dones, env_infos), lists of length M*E."""
         import torch
         assert len(actions) == self.num_envs
+        if getattr(self, '_per_env_tasks_stale', False):
+            self.task_params.copy_(self.task_params_per_task.repeat_interleave(self.envs_per_task, dim=0))
+            self._per_env_tasks_stale = False
         act = torch.from_numpy(np.asarray(actions, dtype=np.float32).reshape(self.n_envs, -1)).to(self.device)
         s = self.spec
         _lib.call('promp_env_step', s['env_kind'], s['reward_type'], s['radius'], int(s.get('normalized', False)), self.n_envs,
