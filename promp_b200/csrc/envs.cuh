@@ -225,28 +225,44 @@ __device__ __forceinline__ float sum8(float v) {
 }
 __device__ __forceinline__ void step_warp(const JointConst& jc, float u, float& q, float& qd, float (&root)[6], float task, int mode,
                                           float& reward, float& r_run, float& r_ctrl, float& fwd_vel) {
-    float x0 = root[0];
-    const float twist = sum8(jc.p * u);          // the torques are constant over the sub-steps: one reduction, not five
-#pragma unroll 1
+    // The joints (q, qd) and the pitch (root[2], root[5]) evolve independently of the two quantities that need a
+    // reduction over the joints (thrust -> x, lift -> z), and the x / z recurrences are LINEAR in thrust / lift.  So every
+    // lane integrates the response of (xd, x, zd, z) to ITS OWN joint's thrust / lift from zero initial conditions, all
+    // lanes integrate the homogeneous part from the real initial conditions, and one 8-lane reduction per env step (instead
+    // of two per sub-step on the critical path: 1 790 -> ~600 clk per step, tools/rollout_time.py) adds them up.  Same
+    // equations as step_serial / oracle/cheetah_surrogate.py; the summation order differs at float32 round-off.
+    const float x0 = root[0];
+    const float twist = sum8(jc.p * u);          // the torques are constant over the sub-steps
+    const float su = sum8(u * u);
+    float xdh = root[3], xh = root[0], zdh = root[4], zh = root[1];      // homogeneous parts
+    float xdp = 0.f, xp = 0.f, zdp = 0.f, zp = 0.f;                      // this lane's driven parts
+    float pitch = root[2], pd = root[5];
+#pragma unroll
     for (int s = 0; s < FRAME_SKIP; ++s) {
-        float acc = jc.g * u - jc.k * q - jc.d * qd;
+        const float acc = jc.g * u - jc.k * q - jc.d * qd;
         qd = qd + HS * acc;
         q = q + HS * qd;
         float sn, cs;
-        __sincosf(q + root[2] + jc.ph, &sn, &cs);   // |angle| stays O(1): fast path error ~5e-7
-        float thrust = sum8(jc.c * qd * sn);
-        float lift = sum8(jc.c * qd * cs);
-        float xd = root[3] + HS * (thrust - BX * root[3]);
-        root[3] = xd;
-        root[0] = root[0] + HS * xd;
-        float zd = root[4] + HS * (LZ * lift - KZ * root[1] - DZ * root[4]);
-        root[4] = zd;
-        root[1] = root[1] + HS * zd;
-        float pd = root[5] + HS * (twist - KP * root[2] - DP * root[5]);
-        root[5] = pd;
-        root[2] = root[2] + HS * pd;
+        __sincosf(q + pitch + jc.ph, &sn, &cs);   // pitch of the START of the sub-step, as in step_serial
+        const float t = jc.c * qd * sn, l = jc.c * qd * cs;
+        xdp = xdp + HS * (t - BX * xdp);
+        xp = xp + HS * xdp;
+        zdp = zdp + HS * (LZ * l - KZ * zp - DZ * zdp);
+        zp = zp + HS * zdp;
+        xdh = xdh + HS * (0.f - BX * xdh);
+        xh = xh + HS * xdh;
+        zdh = zdh + HS * (0.f - KZ * zh - DZ * zdh);
+        zh = zh + HS * zdh;
+        pd = pd + HS * (twist - KP * pitch - DP * pd);
+        pitch = pitch + HS * pd;
     }
-    r_ctrl = -0.05f * sum8(u * u);
+    root[3] = xdh + sum8(xdp);
+    root[0] = xh + sum8(xp);
+    root[4] = zdh + sum8(zdp);
+    root[1] = zh + sum8(zp);
+    root[5] = pd;
+    root[2] = pitch;
+    r_ctrl = -0.05f * su;
     fwd_vel = (root[0] - x0) / DT;
     r_run = mode ? -fabsf(fwd_vel - task) : task * fwd_vel;
     reward = r_ctrl + r_run;
