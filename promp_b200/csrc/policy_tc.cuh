@@ -4,14 +4,17 @@
 // cores as tcgen05.mma.kind::tf32 with the 3-term split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (a_hi = the fp32
 // value itself, which the tensor core truncates to TF32; a_lo = a - trunc_tf32(a)), i.e. fp32-level accuracy
 // (1.5e-6 relative, tools/ubench/umma_test.cu) at 24 MMAs per GEMM.  Accumulators live in TMEM (2 x 64 columns) and
-// are read back with tcgen05.ld (one sample row per thread, 32 columns each); operands are written by the epilogue
+// are read back with tcgen05.ld (one sample row per thread, 64 / NQ columns each; NQ = 2 or 4 column groups = 256 or 512
+// threads per CTA); operands are written by the epilogue
 // threads straight into the UMMA canonical K-major layout WITHOUT swizzle: 8x4-float core matrices (128 contiguous
 // bytes, rows 16 B apart), next 8 rows at +128 B (SBO), next 4 columns at +S_c (LBO).  S_c = rows*16 + 16 bytes: the
 // extra 16 B make both the row-wise 16-byte stores of the epilogue and the column-wise scalar reads of the SIMT
 // reductions bank-conflict free, and the same bytes stay readable as a plain fp32 tile by the CUDA-core code.
 // The weight-gradient GEMM H1^T.D2 contracts over samples, i.e. needs MN-major operands, which for tf32 exist only
-// in the 128B_BASE32B layout (a second copy of every tile): it stays on the CUDA cores and runs CONCURRENTLY with the
-// backward MMA (different pipes).  One elected thread issues the MMAs; completion is an mbarrier (tcgen05.commit).
+// in the 128B_BASE32B layout (a second copy of every tile): it runs on the warp-level tensor-core path (mma.sync
+// m16n8k8 tf32, same 3-term split, fragments loaded straight from the K-major tiles: wgrad_mma_tile below) CONCURRENTLY
+// with the backward tcgen05 MMA.  One elected thread of a warp-uniform branch issues the tcgen05 MMAs; completion is
+// an mbarrier (tcgen05.commit).
 #pragma once
 #include "mlp_tile.cuh"
 
