@@ -258,3 +258,18 @@ def test_logger_file_formats_and_snapshot_modes(tmp_path):
             logger.configure(dir=d, format_strs=['tensorboard'])
     finally:
         logger.reset()
+
+
+def test_ragged_phase_path_table():
+    """RaggedPhaseData (variable-length paths): prefix-sum path table, per-task counts, padding to a multiple of 4 rows -
+    the host-side contract promp_process_samples_ragged / promp_policy_*_ragged read (include/promp_b200.h)."""
+    import torch
+    from promp_b200.samplers.device_data import RaggedPhaseData
+    lens = [[5, 17, 1], [40], [9, 9, 9, 25, 2]]
+    ph = RaggedPhaseData(lens, 2, 2, torch.device('cpu'))
+    assert ph.M == 3 and ph.E == 5 and ph.N == 56 and ph.N % 4 == 0          # Pmax = 5, Nmax = max(23, 40, 54) -> 56
+    np.testing.assert_array_equal(ph.n_valid_host, [23, 40, 54])
+    np.testing.assert_array_equal(ph.n_paths_host, [3, 1, 5])
+    np.testing.assert_array_equal(ph.path_off_host, [[0, 5, 22, 23, 23, 23], [0, 40, 40, 40, 40, 40], [0, 9, 18, 27, 52, 54]])
+    assert ph.path_off.dtype == torch.int32 and ph.n_valid.dtype == torch.int32 and ph.total_paths == 9
+    assert ph.obs.shape == (3, 56, 2) and float(ph.obs.abs().sum()) == 0.0       # padding rows start zeroed
