@@ -1085,12 +1085,13 @@ extern "C" int64_t promp_policy_workspace_bytes(int M, int N, int obs_dim, int a
     // upper bound over the occupancies the kernels can have (1..4 CTAs per SM on 148..160 SMs)
     const int P = promp::num_params(obs_dim, act_dim, hidden);
     int64_t worst = 0;
-    for (int occ = 1; occ <= 4; ++occ) {
-        const TilePlan p = plan_tiles(M, N, 160 * occ, P);
-        if (p.partial_floats > worst) worst = p.partial_floats;
-        const TilePlan p2 = plan_tiles(M, N, 148 * occ, P);
-        if (p2.partial_floats > worst) worst = p2.partial_floats;
-    }
+    for (int occ = 1; occ <= 4; ++occ)
+        for (int tb : {TB, TBT}) {            // CUDA-core kernels tile by 64 samples, the tensor-core kernels by 128
+            const TilePlan p = plan_tiles(M, N, 160 * occ, P, tb);
+            if (p.partial_floats > worst) worst = p.partial_floats;
+            const TilePlan p2 = plan_tiles(M, N, 148 * occ, P, tb);
+            if (p2.partial_floats > worst) worst = p2.partial_floats;
+        }
     return counters_bytes(M) + worst * (int64_t)sizeof(float) + 16;
 }
 
