@@ -32,6 +32,8 @@ class TRPOMAML(MAMLAlgo):
         device from the processing kernel's per-task sums (global over ranks)."""
         import torch
         last = phases[-1]
+        if getattr(last, 'n_valid', None) is not None or getattr(phases[0], 'n_valid', None) is not None:
+            raise NotImplementedError("promp_b200: the E-MAML exploration term is implemented for fixed-horizon paths only")
         if getattr(last, '_explore_adv', None) is None:
             st = last.stats[:, 5:7]                                    # per task: sum r, sum r^2
             tot = torch.cat([st.sum(0), torch.tensor([float(last.M * last.N)], dtype=torch.float64, device=st.device)])
