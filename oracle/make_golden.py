@@ -195,6 +195,46 @@ def gen_point_variants_steps():
     np.savez_compressed(os.path.join(OUT, 'point_variants_steps.npz'), **out)
 
 
+def gen_tf_half_numpy_known():
+    """The numpy-executable pieces of the reference's TF1 half (TensorFlow itself is absent; `import tensorflow` inside
+    these modules is satisfied by the inert oracle/stubs_tf stand-in, which these functions never touch):
+    DiagonalGaussian.kl / log_likelihood / entropy (policies/distributions/diagonal_gaussian.py:46-69, 111-127, 142-153)
+    and conjugate_gradients (optimizers/conjugate_gradient_optimizer.py:325-354)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'stubs_tf'))      # import-only TensorFlow stand-in (nothing of it is executed)
+    from meta_policy_search.policies.distributions.diagonal_gaussian import DiagonalGaussian
+    if not hasattr(np, 'cast'):          # removed in NumPy 2; the optimizer module evaluates np.cast['float32'](1e-5) at import
+        class _Cast(dict):
+            def __missing__(self, k):
+                return lambda x: np.asarray(x, dtype=k)
+        np.cast = _Cast()
+    from meta_policy_search.optimizers.conjugate_gradient_optimizer import conjugate_gradients
+    rng = np.random.RandomState(31)
+    out = {}
+    for Da, N in ((2, 257), (6, 140)):
+        pre = 'dist%d_' % Da
+        old_mean, new_mean = rng.randn(N, Da), rng.randn(N, Da)
+        old_ls, new_ls = 0.3 * rng.randn(N, Da) - 0.5, 0.3 * rng.randn(N, Da) - 0.5
+        new_ls[:5] = np.log(1e-6)                      # the clip floor of gaussian_mlp_policy.py:71
+        x = old_mean + np.exp(old_ls) * rng.randn(N, Da)
+        dist = DiagonalGaussian(Da)
+        old, new = dict(mean=old_mean, log_std=old_ls), dict(mean=new_mean, log_std=new_ls)
+        out[pre + 'old_mean'], out[pre + 'old_ls'], out[pre + 'new_mean'], out[pre + 'new_ls'], out[pre + 'x'] = \
+            old_mean, old_ls, new_mean, new_ls, x
+        out[pre + 'kl'] = dist.kl(old, new)
+        out[pre + 'll_old'] = dist.log_likelihood(x, old)
+        out[pre + 'll_new'] = dist.log_likelihood(x, new)
+        out[pre + 'entropy'] = dist.entropy(new)
+    n = 60
+    A = rng.randn(n, n)
+    A = (A @ A.T / n + 0.5 * np.eye(n)).astype(np.float32)
+    b = rng.randn(n).astype(np.float32)
+    out['cg_A'], out['cg_b'] = A, b
+    out['cg_x10'] = conjugate_gradients(lambda p: A.dot(p), b, cg_iters=10)
+    out['cg_x3'] = conjugate_gradients(lambda p: A.dot(p), b, cg_iters=3)
+    out['cg_x_tol'] = conjugate_gradients(lambda p: A.dot(p), b, cg_iters=200, residual_tol=1e-6)
+    np.savez_compressed(os.path.join(OUT, 'tf_half_known.npz'), **out)
+
+
 def gen_process_samples_ragged():
     """MetaSampleProcessor + LinearFeatureBaseline on VARIABLE-LENGTH paths (early termination,
     meta_sampler.py:116-125): per task a different number of paths and samples.  Stored flat with offsets."""
@@ -309,5 +349,6 @@ if __name__ == '__main__':
     gen_baseline_known()
     gen_process_samples_ragged()
     gen_point_variants_steps()
+    gen_tf_half_numpy_known()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -2,7 +2,8 @@
 
 TensorFlow 1.x is not installable here (no network), so the graph the reference builds in
 policies/*, meta_algos/* and optimizers/* is restated on torch autograd (float32 or float64).
-PARITY UNPINNED by reference outputs - see oracle/__init__.py for what pins it instead.
+PARITY UNPINNED by reference outputs except the distribution math and the CG solver (tests/golden/tf_half_known.npz)
+- see oracle/__init__.py for what pins the rest.
 `ref:` citations are relative to /root/reference/meta_policy_search/.
 
 Conventions

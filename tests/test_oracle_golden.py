@@ -244,3 +244,36 @@ def test_reference_advantage_identity():
             np.testing.assert_allclose(data[m]['advantages'][off:off + L], np.cumsum(p['rewards'][::-1])[::-1], atol=1e-10)
             off += L
         assert len(data[m].keys()) == 8
+
+
+@pytest.mark.parametrize('Da', [2, 6])
+def test_tf_half_distribution_math_matches_reference_numpy(golden_dir, Da):
+    """The numpy-executable part of the reference's TF1 half pins the oracle's distribution math: DiagonalGaussian.kl /
+    log_likelihood (policies/distributions/diagonal_gaussian.py:46-69, 111-127; the *_sym graph versions are the same
+    expressions in TF ops) for random distributions incl. log_std at the 1e-6 clip floor.  float64, 1e-12."""
+    import torch
+    from oracle import tf_half as th
+    g = _load(golden_dir, 'tf_half_known.npz')
+    pre = 'dist%d_' % Da
+    t = {k: torch.from_numpy(g[pre + k]) for k in ('old_mean', 'old_ls', 'new_mean', 'new_ls', 'x')}
+    np.testing.assert_allclose(th.kl(t['old_mean'], t['old_ls'], t['new_mean'], t['new_ls']).numpy(), g[pre + 'kl'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(th.log_likelihood(t['x'], t['old_mean'], t['old_ls']).numpy(), g[pre + 'll_old'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(th.log_likelihood(t['x'], t['new_mean'], t['new_ls']).numpy(), g[pre + 'll_new'], rtol=1e-12, atol=1e-12)
+    ratio = th.likelihood_ratio(t['x'], t['old_mean'], t['old_ls'], t['new_mean'], t['new_ls']).numpy()
+    np.testing.assert_allclose(ratio, np.exp(g[pre + 'll_new'] - g[pre + 'll_old']), rtol=1e-12, atol=0)
+    # entropy (diagonal_gaussian.py:142-153) = sum(log_std + log sqrt(2 pi e)): consistency of the fixture itself
+    np.testing.assert_allclose(g[pre + 'entropy'], np.sum(g[pre + 'new_ls'] + np.log(np.sqrt(2 * np.pi * np.e)), axis=-1), rtol=1e-12)
+
+
+def test_conjugate_gradients_match_reference(golden_dir):
+    """conjugate_gradients (optimizers/conjugate_gradient_optimizer.py:325-354) run from the unmodified reference: the
+    oracle's restatement AND the product's host-side CG (promp_b200/optimizers) reproduce it bit for bit (float32)."""
+    from oracle import tf_half as th
+    from promp_b200.optimizers.conjugate_gradient_optimizer import conjugate_gradients as cg_product
+    g = _load(golden_dir, 'tf_half_known.npz')
+    A, b = g['cg_A'], g['cg_b']
+    for fn in (th.conjugate_gradients, cg_product):
+        assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=10), g['cg_x10'])
+        assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=3), g['cg_x3'])
+        assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=200, residual_tol=1e-6), g['cg_x_tol'])
+    assert np.linalg.norm(A.dot(g['cg_x_tol']) - b) < 1e-2 * np.linalg.norm(b)
