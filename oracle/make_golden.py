@@ -232,6 +232,13 @@ def gen_tf_half_numpy_known():
     out['cg_x10'] = conjugate_gradients(lambda p: A.dot(p), b, cg_iters=10)
     out['cg_x3'] = conjugate_gradients(lambda p: A.dot(p), b, cg_iters=3)
     out['cg_x_tol'] = conjugate_gradients(lambda p: A.dot(p), b, cg_iters=200, residual_tol=1e-6)
+    # adaptive inner-KL penalty rule (meta_algos/pro_mp.py:201-214), incl. the exact thresholds
+    from meta_policy_search.meta_algos.pro_mp import _adapt_kl_coeff
+    target = 0.01
+    kls = np.concatenate([rng.uniform(0.0, 0.03, size=40), [target / 1.5, target * 1.5, 0.0, target]])
+    coeffs = np.concatenate([rng.uniform(1e-4, 1e-2, size=40), [5e-4, 5e-4, 5e-4, 5e-4]])
+    out['klc_target'], out['klc_kl'], out['klc_in'] = np.asarray(target), kls, coeffs
+    out['klc_out'] = np.asarray([_adapt_kl_coeff(float(c), float(k), target) for c, k in zip(coeffs, kls)])
     np.savez_compressed(os.path.join(OUT, 'tf_half_known.npz'), **out)
 
 

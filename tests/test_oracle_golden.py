@@ -277,3 +277,21 @@ def test_conjugate_gradients_match_reference(golden_dir):
         assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=3), g['cg_x3'])
         assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=200, residual_tol=1e-6), g['cg_x_tol'])
     assert np.linalg.norm(A.dot(g['cg_x_tol']) - b) < 1e-2 * np.linalg.norm(b)
+
+
+def test_adaptive_kl_coefficient_rule_matches_reference(golden_dir):
+    """_adapt_kl_coeff (meta_algos/pro_mp.py:201-214) from the unmodified reference, incl. the exact /1.5 and *1.5
+    thresholds: the oracle's and the product's restatements give the same coefficients."""
+    import ast
+    from oracle import tf_half as th
+    g = _load(golden_dir, 'tf_half_known.npz')
+    target = float(g['klc_target'])
+    np.testing.assert_array_equal(th.adapt_kl_coeff(g['klc_in'], g['klc_kl'], target), g['klc_out'])
+    # the product's rule lives in promp_b200/meta_algos/pro_mp.py (module import needs the CUDA library: evaluate the
+    # function's source alone)
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'promp_b200', 'meta_algos', 'pro_mp.py')).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == '_adapt_kl_coeff'][0]
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'pro_mp._adapt_kl_coeff', 'exec'), ns)
+    got = np.asarray([ns['_adapt_kl_coeff'](float(c), float(k), target) for c, k in zip(g['klc_in'], g['klc_kl'])])
+    np.testing.assert_array_equal(got, g['klc_out'])
