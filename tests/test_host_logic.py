@@ -273,3 +273,24 @@ def test_ragged_phase_path_table():
     np.testing.assert_array_equal(ph.path_off_host, [[0, 5, 22, 23, 23, 23], [0, 40, 40, 40, 40, 40], [0, 9, 18, 27, 52, 54]])
     assert ph.path_off.dtype == torch.int32 and ph.n_valid.dtype == torch.int32 and ph.total_paths == 9
     assert ph.obs.shape == (3, 56, 2) and float(ph.obs.abs().sum()) == 0.0       # padding rows start zeroed
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/meta_policy_search'), reason='reference tree not present')
+def test_path_stacking_matches_reference_utils():
+    """Trajectory bookkeeping of the stepwise sampler: per-step info dicts -> one dict of stacked arrays,
+    nested dicts included, exactly like utils.stack_tensor_dict_list (meta_policy_search/utils/utils.py) run from the
+    unmodified reference."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_utils', '/root/reference/meta_policy_search/utils/utils.py')
+    ref_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_utils)
+    from promp_b200.samplers.meta_sampler import _stack
+    rng = np.random.RandomState(0)
+    steps = [dict(mean=rng.randn(3), log_std=rng.randn(3), nested=dict(a=rng.randn(2), b=float(i))) for i in range(7)]
+    want, got = ref_utils.stack_tensor_dict_list(steps), _stack(steps)
+    assert set(want) == set(got) and set(want['nested']) == set(got['nested'])
+    for k in ('mean', 'log_std'):
+        np.testing.assert_array_equal(got[k], want[k])
+    for k in ('a', 'b'):
+        np.testing.assert_array_equal(got['nested'][k], want['nested'][k])
+    assert _stack([]) == {} and _stack([{}, {}]) == {}
