@@ -16,7 +16,8 @@ metric = env-steps/s = (M*E*H*2 env steps per meta-iteration) / (time per meta-i
   roofline     : dominant kernel (policy_hvp_kernel), algorithmic bytes / CUDA-event time vs the measured
                  HBM peak (MEASURED_PEAKS.json).  NOTE: that kernel is fp32-FMA bound (AI ~ 500 FLOP/B), so
                  the HBM fraction is small by construction; `fp32_tflops` gives the compute-side view.
-  cpu_baseline : the CPU oracle port of the reference (oracle/) on the host cores, bounded sample.
+  cpu_baseline : the CPU oracle port of the reference (oracle/) on the host cores: numpy half in min(tasks, cores) worker
+                 processes (like the reference's parallel=True executor), TF1 half on PyTorch-CPU threads.
 
 --impl reference times the reference's CPU implementation (oracle port: /root/reference is absent on the
 GPU box and TF1 is not installable) on the same metric.
@@ -312,7 +313,17 @@ def run_gpu(args):
         roof['rollout_kernel'] = dict(achieved=ro_bytes / (ro_ms * 1e-3) / 1e9, frac=ro_bytes / (ro_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                                       algorithmic_bytes_per_launch=ro_bytes, avg_launch_ms=ro_ms,
                                       env_steps_per_s=M * N / (ro_ms * 1e-3))
-        cpu = run_cpu_baseline(wl, steps=2, warmup=1, m_sample=10) if not args.no_cpu_baseline else None
+        cpu = None
+        if not args.no_cpu_baseline:
+            # a separate process: the CPU arm forks worker processes, which must not inherit this process's CUDA context
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', args.workload,
+                                    '--steps', '2', '--warmup', '1'], capture_output=True, text=True, timeout=900,
+                                   env=dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1'))
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])['cpu_baseline']
+            except Exception as e:      # keep the bench line: fall back to the in-process single-worker port
+                sys.stderr.write('cpu_baseline subprocess failed (%r); single-process fallback\n' % (e,))
+                cpu = run_cpu_baseline(wl, steps=2, warmup=1, m_sample=10, parallel=False)
         value = steps_per_iter * args.steps / (ms_dev * 1e-3)
         e2e_val = steps_per_iter * args.steps / (ms_e2e * 1e-3)
         out = {
@@ -406,38 +417,143 @@ def cpu_meta_iteration(wl, m_sample, state):
     return spans
 
 
-def run_cpu_baseline(wl, steps, warmup, m_sample):
+# ---- multi-process numpy half: the reference's parallel=True runs one worker process per task (MetaParallelEnvExecutor,
+#      samplers/vectorized_env_executor.py:88-202); here every worker owns a contiguous block of tasks and runs the oracle's
+#      sampler + sample processor for them (policy forward included, so there is no per-step pipe traffic: a stronger CPU
+#      arm than the reference's own layout).
+_WORKER = {}
+
+
+def _cpu_worker_phase(job):
+    wl_key, goals, theta_tasks, pre_update, seed = job
+    import warnings
+    warnings.filterwarnings('ignore')
+    from oracle import numpy_half as nh, tf_half as th, cheetah_surrogate as cs
+    wl = WORKLOADS[wl_key]
+    m_sub = len(goals)
+    key = (wl_key, m_sub)
+    if key not in _WORKER:
+        try:
+            import torch
+            torch.set_num_threads(1)
+        except Exception:
+            pass
+        env = nh.NormalizedEnv(nh.PointEnvCorner() if wl['env'] == 'MetaPointEnvCorner' else cs.HalfCheetahRandDirecSurrogate())
+        policy = th.OraclePolicy(m_sub, wl['Do'], wl['Da'])
+        _WORKER[key] = (policy, nh.Sampler(env, policy, wl['E'], m_sub, wl['H']),
+                        nh.SampleProcessor(nh.LinearFeatureBaseline(), 0.99, 1, True))
+    policy, sampler, proc = _WORKER[key]
+    np.random.seed(seed)
+    sampler.vec_env.set_tasks(list(goals))
+    if pre_update:
+        policy.theta = np.asarray(theta_tasks[0], dtype=np.float32)
+        policy.switch_to_pre_update()
+    else:
+        policy.update_task_parameters(np.asarray(theta_tasks, dtype=np.float32))
+    data = proc.process_samples(sampler.obtain_samples())
+    f = lambda a: np.stack(a).astype(np.float32)
+    return dict(obs=f([d['observations'] for d in data]), act=f([d['actions'] for d in data]),
+                adv=f([d['advantages'] for d in data]), mean=f([d['agent_infos']['mean'] for d in data]),
+                log_std=f([d['agent_infos']['log_std'] for d in data]))
+
+
+def cpu_meta_iteration_parallel(wl_key, m_sample, state, pool, n_workers):
+    """One meta-iteration on the CPU with the numpy half sharded over `n_workers` processes."""
+    import torch
+    from oracle import numpy_half as nh, tf_half as th, cheetah_surrogate as cs
+    wl = WORKLOADS[wl_key]
+    dims = (wl['Do'], wl['Da'], (64, 64))
+    if 'theta' not in state:
+        env = nh.PointEnvCorner() if wl['env'] == 'MetaPointEnvCorner' else cs.HalfCheetahRandDirecSurrogate()
+        state.update(env=env, theta=th.init_params(*dims), adam=th.TF1Adam(th.num_params(*dims)), itr=0)
+    env, adam = state['env'], state['adam']
+    chunks = np.array_split(np.arange(m_sample), n_workers)
+    chunks = [c for c in chunks if len(c)]
+    spans = {}
+    t0 = time.perf_counter()
+    tasks = env.sample_tasks(m_sample)
+    theta = np.asarray(state['theta'], dtype=np.float32)
+    theta_tasks = np.tile(theta, (m_sample, 1))
+    phases = []
+    for step in range(2):
+        t = time.perf_counter()
+        jobs = [(wl_key, [tasks[i] for i in c], theta_tasks[c], step == 0, 1000003 * state['itr'] + 7919 * step + int(c[0]) + 1)
+                for c in chunks]
+        parts = pool.map(_cpu_worker_phase, jobs)
+        phases.append({k: torch.from_numpy(np.concatenate([p[k] for p in parts])) for k in parts[0]})
+        spans['sampling'] = spans.get('sampling', 0) + time.perf_counter() - t       # sampling + sample processing + IPC
+        if step == 0:
+            t = time.perf_counter()
+            theta_tasks = th.adapt(torch.from_numpy(theta_tasks), phases[0], dims, PROMP['inner_lr']).numpy()
+            spans['inner_step'] = time.perf_counter() - t
+    t = time.perf_counter()
+    new_theta, _ = th.promp_optimize(torch.from_numpy(theta), phases, dims, adam, PROMP['inner_lr'], PROMP['clip_eps'],
+                                     [PROMP['init_inner_kl_penalty']], PROMP['num_ppo_steps'])
+    state['theta'] = new_theta.numpy()
+    state['itr'] += 1
+    spans['outer_step'] = time.perf_counter() - t
+    spans['sample_proc'] = 0.0
+    spans['itr'] = time.perf_counter() - t0
+    return spans
+
+
+def run_cpu_baseline(wl, steps, warmup, m_sample, parallel=True):
+    """CPU arm: the oracle port of the reference's path on this box's host cores.  parallel=True: the numpy half runs in
+    min(tasks, cores) worker processes (like the reference's parallel=True executor), the TF1 half (PyTorch-CPU) with the
+    fastest thread count; the whole M-task workload is timed.  parallel=False: single process, `m_sample` tasks."""
     import torch
     import warnings
     warnings.filterwarnings('ignore')
-    state = {}
-    np.random.seed(1)
-    # choose the torch thread count on a gradient evaluation of the right shape
-    from oracle import tf_half as th
-    dims = (wl['Do'], wl['Da'], (64, 64))
-    N = wl['E'] * wl['H']
-    g = torch.Generator().manual_seed(0)
-    fake = dict(obs=torch.randn(m_sample, N, wl['Do'], generator=g), act=torch.randn(m_sample, N, wl['Da'], generator=g),
-                adv=torch.randn(m_sample, N, generator=g), mean=torch.randn(m_sample, N, wl['Da'], generator=g),
-                log_std=torch.zeros(m_sample, N, wl['Da']))
-    theta = torch.tensor(th.init_params(*dims))
+    wl_key = [k for k, v in WORKLOADS.items() if v is wl][0]
+    cores = os.cpu_count() or 1
+    pool, n_workers = None, 1
+    if parallel and cores > 1:
+        import multiprocessing as mp
+        m_sample = wl['M']
+        n_workers = max(1, min(m_sample, cores))
+        pool = mp.get_context('fork').Pool(n_workers)        # forked BEFORE the parent touches torch's thread pool
+    try:
+        state = {}
+        np.random.seed(1)
+        # choose the torch thread count on a gradient evaluation of the right shape
+        from oracle import tf_half as th
+        dims = (wl['Do'], wl['Da'], (64, 64))
+        N = wl['E'] * wl['H']
+        g = torch.Generator().manual_seed(0)
+        fake = dict(obs=torch.randn(m_sample, N, wl['Do'], generator=g), act=torch.randn(m_sample, N, wl['Da'], generator=g),
+                    adv=torch.randn(m_sample, N, generator=g), mean=torch.randn(m_sample, N, wl['Da'], generator=g),
+                    log_std=torch.zeros(m_sample, N, wl['Da']))
+        theta = torch.tensor(th.init_params(*dims))
 
-    def probe():
-        t = theta.clone().requires_grad_(True)
-        obj, _, _ = th.meta_objective(t, [fake, fake], dims, 0.1, 'promp', 0.3, [5e-4])
-        torch.autograd.grad(obj, t)
-    nthreads = pick_torch_threads(probe)
-    for _ in range(warmup):
-        cpu_meta_iteration(wl, m_sample, state)
-    all_spans = [cpu_meta_iteration(wl, m_sample, state) for _ in range(steps)]
+        def probe():
+            t = theta.clone().requires_grad_(True)
+            obj, _, _ = th.meta_objective(t, [fake, fake], dims, 0.1, 'promp', 0.3, [5e-4])
+            torch.autograd.grad(obj, t)
+        nthreads = pick_torch_threads(probe)
+        if pool is not None:
+            run = lambda: cpu_meta_iteration_parallel(wl_key, m_sample, state, pool, n_workers)
+        else:
+            run = lambda: cpu_meta_iteration(wl, m_sample, state)
+        for _ in range(warmup):
+            run()
+        all_spans = [run() for _ in range(steps)]
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
     itr = float(np.median([s['itr'] for s in all_spans]))
     steps_per_iter = m_sample * wl['E'] * wl['H'] * 2
     med = {k: float(np.median([s[k] for s in all_spans])) for k in all_spans[0]}
-    return dict(value=steps_per_iter / itr, unit='env-steps/s', cores=os.cpu_count(), torch_threads=nthreads, kind='port',
-                sample='%d of %d tasks x %d envs x H=%d, full meta-iteration (tasks are independent; numpy half = per-env Python '
-                       'stepping like the reference, TF1 half = PyTorch-CPU restatement batched over tasks), median of %d'
-                       % (m_sample, wl['M'], wl['E'], wl['H'], steps),
-                sec_per_iter=itr, spans_sec=med,
+    if pool is not None:
+        sample = ('all %d tasks x %d envs x H=%d, full meta-iteration; numpy half (per-env Python stepping like the reference, '
+                  'sampling + sample processing) sharded over %d worker processes, TF1 half = PyTorch-CPU restatement batched over '
+                  'tasks with %d threads; median of %d' % (m_sample, wl['E'], wl['H'], n_workers, nthreads, steps))
+    else:
+        sample = ('%d of %d tasks x %d envs x H=%d, full meta-iteration (tasks are independent; numpy half = per-env Python '
+                  'stepping like the reference, TF1 half = PyTorch-CPU restatement batched over tasks), median of %d'
+                  % (m_sample, wl['M'], wl['E'], wl['H'], steps))
+    return dict(value=steps_per_iter / itr, unit='env-steps/s', cores=max(n_workers, nthreads), host_cores=cores, worker_processes=n_workers,
+                torch_threads=nthreads, kind='port', sample=sample, sec_per_iter=itr, spans_sec=med,
                 sampling_env_steps_per_sec=steps_per_iter / med['sampling'])
 
 
@@ -447,8 +563,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    m_sample = 10
-    cpu = run_cpu_baseline(wl, steps=args.steps, warmup=args.warmup, m_sample=m_sample)
+    cpu = run_cpu_baseline(wl, steps=args.steps, warmup=args.warmup, m_sample=10, parallel=not args.cpu_serial)
     out = {
         'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': cpu['value'], 'unit': 'env-steps/s',
         'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
@@ -472,6 +587,7 @@ def main():
     ap.add_argument('--impl', default='promp_b200', choices=['promp_b200', 'reference'])
     ap.add_argument('--workload', default='point', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-serial', action='store_true', help='CPU arm: single process on a 10-task sample instead of one worker process per task')
     ap.add_argument('--no-graph', action='store_true', help='time the device-resident loop eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else max(args.warmup, 1)
