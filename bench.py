@@ -318,7 +318,7 @@ def run_gpu(args):
             # a separate process: the CPU arm forks worker processes, which must not inherit this process's CUDA context
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', args.workload,
-                                    '--steps', '2', '--warmup', '1'], capture_output=True, text=True, timeout=900,
+                                    '--steps', '2', '--warmup', '1'], capture_output=True, text=True, timeout=300,
                                    env=dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1'))
                 cpu = json.loads(r.stdout.strip().splitlines()[-1])['cpu_baseline']
             except Exception as e:      # keep the bench line: fall back to the in-process single-worker port
