@@ -314,7 +314,7 @@ def run_gpu(args):
                                       algorithmic_bytes_per_launch=ro_bytes, avg_launch_ms=ro_ms,
                                       env_steps_per_s=M * N / (ro_ms * 1e-3))
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # the CPU baseline is reported at N = 1 only (rank 0)
             # a separate process: the CPU arm forks worker processes, which must not inherit this process's CUDA context
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', args.workload,
