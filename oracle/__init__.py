@@ -18,14 +18,24 @@ Pinning status
   ``/root/reference`` (with the stub packages under ``oracle/stubs``) and writes their outputs to
   ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this restatement against them,
   and against the known-answer vectors of the reference's own tests/test_samplers.py.
-* TF1 half: the graph itself (MLP forward, tf.gradients through the inner steps, TF1 Adam) is PARITY UNPINNED by
-  reference outputs (TF1 cannot run here).  Pinned pieces: the distribution math and the conjugate-gradient solver,
-  whose numpy twins inside the reference's TF-half modules (DiagonalGaussian.kl / log_likelihood / entropy,
-  optimizers.conjugate_gradients) ARE executed by make_golden.py (tests/golden/tf_half_known.npz).  The rest is pinned
-  only by (i) the reference tests that touch it and can be restated (likelihood ratio == 1 at the first inner step,
-  tests/test_integration.py:150-175; get_actions == distribution_info, tests/test_policies.py:43-64) and (ii) fp64
-  finite-difference checks of every gradient.
-* HalfCheetah surrogate dynamics: PARITY UNPINNED (new model; MuJoCo absent).
+* TF1 half: PINNED to the reference's own graph code.  ``oracle/stubs_tf/tensorflow`` is a torch-backed, lazily
+  evaluated stand-in for the ~45 TF-1.x symbols the reference uses (placeholders, variables, dense layers, math ops,
+  ``tf.gradients`` via ``torch.autograd.grad(create_graph=True)``, ``Session.run``, the published TF1 Adam rule), so
+  ``make_golden.py`` imports the UNMODIFIED ``policies/*``, ``meta_algos/{base,pro_mp,trpo_maml,vpg_maml}.py``,
+  ``optimizers/*`` and ``meta_trainer.py`` from ``/root/reference`` and records what they compute:
+  ``tests/golden/tf_half_graph.npz`` (adapted parameters, meta objective, inner / outer KL, second-order meta-gradient,
+  5-epoch Adam end point, TRPO-MAML gradients / finite-difference Hx / CG direction / accepted step, E-MAML and VPG-MAML;
+  14 cases incl. the BASELINE.json shapes 40 x 2000 and 40 x 4000, each evaluated in float32 and float64) and
+  ``tests/golden/trainer_run.npz`` (3 meta-iterations of the unmodified ``Trainer`` over the unmodified sampler /
+  processor / baseline / policy / ProMP).  ``tests/test_tf_golden.py`` checks ``tf_half.py`` against them (float32:
+  2e-5, float64: 1e-6 - the reference rounds ``inner_lr`` and ``log(2 pi)`` to float32) and the CUDA path too.  What the
+  stand-in cannot reproduce is TensorFlow's floating-point kernels (Eigen vs torch CPU: last-bit differences) and its
+  random streams (action noise is recorded and injected instead).  The numpy twins inside the TF-half modules
+  (DiagonalGaussian.kl / log_likelihood / entropy, conjugate_gradients, _adapt_kl_coeff) are executed directly
+  (``tests/golden/tf_half_known.npz``).
+* HalfCheetah surrogate dynamics: a NEW analytic model (MuJoCo is absent and the north star asks for a MuJoCo-free
+  surrogate), so there is no reference output to pin its dynamics to; obs/act dims, reward decomposition, task
+  sampling, reset noise and env_infos keys follow the reference source.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import this package.  The product (``promp_b200``) never does.

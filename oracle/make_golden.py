@@ -242,6 +242,234 @@ def gen_tf_half_numpy_known():
     np.savez_compressed(os.path.join(OUT, 'tf_half_known.npz'), **out)
 
 
+
+def _np_cast_shim():
+    if not hasattr(np, 'cast'):          # removed in NumPy 2; the optimizer module evaluates np.cast['float32'](1e-5) at import
+        class _Cast(dict):
+            def __missing__(self, k):
+                return lambda x: np.asarray(x, dtype=k)
+        np.cast = _Cast()
+
+
+def _build_reference_algo(case, torch_dtype):
+    """UNMODIFIED reference policy + algorithm graph for one oracle/tf_cases.py case, on the torch-backed tensorflow
+    stand-in.  Returns (tf, sess, policy, algo)."""
+    import tensorflow as tf
+    from oracle import tf_cases
+    from meta_policy_search.policies.meta_gaussian_mlp_policy import MetaGaussianMLPPolicy
+    from meta_policy_search.meta_algos.pro_mp import ProMP
+    from meta_policy_search.meta_algos.trpo_maml import TRPOMAML
+    from meta_policy_search.meta_algos.vpg_maml import VPGMAML
+    H = tf_cases.HYPER
+    tf.reset_default_graph()
+    tf.set_compute_dtype(torch_dtype)
+    M = case['M']
+    policy = MetaGaussianMLPPolicy(name='meta-policy', obs_dim=case['Do'], action_dim=case['Da'], meta_batch_size=M,
+                                   hidden_sizes=(case['hidden'], case['hidden']))
+    S1 = case['S'] - 1
+    if case['algo'] == 'promp':
+        algo = ProMP(policy=policy, inner_lr=H['inner_lr'], meta_batch_size=M, num_inner_grad_steps=S1,
+                     learning_rate=H['learning_rate'], num_ppo_steps=H['num_ppo_steps'], clip_eps=H['clip_eps'],
+                     target_inner_step=0.01, init_inner_kl_penalty=H['init_inner_kl_penalty'], adaptive_inner_kl_penalty=False)
+    elif case['algo'] == 'trpo':
+        algo = TRPOMAML(policy=policy, step_size=H['step_size'], inner_type=case['inner_type'], inner_lr=H['inner_lr'],
+                        meta_batch_size=M, num_inner_grad_steps=S1, exploration=case.get('exploration', False))
+    else:
+        algo = VPGMAML(policy=policy, learning_rate=H['learning_rate'], inner_type=case['inner_type'], inner_lr=H['inner_lr'],
+                       meta_batch_size=M, num_inner_grad_steps=S1, exploration=case.get('exploration', False))
+    sess = tf.Session()
+    sess.__enter__()
+    uninit = [v for v in tf.global_variables() if not sess.run(tf.is_variable_initialized(v))]     # meta_trainer.py:75-76
+    sess.run(tf.variables_initializer(uninit))
+    policy.set_params(tf_cases.unflatten(case['theta'], case['Do'], case['Da'], case['hidden']))
+    return tf, sess, policy, algo
+
+
+def gen_tf_half_graph(only=None):
+    """Golden OUTPUTS of the reference's TF1 graph half, produced by running its UNMODIFIED graph-building code
+    (policies/*, meta_algos/{base,pro_mp,trpo_maml,vpg_maml}.py, optimizers/*) on the torch-backed `tensorflow`
+    stand-in (oracle/stubs_tf): inner adapt step, meta-objective, inner / outer KL, second-order meta-gradient,
+    the K-epoch TF1-Adam trajectory end point, TRPO-MAML loss / constraint gradients, finite-difference Hx, CG direction
+    and accepted step.  Each case is evaluated twice: float32 (the reference's dtype) and float64 (same graph, no rounding).
+    Inputs come from oracle/tf_cases.py seeds and are not stored."""
+    import torch
+    torch.set_num_threads(1)          # many tiny ops: intra-op threading only adds synchronisation cost
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'stubs_tf'))
+    _np_cast_shim()
+    from oracle import tf_cases
+    from meta_policy_search.utils import logger
+    from meta_policy_search.optimizers.conjugate_gradient_optimizer import conjugate_gradients
+    logger.set_level(logger.DISABLED) if hasattr(logger, 'set_level') else None
+    path = os.path.join(OUT, 'tf_half_graph.npz')
+    out = dict(np.load(path)) if (only and os.path.exists(path)) else {}
+    for name in tf_cases.CASES:
+        if only and name not in only:
+            continue
+        case = tf_cases.make_case(name)
+        samples = tf_cases.reference_samples(case)
+        M, P, big = case['M'], case['P'], case['M'] >= 40
+        keep_tasks = [0, 13, M - 1] if big else list(range(M))
+        for tag, tdt in (('f32', torch.float32), ('f64', torch.float64)):
+            pre = '%s/%s/' % (name, tag)
+            tf, sess, policy, algo = _build_reference_algo(case, tdt)
+            try:
+                flat = lambda od: np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in od.values()])
+                # ---- inner adapt steps (meta_algos/base.py:217-242), from the pre-update parameters
+                policy.switch_to_pre_update()
+                for s in range(case['S'] - 1):
+                    algo._adapt(samples[s])
+                    tp = np.stack([flat(od) for od in policy.policies_params_vals])            # [M, P]
+                    delta = tp - case['theta'].astype(np.float64)[None]
+                    out[pre + 'adapt%d_tasks' % s] = tp[keep_tasks]
+                    out[pre + 'adapt%d_delta_sum' % s] = delta.sum(1)
+                    out[pre + 'adapt%d_delta_norm' % s] = np.sqrt((delta ** 2).sum(1))
+                out[name + '/keep_tasks'] = np.asarray(keep_tasks)
+                # ---- outer objective / gradient at theta
+                inp = algo._extract_input_dict_meta_op(samples, algo._optimization_keys)
+                params = list(policy.get_params().values())
+                opt = algo.optimizer
+                if case['algo'] == 'promp':
+                    inp['inner_kl_coeff'] = algo.inner_kl_coeff
+                    inp['clip_eps'] = algo.clip_eps
+                    feed = opt.create_feed_dict(inp)
+                    loss, ikl, okl, grads = sess.run([opt._loss, opt._inner_kl, opt._outer_kl, tf.gradients(opt._loss, params)], feed)
+                    out[pre + 'loss'], out[pre + 'inner_kl'], out[pre + 'outer_kl'] = np.float64(loss), np.asarray(ikl, np.float64), np.float64(okl)
+                    out[pre + 'grad'] = np.concatenate([np.asarray(g, np.float64).reshape(-1) for g in grads])
+                    algo.optimize_policy(samples, log=False)                                       # pro_mp.py:165-199, K = 5 epochs
+                    out[pre + 'theta_after_adam5'] = flat(policy.get_param_values())
+                    la, ikl2, okl2 = opt.compute_stats(inp)
+                    out[pre + 'loss_after'], out[pre + 'inner_kl_after'], out[pre + 'outer_kl_after'] = \
+                        np.float64(la), np.asarray(ikl2, np.float64), np.float64(okl2)
+                    if not big:
+                        # first epoch alone (fresh graph = fresh Adam slots; only the epoch count of the optimizer changes)
+                        sess.__exit__(None, None, None)
+                        tf, sess, policy, algo = _build_reference_algo(case, tdt)
+                        algo.optimizer._max_epochs = 1
+                        algo.optimize_policy(samples, log=False)
+                        out[pre + 'theta_after_adam1'] = flat(policy.get_param_values())
+                elif case['algo'] == 'trpo':
+                    out[pre + 'loss'] = np.float64(opt.loss(inp))
+                    out[pre + 'outer_kl'] = np.float64(opt.constraint_val(inp))
+                    g = opt.gradient(inp)
+                    out[pre + 'grad'] = np.asarray(g, np.float64)
+                    out[pre + 'kl_grad'] = np.asarray(opt._hvp_approach.constraint_gradient(inp), np.float64)
+                    x = (g / (np.linalg.norm(g) + 1e-12)).astype(g.dtype)
+                    out[pre + 'hx_dir'] = np.asarray(x, np.float64)
+                    out[pre + 'hx'] = np.asarray(opt._hvp_approach.Hx(inp, x), np.float64)           # conjugate_gradient_optimizer.py:59-89
+                    if not big or tag == 'f64':
+                        Hx = opt._hvp_approach.build_eval(inp)
+                        out[pre + 'cg_dir'] = np.asarray(conjugate_gradients(Hx, g, cg_iters=10), np.float64)
+                    algo.optimize_policy(samples, log=False)                                         # trpo_maml.py:161-192
+                    out[pre + 'theta_after'] = flat(policy.get_param_values())
+                    out[pre + 'loss_after'] = np.float64(opt.loss(inp))
+                    out[pre + 'kl_after'] = np.float64(opt.constraint_val(inp))
+                else:
+                    feed = opt.create_feed_dict(inp)
+                    loss, grads = sess.run([opt._loss, tf.gradients(opt._loss, params)], feed)
+                    out[pre + 'loss'] = np.float64(loss)
+                    out[pre + 'grad'] = np.concatenate([np.asarray(g, np.float64).reshape(-1) for g in grads])
+                    algo.optimize_policy(samples, log=False)                                         # vpg_maml.py:147-166 (1 Adam step)
+                    out[pre + 'theta_after'] = flat(policy.get_param_values())
+            finally:
+                sess.__exit__(None, None, None)
+            print('tf_half_graph', name, tag, 'done', flush=True)
+        # values of the float32 evaluation are float32 numbers: store them as such
+        out = {k: (v.astype(np.float32) if ('/f32/' in k and np.asarray(v).dtype == np.float64) else v) for k, v in out.items()}
+        np.savez_compressed(path, **out)
+
+
+
+def gen_trainer_run():
+    """End-to-end pin: the UNMODIFIED reference Trainer (meta_trainer.py:59-152) driving the unmodified reference
+    MetaSampler(parallel=False) / MetaSampleProcessor / LinearFeatureBaseline / MetaGaussianMLPPolicy / ProMP on
+    normalize(MetaPointEnvCorner) at BASELINE.json configs[0] (5 tasks x 4 envs x H=100, run-script hyper-parameters)
+    for 3 meta-iterations.  TensorFlow is the torch-backed stand-in (oracle/stubs_tf); its tf.random_normal draws are
+    recorded so the CUDA path can be fed the same action noise.  Stored: theta_0, the noise, per-iteration goals,
+    theta after every iteration and the logged scalars."""
+    import torch
+    torch.set_num_threads(1)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'stubs_tf'))
+    _np_cast_shim()
+    import tensorflow as tf
+    from oracle import tf_cases
+    from meta_policy_search.baselines.linear_baseline import LinearFeatureBaseline
+    from meta_policy_search.envs.point_envs.point_env_2d_corner import MetaPointEnvCorner
+    from meta_policy_search.envs.normalized_env import normalize
+    from meta_policy_search.meta_algos.pro_mp import ProMP
+    from meta_policy_search.meta_trainer import Trainer
+    from meta_policy_search.samplers.meta_sampler import MetaSampler
+    from meta_policy_search.samplers.meta_sample_processor import MetaSampleProcessor
+    from meta_policy_search.policies.meta_gaussian_mlp_policy import MetaGaussianMLPPolicy
+    from meta_policy_search.utils import logger
+    M, E, H, n_itr = 5, 4, 100, 3
+    out = {}
+    for rtype in ('sparse', 'dense'):
+        tf.reset_default_graph()
+        tf.set_compute_dtype(torch.float32)
+        draws = []
+        noise_rng = np.random.RandomState(77)
+
+        def normal_hook(shape):
+            a = noise_rng.standard_normal(shape).astype(np.float32)
+            draws.append(a)
+            return a
+        tf.set_random_normal_hook(normal_hook)
+        try:
+            env = normalize(MetaPointEnvCorner(reward_type=rtype))
+            baseline = LinearFeatureBaseline()
+            policy = MetaGaussianMLPPolicy(name='meta-policy', obs_dim=2, action_dim=2, meta_batch_size=M, hidden_sizes=(64, 64))
+            sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H,
+                                  parallel=False)
+            proc = MetaSampleProcessor(baseline=baseline, discount=0.99, gae_lambda=1, normalize_adv=True)
+            algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3,
+                         num_ppo_steps=5, clip_eps=0.3, target_inner_step=0.01, init_inner_kl_penalty=5e-4,
+                         adaptive_inner_kl_penalty=False)
+            sess = tf.Session()
+            with sess.as_default():
+                sess.run(tf.global_variables_initializer())
+                theta0 = tf_cases.make_case('promp_iter0')['theta']          # a fixed, seeded parameter vector (P = 4484)
+                policy.set_params(tf_cases.unflatten(theta0, 2, 2, 64))
+            thetas, kvs, goals = [], [], []
+            flat = lambda od: np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in od.values()])
+            orig_opt, orig_update = algo.optimize_policy, sampler.update_tasks
+
+            def optimize_and_record(*a, **k):
+                orig_opt(*a, **k)
+                thetas.append(flat(policy.get_param_values()))
+                kvs.append({k_: float(v) for k_, v in logger.getkvs().items() if not k_.startswith('Time')})
+
+            def update_and_record():
+                orig_update()
+                goals.append(np.asarray([e.get_task() for e in sampler.vec_env.envs[::E]], dtype=np.float64))
+            algo.optimize_policy, sampler.update_tasks = optimize_and_record, update_and_record
+            trainer = Trainer(algo=algo, env=env, sampler=sampler, sample_processor=proc, policy=policy, n_itr=n_itr,
+                              num_inner_grad_steps=1, sess=sess)
+            np.random.seed(1)
+            trainer.train()
+            rng_probe = np.random.uniform(size=4)
+        finally:
+            tf.set_random_normal_hook(None)
+        # reassemble the recorded draws: per iteration, phase 0 (pre-update) = H draws of [M*E, Da];
+        # phase 1 (post-update) = H x M draws of [E, Da] in task order
+        noise = np.zeros((n_itr, 2, M, E, H, 2), np.float32)
+        k = 0
+        for it in range(n_itr):
+            for t in range(H):
+                noise[it, 0, :, :, t] = draws[k].reshape(M, E, 2); k += 1
+            for t in range(H):
+                for m in range(M):
+                    noise[it, 1, m, :, t] = draws[k]; k += 1
+        assert k == len(draws), (k, len(draws))
+        pre = rtype + '_'
+        out[pre + 'theta0'], out[pre + 'noise'], out[pre + 'goals'] = theta0, noise, np.stack(goals)
+        out[pre + 'thetas'] = np.stack(thetas)
+        keys = sorted(kvs[0])
+        out[pre + 'log_keys'] = np.asarray(keys)
+        out[pre + 'log_vals'] = np.asarray([[kv[k_] for k_ in keys] for kv in kvs])
+        out[pre + 'rng_probe_after'] = rng_probe
+    np.savez_compressed(os.path.join(OUT, 'trainer_run.npz'), **out)
+
+
 def gen_process_samples_ragged():
     """MetaSampleProcessor + LinearFeatureBaseline on VARIABLE-LENGTH paths (early termination,
     meta_sampler.py:116-125): per task a different number of paths and samples.  Stored flat with offsets."""
@@ -349,6 +577,12 @@ def gen_baseline_known():
 if __name__ == '__main__':
     _import_reference()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'tf_half_graph':      # python oracle/make_golden.py tf_half_graph [case ...]
+        gen_tf_half_graph(only=sys.argv[2:] or None)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'trainer_run':
+        gen_trainer_run()
+        sys.exit(0)
     gen_point_corner_steps()
     gen_point_env_steps()
     gen_process_samples()
@@ -357,5 +591,7 @@ if __name__ == '__main__':
     gen_process_samples_ragged()
     gen_point_variants_steps()
     gen_tf_half_numpy_known()
+    gen_tf_half_graph()
+    gen_trainer_run()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -36,13 +36,20 @@ __global__ void __launch_bounds__(1024) allreduce_p2p_kernel(int world, int rank
         const long long t0 = clock64();
         while (*f != epoch) {
             if (clock64() - t0 > 4000000000LL) {   // ~2 s
-                *error_flag = 1;
+                *error_flag = 1;                   // sticky: every later call poisons its output too
                 break;
             }
         }
     }
     __threadfence_system();
     __syncthreads();
+    if (*reinterpret_cast<volatile uint32_t*>(error_flag) != 0) {
+        // A peer never arrived.  Summing whatever is in its slot would silently apply a partial / stale meta-gradient and
+        // let the replicas diverge; poison the result instead so the failure is loud (NaN loss / parameters on this rank,
+        // P2PComm.check() raises) and leave the epoch untouched.
+        for (int p = tid; p < n; p += blockDim.x) out[p] = __int_as_float(0x7fc00000);
+        return;
+    }
     for (int p = tid; p < n; p += blockDim.x) {
         float s = 0.f;
         for (int r = 0; r < world; ++r) {

@@ -73,6 +73,10 @@ class MAMLAlgo(object):
         phase.adv = up('advantages').reshape(self.meta_batch_size, N)
         phase.mean = up('agent_infos', 'mean').reshape(self.meta_batch_size, N, p.action_dim)
         phase.log_std_full = up('agent_infos', 'log_std').reshape(self.meta_batch_size, N, p.action_dim)
+        if 'adj_avg_rewards' in first:
+            # E-MAML (trpo_maml.py:137-144 / vpg_maml.py:137-144) only uses mean_n adj_avg_rewards_i: keep that per task
+            c = np.asarray([np.mean(np.asarray(s['adj_avg_rewards'], dtype=np.float64)) for s in samples], dtype=np.float32)
+            phase.adj_avg_rewards_mean = torch.from_numpy(c).to(p.device)
         return phase
 
     def _grad(self, phase, params, stride, obj_kind, obj_scale=1.0, clip_eps=0.0, kl_coeff=0.0, clip_log_std=0,

@@ -34,6 +34,12 @@ class TRPOMAML(MAMLAlgo):
         last = phases[-1]
         if getattr(last, 'n_valid', None) is not None or getattr(phases[0], 'n_valid', None) is not None:
             raise NotImplementedError("promp_b200: the E-MAML exploration term is implemented for fixed-horizon paths only")
+        if getattr(last, 'adj_avg_rewards_mean', None) is not None:
+            # reference-style sample dicts (MAMLAlgo._phase_of): the caller's processor already computed adj_avg_rewards
+            return last.adj_avg_rewards_mean.view(-1, 1).expand(last.M, phases[0].N).contiguous()
+        if getattr(last, 'stats', None) is None:
+            raise NotImplementedError("exploration=True needs 'adj_avg_rewards' in the sample dicts or a phase processed by "
+                                      "promp_b200's MetaSampleProcessor")
         if getattr(last, '_explore_adv', None) is None:
             st = last.stats[:, 5:7]                                    # per task: sum r, sum r^2
             tot = torch.cat([st.sum(0), torch.tensor([float(last.M * last.N)], dtype=torch.float64, device=st.device)])

@@ -13,6 +13,13 @@ import numpy as np
 from promp_b200.utils import logger
 
 
+def _check_collectives():
+    """N > 1: raise if the peer-memory all-reduce timed out on a missing rank (its output is NaN-poisoned from then on)."""
+    from promp_b200.utils import dist
+    if dist._p2p is not None:
+        dist._p2p.check()
+
+
 class Trainer(object):
     def __init__(self, algo, env, sampler, sample_processor, policy, n_itr, start_itr=0, num_inner_grad_steps=1,
                  sess=None, use_cuda_graph=False, prefetch_host_inputs=False):
@@ -50,6 +57,7 @@ class Trainer(object):
         t_outer = time.time()
         self.algo.optimize_policy(all_samples_data, log=log)
         if log:
+            _check_collectives()
             logger.logkv('Itr', itr)
             logger.logkv('n_timesteps', self.sampler.total_timesteps_sampled)
             logger.logkv('Time-OuterStep', time.time() - t_outer)
@@ -159,6 +167,7 @@ class Trainer(object):
             sampler.total_timesteps_sampled += n_steps
             if log:
                 torch.cuda.current_stream().synchronize()
+                _check_collectives()
                 vals = state['pinned'].numpy()
                 for k, v in zip(keys, vals):
                     logger.logkv(k, int(v) if k.endswith('NumTrajs') else float(v))

@@ -129,6 +129,11 @@ class MetaSampler(object):
             self._pinned_init = [[torch.empty(M, E, sd, dtype=torch.float32).pin_memory() for _ in range(n_phases)] for _ in range(2)]
             self._pinned_tasks = [torch.empty(M, td, dtype=torch.float32).pin_memory() for _ in range(2)]
             self._staged_tasks = [None, None]
+            self._upload_done = [None, None]
+        if self._upload_done[slot] is not None:
+            # the H2D copies issued from this pinned slot may still be queued behind an unfinished replay: the host must
+            # not overwrite the staging memory before they have executed (it would tear tasks / reset states)
+            self._upload_done[slot].synchronize()
         tasks = self._draw_tasks()
         assert len(tasks) == self.meta_batch_size
         self._staged_tasks[slot] = list(tasks)
@@ -148,6 +153,10 @@ class MetaSampler(object):
         n_phases = len(self._static_init)
         for s in range(n_phases):
             self._static_init[s].copy_(self._pinned_init[slot][s], non_blocking=True)
+        import torch
+        if self._upload_done[slot] is None:
+            self._upload_done[slot] = torch.cuda.Event()
+        self._upload_done[slot].record()       # draw_host_inputs(slot) waits on this before reusing the pinned buffers
         M, E = self.meta_batch_size, self.envs_per_task
         return 4 * (M * self.spec['task_dim'] + n_phases * M * E * self.spec['state_dim'])
 

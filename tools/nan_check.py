@@ -1,5 +1,5 @@
 import os, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, torch
 from promp_b200.utils import logger
 logger.set_quiet(True)
