@@ -123,10 +123,10 @@ def build_stack(wl, reset_mode, task_shard=None):
 
 class LaunchCounter(object):
     """Counts OUR kernel launches by wrapping the ctypes entry points (kernels per call from the .cu files)."""
-    KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=2,
+    KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=1,
                    promp_adj_avg_rewards=1, promp_policy_grad=1, promp_policy_hvp=1, promp_reduce_tasks=1,
                    promp_adam_tf1=2, promp_policy_forward=1, promp_counter_add=1, promp_meta_loss_terms=1,
-                   promp_policy_grad_ragged=1, promp_policy_hvp_ragged=1, promp_process_samples_ragged=2)
+                   promp_policy_grad_ragged=1, promp_policy_hvp_ragged=1, promp_process_samples_ragged=1)
 
     def __init__(self, time_kernels=False):
         from promp_b200 import _lib

@@ -140,7 +140,10 @@ int promp_env_observe(int env_kind, int n_env, const float* state, float* obs, v
  *   coeffs  [M,F] float64, F = 2*Do+4 (may be NULL)
  *   stats   [M,8] float64: sum R_0, sum G, sum G^2, max G, min G (G = undiscounted return per path),
  *           sum r, sum r^2, reg_coeff finally used            (may be NULL)
- *   workspace: float64 scratch, >= promp_process_workspace_bytes(M,E,H,Do) bytes
+ *   workspace: scratch, >= promp_process_workspace_bytes(M,E,H,Do) bytes.  It must be ZERO-FILLED before its first
+ *           use (per-task arrival tickets live at its start); every call leaves it ready for the next one.
+ * One launch: grid (chunks of a task's trajectories, M); the last CTA of a task to arrive finishes the task
+ * (fit / predict / GAE / normalisation).
  */
 int64_t promp_process_workspace_bytes(int M, int E, int H, int obs_dim);
 int promp_process_samples(int M, int E, int H, int obs_dim, const float* obs, const float* rew,
@@ -165,6 +168,22 @@ int promp_process_samples_ragged(int M, int max_paths, int max_samples, int obs_
                                  double reg_coeff, int baseline_kind, int normalize_adv, int positive_adv,
                                  float* returns, float* adv, double* coeffs, double* stats,
                                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Standalone LinearFeatureBaseline (baselines/linear_baseline.py): fit(paths, target_key) (:55-77) and predict(path)
+ * (:17-33) for a flat list of n_paths paths stored back to back (path e = samples [path_off[e], path_off[e+1]), path_off
+ * [n_paths+1] int32 device memory; the time feature restarts at 0 in every path, :101-106).
+ *   fit:     obs [n_samples,Do] float32, target [n_samples] float64 (the caller's path[target_key]) ->
+ *            coeffs [F] float64, F = 2*Do+4; *reg_used (device float64, may be NULL) = ridge finally used by the
+ *            reference's x10-on-NaN retry rule.  workspace: zero-filled before first use, like promp_process_samples.
+ *   predict: out [n_samples] float64 = features . coeffs
+ */
+int64_t promp_baseline_fit_workspace_bytes(int n_paths, int n_samples, int obs_dim);
+int promp_baseline_fit(int n_paths, int n_samples, int obs_dim, const float* obs, const double* target,
+                       const int32_t* path_off, double reg_coeff, double* coeffs, double* reg_used,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+int promp_baseline_predict(int n_paths, int n_samples, int obs_dim, const float* obs, const int32_t* path_off,
+                           const double* coeffs, double* out, void* stream);
 
 /* adj_avg_rewards = (r - mean_all)/(std_all + 1e-8) (samplers/meta_sample_processor.py:40-44);
  * mean/std are passed by the caller (reduced over all tasks / ranks from `stats`). */

@@ -36,6 +36,9 @@ _SIGNATURES = {
     'promp_process_samples_ragged': (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_double, c_double, c_double, c_int,
                                              c_int, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     'promp_adj_avg_rewards': (c_int, [c_int64, _P, c_double, c_double, _P, _P]),
+    'promp_baseline_fit_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
+    'promp_baseline_fit': (c_int, [c_int, c_int, c_int, _P, _P, _P, c_double, _P, _P, _P, c_int64, _P]),
+    'promp_baseline_predict': (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     'promp_policy_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     'promp_policy_grad': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                   c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, c_int64, _P]),

@@ -4,8 +4,9 @@ On the hot path the fit (float64 Gram + Cholesky with the reference's ridge / Na
 prediction happen inside promp_process_samples, one fit per task; this object carries `reg_coeff`
 in, and receives the coefficients of the LAST fitted task out - exactly the state the reference's
 shared baseline object is left in after MetaSampleProcessor.process_samples
-(samplers/meta_sample_processor.py:31-34).  `predict` / `_features` on the host exist for API
-compatibility (diagnostics, pickling round trips); they are not used by the product path.
+(samplers/meta_sample_processor.py:31-34).  Called on its own (the reference's tests/test_baselines.py:67-98 do),
+`fit(paths, target_key)` and `predict(path)` run the same float64 Gram / ridge-solve / feature code through the
+standalone entry points promp_baseline_fit / promp_baseline_predict; `_features` is a host helper for diagnostics.
 """
 import numpy as np
 
@@ -30,12 +31,14 @@ class LinearFeatureBaseline(object):
         return np.concatenate([obs, obs ** 2, t, t ** 2, t ** 3, np.ones((n, 1))], axis=1)
 
     def predict(self, path):
+        """linear_baseline.py:17-33: zeros if never fitted, else features . coeffs (on the device)."""
         if self._coeffs is None:
             return np.zeros(len(path["observations"]))
-        return self._features(path).dot(self._coeffs)
+        from promp_b200.samplers.meta_sample_processor import predict_baseline_on_path
+        return predict_baseline_on_path(path, np.asarray(self._coeffs, dtype=np.float64))
 
     def fit(self, paths, target_key='returns'):
-        """Fit on a list of paths through the device kernel (one pseudo-task)."""
+        """linear_baseline.py:55-77 on a flat list of (variable-length) paths, through promp_baseline_fit."""
         from promp_b200.samplers.meta_sample_processor import fit_baseline_on_paths
         self._coeffs = fit_baseline_on_paths(paths, target_key, self._reg_coeff)
 

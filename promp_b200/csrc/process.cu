@@ -1,288 +1,339 @@
-// Sample processing: returns -> linear-feature baseline fit/predict -> GAE -> normalisation -> stats.
+// Sample processing: returns -> linear-feature baseline fit/predict -> GAE -> normalisation -> stats, ONE launch.
 // Tasks are independent (the reference re-fits the shared baseline inside its task loop,
-// samplers/meta_sample_processor.py:31-34); a task is split over C CTAs for the returns + Gram stage and
-// finished by one CTA.  The scans, Gram matrix, Cholesky solve and
-// moments run in float64 like the reference's numpy/LAPACK path; inputs/outputs are float32.
-//
-// HBM-bound stage (AI < 1 FLOP/B): per env-step it reads obs (4*Do B) twice + rew (4 B) twice and
-// writes returns + advantages (8 B); fp64 intermediates live in an L2-resident workspace.
+// samplers/meta_sample_processor.py:31-34).  Grid (C, M): CTA (c, m) owns a chunk of task m's trajectories:
+//   front stage  rewards -> shared memory (one coalesced round trip), discounted-return scans out of shared memory,
+//                returns written back coalesced, path statistics, and the chunk's slice of the Gram matrix
+//                Phi^T [Phi | y] in float64 (4x4 register blocks over 32-sample feature tiles);
+//   ticket       the chunk's partials go to the workspace, then one atomic ticket per task; the LAST CTA of a task
+//   finish stage reduces the partials in fixed chunk order (deterministic), solves the ridge system (Crout Cholesky over
+//                the whole CTA, the reference's x10 ridge / NaN retry rule), predicts, runs the GAE scans out of shared
+//                memory, and writes normalised advantages.
+// The scans, Gram matrix, solve and moments run in float64 like the reference's numpy/LAPACK path; inputs/outputs are
+// float32.  HBM-bound stage (AI < 1 FLOP/B): per env-step it reads obs (4*Do B) twice + rew (4 B) twice and writes
+// returns + advantages (8 B).
+// Round-1 version (two launches, per-trajectory scans walking global memory in a load->fma->store chain, finish stage on
+// M CTAs re-reading float64 intermediates from L2): 74 us at 40x20x100 / 285 us at 40x20x200x(17,6).
 #include "common.cuh"
 
 namespace promp {
 
 constexpr int PS_THREADS = 256;
-constexpr int PS_TS = 32;          // samples per Gram tile
-constexpr int PS_MAXCOL = 44;      // F+1 <= 44  (obs_dim <= 19)
-constexpr int PS_MAXPAIR = PS_MAXCOL * (PS_MAXCOL + 1) / 2;   // 990
-constexpr int PS_MAXITEM = 4;      // pair-items per thread
+constexpr int PS_WARPS = PS_THREADS / 32;
+constexpr int PS_TS = 32;           // samples per Gram tile
+constexpr int PS_MAXCOL = 44;       // NC = F+1 <= 44  (obs_dim <= 19)
+constexpr int PS_MAXBLK = 66;       // 4x4 blocks of the upper triangle, nb = 11
+constexpr int PS_GP = PS_MAXBLK * 16;   // doubles per partial Gram
+constexpr int PS_SMEM_SAMPLES_BYTES = 12;   // per staged sample: float64 value + float32 reward
+constexpr int PS_SMEM_BUDGET = 160 * 1024;  // above this the sample arrays stay in the (L2-resident) workspace
 
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    v = warp_sum(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < PS_THREADS / 32; ++i) t += red[i];
-    return t;
-}
-__device__ __forceinline__ double block_max(double v, double* red) {
-    v = warp_max(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    double t = red[0];
-#pragma unroll
-    for (int i = 1; i < PS_THREADS / 32; ++i) t = fmax(t, red[i]);
-    return t;
-}
-__device__ __forceinline__ double block_min(double v, double* red) {
-    v = warp_min(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    double t = red[0];
-#pragma unroll
-    for (int i = 1; i < PS_THREADS / 32; ++i) t = fmin(t, red[i]);
-    return t;
-}
+enum { PS_MODE_PROCESS = 0, PS_MODE_FIT_ONLY = 1 };
 
 struct ProcArgs {
     int M, E, H, Do;
-    const float* obs;
-    const float* rew;
+    const float* __restrict__ obs;
+    const float* __restrict__ rew;
     double discount, gae_lambda, reg_coeff;
     int baseline_kind, normalize_adv, positive_adv;
-    float* returns;
-    float* adv;
+    float* __restrict__ returns;
+    float* __restrict__ adv;
     double* coeffs;
     double* stats;
-    double* ws;      // [M][2][N] float64 (returns, baseline->advantages), then partials
-    double* gram_p;  // [M][C][PS_MAXPAIR] partial Gram matrices
-    double* stat_p;  // [M][C][8] partial path statistics
-    int C, EPC;      // trajectory chunks per task, trajectories per chunk
+    // workspace
+    unsigned int* counters;   // [M] tickets, zero on entry, left zero
+    double* gram_p;           // [M][C][PS_GP] partial Gram blocks
+    double* stat_p;           // [M][C][8] partial path statistics
+    double* ws64;             // [M][2][NS] float64 (returns | baseline->advantages): only used when the arrays do not fit smem
+    int C, EPC;               // trajectory chunks per task, trajectories per chunk
     // variable-length paths (early termination, meta_sampler.py:116-125); path_off == nullptr: E paths of H steps each
-    const int32_t* path_off;   // [M][Pmax+1] sample offset of every path inside its task (prefix sums), E := Pmax
-    const int32_t* n_paths;    // [M] number of paths of each task (<= Pmax)
-    int NS;                    // sample stride between tasks (E*H, or Nmax for variable-length paths)
-    int32_t* tpos;             // [M][NS] workspace: time index of every sample inside its path (variable-length only)
+    const int32_t* __restrict__ path_off;   // [M][Pmax+1] prefix sums, E := Pmax
+    const int32_t* __restrict__ n_paths;    // [M]
+    int NS;                   // sample stride between tasks (E*H, or Nmax for variable-length paths)
+    int32_t* tpos;            // [M][NS] time index of every sample inside its path (variable-length only)
+    // standalone LinearFeatureBaseline.fit: targets given by the caller instead of the return scan
+    const double* __restrict__ target;      // [M][NS] or nullptr
+    int mode;
+    int chunk_cap;            // samples a front-stage CTA can stage in shared memory (0: use ws64)
+    int finish_cap;           // samples the finish stage can stage in shared memory (0: use ws64)
 };
-// path table helpers: number of paths of task m, offset of path e
-__device__ __forceinline__ int n_paths_of(const ProcArgs& A, int m) { return A.path_off ? __ldg(A.n_paths + m) : A.E; }
+__device__ __forceinline__ int n_paths_of(const ProcArgs& A, int m) { return (A.path_off && A.n_paths) ? __ldg(A.n_paths + m) : A.E; }
 __device__ __forceinline__ int path_begin(const ProcArgs& A, int m, int e) {
     return A.path_off ? __ldg(A.path_off + (int64_t)m * (A.E + 1) + e) : e * A.H;
 }
 
-// LinearFeatureBaseline._features (baselines/linear_baseline.py:101-106) for one sample, float64:
+// block-wide reductions of K values at once: warp shuffles, one smem exchange
+template <int K>
+__device__ __forceinline__ void block_reduce(double (&v)[K], const int (&op)[K], double* red /* [PS_WARPS][K] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = op[k] == 0 ? warp_sum(v[k]) : op[k] == 1 ? warp_max(v[k]) : warp_min(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[w * K + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = red[k];
+#pragma unroll
+        for (int i = 1; i < PS_WARPS; ++i) {
+            const double x = red[i * K + k];
+            t = op[k] == 0 ? t + x : op[k] == 1 ? fmax(t, x) : fmin(t, x);
+        }
+        v[k] = t;
+    }
+}
+
+// LinearFeatureBaseline._features (baselines/linear_baseline.py:101-106), column `col` of one sample, float64:
 //   [clip(o,-10,10), clip(o)^2, t, t^2, t^3, 1] with t = step/100
-__device__ __forceinline__ void features(const float* o, int Do, int step, double* f) {
-    for (int i = 0; i < Do; ++i) {
-        double c = fmin(fmax((double)o[i], -10.0), 10.0);
-        f[i] = c;
-        f[Do + i] = c * c;
+__device__ __forceinline__ double feature_col(const float* __restrict__ o, int Do, int step, int col) {
+    if (col < 2 * Do) {
+        const double c = fmin(fmax((double)__ldg(o + (col < Do ? col : col - Do)), -10.0), 10.0);
+        return col < Do ? c : c * c;
     }
     const double tt = (double)step / 100.0;
-    f[2 * Do] = tt;
-    f[2 * Do + 1] = tt * tt;
-    f[2 * Do + 2] = tt * tt * tt;
-    f[2 * Do + 3] = 1.0;
+    const int k = col - 2 * Do;
+    return k == 0 ? tt : k == 1 ? tt * tt : k == 2 ? tt * tt * tt : 1.0;
 }
 
-__device__ __forceinline__ void pair_tables(int NC, int n_pairs, unsigned char* pair_i, unsigned char* pair_j) {
-    for (int p = threadIdx.x; p < n_pairs; p += PS_THREADS) {   // packed (i<=j) index tables
-        int i = 0, rem = p;
-        while (rem >= NC - i) { rem -= NC - i; ++i; }
-        pair_i[p] = (unsigned char)i;
-        pair_j[p] = (unsigned char)(i + rem);
-    }
-}
+// shared-memory carve-up (dynamic): [tile | red | (front: val, rewf) or (finish: A, L, w, bval, rall)]
 
-// Stage 1, grid (C, M): CTA (c, m) owns trajectories [c*EPC, (c+1)*EPC) of task m: discounted returns, path
-// statistics, and its slice of the Gram matrix Phi^T [Phi | y] in float64.  Splitting a task over C CTAs puts
-// ~2 CTAs on every SM (a task-per-CTA launch uses only M of the 148 SMs and is fp64-FMA bound for F = 38).
-__global__ void __launch_bounds__(PS_THREADS) process_gram_kernel(ProcArgs A) {
-    const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x;
+// ---------------------------------------------------------------------------------------------------------------
+// One launch.  STAGE_F / STAGE_L: the front / finish stage keeps its sample arrays in shared memory.
+template <bool STAGE_F, bool STAGE_L>
+__global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int E = n_paths_of(A, m), H = A.H, Do = A.Do, NS = A.NS;
-    const int F = 2 * Do + 4, NC = F + 1;
-    const int n_pairs = NC * (NC + 1) / 2;
+    const int F = 2 * Do + 4, NC = F + 1, nb = (NC + 3) >> 2, NCP = nb * 4, nblk = nb * (nb + 1) / 2;
+    const bool linear = A.baseline_kind == PROMP_BASELINE_LINEAR_FEATURE;
     const int e_lo = min(E, c * A.EPC), e_hi = min(E, e_lo + A.EPC);
-    const float* obs = A.obs + (int64_t)m * NS * Do;
-    const float* rew = A.rew + (int64_t)m * NS;
-    double* ret64 = A.ws + (int64_t)m * 2 * NS;
+    const float* __restrict__ obs = A.obs + (int64_t)m * NS * Do;
+    const float* __restrict__ rew = A.rew ? A.rew + (int64_t)m * NS : nullptr;
     int32_t* tpos = A.tpos ? A.tpos + (int64_t)m * NS : nullptr;
 
-    __shared__ double red[PS_THREADS / 32];
-    __shared__ double tile[PS_TS * PS_MAXCOL];
-    __shared__ double gram[PS_MAXPAIR];
-    __shared__ unsigned char pair_i[PS_MAXPAIR], pair_j[PS_MAXPAIR];
+    __shared__ unsigned char blk_i[PS_MAXBLK], blk_j[PS_MAXBLK];
+    __shared__ int s_last, s_flag;
+    __shared__ double s_piv, s_reg;
+    __shared__ unsigned char s_def[PS_MAXCOL];
 
-    // ---- discounted returns R_t = r_t + g R_{t+1}  (utils/utils.py:74-81) + path statistics
-    double sR0 = 0, sG = 0, sG2 = 0, mxG = -1e300, mnG = 1e300, sr = 0, sr2 = 0;
-    for (int e = e_lo + tid; e < e_hi; e += PS_THREADS) {
-        double R = 0.0, G = 0.0;
-        const int o = path_begin(A, m, e), L = path_begin(A, m, e + 1) - o;
-        for (int t = L - 1; t >= 0; --t) {
-            const double r = (double)rew[o + t];
-            R = r + A.discount * R;
-            G += r;
-            sr += r;
-            sr2 += r * r;
-            ret64[o + t] = R;
-            if (tpos) tpos[o + t] = t;
-        }
-        sR0 += R;
-        sG += G;
-        sG2 += G * G;
-        mxG = fmax(mxG, G);
-        mnG = fmin(mnG, G);
-    }
-    sR0 = block_sum(sR0, red); sG = block_sum(sG, red); sG2 = block_sum(sG2, red);
-    sr = block_sum(sr, red); sr2 = block_sum(sr2, red);
-    mxG = block_max(mxG, red); mnG = block_min(mnG, red);
-    if (tid == 0) {
-        double* sp = A.stat_p + ((int64_t)m * A.C + c) * 8;
-        sp[0] = sR0; sp[1] = sG; sp[2] = sG2; sp[3] = mxG; sp[4] = mnG; sp[5] = sr; sp[6] = sr2; sp[7] = 0.0;
-    }
-    __syncthreads();   // ret64 of this CTA's trajectories visible to the whole CTA
-    const int n_lo = path_begin(A, m, e_lo), n_hi = path_begin(A, m, e_hi);
-    for (int n = n_lo + tid; n < n_hi; n += PS_THREADS) A.returns[(int64_t)m * NS + n] = (float)ret64[n];
-    if (A.baseline_kind != PROMP_BASELINE_LINEAR_FEATURE) return;
+    double* tile = reinterpret_cast<double*>(smem_raw);
+    double* red = tile + PS_TS * NCP;
+    double* rest = red + PS_THREADS * 8;
 
-    // ---- partial Gram matrix over this CTA's samples (baselines/linear_baseline.py:66-73)
-    pair_tables(NC, n_pairs, pair_i, pair_j);
-    const int G = max(1, PS_THREADS / n_pairs);        // sample groups per pair
-    const int n_items = n_pairs * G;
-    double acc[PS_MAXITEM] = {0, 0, 0, 0};
-    for (int n0 = n_lo; n0 < n_hi; n0 += PS_TS) {
-        const int ns = min(PS_TS, n_hi - n0);
-        __syncthreads();
-        for (int s = tid; s < ns; s += PS_THREADS) {     // one thread builds one sample's feature row
-            const int n = n0 + s;
-            features(obs + (int64_t)n * Do, Do, tpos ? tpos[n] : n % H, &tile[s * NC]);
-            tile[s * NC + F] = ret64[n];
+    if (tid < nblk) {      // packed (bi <= bj) block index tables
+        int i = 0, rem = tid;
+        while (rem >= nb - i) { rem -= nb - i; ++i; }
+        blk_i[tid] = (unsigned char)i;
+        blk_j[tid] = (unsigned char)(i + rem);
+    }
+
+    // ================================================================================================ front stage
+    const int n_lo = path_begin(A, m, e_lo), n_hi = path_begin(A, m, e_hi), ns = n_hi - n_lo;
+    double* val = STAGE_F ? rest : A.ws64 + (int64_t)m * 2 * NS + n_lo;          // returns / targets of this chunk, float64
+    float* rewf = STAGE_F ? reinterpret_cast<float*>(rest + A.chunk_cap) : nullptr;
+    if (A.target) {
+        const double* __restrict__ tg = A.target + (int64_t)m * NS + n_lo;
+        for (int i = tid; i < ns; i += PS_THREADS) val[i] = tg[i];
+    } else if (STAGE_F) {
+        for (int i = tid; i < ns; i += PS_THREADS) rewf[i] = __ldg(rew + n_lo + i);
+    }
+    __syncthreads();
+    {
+        // ---- discounted returns R_t = r_t + g R_{t+1}  (utils/utils.py:74-81) + path statistics; one thread per path,
+        //      walking shared memory (no global round trip on the dependent chain)
+        double st[7] = {0, 0, 0, -1e300, 1e300, 0, 0};   // sum R0, sum G, sum G^2, max G, min G, sum r, sum r^2
+        for (int e = e_lo + tid; e < e_hi; e += PS_THREADS) {
+            const int o = path_begin(A, m, e) - n_lo, L = path_begin(A, m, e + 1) - n_lo - o;
+            if (A.target) {
+                if (tpos) for (int t = 0; t < L; ++t) tpos[n_lo + o + t] = t;
+                continue;
+            }
+            double R = 0.0, G = 0.0, sr = 0.0, sr2 = 0.0;
+            for (int t = L - 1; t >= 0; --t) {
+                const double r = (double)(STAGE_F ? rewf[o + t] : __ldg(rew + n_lo + o + t));
+                R = r + A.discount * R;
+                G += r;
+                sr += r;
+                sr2 += r * r;
+                val[o + t] = R;
+                if (tpos) tpos[n_lo + o + t] = t;
+            }
+            st[0] += R; st[1] += G; st[2] += G * G; st[3] = fmax(st[3], G); st[4] = fmin(st[4], G); st[5] += sr; st[6] += sr2;
+        }
+        if (!A.target) {
+            const int op[7] = {0, 0, 0, 1, 2, 0, 0};
+            block_reduce<7>(st, op, red);
+            if (tid < 7) A.stat_p[((int64_t)m * A.C + c) * 8 + tid] = st[tid];
         }
         __syncthreads();
+        if (A.returns && !A.target)
+            for (int i = tid; i < ns; i += PS_THREADS) A.returns[(int64_t)m * NS + n_lo + i] = (float)val[i];
+    }
+
+    // ---- partial Gram matrix over this chunk's samples (baselines/linear_baseline.py:66-73): thread = (4x4 block, group)
+    if (linear) {
+        const int G = max(1, PS_THREADS / nblk);
+        const int blk = tid % nblk, g = tid / nblk;
+        const bool active = g < G;
+        const int bi = blk_i[active ? blk : 0], bj = blk_j[active ? blk : 0];
+        double acc[16];
 #pragma unroll
-        for (int it = 0; it < PS_MAXITEM; ++it) {
-            const int item = tid + it * PS_THREADS;
-            if (item < n_items) {
-                const int p = item % n_pairs, g = item / n_pairs;
-                const int i = pair_i[p], j = pair_j[p];
-                double a = acc[it];
-                for (int s = g; s < ns; s += G) a = fma(tile[s * NC + i], tile[s * NC + j], a);
-                acc[it] = a;
+        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+        for (int n0 = 0; n0 < ns; n0 += PS_TS) {
+            const int tn = min(PS_TS, ns - n0);
+            __syncthreads();
+            {   // feature rows: thread (sample s, column part)
+                const int s = tid >> 3, part = tid & 7;
+                if (s < tn) {
+                    const int n = n_lo + n0 + s;
+                    const int step = tpos ? tpos[n] : n % H;
+                    const float* o = obs + (int64_t)n * Do;
+                    for (int col = part; col < NCP; col += 8)
+                        tile[s * NCP + col] = col < F ? feature_col(o, Do, step, col) : col == F ? val[n0 + s] : 0.0;
+                }
+            }
+            __syncthreads();
+            if (active) {
+                for (int s = g; s < tn; s += G) {
+                    const double2* ra = reinterpret_cast<const double2*>(tile + s * NCP + 4 * bi);
+                    const double2* rb = reinterpret_cast<const double2*>(tile + s * NCP + 4 * bj);
+                    const double2 a01 = ra[0], a23 = ra[1], b01 = rb[0], b23 = rb[1];
+                    const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[r * 4 + q] = fma(a[r], b[q], acc[r * 4 + q]);
+                }
+            }
+        }
+        // deterministic group reduction (groups added in order g = 0..G-1), two halves of 8 accumulators
+        double* gp = A.gram_p + ((int64_t)m * A.C + c) * PS_GP;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[tid * 8 + i] = active ? acc[half * 8 + i] : 0.0;
+            __syncthreads();
+            for (int idx = tid; idx < nblk * 8; idx += PS_THREADS) {
+                const int b = idx >> 3, i = idx & 7;
+                double sum = 0.0;
+                for (int gg = 0; gg < G; ++gg) sum += red[(gg * nblk + b) * 8 + i];
+                gp[b * 16 + half * 8 + i] = sum;
             }
         }
     }
+
+    // ================================================================================================ ticket
+    __threadfence();
     __syncthreads();
-    for (int p = tid; p < n_pairs; p += PS_THREADS) gram[p] = 0.0;
-    __syncthreads();
-    for (int g = 0; g < G; ++g) {      // deterministic group reduction: groups added in order g = 0..G-1
-#pragma unroll
-        for (int it = 0; it < PS_MAXITEM; ++it) {
-            const int item = tid + it * PS_THREADS;
-            if (item < n_items && item / n_pairs == g) gram[item % n_pairs] += acc[it];
-        }
-        __syncthreads();
+    if (tid == 0) {
+        const unsigned int old = atomicAdd(A.counters + m, 1u);
+        s_last = (old == (unsigned int)(A.C - 1));
+        if (s_last) A.counters[m] = 0u;        // self-cleaning: the workspace is left ready for the next launch
     }
-    double* gp = A.gram_p + ((int64_t)m * A.C + c) * PS_MAXPAIR;
-    for (int p = tid; p < n_pairs; p += PS_THREADS) gp[p] = gram[p];
-}
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
 
-// Stage 2, one CTA per task: reduce the partials (fixed chunk order), Cholesky solve with the reference's
-// ridge / NaN-retry rule, predict, GAE scan, per-task moments, advantages.
-__global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) {
-    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int E = n_paths_of(A, m), H = A.H, Do = A.Do, NS = A.NS;
+    // ================================================================================================ finish stage
     const int N = path_begin(A, m, E);                 // valid samples of this task
-    const int F = 2 * Do + 4, NC = F + 1;
-    const int n_pairs = NC * (NC + 1) / 2;
-    const float* obs = A.obs + (int64_t)m * NS * Do;
-    const float* rew = A.rew + (int64_t)m * NS;
-    double* adv64 = A.ws + (int64_t)m * 2 * NS + NS;
-    const int32_t* tpos = A.tpos ? A.tpos + (int64_t)m * NS : nullptr;
+    double* Afull = rest;                              // [NCP][NCP]
+    const int LD = F | 1;
+    double* Lm = Afull + NCP * NCP;                    // [F][LD] lower triangle
+    double* wv = Lm + PS_MAXCOL * (PS_MAXCOL + 1);     // [PS_MAXCOL]
+    double* bval = STAGE_L ? wv + PS_MAXCOL + 4 : A.ws64 + (int64_t)m * 2 * NS + NS;   // baseline -> advantages, float64
+    float* rall = STAGE_L ? reinterpret_cast<float*>(bval + A.finish_cap) : nullptr;
 
-    __shared__ double red[PS_THREADS / 32];
-    __shared__ double gram[PS_MAXPAIR];                 // packed upper triangle over NC columns
-    __shared__ double Lm[(PS_MAXCOL - 1) * (PS_MAXCOL - 1)];
-    __shared__ double wv[PS_MAXCOL];
-    __shared__ unsigned char pair_i[PS_MAXPAIR], pair_j[PS_MAXPAIR];
-    __shared__ int s_flag;
-    __shared__ double s_reg;
-
-    if (tid < 8) {   // path statistics: sums for 0,1,2,5,6; max for 3; min for 4
+    if (tid < 8 && A.mode == PS_MODE_PROCESS) {   // path statistics: sums for 0,1,2,5,6; max for 3; min for 4
         const double* sp = A.stat_p + (int64_t)m * A.C * 8 + tid;
-        double v = sp[0];
-        for (int c = 1; c < A.C; ++c) {
-            const double x = sp[c * 8];
+        double v = __ldcg(sp);
+        for (int cc = 1; cc < A.C; ++cc) {
+            const double x = __ldcg(sp + cc * 8);
             v = (tid == 3) ? fmax(v, x) : (tid == 4) ? fmin(v, x) : v + x;
         }
         if (A.stats && tid < 7) A.stats[(int64_t)m * 8 + tid] = v;
     }
+    if (STAGE_L && A.mode == PS_MODE_PROCESS)
+        for (int n = tid; n < N; n += PS_THREADS) rall[n] = __ldg(rew + n);
 
     double reg_used = 0.0;
-    if (A.baseline_kind == PROMP_BASELINE_LINEAR_FEATURE) {
-        pair_tables(NC, n_pairs, pair_i, pair_j);
-        for (int p = tid; p < n_pairs; p += PS_THREADS) {
-            const double* gp = A.gram_p + (int64_t)m * A.C * PS_MAXPAIR + p;
+    if (linear) {
+        for (int idx = tid; idx < nblk * 16; idx += PS_THREADS) {   // reduce the chunk partials in chunk order
+            const double* gp = A.gram_p + (int64_t)m * A.C * PS_GP + idx;
             double v = 0.0;
-            for (int c = 0; c < A.C; ++c) v += gp[(int64_t)c * PS_MAXPAIR];
-            gram[p] = v;
+            for (int cc = 0; cc < A.C; ++cc) v += __ldcg(gp + (int64_t)cc * PS_GP);
+            const int b = idx >> 4, r = (idx >> 2) & 3, q = idx & 3;
+            const int i = 4 * blk_i[b] + r, j = 4 * blk_j[b] + q;
+            Afull[i * NCP + j] = v;
+            Afull[j * NCP + i] = v;
         }
-        __syncthreads();
-
-        // ---- solve (Phi^T Phi + reg I) w = Phi^T y; retry with 10x reg on NaN, up to 5 tries (:68-77)
         if (tid == 0) { s_reg = A.reg_coeff; s_flag = 0; }
         __syncthreads();
+        // ---- solve (Phi^T Phi + reg I) w = Phi^T y; retry with 10x reg on NaN, up to 5 tries (:68-77).
+        //      Crout Cholesky, 4 lanes per row.  A pivot that vanishes relative to its diagonal entry (only possible with
+        //      reg_coeff = 0 and collinear features) marks the column rank-deficient: w_j = 0, which gives the same fitted
+        //      values as the reference's minimum-norm lstsq solution (least-squares fits are unique in Phi w).
+        const int row = tid >> 2, q4 = tid & 3;
         for (int attempt = 0; attempt < 5; ++attempt) {
             const double reg = s_reg;
-            // unpack A into Lm (lower triangle incl. diagonal)
-            for (int p = tid; p < n_pairs; p += PS_THREADS) {
-                const int i = pair_i[p], j = pair_j[p];
-                if (j < F) Lm[j * F + i] = gram[p] + (i == j ? reg : 0.0);
+            for (int idx = tid; idx < F * F; idx += PS_THREADS) {
+                const int i = idx / F, j = idx - i * F;
+                if (j <= i) Lm[i * LD + j] = Afull[i * NCP + j] + (i == j ? reg : 0.0);
             }
+            if (tid < PS_MAXCOL) s_def[tid] = 0;
             __syncthreads();
+            bool bad = false;
+            for (int j = 0; j < F; ++j) {
+                double s = 0.0;
+                if (row >= j && row < F)
+                    for (int k = q4; k < j; k += 4) s = fma(Lm[row * LD + k], Lm[j * LD + k], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (row == j && q4 == 0) {
+                    const double ajj = Lm[j * LD + j], d = ajj - s;
+                    if (d <= 1e-14 * fabs(ajj) && d == d && ajj == ajj && isfinite(ajj)) {
+                        s_def[j] = 1;
+                        s_piv = 1.0;
+                        Lm[j * LD + j] = 1.0;
+                    } else {
+                        const double ljj = sqrt(d);     // NaN input -> NaN -> retry with a larger ridge
+                        s_piv = ljj;
+                        Lm[j * LD + j] = ljj;
+                    }
+                }
+                __syncthreads();
+                const double piv = s_piv;
+                if (!(piv > 0.0)) bad = true;
+                if (row > j && row < F && q4 == 0) Lm[row * LD + j] = s_def[j] ? 0.0 : (Lm[row * LD + j] - s) / piv;
+                __syncthreads();
+            }
+            // forward L z = b, backward L^T w = z on one warp: lane l owns rows l and l+32   (b = Gram column F)
             if (tid < 32) {
-                bool bad = false;
-                // Cholesky A = L L^T, column by column; lanes own rows
-                for (int j = 0; j < F; ++j) {
-                    double d = 0.0;
-                    for (int k = lane; k < j; k += 32) d += Lm[j * F + k] * Lm[j * F + k];
-                    d = Lm[j * F + j] - warp_sum(d);
-                    const double ljj = sqrt(d);     // d <= 0 -> NaN -> retry with a larger ridge
-                    if (!(ljj > 0.0)) bad = true;
-                    __syncwarp();
-                    if (lane == 0) Lm[j * F + j] = ljj;
-                    for (int i = j + 1 + lane; i < F; i += 32) {
-                        double s = Lm[i * F + j];
-                        for (int k = 0; k < j; ++k) s -= Lm[i * F + k] * Lm[j * F + k];
-                        Lm[i * F + j] = s / ljj;
-                    }
-                    __syncwarp();
+                double b0 = lane < F ? Afull[lane * NCP + F] : 0.0, b1 = lane + 32 < F ? Afull[(lane + 32) * NCP + F] : 0.0;
+                if (lane < F && s_def[lane]) b0 = 0.0;
+                if (lane + 32 < F && s_def[lane + 32]) b1 = 0.0;
+                for (int k = 0; k < F; ++k) {
+                    const double mine = (k < 32 ? b0 : b1) / Lm[k * LD + k];
+                    const double zk = s_def[k] ? 0.0 : __shfl_sync(0xffffffffu, mine, k & 31);
+                    if (lane == (k & 31)) { if (k < 32) b0 = zk; else b1 = zk; }
+                    if (lane > k && lane < F) b0 = fma(-Lm[lane * LD + k], zk, b0);
+                    if (lane + 32 > k && lane + 32 < F) b1 = fma(-Lm[(lane + 32) * LD + k], zk, b1);
                 }
-                // forward: L z = b ; backward: L^T w = z   (b = Phi^T y = gram column F)
-                if (lane == 0) {
-                    for (int i = 0; i < F; ++i) {
-                        // packed index of (i, F): row i starts at i*NC - i(i-1)/2, column offset F-i
-                        double s = gram[i * NC - i * (i - 1) / 2 + (F - i)];
-                        for (int k = 0; k < i; ++k) s -= Lm[i * F + k] * wv[k];
-                        wv[i] = s / Lm[i * F + i];
-                    }
-                    for (int i = F - 1; i >= 0; --i) {
-                        double s = wv[i];
-                        for (int k = i + 1; k < F; ++k) s -= Lm[k * F + i] * wv[k];
-                        wv[i] = s / Lm[i * F + i];
-                    }
-                    for (int i = 0; i < F; ++i)
-                        if (isnan(wv[i]) || isinf(wv[i])) bad = true;
+                for (int k = F - 1; k >= 0; --k) {
+                    const double mine = (k < 32 ? b0 : b1) / Lm[k * LD + k];
+                    const double wk = s_def[k] ? 0.0 : __shfl_sync(0xffffffffu, mine, k & 31);
+                    if (lane == (k & 31)) { if (k < 32) b0 = wk; else b1 = wk; }
+                    if (lane < k) b0 = fma(-Lm[k * LD + lane], wk, b0);
+                    if (lane + 32 < k) b1 = fma(-Lm[k * LD + lane + 32], wk, b1);
                 }
-                bad = __any_sync(0xffffffffu, bad);
+                if (lane < F) wv[lane] = b0;
+                if (lane + 32 < F) wv[lane + 32] = b1;
+                bool nf = (lane < F && !isfinite(b0)) || (lane + 32 < F && !isfinite(b1));
+                nf = __any_sync(0xffffffffu, nf) || bad;
                 if (lane == 0) {
-                    s_flag = bad ? 0 : 1;
-                    if (bad) s_reg = reg * 10.0;
+                    s_flag = nf ? 0 : 1;
+                    if (nf) s_reg = reg * 10.0;
                 }
             }
             __syncthreads();
@@ -291,31 +342,44 @@ __global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) 
         }
         if (A.coeffs)
             for (int i = tid; i < F; i += PS_THREADS) A.coeffs[(int64_t)m * F + i] = wv[i];
+        if (A.mode == PS_MODE_FIT_ONLY) {
+            if (A.stats && tid == 0) A.stats[(int64_t)m * 8 + 7] = reg_used;
+            return;
+        }
         // ---- predict b_n = phi_n . w (baselines/linear_baseline.py:17-33)
         for (int n = tid; n < N; n += PS_THREADS) {
-            double f[PS_MAXCOL];
-            features(obs + (int64_t)n * Do, Do, tpos ? tpos[n] : n % H, f);
+            const float* o = obs + (int64_t)n * Do;
+            const int step = tpos ? tpos[n] : n % H;
             double b = 0.0;
-            for (int i = 0; i < F; ++i) b = fma(f[i], wv[i], b);
-            adv64[n] = b;
+            for (int i = 0; i < Do; ++i) {
+                const double cl = fmin(fmax((double)__ldg(o + i), -10.0), 10.0);
+                b = fma(cl, wv[i], b);
+                b = fma(cl * cl, wv[Do + i], b);
+            }
+            const double tt = (double)step / 100.0;
+            b = fma(tt, wv[2 * Do], b);
+            b = fma(tt * tt, wv[2 * Do + 1], b);
+            b = fma(tt * tt * tt, wv[2 * Do + 2], b);
+            bval[n] = b + wv[2 * Do + 3];
         }
     } else {
-        for (int n = tid; n < N; n += PS_THREADS) adv64[n] = 0.0;   // ZeroBaseline.predict
+        if (A.mode == PS_MODE_FIT_ONLY) return;
+        for (int n = tid; n < N; n += PS_THREADS) bval[n] = 0.0;   // ZeroBaseline.predict
     }
     __syncthreads();
 
     // ---- GAE: delta_t = r_t + g b_{t+1} - b_t (b_H = 0); A_t = delta_t + g*lam A_{t+1}  (samplers/base.py:151-162)
     const double gl = A.discount * A.gae_lambda;
-    double s1 = 0.0;
+    double mom[2] = {0.0, 0.0};
     for (int e = tid; e < E; e += PS_THREADS) {
         double b_next = 0.0, a_next = 0.0;
         const int o = path_begin(A, m, e), L = path_begin(A, m, e + 1) - o;
         for (int t = L - 1; t >= 0; --t) {
-            const double b = adv64[o + t];
-            const double delta = (double)rew[o + t] + A.discount * b_next - b;
-            const double a = delta + gl * a_next;
-            adv64[o + t] = a;
-            s1 += a;
+            const double b = bval[o + t];
+            const double r = (double)(STAGE_L ? rall[o + t] : __ldg(rew + o + t));
+            const double a = (r + A.discount * b_next - b) + gl * a_next;
+            bval[o + t] = a;
+            mom[0] += a;
             a_next = a;
             b_next = b;
         }
@@ -325,23 +389,31 @@ __global__ void __launch_bounds__(PS_THREADS) process_finish_kernel(ProcArgs A) 
     // ---- per-task normalisation / positive shift (utils/utils.py:59-71; population std)
     double mean = 0.0, inv = 1.0;
     if (A.normalize_adv) {
-        mean = block_sum(s1, red) / (double)N;
-        double s2 = 0.0;
-        for (int n = tid; n < N; n += PS_THREADS) {
-            const double d = adv64[n] - mean;
-            s2 += d * d;
+        {
+            double v[1] = {mom[0]};
+            const int op[1] = {0};
+            block_reduce<1>(v, op, red);
+            mean = v[0] / (double)N;
         }
-        const double var = block_sum(s2, red) / (double)N;
-        inv = 1.0 / (sqrt(var) + 1e-8);
+        double v[1] = {0.0};
+        for (int n = tid; n < N; n += PS_THREADS) {
+            const double d = bval[n] - mean;
+            v[0] += d * d;
+        }
+        const int op[1] = {0};
+        block_reduce<1>(v, op, red);
+        inv = 1.0 / (sqrt(v[0] / (double)N) + 1e-8);
     }
     double mn = 0.0;
     if (A.positive_adv) {
-        double lm = 1e300;
-        for (int n = tid; n < N; n += PS_THREADS) lm = fmin(lm, (adv64[n] - mean) * inv);
-        mn = block_min(lm, red);
+        double v[1] = {1e300};
+        for (int n = tid; n < N; n += PS_THREADS) v[0] = fmin(v[0], (bval[n] - mean) * inv);
+        const int op[1] = {2};
+        block_reduce<1>(v, op, red);
+        mn = v[0];
     }
     for (int n = tid; n < N; n += PS_THREADS) {
-        double a = (adv64[n] - mean) * inv;
+        double a = (bval[n] - mean) * inv;
         if (A.positive_adv) a = (a - mn) + 1e-8;
         A.adv[(int64_t)m * NS + n] = (float)a;
     }
@@ -354,23 +426,98 @@ __global__ void adj_avg_rewards_kernel(int64_t n, const float* rew, double mean,
     if (i < n) out[i] = (float)(((double)rew[i] - mean) * inv);
 }
 
+// LinearFeatureBaseline.predict (baselines/linear_baseline.py:17-33) for a flat list of paths
+__global__ void baseline_predict_kernel(int n_paths, const int32_t* __restrict__ path_off, int Do, const float* __restrict__ obs,
+                                        const double* __restrict__ coeffs, double* __restrict__ out) {
+    const int n_total = __ldg(path_off + n_paths);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_total; n += gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_paths;           // path containing sample n: path_off[lo] <= n < path_off[lo+1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(path_off + mid) <= n) lo = mid; else hi = mid;
+        }
+        const int step = n - __ldg(path_off + lo);
+        const float* o = obs + (int64_t)n * Do;
+        double b = 0.0;
+        for (int i = 0; i < Do; ++i) {
+            const double cl = fmin(fmax((double)__ldg(o + i), -10.0), 10.0);
+            b = fma(cl, coeffs[i], b);
+            b = fma(cl * cl, coeffs[Do + i], b);
+        }
+        const double tt = (double)step / 100.0;
+        b = fma(tt, coeffs[2 * Do], b);
+        b = fma(tt * tt, coeffs[2 * Do + 1], b);
+        b = fma(tt * tt * tt, coeffs[2 * Do + 2], b);
+        out[n] = b + coeffs[2 * Do + 3];
+    }
+}
+
 }  // namespace promp
 
 using namespace promp;
 
+// Chunking: enough CTAs for ~4 per SM (each CTA's front stage is latency-bound), never more than one per trajectory.
 static void proc_chunks(int M, int E, int* C, int* EPC) {
-    int target = (2 * 148 + M - 1) / M;          // ~2 CTAs per SM
+    int target = (4 * 148 + M - 1) / M;
     if (target > E) target = E;
     if (target < 1) target = 1;
     *EPC = (E + target - 1) / target;
     *C = (E + *EPC - 1) / *EPC;
 }
 
+struct ProcLayout {
+    int C, EPC;
+    int64_t off_gram, off_stat, off_ws64, off_tpos, total;
+};
+static ProcLayout proc_layout(int M, int E, int NS, bool ragged) {
+    ProcLayout L;
+    proc_chunks(M, E, &L.C, &L.EPC);
+    int64_t o = ((int64_t)M * 4 + 15) / 16 * 16;            // counters
+    L.off_gram = o;  o += (int64_t)M * L.C * PS_GP * 8;
+    L.off_stat = o;  o += (int64_t)M * L.C * 8 * 8;
+    L.off_ws64 = o;  o += (int64_t)M * 2 * NS * 8;
+    L.off_tpos = o;  if (ragged) o += ((int64_t)M * NS * 4 + 7) / 8 * 8;
+    L.total = o;
+    return L;
+}
+
+static size_t proc_smem_fixed(int Do) {
+    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
+    return (size_t)(PS_TS * NCP + PS_THREADS * 8) * 8;
+}
+static size_t proc_smem_finish_fixed(int Do) {
+    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
+    return (size_t)(NCP * NCP + PS_MAXCOL * (PS_MAXCOL + 1) + PS_MAXCOL + 4) * 8;
+}
+
+static int launch_process(ProcArgs& A, bool ragged, cudaStream_t stream) {
+    // shared-memory staging: front stage holds a chunk's rewards + returns, the finish stage a task's rewards + baseline
+    const int chunk_samples = ragged ? A.NS : A.EPC * A.H;
+    const size_t fixed = proc_smem_fixed(A.Do);
+    size_t front = fixed + (size_t)chunk_samples * PS_SMEM_SAMPLES_BYTES;
+    size_t fin = fixed + proc_smem_finish_fixed(A.Do) + (size_t)A.NS * PS_SMEM_SAMPLES_BYTES;
+    const bool stage_f = front <= (size_t)PS_SMEM_BUDGET, stage_l = fin <= (size_t)PS_SMEM_BUDGET;
+    if (!stage_f) front = fixed;
+    if (!stage_l) fin = fixed + proc_smem_finish_fixed(A.Do);
+    A.chunk_cap = stage_f ? chunk_samples : 0;
+    A.finish_cap = stage_l ? A.NS : 0;
+    const size_t smem = (front > fin ? front : fin) + 16;
+    auto kern = stage_f ? (stage_l ? process_fused_kernel<true, true> : process_fused_kernel<true, false>)
+                        : (stage_l ? process_fused_kernel<false, true> : process_fused_kernel<false, false>);
+    static size_t configured[4] = {0, 0, 0, 0};
+    const int which = (stage_f ? 2 : 0) + (stage_l ? 1 : 0);
+    if (smem > configured[which]) {
+        PROMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[which] = smem;
+    }
+    kern<<<dim3(A.C, A.M), PS_THREADS, smem, stream>>>(A);
+    PROMP_LAUNCH_CHECK("process_fused_kernel");
+    return PROMP_OK;
+}
+
 extern "C" int64_t promp_process_workspace_bytes(int M, int E, int H, int obs_dim) {
     (void)obs_dim;
-    int C, EPC;
-    proc_chunks(M, E, &C, &EPC);
-    return ((int64_t)M * 2 * E * H + (int64_t)M * C * (PS_MAXPAIR + 8)) * (int64_t)sizeof(double);
+    return proc_layout(M, E, E * H, false).total;
 }
 
 extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const float* obs, const float* rew,
@@ -386,23 +533,22 @@ extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const flo
                   "promp_process_samples: unknown baseline kind %d", baseline_kind);
     PROMP_REQUIRE(discount >= 0.0 && discount <= 1.0 && gae_lambda >= 0.0 && gae_lambda <= 1.0,
                   "promp_process_samples: discount and gae_lambda must be in [0,1]");   // samplers/base.py:56-57
-    if (workspace_bytes < promp_process_workspace_bytes(M, E, H, obs_dim)) {
-        set_error("promp_process_samples: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
-                  (long long)promp_process_workspace_bytes(M, E, H, obs_dim));
+    const ProcLayout L = proc_layout(M, E, E * H, false);
+    if (workspace_bytes < L.total) {
+        set_error("promp_process_samples: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)L.total);
         return PROMP_ERR_WORKSPACE;
     }
-    int C, EPC;
-    proc_chunks(M, E, &C, &EPC);
-    double* ws = (double*)workspace;
-    double* gram_p = ws + (int64_t)M * 2 * E * H;
-    double* stat_p = gram_p + (int64_t)M * C * PS_MAXPAIR;
-    ProcArgs A{M, E, H, obs_dim, obs, rew, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv,
-               returns, adv, coeffs, stats, ws, gram_p, stat_p, C, EPC, nullptr, nullptr, E * H, nullptr};
-    process_gram_kernel<<<dim3(C, M), PS_THREADS, 0, (cudaStream_t)stream>>>(A);
-    PROMP_LAUNCH_CHECK("process_gram_kernel");
-    process_finish_kernel<<<M, PS_THREADS, 0, (cudaStream_t)stream>>>(A);
-    PROMP_LAUNCH_CHECK("process_finish_kernel");
-    return PROMP_OK;
+    unsigned char* w = (unsigned char*)workspace;
+    ProcArgs A{};
+    A.M = M; A.E = E; A.H = H; A.Do = obs_dim; A.obs = obs; A.rew = rew;
+    A.discount = discount; A.gae_lambda = gae_lambda; A.reg_coeff = reg_coeff;
+    A.baseline_kind = baseline_kind; A.normalize_adv = normalize_adv; A.positive_adv = positive_adv;
+    A.returns = returns; A.adv = adv; A.coeffs = coeffs; A.stats = stats;
+    A.counters = (unsigned int*)w; A.gram_p = (double*)(w + L.off_gram); A.stat_p = (double*)(w + L.off_stat);
+    A.ws64 = (double*)(w + L.off_ws64);
+    A.C = L.C; A.EPC = L.EPC; A.path_off = nullptr; A.n_paths = nullptr; A.NS = E * H; A.tpos = nullptr;
+    A.target = nullptr; A.mode = PS_MODE_PROCESS;
+    return launch_process(A, false, (cudaStream_t)stream);
 }
 
 extern "C" int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, double std, float* out, void* stream) {
@@ -414,13 +560,10 @@ extern "C" int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, d
     return PROMP_OK;
 }
 
-// ---- variable-length paths: same kernels driven by a per-task path table ------------------------------------------
+// ---- variable-length paths: same kernel driven by a per-task path table ------------------------------------------
 extern "C" int64_t promp_process_workspace_bytes_ragged(int M, int max_paths, int max_samples, int obs_dim) {
     (void)obs_dim;
-    int C, EPC;
-    proc_chunks(M, max_paths, &C, &EPC);
-    return ((int64_t)M * 2 * max_samples + (int64_t)M * C * (PS_MAXPAIR + 8)) * (int64_t)sizeof(double) +
-           (int64_t)M * max_samples * (int64_t)sizeof(int32_t);
+    return proc_layout(M, max_paths, max_samples, true).total;
 }
 
 extern "C" int promp_process_samples_ragged(int M, int max_paths, int max_samples, int obs_dim, const float* obs,
@@ -437,22 +580,67 @@ extern "C" int promp_process_samples_ragged(int M, int max_paths, int max_sample
                   "promp_process_samples_ragged: unknown baseline kind %d", baseline_kind);
     PROMP_REQUIRE(discount >= 0.0 && discount <= 1.0 && gae_lambda >= 0.0 && gae_lambda <= 1.0,
                   "promp_process_samples_ragged: discount and gae_lambda must be in [0,1]");
-    const int64_t need = promp_process_workspace_bytes_ragged(M, max_paths, max_samples, obs_dim);
-    if (workspace_bytes < need) {
-        set_error("promp_process_samples_ragged: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need);
+    const ProcLayout L = proc_layout(M, max_paths, max_samples, true);
+    if (workspace_bytes < L.total) {
+        set_error("promp_process_samples_ragged: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)L.total);
         return PROMP_ERR_WORKSPACE;
     }
-    int C, EPC;
-    proc_chunks(M, max_paths, &C, &EPC);
-    double* ws = (double*)workspace;
-    double* gram_p = ws + (int64_t)M * 2 * max_samples;
-    double* stat_p = gram_p + (int64_t)M * C * PS_MAXPAIR;
-    int32_t* tpos = (int32_t*)(stat_p + (int64_t)M * C * 8);
-    ProcArgs A{M, max_paths, 0, obs_dim, obs, rew, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv,
-               returns, adv, coeffs, stats, ws, gram_p, stat_p, C, EPC, path_off, n_paths, max_samples, tpos};
-    process_gram_kernel<<<dim3(C, M), PS_THREADS, 0, (cudaStream_t)stream>>>(A);
-    PROMP_LAUNCH_CHECK("process_gram_kernel");
-    process_finish_kernel<<<M, PS_THREADS, 0, (cudaStream_t)stream>>>(A);
-    PROMP_LAUNCH_CHECK("process_finish_kernel");
+    unsigned char* w = (unsigned char*)workspace;
+    ProcArgs A{};
+    A.M = M; A.E = max_paths; A.H = 0; A.Do = obs_dim; A.obs = obs; A.rew = rew;
+    A.discount = discount; A.gae_lambda = gae_lambda; A.reg_coeff = reg_coeff;
+    A.baseline_kind = baseline_kind; A.normalize_adv = normalize_adv; A.positive_adv = positive_adv;
+    A.returns = returns; A.adv = adv; A.coeffs = coeffs; A.stats = stats;
+    A.counters = (unsigned int*)w; A.gram_p = (double*)(w + L.off_gram); A.stat_p = (double*)(w + L.off_stat);
+    A.ws64 = (double*)(w + L.off_ws64);
+    A.C = L.C; A.EPC = L.EPC; A.path_off = path_off; A.n_paths = n_paths; A.NS = max_samples;
+    A.tpos = (int32_t*)(w + L.off_tpos);
+    A.target = nullptr; A.mode = PS_MODE_PROCESS;
+    return launch_process(A, true, (cudaStream_t)stream);
+}
+
+// ---- standalone LinearFeatureBaseline.fit / predict (baselines/linear_baseline.py:55-77, 17-33) --------------------
+extern "C" int64_t promp_baseline_fit_workspace_bytes(int n_paths, int n_samples, int obs_dim) {
+    (void)obs_dim;
+    return proc_layout(1, n_paths, n_samples, true).total;
+}
+
+extern "C" int promp_baseline_fit(int n_paths, int n_samples, int obs_dim, const float* obs, const double* target,
+                                  const int32_t* path_off, double reg_coeff, double* coeffs, double* reg_used,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+    PROMP_REQUIRE(n_paths > 0 && n_samples > 0 && obs_dim > 0, "promp_baseline_fit: dimensions must be positive");
+    PROMP_REQUIRE(2 * obs_dim + 5 <= PS_MAXCOL, "promp_baseline_fit: obs_dim %d too large (max %d)", obs_dim, (PS_MAXCOL - 5) / 2);
+    PROMP_REQUIRE(obs && target && path_off && coeffs && workspace, "promp_baseline_fit: null pointer argument");
+    const ProcLayout L = proc_layout(1, n_paths, n_samples, true);
+    if (workspace_bytes < L.total) {
+        set_error("promp_baseline_fit: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)L.total);
+        return PROMP_ERR_WORKSPACE;
+    }
+    unsigned char* w = (unsigned char*)workspace;
+    // n_paths lives on the host here; the kernel reads it through the path table of its single task
+    ProcArgs A{};
+    A.M = 1; A.E = n_paths; A.H = 0; A.Do = obs_dim; A.obs = obs; A.rew = nullptr;
+    A.discount = 0.0; A.gae_lambda = 0.0; A.reg_coeff = reg_coeff;
+    A.baseline_kind = PROMP_BASELINE_LINEAR_FEATURE; A.normalize_adv = 0; A.positive_adv = 0;
+    A.returns = nullptr; A.adv = nullptr; A.coeffs = coeffs; A.stats = nullptr;
+    A.counters = (unsigned int*)w; A.gram_p = (double*)(w + L.off_gram); A.stat_p = (double*)(w + L.off_stat);
+    A.ws64 = (double*)(w + L.off_ws64);
+    A.C = L.C; A.EPC = L.EPC; A.path_off = path_off; A.n_paths = nullptr; A.NS = n_samples;
+    A.tpos = (int32_t*)(w + L.off_tpos);
+    A.target = target; A.mode = PS_MODE_FIT_ONLY;
+    // reg_used is reported through an 8-double stats row when requested
+    A.stats = reg_used ? reg_used - 7 : nullptr;
+    return launch_process(A, true, (cudaStream_t)stream);
+}
+
+extern "C" int promp_baseline_predict(int n_paths, int n_samples, int obs_dim, const float* obs, const int32_t* path_off,
+                                      const double* coeffs, double* out, void* stream) {
+    PROMP_REQUIRE(n_paths > 0 && n_samples > 0 && obs_dim > 0, "promp_baseline_predict: dimensions must be positive");
+    PROMP_REQUIRE(obs && path_off && coeffs && out, "promp_baseline_predict: null pointer argument");
+    const int bs = 256;
+    int grid = (n_samples + bs - 1) / bs;
+    if (grid > 148 * 8) grid = 148 * 8;
+    baseline_predict_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(n_paths, path_off, obs_dim, obs, coeffs, out);
+    PROMP_LAUNCH_CHECK("baseline_predict_kernel");
     return PROMP_OK;
 }

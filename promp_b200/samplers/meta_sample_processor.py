@@ -90,6 +90,24 @@ def _ragged_phase_from_host_paths(tasks, device):
     return phase
 
 
+_WS_CACHE = {}
+_WS_KEEP = []       # superseded workspaces stay alive: a captured CUDA graph may still hold their address
+
+
+def _zeroed_workspace(nbytes, dev):
+    """The processing kernel's scratch (arrival tickets + partial Gram blocks): zero-filled ONCE, then left clean by every
+    launch, so it is allocated per device (grown on demand) and shared by all phases - launches are serialised on the
+    stream.  (A per-phase torch.zeros inside a CUDA-graph capture would replay a fill kernel every iteration.)"""
+    import torch
+    ws = _WS_CACHE.get(dev)
+    if ws is None or ws.numel() * 8 < nbytes:
+        ws = torch.zeros((nbytes + 7) // 8 + 64, dtype=torch.float64, device=dev)
+        if dev in _WS_CACHE:
+            _WS_KEEP.append(_WS_CACHE[dev])
+        _WS_CACHE[dev] = ws
+    return ws
+
+
 def run_process_kernel(phase, discount, gae_lambda, reg_coeff, baseline_kind, normalize_adv, positive_adv):
     import torch
     if isinstance(phase, RaggedPhaseData):
@@ -103,15 +121,13 @@ def run_process_kernel(phase, discount, gae_lambda, reg_coeff, baseline_kind, no
         phase.coeffs = (torch.empty if baseline_kind == 1 else torch.zeros)(M, 2 * Do + 4, dtype=torch.float64, device=dev)
         phase.stats = torch.empty(M, 8, dtype=torch.float64, device=dev)
     nbytes = _lib.load().promp_process_workspace_bytes(M, E, H, Do)
-    ws = getattr(phase, '_proc_ws', None)
-    if ws is None or ws.numel() * 8 < nbytes:
-        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
-        phase._proc_ws = ws
+    ws = _zeroed_workspace(nbytes, dev)
     _lib.call('promp_process_samples', M, E, H, Do, _lib.ptr(phase.obs), _lib.ptr(phase.rew), float(discount),
               float(gae_lambda), float(reg_coeff), int(baseline_kind), int(bool(normalize_adv)), int(bool(positive_adv)),
               _lib.ptr(phase.returns), _lib.ptr(phase.adv), _lib.ptr(phase.coeffs), _lib.ptr(phase.stats),
               _lib.ptr(ws), ws.numel() * 8, _lib.stream())
     phase.adj_avg_rewards = None
+    phase._explore_adv = None
     phase.invalidate_host()
 
 
@@ -125,10 +141,7 @@ def _run_process_kernel_ragged(phase, discount, gae_lambda, reg_coeff, baseline_
         phase.coeffs = torch.zeros(M, 2 * Do + 4, dtype=torch.float64, device=dev)
         phase.stats = torch.zeros(M, 8, dtype=torch.float64, device=dev)
     nbytes = _lib.load().promp_process_workspace_bytes_ragged(M, Pmax, N, Do)
-    ws = getattr(phase, '_proc_ws', None)
-    if ws is None or ws.numel() * 8 < nbytes:
-        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
-        phase._proc_ws = ws
+    ws = _zeroed_workspace(nbytes, dev)
     _lib.call('promp_process_samples_ragged', M, Pmax, N, Do, _lib.ptr(phase.obs), _lib.ptr(phase.rew), _lib.ptr(phase.path_off),
               _lib.ptr(phase.n_paths), float(discount), float(gae_lambda), float(reg_coeff), int(baseline_kind),
               int(bool(normalize_adv)), int(bool(positive_adv)), _lib.ptr(phase.returns), _lib.ptr(phase.adv),
@@ -137,15 +150,45 @@ def _run_process_kernel_ragged(phase, discount, gae_lambda, reg_coeff, baseline_
     phase.invalidate_host()
 
 
-def fit_baseline_on_paths(paths, target_key, reg_coeff):
-    """LinearBaseline.fit on a flat list of equal-length paths: runs the device kernel with the paths as one task
-    (discount chosen so that the kernel's `returns` equal the provided target is not possible in general, so the
-    target must be the discounted return the kernel itself computes: only target_key='returns' is supported)."""
+def _flat_paths_to_device(paths, dev):
+    """A flat list of (variable-length) host paths -> (obs [n,Do] float32, path_off [P+1] int32) on the device."""
     import torch
-    if target_key != 'returns':
-        raise NotImplementedError("device LinearFeatureBaseline.fit supports target_key='returns' only")
-    raise NotImplementedError("standalone LinearFeatureBaseline.fit needs the discount: use "
-                              "MetaSampleProcessor.process_samples (the reference never calls fit on its own)")
+    lens = [len(p["observations"]) for p in paths]
+    obs = np.concatenate([np.asarray(p["observations"], dtype=np.float32).reshape(l, -1) for p, l in zip(paths, lens)])
+    off = np.zeros(len(paths) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(lens)
+    return (torch.from_numpy(np.ascontiguousarray(obs)).to(dev), torch.from_numpy(off).to(dev), int(off[-1]), obs.shape[1])
+
+
+def fit_baseline_on_paths(paths, target_key, reg_coeff):
+    """LinearBaseline.fit (baselines/linear_baseline.py:55-77) on the device: float64 Gram matrix of the
+    LinearFeatureBaseline features + ridge solve with the reference's x10-on-NaN retry (promp_baseline_fit).
+    Returns the coefficient vector [2*Do+4] as a host float64 array."""
+    import torch
+    _lib.require_cuda()
+    assert all(target_key in p.keys() for p in paths)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    obs, off, n, Do = _flat_paths_to_device(paths, dev)
+    target = torch.from_numpy(np.concatenate([np.asarray(p[target_key], dtype=np.float64).reshape(-1) for p in paths])).to(dev)
+    assert target.numel() == n, "targets and observations must have the same length"
+    coeffs = torch.empty(2 * Do + 4, dtype=torch.float64, device=dev)
+    ws = _zeroed_workspace(_lib.load().promp_baseline_fit_workspace_bytes(len(paths), n, Do), dev)
+    _lib.call('promp_baseline_fit', len(paths), n, Do, _lib.ptr(obs), _lib.ptr(target), _lib.ptr(off), float(reg_coeff),
+              _lib.ptr(coeffs), None, _lib.ptr(ws), ws.numel() * 8, _lib.stream())
+    return coeffs.cpu().numpy()
+
+
+def predict_baseline_on_path(path, coeffs):
+    """LinearBaseline.predict (baselines/linear_baseline.py:17-33) on the device (promp_baseline_predict)."""
+    import torch
+    _lib.require_cuda()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    obs, off, n, Do = _flat_paths_to_device([path], dev)
+    w = torch.from_numpy(np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64))).to(dev)
+    assert w.numel() == 2 * Do + 4, "coefficient vector does not match the observation dimension"
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    _lib.call('promp_baseline_predict', 1, n, Do, _lib.ptr(obs), _lib.ptr(off), _lib.ptr(w), _lib.ptr(out), _lib.stream())
+    return out.cpu().numpy()
 
 
 class MetaSampleProcessor(object):

@@ -51,9 +51,16 @@ class MetaSampler(object):
         self._phase_counter_dev = None      # device uint64 phase counter (graph mode)
         self._injected_noise = None
         self._injected_init = None
-        self.vec_env = MetaDeviceEnvExecutor(env, self.meta_batch_size, self.envs_per_task, self.max_path_length)
-        self.spec = self.vec_env.spec
-        self.device = self.vec_env.device
+        if hasattr(env, 'device_spec'):
+            self.vec_env = MetaDeviceEnvExecutor(env, self.meta_batch_size, self.envs_per_task, self.max_path_length)
+            self.spec = self.vec_env.spec
+            self.device = self.vec_env.device
+        else:
+            # duck-typed host env (the reference's test fakes, tests/test_samplers.py:13-67): stepped where Python runs,
+            # one env.step per env per step like the reference's iterative executor - slow by construction
+            from promp_b200.samplers.host_env_executor import MetaHostEnvExecutor
+            self.vec_env = MetaHostEnvExecutor(env, self.meta_batch_size, self.envs_per_task, self.max_path_length)
+            self.spec, self.device = None, None
 
     # ------------------------------------------------------------------------------------------
     def update_tasks(self):
@@ -67,8 +74,8 @@ class MetaSampler(object):
         self._injected_noise, self._injected_init = noise, init_state
 
     def _fused_ok(self):
-        return (hasattr(self.policy, 'sampling_params') and self.spec['env_kind'] != _lib.ENV_POINT
-                and self.envs_per_task == self.batch_size)
+        return (self.spec is not None and hasattr(self.policy, 'sampling_params')
+                and self.spec['env_kind'] != _lib.ENV_POINT and self.envs_per_task == self.batch_size)
 
     def obtain_samples(self, log=False, log_prefix=''):
         """meta_sampler.py:59-137."""
