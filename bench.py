@@ -98,26 +98,34 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def build_stack(wl, reset_mode, task_shard=None):
+TRPO = dict(step_size=0.01, inner_type='log_likelihood', inner_lr=0.1, num_inner_grad_steps=1)    # maml_run_mujoco.py defaults
+
+
+def build_stack(wl, reset_mode, task_shard=None, algo='promp', tasks=None, **trainer_kw):
     from promp_b200.envs import normalize, MetaPointEnvCorner, HalfCheetahRandDirecEnv
     from promp_b200.policies import MetaGaussianMLPPolicy
     from promp_b200.samplers import MetaSampler, MetaSampleProcessor
     from promp_b200.baselines import LinearFeatureBaseline
-    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_algos import ProMP, TRPOMAML
     from promp_b200.meta_trainer import Trainer
+    M = wl['M'] if tasks is None else tasks
     env = normalize(MetaPointEnvCorner() if wl['env'] == 'MetaPointEnvCorner' else HalfCheetahRandDirecEnv())
-    policy = MetaGaussianMLPPolicy(name="meta-policy", obs_dim=wl['Do'], action_dim=wl['Da'], meta_batch_size=wl['M'],
+    policy = MetaGaussianMLPPolicy(name="meta-policy", obs_dim=wl['Do'], action_dim=wl['Da'], meta_batch_size=M,
                                    hidden_sizes=(64, 64))
-    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=wl['E'], meta_batch_size=wl['M'],
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=wl['E'], meta_batch_size=M,
                           max_path_length=wl['H'], parallel=True, reset_mode=reset_mode, seed=1, task_shard=task_shard)
     proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
-    algo = ProMP(policy=policy, inner_lr=PROMP['inner_lr'], meta_batch_size=wl['M'],
-                 num_inner_grad_steps=PROMP['num_inner_grad_steps'], learning_rate=PROMP['learning_rate'],
-                 num_ppo_steps=PROMP['num_ppo_steps'], clip_eps=PROMP['clip_eps'],
-                 target_inner_step=PROMP['target_inner_step'], init_inner_kl_penalty=PROMP['init_inner_kl_penalty'],
-                 adaptive_inner_kl_penalty=PROMP['adaptive_inner_kl_penalty'])
-    trainer = Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1,
-                      num_inner_grad_steps=PROMP['num_inner_grad_steps'])
+    if algo == 'promp':
+        alg = ProMP(policy=policy, inner_lr=PROMP['inner_lr'], meta_batch_size=M,
+                    num_inner_grad_steps=PROMP['num_inner_grad_steps'], learning_rate=PROMP['learning_rate'],
+                    num_ppo_steps=PROMP['num_ppo_steps'], clip_eps=PROMP['clip_eps'],
+                    target_inner_step=PROMP['target_inner_step'], init_inner_kl_penalty=PROMP['init_inner_kl_penalty'],
+                    adaptive_inner_kl_penalty=PROMP['adaptive_inner_kl_penalty'])
+    else:
+        alg = TRPOMAML(policy=policy, step_size=TRPO['step_size'], inner_type=TRPO['inner_type'], inner_lr=TRPO['inner_lr'],
+                       meta_batch_size=M, num_inner_grad_steps=TRPO['num_inner_grad_steps'], exploration=False)
+    trainer = Trainer(algo=alg, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1,
+                      num_inner_grad_steps=PROMP['num_inner_grad_steps'], **trainer_kw)
     return trainer
 
 
@@ -126,7 +134,9 @@ class LaunchCounter(object):
     KERNELS = dict(promp_rollout=1, promp_env_step=1, promp_env_observe=1, promp_process_samples=1,
                    promp_adj_avg_rewards=1, promp_policy_grad=1, promp_policy_hvp=1, promp_reduce_tasks=1,
                    promp_adam_tf1=2, promp_policy_forward=1, promp_counter_add=1, promp_meta_loss_terms=1,
-                   promp_policy_grad_ragged=1, promp_policy_hvp_ragged=1, promp_process_samples_ragged=1)
+                   promp_policy_grad_ragged=1, promp_policy_hvp_ragged=1, promp_process_samples_ragged=1,
+                   promp_vec_axpy=1, promp_cg_init=1, promp_cg_step=1, promp_trpo_step=1, promp_trpo_select=1,
+                   promp_allreduce_p2p=1, promp_baseline_fit=1, promp_baseline_predict=1)
 
     def __init__(self, time_kernels=False):
         from promp_b200 import _lib
@@ -226,25 +236,70 @@ def run_gpu(args):
     else:
         ms_dev, wall_dev = ms_eager, wall_eager
     clk = clocks.stop() if clocks else None
-    # ---- e2e: reference-facing API with host inputs / logged outputs ------------------------------
+    # ---- e2e: the default entry point of a run script - Trainer.train() - with host inputs / logged outputs ----------
+    def timed_train(trainer, n_warm, n_steps):
+        """Time n_steps meta-iterations of trainer.train() (device events + wall clock, max over ranks) after n_warm."""
+        trainer.start_itr, trainer.n_itr = 0, n_warm
+        trainer.train()                                   # warm-up iterations (captures the CUDA graph when possible)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        trainer.start_itr, trainer.n_itr = n_warm, n_warm + n_steps
+        t0 = time.perf_counter()
+        a.record()
+        trainer.train()
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([a.elapsed_time(b), wall * 1e3], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
     np.random.seed(1)
-    tr_e2e = build_stack(wl, 'numpy', shard)
+    tr_e2e = build_stack(wl, 'numpy', shard)              # Trainer defaults: use_cuda_graph='auto', prefetch_host_inputs=True
     sd = tr_e2e.sampler.spec
     S = PROMP['num_inner_grad_steps'] + 1
     if use_graph:
-        # the public training entry point with use_cuda_graph=True: host numpy draws of tasks + reset states (reference
-        # RNG order) -> pinned -> H2D, graph replay, one D2H of the packed logged scalars, logger keys emitted
-        e2e_step = tr_e2e.capture_graph(warmup=2, log=True, prefetch_host_inputs=True)
-        ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps, e2e_step)
+        ms_e2e, wall_e2e = timed_train(tr_e2e, args.warmup, args.steps)
         h2d, d2h = tr_e2e.graph_h2d_bytes, tr_e2e.graph_d2h_bytes
-        e2e_api = ('promp_b200.meta_trainer.Trainer.capture_graph(log=True, prefetch_host_inputs=True) step: numpy-drawn tasks + reset states '
-                   '(reference RNG order, reset_mode=numpy; the NEXT iteration is drawn into a second pinned slot while the GPU runs), '
-                   'H2D from pinned memory, graph replay, one D2H of the logged scalars, logger keys emitted')
+        e2e_api = ('promp_b200.meta_trainer.Trainer(...).train() with its defaults - the call an unchanged run script makes '
+                   '(run_scripts/pro-mp_run_point_mass.py:66-77): per iteration numpy-drawn tasks + reset states in the reference RNG '
+                   'order (reset_mode=numpy, next iteration drawn into a second pinned slot while the GPU runs), H2D from pinned memory, '
+                   'one CUDA-graph replay of the device part (captured automatically: fixed-horizon env, fixed KL coefficient), one D2H '
+                   'of the logged scalars, logger.logkv of every reference key, logger.dumpkvs()')
     else:
         ms_e2e, wall_e2e = timed(tr_e2e, True, args.warmup, args.steps)
         h2d = 4 * (M * sd['task_dim'] + S * M * E * sd['state_dim'])
         d2h = S * (M * 8 * 8 + M * sd['act_dim'] * 4 + (2 * M * E * H * 4 * 2 if sd['env_kind'] == 2 else 0)) + 4 * (3 + S - 1)
         e2e_api = 'promp_b200.meta_trainer.Trainer.train_iteration(log=True), reset_mode=numpy'
+    # the same iteration WITHOUT graph replay: Trainer.train_iteration(log=True), what configurations with a host decision
+    # inside the iteration get (adaptive KL coefficient, early-terminating envs, E-MAML)
+    np.random.seed(1)
+    tr_eager = build_stack(wl, 'numpy', shard, use_cuda_graph=False)
+    ms_e2e_eager, wall_e2e_eager = timed(tr_eager, True, args.warmup, args.steps)
+
+    # ---- the other BASELINE.json configurations, measured in the same run (short): HalfCheetah surrogate (configs[2] per GPU =
+    #      configs[4] at N = 8, weak scaling) and TRPO-MAML on PointEnv (configs[3]: 40 tasks in total, STRONG scaling)
+    extras = {}
+    if not args.no_extras:
+        def extra(key, wl_x, algo, tasks_per_gpu, scaling, n_steps):
+            np.random.seed(1)
+            tr = build_stack(wl_x, 'numpy', shard, algo=algo, tasks=tasks_per_gpu)
+            ms, wall = timed_train(tr, 3, n_steps)
+            n_env = tasks_per_gpu * world * wl_x['E'] * wl_x['H'] * 2
+            extras[key] = dict(workload=wl_x['name'] if algo == 'promp' else 'MAML-TRPO (maml_run_mujoco.py config: step_size 0.01, '
+                               'inner_type log_likelihood) on MetaPointEnvCorner, meta_batch=40 in total (BASELINE.json configs[3])',
+                               algo=algo, scaling=scaling, tasks_per_gpu=tasks_per_gpu, tasks_total=tasks_per_gpu * world,
+                               n_gpus=world, steps=n_steps, ms_per_step=ms / n_steps, wall_ms_per_step=wall / n_steps,
+                               value=n_env * n_steps / (ms * 1e-3), unit='env-steps/s', meta_iters_per_sec=n_steps / (ms * 1e-3),
+                               api='Trainer.train() (default entry point; e2e with host-drawn inputs and logged outputs)',
+                               launch_mode='cuda_graph_replay' if tr.graph_capturable() else 'eager')
+            if algo == 'trpo':
+                extras[key]['last_step'] = {k: v for k, v in tr.algo.optimizer.last.items()}
+        other = 'cheetah' if args.workload == 'point' else 'point'
+        extra(other + '_promp_weak', WORKLOADS[other], 'promp', WORKLOADS[other]['M'], 'weak', max(5, args.steps // 2))
+        if 40 % world == 0:
+            extra('point_trpo_strong', WORKLOADS['point'], 'trpo', 40 // world, 'strong', max(3, args.steps // 4))
 
     out = None
     # ---- per-kernel timing pass (instrumented, not part of the timed loops; every rank runs it because the
@@ -266,11 +321,11 @@ def run_gpu(args):
         Do_, Da_ = wl['Do'], wl['Da']
         alg = {
             'promp_policy_grad': dict(
-                bytes=M * N * 4 * (Do_ + 2 * Da_ + 1) + M * 4 * (Da_ + 3 * P),
+                bytes=M * N * 4 * (Do_ + 2 * Da_ + 1),
                 flops=M * N * (3 * 2 * 64 * 64 + 2 * 2 * Do_ * 64 + 3 * 2 * 64 * Da_),
                 gemm_flops=M * N * 3 * 2 * 64 * 64, ncu='policy_grad'),
             'promp_policy_hvp': dict(
-                bytes=M * N * 4 * (Do_ + 2 * Da_ + 1) + M * 4 * (Da_ + 3 * P),
+                bytes=M * N * 4 * (Do_ + 2 * Da_ + 1),
                 flops=M * N * (8 * 2 * 64 * 64 + 6 * 2 * Do_ * 64 + 8 * 2 * 64 * Da_),
                 gemm_flops=M * N * 8 * 2 * 64 * 64, ncu='policy_hvp'),
         }
@@ -282,32 +337,42 @@ def run_gpu(args):
         fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
 
         def kernel_roof(name):
+            """The policy kernels are issue / latency-bound (AI ~ 1 kFLOP/B, inputs L2-resident): `frac` is the compute-side
+            fraction (algorithmic fp32 FLOP/s over the fp32-SIMT peak 148 SM x 128 lanes x 2 x f_max); the HBM view
+            (SURVEY.md section 8d bytes per sample x samples / launch time over the measured copy bandwidth) sits beside it."""
             a_, pk = alg[name], per_kernel.get(name, {})
             ms = pk.get('avg_ms', float('nan'))
-            ach = a_['bytes'] / (ms * 1e-3) / 1e9
+            tfl = a_['flops'] / (ms * 1e-3) / 1e12
+            gbs = a_['bytes'] / (ms * 1e-3) / 1e9
             kk = [k for k in km if k.startswith(a_['ncu'])]
             traffic = (km[kk[0]].get('dram_read_bytes', 0.0) + km[kk[0]].get('dram_write_bytes', 0.0)) if kk else None
-            return dict(kernel=(kk[0] if kk else a_['ncu'] + '_kernel'), bound='hbm', achieved=ach, peak=peaks['hbm_gbs'], unit='GB/s',
-                        frac=ach / peaks['hbm_gbs'], traffic=traffic,
+            return dict(kernel=(kk[0] if kk else a_['ncu'] + '_kernel'), bound='issue', achieved=tfl, peak=fp32_peak, unit='TFLOP/s',
+                        frac=tfl / fp32_peak, peak_source='derived: 148 SM x 128 fp32 lanes x 2 x sm_max_mhz (no measured fp32 peak in MEASURED_PEAKS.json)',
+                        traffic=traffic,
                         traffic_source='profiles/r01_kernel_metrics.json (cold-cache ncu replay; in the live loop the inputs are L2 hits)' if kk else None,
-                        peak_source=peak_src, algorithmic_bytes_per_launch=a_['bytes'], avg_launch_ms=ms,
+                        hbm={'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'peak_source': peak_src,
+                             'algorithmic_bytes_per_launch': a_['bytes'],
+                             'bytes_rule': 'SURVEY.md 8(d): 4*(Do+2*Da+1) B per sample per launch x M*N samples'},
+                        algorithmic_flops_per_launch=a_['flops'], avg_launch_ms=ms,
                         launches_per_iter=pk.get('launches_per_iter'), share_of_iteration=pk.get('total_ms_per_iter', 0.0) / iter_ms,
-                        algorithmic_tflops=a_['flops'] / (ms * 1e-3) / 1e12, fp32_simt_peak_tflops=fp32_peak,
                         tensor={'executed_tf32_tflops': 3 * a_['gemm_flops'] / (ms * 1e-3) / 1e12,
                                 'peak_bf16_tflops': peaks.get('bf16_tflops'),
                                 'note': 'layer GEMMs run as 3xTF32 tcgen05.mma (weight gradients: mma.sync); 3 MMAs per algorithmic GEMM'})
         dom = max(alg, key=lambda n: per_kernel.get(n, {}).get('total_ms_per_iter', 0.0))
         roof = kernel_roof(dom)
         roof['note'] = ('arithmetic intensity ~ %d FLOP/B with everything L2/smem resident: neither HBM- nor tensor-peak-bound; the kernel is '
-                        'issue/latency-bound at 1 CTA/SM (see DESIGN.md section 3 phase table); the HBM fraction is small by construction'
+                        'issue/latency-bound at 1 CTA/SM (see DESIGN.md section 3 phase table); the HBM fraction (roofline.hbm) is small by construction'
                         % (alg[dom]['flops'] / alg[dom]['bytes']))
         other = [n for n in alg if n != dom][0]
         roof['other_policy_kernel'] = kernel_roof(other)
         # HBM-bound scan kernel for reference: promp_process_samples reads obs twice + rew twice, writes ret + adv
-        proc_bytes = M * N * (4 * 2 * wl['Do'] + 8 + 8)
+        proc_bytes = M * N * (8 + 4 * (wl['Do'] + 1) + 4 * (wl['Do'] + 2) + 12)
         proc_ms = per_kernel.get('promp_process_samples', {}).get('avg_ms', float('nan'))
-        roof['process_kernel'] = dict(achieved=proc_bytes / (proc_ms * 1e-3) / 1e9, frac=proc_bytes / (proc_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                                      algorithmic_bytes_per_launch=proc_bytes, avg_launch_ms=proc_ms)
+        roof['process_kernel'] = dict(kernel='process_fused_kernel', bound='hbm', unit='GB/s', peak=peaks['hbm_gbs'],
+                                      achieved=proc_bytes / (proc_ms * 1e-3) / 1e9, frac=proc_bytes / (proc_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                      algorithmic_bytes_per_launch=proc_bytes, avg_launch_ms=proc_ms,
+                                      bytes_rule='SURVEY.md 8(d): returns 8 + Gram 4*(Do+1) + predict/GAE 4*(Do+2) + normalise 12 B per env-step',
+                                      note='2.5-20 MB per launch: latency-bound (one short wave), far from the bandwidth roof by size')
         ro_bytes = M * N * (4 * (wl['Do'] + 2 * wl['Da'] + 1) + 1 + (8 if wl['Da'] == 6 else 0))
         ro_ms = per_kernel.get('promp_rollout', {}).get('avg_ms', float('nan'))
         roof['rollout_kernel'] = dict(achieved=ro_bytes / (ro_ms * 1e-3) / 1e9, frac=ro_bytes / (ro_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
@@ -340,7 +405,12 @@ def run_gpu(args):
             'launch_mode': 'cuda_graph_replay' if use_graph else 'eager', 'eager_ms_per_step': ms_eager / args.steps,
             'e2e': {'value': e2e_val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps, 'wall_ms_per_step': wall_e2e / args.steps,
-                    'api': e2e_api},
+                    'api': e2e_api,
+                    'eager': {'value': steps_per_iter * args.steps / (ms_e2e_eager * 1e-3), 'ms_per_step': ms_e2e_eager / args.steps,
+                              'wall_ms_per_step': wall_e2e_eager / args.steps,
+                              'api': 'Trainer(use_cuda_graph=False).train_iteration(itr, log=True): ~35 kernel launches per iteration '
+                                     'issued one by one, a D2H read of the logged statistics per sampling phase'}},
+            'other_configs': extras,
             'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
             'clocks': clk, 'roofline': roof, 'kernels': per_kernel, 'cpu_baseline': cpu,
         }
@@ -497,7 +567,7 @@ def cpu_meta_iteration_parallel(wl_key, m_sample, state, pool, n_workers):
     return spans
 
 
-def run_cpu_baseline(wl, steps, warmup, m_sample, parallel=True):
+def run_cpu_baseline(wl, steps, warmup, m_sample, parallel=True, n_tasks=None):
     """CPU arm: the oracle port of the reference's path on this box's host cores.  parallel=True: the numpy half runs in
     min(tasks, cores) worker processes (like the reference's parallel=True executor), the TF1 half (PyTorch-CPU) with the
     fastest thread count; the whole M-task workload is timed.  parallel=False: single process, `m_sample` tasks."""
@@ -509,7 +579,7 @@ def run_cpu_baseline(wl, steps, warmup, m_sample, parallel=True):
     pool, n_workers = None, 1
     if parallel and cores > 1:
         import multiprocessing as mp
-        m_sample = wl['M']
+        m_sample = wl['M'] if n_tasks is None else n_tasks        # like for like with an N-GPU run: 40*N tasks
         n_workers = max(1, min(m_sample, cores))
         pool = mp.get_context('fork').Pool(n_workers)        # forked BEFORE the parent touches torch's thread pool
     try:
@@ -563,13 +633,16 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    cpu = run_cpu_baseline(wl, steps=args.steps, warmup=args.warmup, m_sample=10, parallel=not args.cpu_serial)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    # the GPU arm is weak-scaled (wl['M'] tasks per GPU): the CPU arm gets the same wl['M'] * N tasks, on min(tasks, cores) workers
+    cpu = run_cpu_baseline(wl, steps=args.steps, warmup=args.warmup, m_sample=10, parallel=not args.cpu_serial,
+                           n_tasks=wl['M'] * world)
     out = {
         'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': cpu['value'], 'unit': 'env-steps/s',
         'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': cpu['sec_per_iter'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 (TF half) / f64 (numpy half)', 'data': 'synthetic',
-        'config': {'workload': wl['name'], 'sample': cpu['sample'],
+        'config': {'workload': wl['name'], 'tasks_total': wl['M'] * world, 'sample': cpu['sample'],
                    'note': 'reference = jonasrothfuss/ProMP CPU path; /root/reference and TF1 are absent on the GPU box, so the '
                            'oracle port (pinned to the reference by tests/golden) is what runs'},
         'cpu_baseline': cpu,
@@ -587,6 +660,7 @@ def main():
     ap.add_argument('--impl', default='promp_b200', choices=['promp_b200', 'reference'])
     ap.add_argument('--workload', default='point', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the short cheetah / TRPO-MAML measurements (other_configs)')
     ap.add_argument('--cpu-serial', action='store_true', help='CPU arm: single process on a 10-task sample instead of one worker process per task')
     ap.add_argument('--no-graph', action='store_true', help='time the device-resident loop eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()

@@ -185,6 +185,31 @@ int promp_baseline_fit(int n_paths, int n_samples, int obs_dim, const float* obs
 int promp_baseline_predict(int n_paths, int n_samples, int obs_dim, const float* obs, const int32_t* path_off,
                            const double* coeffs, double* out, void* stream);
 
+/*
+ * Device-resident ConjugateGradientOptimizer (optimizers/conjugate_gradient_optimizer.py:239-354) on flat float32 parameter
+ * vectors [n]; one CTA each, dot products accumulated in float64 in a fixed order.  `scal` is a device float[4]:
+ * [0] r.r  [1] converged flag  [2] beta  [3] beta-is-NaN flag.
+ *   promp_vec_axpy    out = y + a*x                      (theta +- eps*p, theta - ratio^k*step; :73-82, :277-279)
+ *   promp_cg_init     p = r = g, x = 0, r.r              (:325-331)
+ *   promp_cg_step     z = (grad_plus - grad_minus)/two_eps + reg*p  (FiniteDifferenceHvp.Hx, :59-89, :101-104), then one
+ *                     CG iteration (:337-349); a no-op once r.r < residual_tol (:350-351)
+ *   promp_trpo_step   beta = sqrt(2*delta / (x.Hx(x) + 1e-8)), step = beta*x  (:262-269)
+ *   promp_trpo_select verdict of the backtracking line search (:274-300) over candidates k0..k0+K-1 whose
+ *                     [loss, ..., kl] rows (n_terms floats, promp_meta_loss_terms layout) are in `terms` and whose
+ *                     parameter vectors are in `candidates` [K][n]: theta_out = accepted candidate, or theta_prev when the
+ *                     step is rejected; untouched while undecided.
+ *                     result float[8]: loss_before, kl_before, loss_after, kl_after, accepted k (-1), rejected, need_more, beta
+ */
+int promp_vec_axpy(int n, float a, const float* x, const float* y, float* out, void* stream);
+int promp_cg_init(int n, const float* g, float* p, float* r, float* x, float* scal, void* stream);
+int promp_cg_step(int n, const float* grad_plus, const float* grad_minus, float two_eps, float reg_coeff, float* p, float* r,
+                  float* x, float* scal, float residual_tol, void* stream);
+int promp_trpo_step(int n, const float* grad_plus, const float* grad_minus, float two_eps, float reg_coeff, const float* x,
+                    float max_constraint, float* step, float* scal, void* stream);
+int promp_trpo_select(int n, int n_candidates, int n_terms, int k0, int max_backtracks, const float* terms,
+                      const float* base_terms, float max_constraint, const float* theta_prev, const float* candidates,
+                      const float* scal, float* theta_out, float* result, void* stream);
+
 /* adj_avg_rewards = (r - mean_all)/(std_all + 1e-8) (samplers/meta_sample_processor.py:40-44);
  * mean/std are passed by the caller (reduced over all tasks / ranks from `stats`). */
 int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, double std, float* out, void* stream);

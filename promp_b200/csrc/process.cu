@@ -472,7 +472,9 @@ struct ProcLayout {
 static ProcLayout proc_layout(int M, int E, int NS, bool ragged) {
     ProcLayout L;
     proc_chunks(M, E, &L.C, &L.EPC);
-    int64_t o = ((int64_t)M * 4 + 15) / 16 * 16;            // counters
+    // arrival tickets: a FIXED-size header (grid.y <= 65535 tasks), so a workspace shared by launches of different
+    // shapes never finds stale partials where a later layout expects zeroed tickets
+    int64_t o = 65536 * 4;
     L.off_gram = o;  o += (int64_t)M * L.C * PS_GP * 8;
     L.off_stat = o;  o += (int64_t)M * L.C * 8 * 8;
     L.off_ws64 = o;  o += (int64_t)M * 2 * NS * 8;

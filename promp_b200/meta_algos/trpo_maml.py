@@ -67,17 +67,24 @@ class TRPOMAML(MAMLAlgo):
         return st[:, 0], g
 
     # meta objective = mean_i -mean(ratio*adv) (:135,152); constraint = mean_i mean KL(old || theta_i') (:133,149)
-    def eval_scalars(self, theta, phases):
+    def loss_terms_dev(self, theta, phases, out=None):
+        """[loss, inner KLs.., outer KL] at `theta` as a device float32 vector (global means over tasks and ranks), written
+        into `out` when given.  No host interaction."""
         import torch
-        res = self._meta_pass(theta, phases, _lib.OBJ_RATIO, 0.0, [0.0] * self.num_inner_grad_steps, want_grad=False)
+        S1 = self.num_inner_grad_steps
+        res = self._meta_pass(theta, phases, _lib.OBJ_RATIO, 0.0, [0.0] * S1, want_grad=False)
+        if out is None:
+            out = torch.empty(S1 + 2, dtype=torch.float32, device=self.policy.device)
+        _lib.call('promp_meta_loss_terms', S1 + 1, self.meta_batch_size, _lib.ptr(res['stats_all']),
+                  1.0 / (self.meta_batch_size * world_size()), None, S1 + 2, _lib.ptr(out), _lib.stream())
         if self.exploration:
-            res['surr'] = res['surr'] + self._exploration_term(theta, phases, False)[0]
-        vec = torch.stack([res['surr'].sum(), res['outer_kl'].sum()]) / (self.meta_batch_size * world_size())
-        allreduce_sum_(vec)
-        host = vec.cpu().numpy()
-        return float(host[0]), float(host[1])
+            out[0] += self._exploration_term(theta, phases, False)[0].sum() / (self.meta_batch_size * world_size())
+        allreduce_sum_(out)
+        return out
 
-    def eval_gradient(self, theta, phases, which):
+    def eval_gradient_dev(self, theta, phases, which):
+        """Flat gradient [P] of the meta objective ('loss') or of the KL constraint ('kl') at `theta`, all-reduced over
+        ranks, on the device."""
         zeros = [0.0] * self.num_inner_grad_steps
         if which == 'loss':
             res = self._meta_pass(theta, phases, _lib.OBJ_RATIO, 0.0, zeros, want_grad=True)
@@ -91,18 +98,49 @@ class TRPOMAML(MAMLAlgo):
         else:
             res = self._meta_pass(theta, phases, _lib.OBJ_NONE, 0.0, zeros, want_grad=True, outer_kl_coeff=1.0)
         allreduce_sum_(res['grad'])
-        return res['grad'].cpu().numpy().astype(np.float32)
+        return res['grad']
+
+    def eval_scalars(self, theta, phases):
+        """(loss, mean KL) as host floats (one device->host read; diagnostics / tests)."""
+        host = self.loss_terms_dev(theta, phases).cpu().numpy()
+        return float(host[0]), float(host[-1])
+
+    def eval_gradient(self, theta, phases, which):
+        return self.eval_gradient_dev(theta, phases, which).cpu().numpy().astype(np.float32)
+
+    LOG_KEYS = ('LossBefore', 'MeanKLBefore', 'LossAfter', 'MeanKL', '_accepted_k', '_rejected', '_need_more', '_beta')
+
+    @property
+    def graph_capturable(self):
+        return not self.exploration      # the E-MAML coefficient is assembled with host scalars
+
+    def optimize_phases(self, phases):
+        """optimize_policy on PhaseData objects up to the verdict on the first line-search group, everything left on the
+        device: the CUDA-graph Trainer captures this and reads the float64 result vector back with its logged scalars; if
+        the verdict is `need_more` (rare) post_replay() finishes the backtracking eagerly."""
+        self._last_phases = phases
+        return self.optimizer.optimize_device(phases).double()
+
+    def post_replay(self, hidden, phases):
+        """Called by the CUDA-graph Trainer after its one device->host read; `hidden` holds the `_`-prefixed LOG_KEYS."""
+        need_more = hidden['_need_more'] != 0.0 if hidden is not None else True     # log=False: the verdict was not read yet
+        res = None
+        if need_more:
+            res = self.optimizer.continue_line_search(phases, self.optimizer._buffers()['result'].cpu().numpy())
+        if hidden is not None:
+            if res is not None:
+                logger.logkv('LossAfter', float(res[2]))
+                logger.logkv('MeanKL', float(res[3]))
+            kv = logger.getkvs()
+            logger.logkv('dLoss', float(kv['LossBefore']) - float(kv['LossAfter']))
 
     def optimize_policy(self, all_samples_data, log=True):
         """trpo_maml.py:161-192."""
         assert len(all_samples_data) == self.num_inner_grad_steps + 1
         phases = [self._phase_of(s) for s in all_samples_data]
-        theta = self.policy.theta
-        logger.log("Computing KL before")
-        loss_before, mean_kl_before = self.eval_scalars(theta, phases)
         logger.log("Optimizing")
-        self.optimizer.optimize(phases)
-        loss_after, mean_kl = self.eval_scalars(self.policy.theta, phases)
+        res = self.optimizer.optimize(phases)
+        loss_before, mean_kl_before, loss_after, mean_kl = (float(v) for v in res[:4])
         self.last_stats = dict(loss_before=loss_before, loss_after=loss_after, kl_before=mean_kl_before, kl=mean_kl)
         if log:
             logger.logkv('MeanKLBefore', mean_kl_before)

@@ -22,14 +22,16 @@ def _check_collectives():
 
 class Trainer(object):
     def __init__(self, algo, env, sampler, sample_processor, policy, n_itr, start_itr=0, num_inner_grad_steps=1,
-                 sess=None, use_cuda_graph=False, prefetch_host_inputs=False):
+                 sess=None, use_cuda_graph='auto', prefetch_host_inputs=True):
         self.algo, self.env, self.sampler, self.sample_processor = algo, env, sampler, sample_processor
         self.baseline = sample_processor.baseline
         self.policy = policy
         self.n_itr, self.start_itr = n_itr, start_itr
         self.num_inner_grad_steps = num_inner_grad_steps
         self.sess = sess
-        self.use_cuda_graph = use_cuda_graph      # replay the device part of every iteration as one CUDA graph
+        # 'auto' (default): train() replays the device part of every iteration as one CUDA graph whenever the configuration
+        # allows it (fused fixed-horizon rollouts, ProMP with a fixed KL coefficient), else runs train_iteration eagerly
+        self.use_cuda_graph = use_cuda_graph
         self.prefetch_host_inputs = prefetch_host_inputs   # graph mode: draw iteration i+1's host inputs while the GPU runs i
         self._graph_step = None
 
@@ -61,6 +63,8 @@ class Trainer(object):
             logger.logkv('Itr', itr)
             logger.logkv('n_timesteps', self.sampler.total_timesteps_sampled)
             logger.logkv('Time-OuterStep', time.time() - t_outer)
+            logger.logkv('Time-MAMLSteps', time.time() - t_outer)
+            logger.logkv('Time-TotalInner', t_outer - t_itr)
             logger.logkv('Time-InnerStep', t_inner)
             logger.logkv('Time-SampleProc', t_proc)
             logger.logkv('Time-Sampling', t_sampling)
@@ -86,7 +90,7 @@ class Trainer(object):
         sampler, proc, algo, policy = self.sampler, self.sample_processor, self.algo, self.policy
         assert sampler._fused_ok(), "graph mode needs the fused rollout path"
         assert not getattr(algo, 'adaptive_inner_kl_penalty', False), "adaptive KL coefficient is a host decision"
-        assert hasattr(algo, 'optimize_phases'), "graph mode is implemented for ProMP"
+        assert hasattr(algo, 'optimize_phases'), "graph mode needs an algorithm with a device-only outer step (ProMP, TRPOMAML)"
         S = self.num_inner_grad_steps + 1
         M, E, H = sampler.meta_batch_size, sampler.envs_per_task, sampler.max_path_length
         numpy_resets = sampler.reset_mode == 'numpy'
@@ -132,6 +136,15 @@ class Trainer(object):
                 state['pinned'].copy_(vec, non_blocking=True)        # the ONE device->host copy of the iteration
             state['phases'] = phases
 
+        # The warm-up passes below are REAL meta-iterations (they size the allocator pools and JIT nothing, but they do train
+        # the policy and consume random numbers).  Everything they touch is saved here and put back after the capture, so
+        # that step(0) is the run's first iteration exactly as in eager mode: parameters, Adam slots, the device Philox phase
+        # counter, the global numpy stream.
+        opt = getattr(algo, 'optimizer', None)
+        torch.cuda.synchronize()
+        saved = dict(theta=policy.theta.clone(), np_state=np.random.get_state(),
+                     phase_counter_dev=sampler._phase_counter_dev.clone(),
+                     adam=[t.clone() for t in (opt.m, opt.v, opt.step)] if hasattr(opt, 'm') else None)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -144,6 +157,13 @@ class Trainer(object):
         host_part()
         with torch.cuda.graph(graph):
             device_part()
+        policy.theta.copy_(saved['theta'])
+        if saved['adam'] is not None:
+            for dst, src in zip((opt.m, opt.v, opt.step), saved['adam']):
+                dst.copy_(src)
+        sampler._phase_counter_dev.copy_(saved['phase_counter_dev'])
+        np.random.set_state(saved['np_state'])
+        torch.cuda.synchronize()
         self._graph = graph
         self.graph_d2h_bytes = 8 * len(keys) if log else 0
         n_steps = M * E * H * S
@@ -151,7 +171,7 @@ class Trainer(object):
         prefetch = bool(prefetch_host_inputs) and numpy_resets
         state['slot'], state['drawn'] = 0, False
 
-        def step(itr=0):
+        def step(itr=0, last=False):
             t0 = time.time()
             if prefetch:
                 if not state['drawn']:
@@ -160,32 +180,61 @@ class Trainer(object):
             else:
                 self.graph_h2d_bytes = host_part()
             graph.replay()
-            if prefetch:          # next iteration's host draws overlap the replay that was just enqueued
+            if prefetch and not last:   # next iteration's host draws overlap the replay that was just enqueued
                 state['slot'] ^= 1
                 sampler.draw_host_inputs(S, state['slot'])
                 state['drawn'] = True
+            else:
+                state['drawn'] = False   # `last`: the numpy stream ends exactly where the reference's would
             sampler.total_timesteps_sampled += n_steps
             if log:
                 torch.cuda.current_stream().synchronize()
                 _check_collectives()
                 vals = state['pinned'].numpy()
+                hidden = {}
                 for k, v in zip(keys, vals):
-                    logger.logkv(k, int(v) if k.endswith('NumTrajs') else float(v))
-                logger.logkv('KLCoeffInner', float(np.mean(algo.inner_kl_coeff)))
+                    if k.startswith('_'):
+                        hidden[k] = float(v)          # algorithm-private flags (e.g. TRPO line-search verdict)
+                    else:
+                        logger.logkv(k, int(v) if k.endswith('NumTrajs') else float(v))
+                if hasattr(algo, 'post_replay'):
+                    algo.post_replay(hidden, state['phases'])
+                if hasattr(algo, 'inner_kl_coeff'):
+                    logger.logkv('KLCoeffInner', float(np.mean(algo.inner_kl_coeff)))
                 logger.logkv('Itr', itr)
                 logger.logkv('n_timesteps', sampler.total_timesteps_sampled)
-                logger.logkv('ItrTime', time.time() - t0)
+                # the reference's per-span timers (meta_trainer.py:131-142) have no meaning inside one graph replay: the
+                # columns are kept (progress.csv layout) with the whole replay booked under Time-TotalInner / ItrTime
+                dt = time.time() - t0
+                for k in ('Time-OuterStep', 'Time-InnerStep', 'Time-SampleProc', 'Time-Sampling', 'Time-MAMLSteps'):
+                    logger.logkv(k, float('nan'))
+                for s_ in range(S):
+                    logger.logkv('Step_%d-PolicyExecTime' % s_, float('nan'))
+                    logger.logkv('Step_%d-EnvExecTime' % s_, float('nan'))
+                logger.logkv('Time-TotalInner', dt)
+                logger.logkv('ItrTime', dt)
+            elif hasattr(algo, 'post_replay'):
+                algo.post_replay(None, state['phases'])     # e.g. TRPO: read the line-search verdict, finish it if needed
             return state['phases']
         return step
 
+    def graph_capturable(self):
+        """True when a meta-iteration has no data-dependent host decision: fused fixed-horizon rollouts and an algorithm
+        with a device-only outer step (ProMP with a fixed KL coefficient)."""
+        return bool(self.sampler._fused_ok() and hasattr(self.algo, 'optimize_phases')
+                    and getattr(self.algo, 'graph_capturable', True)
+                    and not getattr(self.algo, 'adaptive_inner_kl_penalty', False))
+
     def train(self):
+        """meta_trainer.py:59-152.  The default entry point of a run script."""
         start = time.time()
+        use_graph = self.graph_capturable() if self.use_cuda_graph == 'auto' else bool(self.use_cuda_graph)
         for itr in range(self.start_itr, self.n_itr):
             logger.log("\n ---------------- Iteration %d ----------------" % itr)
-            if self.use_cuda_graph:
+            if use_graph:
                 if self._graph_step is None:
                     self._graph_step = self.capture_graph(log=True, prefetch_host_inputs=self.prefetch_host_inputs)
-                self._graph_step(itr)
+                self._graph_step(itr, last=(itr == self.n_itr - 1))
             else:
                 self.train_iteration(itr)
             logger.logkv('Time', time.time() - start)

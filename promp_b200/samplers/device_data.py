@@ -168,6 +168,58 @@ class LazyPath(dict):
         return self.phase.H
 
 
+class LazyPathList(object):
+    """A list of LazyPath views created on first access.  Building 800 dict objects per sampling phase cost more host time
+    than the rollout kernel takes; the reference Trainer only indexes / concatenates / iterates these lists
+    (meta_trainer.py:113: `sum(list(paths.values()), [])`), which this sequence supports."""
+
+    def __init__(self, phase, tasks):
+        self.phase = phase
+        self._tasks = list(tasks)          # task ids, E paths each
+        # one LazyPath object per (task, env) of a phase, shared by every list that views it (callers may annotate paths)
+        self._cache = phase.__dict__.setdefault('_path_cache', {})
+
+    def __len__(self):
+        return len(self._tasks) * self.phase.E
+
+    def _make(self, i):
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        m, e = divmod(i, self.phase.E)
+        key = (self._tasks[m], e)
+        p = self._cache.get(key)
+        if p is None:
+            p = self._cache[key] = LazyPath(self.phase, key[0], e)
+        return p
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._make(j) for j in range(*i.indices(len(self)))]
+        return self._make(i)
+
+    def __iter__(self):
+        return (self._make(i) for i in range(len(self)))
+
+    def _concat(self, a, b):
+        if isinstance(a, LazyPathList) and isinstance(b, LazyPathList) and a.phase is b.phase:
+            return LazyPathList(a.phase, a._tasks + b._tasks)
+        return list(a) + list(b)
+
+    def __add__(self, other):
+        return self._concat(self, other)
+
+    def __radd__(self, other):
+        if isinstance(other, list) and not other:
+            return self                     # `[] + lazy` (the start value of sum(..., []))
+        return self._concat(other, self)
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
 class PathsMetaBatch(OrderedDict):
     """OrderedDict{task -> [path]*E} (what MetaSampler.obtain_samples returns) + the device phase."""
     phase = None

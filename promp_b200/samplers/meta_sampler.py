@@ -11,7 +11,7 @@ from collections import OrderedDict
 import numpy as np
 
 from promp_b200 import _lib
-from promp_b200.samplers.device_data import PhaseData, LazyPath, PathsMetaBatch
+from promp_b200.samplers.device_data import PhaseData, LazyPath, LazyPathList, PathsMetaBatch
 from promp_b200.samplers.vectorized_env_executor import MetaDeviceEnvExecutor
 from promp_b200.utils import logger
 from promp_b200.utils.dist import shard_tasks
@@ -201,7 +201,7 @@ class MetaSampler(object):
         self._injected_noise = self._injected_init = None
         paths = PathsMetaBatch()
         for m in range(M):
-            paths[m] = [LazyPath(phase, m, e) for e in range(E)]
+            paths[m] = LazyPathList(phase, (m,))
         paths.phase = phase
         return paths
 

@@ -495,10 +495,79 @@ def test_trpo_maml_optimize_policy_runs_and_matches_first_quantities():
     assert ls['kl_before'] < 1e-6
     assert np.isfinite(ls['loss_after']) and ls['kl'] <= 0.01 + 1e-6
     assert ls['loss_after'] < ls['loss_before'] and not algo.optimizer.last['rejected']
+    assert algo.optimizer.last['backtracks'] >= 0
     # same decision sequence as the oracle's host loop
     th_o, st_o = orc.optimize(theta0, cpus)
     assert st_o['rejected'] is False
     assert abs(st_o['loss'] - ls['loss_after']) < 0.05 * abs(ls['loss_before'] - ls['loss_after']) + 1e-5
+
+
+def test_device_cg_and_line_search_kernels(golden_dir):
+    """promp_cg_init / promp_cg_step against the UNMODIFIED reference's conjugate_gradients outputs
+    (tests/golden/tf_half_known.npz: cg_x10, cg_x3, early exit at residual_tol), driven with grad_plus = A p, grad_minus = 0,
+    two_eps = 1 (so that Hx(p) = A p); then promp_trpo_step and the accept / violate / restore rule of promp_trpo_select
+    (conjugate_gradient_optimizer.py:262-300) on hand-made candidate tables."""
+    torch = _cuda()
+    from promp_b200 import _lib
+    g = _load(golden_dir, 'tf_half_known.npz')
+    A = torch.from_numpy(g['cg_A']).cuda()
+    b = torch.from_numpy(g['cg_b']).cuda()
+    n = b.numel()
+    zero = torch.zeros(n, device='cuda')
+
+    def cg(iters, tol):
+        p, r, x = (torch.empty(n, device='cuda') for _ in range(3))
+        scal = torch.zeros(4, device='cuda')
+        _lib.call('promp_cg_init', n, _lib.ptr(b), _lib.ptr(p), _lib.ptr(r), _lib.ptr(x), _lib.ptr(scal), _lib.stream())
+        for _ in range(iters):
+            z = (A @ p).contiguous()
+            _lib.call('promp_cg_step', n, _lib.ptr(z), _lib.ptr(zero), 1.0, 0.0, _lib.ptr(p), _lib.ptr(r), _lib.ptr(x),
+                      _lib.ptr(scal), float(tol), _lib.stream())
+        return x.cpu().numpy(), scal.cpu().numpy()
+    for iters, key, tol in ((10, 'cg_x10', 1e-10), (3, 'cg_x3', 1e-10), (200, 'cg_x_tol', 1e-6)):
+        x, scal = cg(iters, tol)
+        assert rel_err(x, g[key]) < 2e-5, (key, rel_err(x, g[key]))       # float32 vectors, float64-accumulated dots
+        assert (scal[1] == 1.0) == (key == 'cg_x_tol')                       # the early exit fired only with the loose tolerance
+    # step length: beta = sqrt(2 delta / (x.Hx + 1e-8))
+    x = torch.from_numpy(g['cg_x10']).cuda()
+    hx = (A @ x).contiguous()
+    step, scal = torch.empty(n, device='cuda'), torch.zeros(4, device='cuda')
+    _lib.call('promp_trpo_step', n, _lib.ptr(hx), _lib.ptr(zero), 1.0, 0.0, _lib.ptr(x), 0.01, _lib.ptr(step), _lib.ptr(scal), _lib.stream())
+    beta = np.sqrt(2.0 * 0.01 / (float(g['cg_x10'].dot(g['cg_A'].dot(g['cg_x10']))) + 1e-8))
+    np.testing.assert_allclose(step.cpu().numpy(), beta * g['cg_x10'], rtol=2e-6)
+    assert scal[3].item() == 0.0
+    _lib.call('promp_trpo_step', n, _lib.ptr(-hx), _lib.ptr(zero), 1.0, 0.0, _lib.ptr(x), 0.01, _lib.ptr(step), _lib.ptr(scal), _lib.stream())
+    assert scal[3].item() == 1.0                      # x.Hx < 0 -> NaN step -> the verdict kernel rejects
+    # line-search verdicts: rows are [loss, (inner kl), kl]; loss_before = 1.0, delta = 0.01
+    prev = torch.arange(n, dtype=torch.float32, device='cuda')
+    cands = torch.stack([prev + 10 * (k + 1) for k in range(4)]).contiguous()
+    base = torch.tensor([1.0, 0.0, 0.001], device='cuda')
+
+    def verdict(rows, k0=0, nan_beta=False, kmax=15):
+        terms = torch.tensor(rows, dtype=torch.float32, device='cuda')
+        sc = torch.tensor([0, 0, 0.5, 1.0 if nan_beta else 0.0], dtype=torch.float32, device='cuda')
+        out = torch.full((n,), -7.0, device='cuda')
+        res = torch.zeros(8, device='cuda')
+        _lib.call('promp_trpo_select', n, len(rows), 3, k0, kmax, _lib.ptr(terms), _lib.ptr(base), 0.01, _lib.ptr(prev),
+                  _lib.ptr(cands), _lib.ptr(sc), _lib.ptr(out), _lib.ptr(res), _lib.stream())
+        return out.cpu().numpy(), res.cpu().numpy()
+    ok, bad_loss, bad_kl = [0.9, 0, 0.005], [1.1, 0, 0.005], [0.9, 0, 0.02]
+    out, res = verdict([ok, ok, ok, ok])
+    assert res[4] == 0 and res[5] == 0 and res[6] == 0 and np.array_equal(out, cands[0].cpu().numpy()) and res[2] == np.float32(0.9)
+    out, res = verdict([bad_loss, bad_kl, ok, ok])
+    assert res[4] == 2 and res[5] == 0 and np.array_equal(out, cands[2].cpu().numpy())
+    out, res = verdict([bad_loss, bad_kl, bad_kl, bad_loss])
+    assert res[4] == -1 and res[6] == 1 and np.all(out == -7.0)                       # undecided: parameters untouched
+    out, res = verdict([bad_loss, bad_kl, ok], k0=12)                                  # third group accepts k = 14
+    assert res[4] == 14 and np.array_equal(out, cands[2].cpu().numpy())
+    out, res = verdict([bad_loss, bad_kl, bad_kl], k0=12)                              # budget exhausted -> restored
+    assert res[5] == 1 and res[6] == 0 and np.array_equal(out, prev.cpu().numpy()) and res[2] == 1.0
+    out, res = verdict([[0.9, 0, 0.01]])                                               # kl == delta: accepted by the loop, then "violated"
+    assert res[4] == 0 and res[5] == 1 and np.array_equal(out, prev.cpu().numpy())
+    out, res = verdict([[float('nan'), 0, 0.001], ok])                                 # NaN loss is never accepted
+    assert res[4] == 1
+    out, res = verdict([ok, ok], nan_beta=True)
+    assert res[5] == 1 and res[4] == -1 and np.array_equal(out, prev.cpu().numpy())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -79,18 +79,6 @@ def test_adapt_kl_coeff_rule():
     np.testing.assert_array_equal(adapt_kl_coeff([1.0, 1.0], [0.001, 0.1], 0.01), [0.5, 2.0])
 
 
-def test_conjugate_gradients_solves_spd_system():
-    from promp_b200.optimizers.conjugate_gradient_optimizer import conjugate_gradients
-    from oracle.tf_half import conjugate_gradients as cg_oracle
-    rng = np.random.RandomState(0)
-    A = rng.randn(20, 20).astype(np.float32)
-    A = A @ A.T + 20 * np.eye(20, dtype=np.float32)
-    b = rng.randn(20).astype(np.float32)
-    x = conjugate_gradients(lambda p: A @ p, b, cg_iters=25)
-    np.testing.assert_allclose(A @ x, b, rtol=1e-3, atol=1e-3)
-    np.testing.assert_array_equal(conjugate_gradients(lambda p: A @ p, b), cg_oracle(lambda p: A @ p, b))
-
-
 def test_logger_and_lazy_containers():
     from promp_b200.utils import logger
     logger.set_quiet(True)

@@ -267,12 +267,12 @@ def test_tf_half_distribution_math_matches_reference_numpy(golden_dir, Da):
 
 def test_conjugate_gradients_match_reference(golden_dir):
     """conjugate_gradients (optimizers/conjugate_gradient_optimizer.py:325-354) run from the unmodified reference: the
-    oracle's restatement AND the product's host-side CG (promp_b200/optimizers) reproduce it bit for bit (float32)."""
+    oracle's restatement reproduces it bit for bit (float32).  The product's CG runs on the device (promp_cg_init /
+    promp_cg_step) and is checked against the same vectors in tests/test_gpu_parity.py::test_device_cg_and_line_search_kernels."""
     from oracle import tf_half as th
-    from promp_b200.optimizers.conjugate_gradient_optimizer import conjugate_gradients as cg_product
     g = _load(golden_dir, 'tf_half_known.npz')
     A, b = g['cg_A'], g['cg_b']
-    for fn in (th.conjugate_gradients, cg_product):
+    for fn in (th.conjugate_gradients,):
         assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=10), g['cg_x10'])
         assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=3), g['cg_x3'])
         assert np.array_equal(fn(lambda p: A.dot(p), b, cg_iters=200, residual_tol=1e-6), g['cg_x_tol'])
