@@ -24,9 +24,17 @@ constexpr int PS_MAXCOL = 44;       // NC = F+1 <= 44  (obs_dim <= 19)
 constexpr int PS_MAXBLK = 66;       // 4x4 blocks of the upper triangle, nb = 11
 constexpr int PS_GP = PS_MAXBLK * 16;   // doubles per partial Gram
 constexpr int PS_SMEM_SAMPLES_BYTES = 12;   // per staged sample: float64 value + float32 reward
+constexpr int PS_RING = 4;          // TMA stages of the Gram loop (observation tiles in flight)
 constexpr int PS_SMEM_BUDGET = 160 * 1024;  // above this the sample arrays stay in the (L2-resident) workspace
 
 enum { PS_MODE_PROCESS = 0, PS_MODE_FIT_ONLY = 1 };
+
+#ifdef PROMP_EXP_CLOCKS
+__device__ unsigned long long g_proc_clk[16];
+#define PCLK(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.y == 0 && (i >= 8 || blockIdx.x == 0)) { const long long t_ = clock64(); g_proc_clk[i] += (unsigned long long)(t_ - t_prev); t_prev = t_; } } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
 
 struct ProcArgs {
     int M, E, H, Do;
@@ -54,6 +62,8 @@ struct ProcArgs {
     int mode;
     int chunk_cap;            // samples a front-stage CTA can stage in shared memory (0: use ws64)
     int finish_cap;           // samples the finish stage can stage in shared memory (0: use ws64)
+    int tt_cap;               // entries of the shared-memory time-feature table t/100 (covers every step of fixed-horizon paths)
+    int pred_tile;            // samples per TMA tile of the predict stage (0: no TMA ring there)
 };
 __device__ __forceinline__ int n_paths_of(const ProcArgs& A, int m) { return (A.path_off && A.n_paths) ? __ldg(A.n_paths + m) : A.E; }
 __device__ __forceinline__ int path_begin(const ProcArgs& A, int m, int e) {
@@ -99,7 +109,26 @@ __device__ __forceinline__ double feature_col(const float* __restrict__ o, int D
 // shared-memory carve-up (dynamic): [tile | red | (front: val, rewf) or (finish: A, L, w, bval, rall)]
 
 // ---------------------------------------------------------------------------------------------------------------
+// Sum `cnt` values spaced `stride` doubles apart in chunk order, with the (independent) L2 loads issued 8 at a time so
+// that a reduction over C partials costs ceil(C/8) memory round trips instead of C.
+__device__ __forceinline__ double ordered_sum_ldcg(const double* p, int cnt, int64_t stride) {
+    double v = 0.0;
+    for (int c0 = 0; c0 < cnt; c0 += 8) {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (c0 + k < cnt) ? __ldcg(p + (int64_t)(c0 + k) * stride) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += x[k];
+    }
+    return v;
+}
+
 // One launch.  STAGE_F / STAGE_L: the front / finish stage keeps its sample arrays in shared memory.
+// Latency notes (B200, clock64 phase counters of tools/process_time.py): fp64 divide / sqrt cost 200-400 clk each and a
+// dependent shared-memory load -> DFMA -> store step ~75 clk, so (i) the time features t/100 come from a per-CTA table
+// (one divide per table entry, exact like the reference), (ii) the serial scans run in blocks of 4 steps whose loads are
+// issued before the dependent DFMA chain, (iii) the Cholesky uses one rsqrt per column and multiplies by stored inverse
+// pivots, (iv) partials written by other CTAs are fetched with batched independent loads.
 template <bool STAGE_F, bool STAGE_L>
 __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -116,22 +145,37 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
     __shared__ int s_last, s_flag;
     __shared__ double s_piv, s_reg;
     __shared__ unsigned char s_def[PS_MAXCOL];
+    __shared__ double s_inv[PS_MAXCOL];
 
-    double* tile = reinterpret_cast<double*>(smem_raw);
-    double* red = tile + PS_TS * NCP;
-    double* rest = red + PS_THREADS * 8;
+    // dynamic shared memory: [red | tt_s | tile x2 | rest]; front rest = [val | rewf | obs ring], finish rest = [A | L | w |
+    // bval | rall] (the predict stage re-uses tile..L as its observation ring)
+    double* red = reinterpret_cast<double*>(smem_raw);      // 256 x 8: Gram group reduction / block_reduce scratch / tw table
+    double* tt_s = red + PS_THREADS * 8;                     // A.tt_cap (even) time features t/100
+    double* tile = tt_s + A.tt_cap;                          // 2 x (PS_TS x NCP) feature rows, double-buffered
+    double* rest = tile + 2 * PS_TS * NCP;
+    __shared__ __align__(8) uint64_t s_bar_g[PS_RING], s_bar_p[2];
 
+#ifdef PROMP_EXP_CLOCKS
+    long long t_prev = clock64();
+#endif
     if (tid < nblk) {      // packed (bi <= bj) block index tables
         int i = 0, rem = tid;
         while (rem >= nb - i) { rem -= nb - i; ++i; }
         blk_i[tid] = (unsigned char)i;
         blk_j[tid] = (unsigned char)(i + rem);
     }
+    for (int t = tid; t < A.tt_cap; t += PS_THREADS) tt_s[t] = (double)t / 100.0;      // exact divide, once per table entry
+    if (tid == 0) {
+        for (int i = 0; i < PS_RING; ++i) tma_mbar_init(&s_bar_g[i], 1);
+        tma_mbar_init(&s_bar_p[0], 1);
+        tma_mbar_init(&s_bar_p[1], 1);
+        tma_mbar_fence_init();
+    }
 
     // ================================================================================================ front stage
     const int n_lo = path_begin(A, m, e_lo), n_hi = path_begin(A, m, e_hi), ns = n_hi - n_lo;
     double* val = STAGE_F ? rest : A.ws64 + (int64_t)m * 2 * NS + n_lo;          // returns / targets of this chunk, float64
-    float* rewf = STAGE_F ? reinterpret_cast<float*>(rest + A.chunk_cap) : nullptr;
+    float* rewf = STAGE_F ? reinterpret_cast<float*>(rest + A.chunk_cap) : nullptr;      // then the TMA ring (16-byte aligned)
     if (A.target) {
         const double* __restrict__ tg = A.target + (int64_t)m * NS + n_lo;
         for (int i = tid; i < ns; i += PS_THREADS) val[i] = tg[i];
@@ -139,65 +183,148 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
         for (int i = tid; i < ns; i += PS_THREADS) rewf[i] = __ldg(rew + n_lo + i);
     }
     __syncthreads();
+    PCLK(0);
     {
         // ---- discounted returns R_t = r_t + g R_{t+1}  (utils/utils.py:74-81) + path statistics; one thread per path,
-        //      walking shared memory (no global round trip on the dependent chain)
+        //      walking shared memory in blocks of 4 steps (loads first, then the dependent DFMA chain)
         double st[7] = {0, 0, 0, -1e300, 1e300, 0, 0};   // sum R0, sum G, sum G^2, max G, min G, sum r, sum r^2
+        const double g = A.discount;
         for (int e = e_lo + tid; e < e_hi; e += PS_THREADS) {
             const int o = path_begin(A, m, e) - n_lo, L = path_begin(A, m, e + 1) - n_lo - o;
             if (A.target) {
                 if (tpos) for (int t = 0; t < L; ++t) tpos[n_lo + o + t] = t;
                 continue;
             }
-            double R = 0.0, G = 0.0, sr = 0.0, sr2 = 0.0;
-            for (int t = L - 1; t >= 0; --t) {
-                const double r = (double)(STAGE_F ? rewf[o + t] : __ldg(rew + n_lo + o + t));
-                R = r + A.discount * R;
-                G += r;
-                sr += r;
-                sr2 += r * r;
-                val[o + t] = R;
-                if (tpos) tpos[n_lo + o + t] = t;
+            double R = 0.0, G = 0.0, sr2 = 0.0;
+            int t = L - 1;
+            for (; t >= 3; t -= 4) {
+                double r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r[k] = (double)(STAGE_F ? rewf[o + t - k] : __ldg(rew + n_lo + o + t - k));
+                double Rk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { R = fma(g, R, r[k]); Rk[k] = R; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { val[o + t - k] = Rk[k]; G += r[k]; sr2 = fma(r[k], r[k], sr2); }
             }
-            st[0] += R; st[1] += G; st[2] += G * G; st[3] = fmax(st[3], G); st[4] = fmin(st[4], G); st[5] += sr; st[6] += sr2;
+            for (; t >= 0; --t) {
+                const double r = (double)(STAGE_F ? rewf[o + t] : __ldg(rew + n_lo + o + t));
+                R = fma(g, R, r);
+                val[o + t] = R;
+                G += r;
+                sr2 = fma(r, r, sr2);
+            }
+            if (tpos) for (int k = 0; k < L; ++k) tpos[n_lo + o + k] = k;
+            st[0] += R; st[1] += G; st[2] += G * G; st[3] = fmax(st[3], G); st[4] = fmin(st[4], G); st[5] += G; st[6] += sr2;
         }
+        PCLK(1);
         if (!A.target) {
             const int op[7] = {0, 0, 0, 1, 2, 0, 0};
-            block_reduce<7>(st, op, red);
-            if (tid < 7) A.stat_p[((int64_t)m * A.C + c) * 8 + tid] = st[tid];
+            if (A.EPC <= 32) {            // only warp 0 holds paths: no block-wide exchange needed
+                if (tid < 32) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) st[k] = op[k] == 0 ? warp_sum(st[k]) : op[k] == 1 ? warp_max(st[k]) : warp_min(st[k]);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) A.stat_p[((int64_t)m * A.C + c) * 8 + k] = st[k];
+                    }
+                }
+            } else {
+                block_reduce<7>(st, op, red);
+                if (tid < 7) A.stat_p[((int64_t)m * A.C + c) * 8 + tid] = st[tid];
+            }
         }
         __syncthreads();
         if (A.returns && !A.target)
             for (int i = tid; i < ns; i += PS_THREADS) A.returns[(int64_t)m * NS + n_lo + i] = (float)val[i];
     }
 
+    PCLK(2);
     // ---- partial Gram matrix over this chunk's samples (baselines/linear_baseline.py:66-73): thread = (4x4 block, group)
     if (linear) {
-        const int G = max(1, PS_THREADS / nblk);
+        const int G = max(1, min(PS_THREADS / nblk, 8));
         const int blk = tid % nblk, g = tid / nblk;
         const bool active = g < G;
         const int bi = blk_i[active ? blk : 0], bj = blk_j[active ? blk : 0];
         double acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        for (int n0 = 0; n0 < ns; n0 += PS_TS) {
+        const int s_row = tid >> 3, part = tid & 7;          // feature rows: thread (sample s_row, column part)
+        constexpr int RAWMAX = (PS_MAXCOL + 7) / 8;          // columns per thread
+        float raw[RAWMAX];
+        int raw_step = 0;
+        // raw inputs of one tile row -> registers (global loads in flight while the previous tile is being multiplied)
+        auto fetch = [&](int n0) {
             const int tn = min(PS_TS, ns - n0);
-            __syncthreads();
-            {   // feature rows: thread (sample s, column part)
-                const int s = tid >> 3, part = tid & 7;
-                if (s < tn) {
-                    const int n = n_lo + n0 + s;
-                    const int step = tpos ? tpos[n] : n % H;
-                    const float* o = obs + (int64_t)n * Do;
-                    for (int col = part; col < NCP; col += 8)
-                        tile[s * NCP + col] = col < F ? feature_col(o, Do, step, col) : col == F ? val[n0 + s] : 0.0;
+            if (s_row < tn) {
+                const int n = n_lo + n0 + s_row;
+                raw_step = tpos ? tpos[n] : n % H;
+                const float* o = obs + (int64_t)n * Do;
+#pragma unroll
+                for (int k = 0; k < RAWMAX; ++k) {
+                    const int col = part + 8 * k;
+                    raw[k] = col < 2 * Do ? __ldg(o + (col < Do ? col : col - Do)) : 0.f;
                 }
             }
-            __syncthreads();
+        };
+        auto build = [&](int n0, double* dst) {
+            const int tn = min(PS_TS, ns - n0);
+            if (s_row < tn) {
+                const double tt = raw_step < A.tt_cap ? tt_s[raw_step] : (double)raw_step / 100.0;
+#pragma unroll
+                for (int k = 0; k < RAWMAX; ++k) {
+                    const int col = part + 8 * k;
+                    if (col < NCP) {
+                        double v;
+                        if (col < 2 * Do) {
+                            const double cl = fmin(fmax((double)raw[k], -10.0), 10.0);
+                            v = col < Do ? cl : cl * cl;
+                        } else {
+                            const int kk = col - 2 * Do;      // t, t^2, t^3, 1, target, zero padding
+                            v = kk == 0 ? tt : kk == 1 ? tt * tt : kk == 2 ? tt * tt * tt : kk == 3 ? 1.0 : kk == 4 ? val[n0 + s_row] : 0.0;
+                        }
+                        dst[s_row * NCP + col] = v;
+                    }
+                }
+            }
+        };
+        double* tile2 = tile + PS_TS * NCP;                  // second tile buffer
+        // Observation tiles (PS_TS consecutive samples = one contiguous block of PS_TS*Do floats) stream through a ring of
+        // PS_RING shared-memory stages filled by 1-D TMA bulk copies (one elected thread, mbarrier completion): the L2 / HBM
+        // latency of a tile is paid PS_RING-1 tiles ahead of its use.  Needs 16-byte aligned sources; otherwise (and for
+        // the last partial tile) the rows are fetched with plain loads.
+        float* ring = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(rest) +
+                                               ((size_t)A.chunk_cap * PS_SMEM_SAMPLES_BYTES + 15) / 16 * 16);
+        const float* obs_chunk = obs + (int64_t)n_lo * Do;
+        const int tile_floats = PS_TS * Do;
+        const int full_tiles = ns / PS_TS;
+        const bool use_tma = STAGE_F && full_tiles > 0 && ((reinterpret_cast<uintptr_t>(obs_chunk) & 15) == 0);
+        auto issue = [&](int t) {       // thread 0 only
+            tma_load_1d(ring + (t % PS_RING) * tile_floats, obs_chunk + (int64_t)t * tile_floats, (uint32_t)tile_floats * 4u,
+                        &s_bar_g[t % PS_RING]);
+        };
+        auto build_from_ring = [&](int t, double* dst) {
+            const float* src = ring + (t % PS_RING) * tile_floats + s_row * Do;
+            const int n = n_lo + t * PS_TS + s_row;
+            const int step = tpos ? tpos[n] : n % H;
+            const double tt = step < A.tt_cap ? tt_s[step] : (double)step / 100.0;
+            for (int col = part; col < NCP; col += 8) {
+                double v;
+                if (col < 2 * Do) {
+                    const double cl = fmin(fmax((double)src[col < Do ? col : col - Do], -10.0), 10.0);
+                    v = col < Do ? cl : cl * cl;
+                } else {
+                    const int kk = col - 2 * Do;
+                    v = kk == 0 ? tt : kk == 1 ? tt * tt : kk == 2 ? tt * tt * tt : kk == 3 ? 1.0 : kk == 4 ? val[t * PS_TS + s_row] : 0.0;
+                }
+                dst[s_row * NCP + col] = v;
+            }
+        };
+        auto multiply = [&](const double* tb, int tn) {
             if (active) {
                 for (int s = g; s < tn; s += G) {
-                    const double2* ra = reinterpret_cast<const double2*>(tile + s * NCP + 4 * bi);
-                    const double2* rb = reinterpret_cast<const double2*>(tile + s * NCP + 4 * bj);
+                    const double2* ra = reinterpret_cast<const double2*>(tb + s * NCP + 4 * bi);
+                    const double2* rb = reinterpret_cast<const double2*>(tb + s * NCP + 4 * bj);
                     const double2 a01 = ra[0], a23 = ra[1], b01 = rb[0], b23 = rb[1];
                     const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
@@ -206,14 +333,51 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
                         for (int q = 0; q < 4; ++q) acc[r * 4 + q] = fma(a[r], b[q], acc[r * 4 + q]);
                 }
             }
+        };
+        int cur = 0;
+        int done_tiles = 0;
+        if (use_tma) {
+            if (tid == 0)
+                for (int t = 0; t < min(PS_RING - 1, full_tiles); ++t) issue(t);
+            for (int t = 0; t < full_tiles; ++t) {
+                tma_mbar_wait(&s_bar_g[t % PS_RING], (uint32_t)((t / PS_RING) & 1));
+                build_from_ring(t, cur ? tile2 : tile);
+                __syncthreads();                  // tile t complete; stage (t-1) % PS_RING is free (its tile was built before the previous barrier)
+                if (tid == 0 && t + PS_RING - 1 < full_tiles) issue(t + PS_RING - 1);
+                multiply(cur ? tile2 : tile, PS_TS);
+                cur ^= 1;
+            }
+            done_tiles = full_tiles;
         }
+        // remaining samples (everything when TMA is not usable): plain loads, one tile ahead in registers
+        {
+            const int n_start = done_tiles * PS_TS;
+            if (n_start < ns) {
+                __syncthreads();
+                fetch(n_start);
+                build(n_start, cur ? tile2 : tile);
+                __syncthreads();
+                for (int n0 = n_start; n0 < ns; n0 += PS_TS) {
+                    const int tn = min(PS_TS, ns - n0);
+                    const bool more = n0 + PS_TS < ns;
+                    if (more) fetch(n0 + PS_TS);
+                    multiply(cur ? tile2 : tile, tn);
+                    if (more) build(n0 + PS_TS, cur ? tile : tile2);
+                    __syncthreads();
+                    cur ^= 1;
+                }
+            }
+        }
+        PCLK(3);
         // deterministic group reduction (groups added in order g = 0..G-1), two halves of 8 accumulators
         double* gp = A.gram_p + ((int64_t)m * A.C + c) * PS_GP;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             __syncthreads();
+            if (active) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) red[tid * 8 + i] = active ? acc[half * 8 + i] : 0.0;
+                for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc[half * 8 + i];
+            }
             __syncthreads();
             for (int idx = tid; idx < nblk * 8; idx += PS_THREADS) {
                 const int b = idx >> 3, i = idx & 7;
@@ -224,6 +388,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
         }
     }
 
+    PCLK(4);
     // ================================================================================================ ticket
     __threadfence();
     __syncthreads();
@@ -233,6 +398,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
         if (s_last) A.counters[m] = 0u;        // self-cleaning: the workspace is left ready for the next launch
     }
     __syncthreads();
+    PCLK(5);
     if (!s_last) return;
     __threadfence();
 
@@ -247,10 +413,15 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
 
     if (tid < 8 && A.mode == PS_MODE_PROCESS) {   // path statistics: sums for 0,1,2,5,6; max for 3; min for 4
         const double* sp = A.stat_p + (int64_t)m * A.C * 8 + tid;
-        double v = __ldcg(sp);
-        for (int cc = 1; cc < A.C; ++cc) {
-            const double x = __ldcg(sp + cc * 8);
-            v = (tid == 3) ? fmax(v, x) : (tid == 4) ? fmin(v, x) : v + x;
+        double v;
+        if (tid == 3 || tid == 4) {
+            v = __ldcg(sp);
+            for (int cc = 1; cc < A.C; ++cc) {
+                const double x = __ldcg(sp + cc * 8);
+                v = (tid == 3) ? fmax(v, x) : fmin(v, x);
+            }
+        } else {
+            v = ordered_sum_ldcg(sp, A.C, 8);
         }
         if (A.stats && tid < 7) A.stats[(int64_t)m * 8 + tid] = v;
     }
@@ -260,9 +431,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
     double reg_used = 0.0;
     if (linear) {
         for (int idx = tid; idx < nblk * 16; idx += PS_THREADS) {   // reduce the chunk partials in chunk order
-            const double* gp = A.gram_p + (int64_t)m * A.C * PS_GP + idx;
-            double v = 0.0;
-            for (int cc = 0; cc < A.C; ++cc) v += __ldcg(gp + (int64_t)cc * PS_GP);
+            const double v = ordered_sum_ldcg(A.gram_p + (int64_t)m * A.C * PS_GP + idx, A.C, PS_GP);
             const int b = idx >> 4, r = (idx >> 2) & 3, q = idx & 3;
             const int i = 4 * blk_i[b] + r, j = 4 * blk_j[b] + q;
             Afull[i * NCP + j] = v;
@@ -270,11 +439,18 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
         }
         if (tid == 0) { s_reg = A.reg_coeff; s_flag = 0; }
         __syncthreads();
+        PCLK(8);
         // ---- solve (Phi^T Phi + reg I) w = Phi^T y; retry with 10x reg on NaN, up to 5 tries (:68-77).
-        //      Crout Cholesky, 4 lanes per row.  A pivot that vanishes relative to its diagonal entry (only possible with
-        //      reg_coeff = 0 and collinear features) marks the column rank-deficient: w_j = 0, which gives the same fitted
-        //      values as the reference's minimum-norm lstsq solution (least-squares fits are unique in Phi w).
+        //      Crout Cholesky, 4 lanes per row, one rsqrt per column (L_jj = d * rsqrt(d), inverse pivot kept for the
+        //      solves).  A pivot that vanishes relative to its diagonal entry (only possible with reg_coeff = 0 and collinear
+        //      features) marks the column rank-deficient: w_j = 0, which gives the same fitted values as the reference's
+        //      minimum-norm lstsq solution (least-squares fits are unique in Phi w).
         const int row = tid >> 2, q4 = tid & 3;
+        const int chol_threads = ((F + 7) >> 3) * 32;        // 4 lanes per row: only the warps that own rows take part
+        auto chol_sync = [&]() {
+            if (chol_threads == 32) __syncwarp();
+            else asm volatile("bar.sync 1, %0;" ::"r"(chol_threads) : "memory");
+        };
         for (int attempt = 0; attempt < 5; ++attempt) {
             const double reg = s_reg;
             for (int idx = tid; idx < F * F; idx += PS_THREADS) {
@@ -284,45 +460,45 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
             if (tid < PS_MAXCOL) s_def[tid] = 0;
             __syncthreads();
             bool bad = false;
-            for (int j = 0; j < F; ++j) {
-                double s = 0.0;
-                if (row >= j && row < F)
-                    for (int k = q4; k < j; k += 4) s = fma(Lm[row * LD + k], Lm[j * LD + k], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (row == j && q4 == 0) {
-                    const double ajj = Lm[j * LD + j], d = ajj - s;
-                    if (d <= 1e-14 * fabs(ajj) && d == d && ajj == ajj && isfinite(ajj)) {
-                        s_def[j] = 1;
-                        s_piv = 1.0;
-                        Lm[j * LD + j] = 1.0;
-                    } else {
-                        const double ljj = sqrt(d);     // NaN input -> NaN -> retry with a larger ridge
-                        s_piv = ljj;
-                        Lm[j * LD + j] = ljj;
+            if (tid < chol_threads) {
+                for (int j = 0; j < F; ++j) {
+                    double s = 0.0;
+                    if (row >= j && row < F)
+                        for (int k = q4; k < j; k += 4) s = fma(Lm[row * LD + k], Lm[j * LD + k], s);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (row == j && q4 == 0) {
+                        const double ajj = Lm[j * LD + j], d = ajj - s;
+                        if (d <= 1e-14 * fabs(ajj) && d == d && ajj == ajj && isfinite(ajj)) {
+                            s_def[j] = 1;
+                            s_piv = 1.0;
+                            s_inv[j] = 0.0;
+                        } else {
+                            const double inv = rsqrt(d);     // d < 0 or NaN input -> NaN -> retry with a larger ridge
+                            s_piv = inv;
+                            s_inv[j] = inv;
+                        }
                     }
+                    chol_sync();
+                    const double inv = s_piv;
+                    if (!(inv > 0.0) || !isfinite(inv)) bad = true;
+                    if (row > j && row < F && q4 == 0) Lm[row * LD + j] = s_def[j] ? 0.0 : (Lm[row * LD + j] - s) * inv;
+                    chol_sync();
                 }
-                __syncthreads();
-                const double piv = s_piv;
-                if (!(piv > 0.0)) bad = true;
-                if (row > j && row < F && q4 == 0) Lm[row * LD + j] = s_def[j] ? 0.0 : (Lm[row * LD + j] - s) / piv;
-                __syncthreads();
             }
             // forward L z = b, backward L^T w = z on one warp: lane l owns rows l and l+32   (b = Gram column F)
             if (tid < 32) {
                 double b0 = lane < F ? Afull[lane * NCP + F] : 0.0, b1 = lane + 32 < F ? Afull[(lane + 32) * NCP + F] : 0.0;
-                if (lane < F && s_def[lane]) b0 = 0.0;
-                if (lane + 32 < F && s_def[lane + 32]) b1 = 0.0;
                 for (int k = 0; k < F; ++k) {
-                    const double mine = (k < 32 ? b0 : b1) / Lm[k * LD + k];
-                    const double zk = s_def[k] ? 0.0 : __shfl_sync(0xffffffffu, mine, k & 31);
+                    const double mine = (k < 32 ? b0 : b1) * s_inv[k];         // s_inv = 0 for rank-deficient columns
+                    const double zk = __shfl_sync(0xffffffffu, mine, k & 31);
                     if (lane == (k & 31)) { if (k < 32) b0 = zk; else b1 = zk; }
                     if (lane > k && lane < F) b0 = fma(-Lm[lane * LD + k], zk, b0);
                     if (lane + 32 > k && lane + 32 < F) b1 = fma(-Lm[(lane + 32) * LD + k], zk, b1);
                 }
                 for (int k = F - 1; k >= 0; --k) {
-                    const double mine = (k < 32 ? b0 : b1) / Lm[k * LD + k];
-                    const double wk = s_def[k] ? 0.0 : __shfl_sync(0xffffffffu, mine, k & 31);
+                    const double mine = (k < 32 ? b0 : b1) * s_inv[k];
+                    const double wk = __shfl_sync(0xffffffffu, mine, k & 31);
                     if (lane == (k & 31)) { if (k < 32) b0 = wk; else b1 = wk; }
                     if (lane < k) b0 = fma(-Lm[k * LD + lane], wk, b0);
                     if (lane + 32 < k) b1 = fma(-Lm[k * LD + lane + 32], wk, b1);
@@ -340,44 +516,116 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
             reg_used = reg;
             if (s_flag) break;
         }
+        PCLK(9);
         if (A.coeffs)
             for (int i = tid; i < F; i += PS_THREADS) A.coeffs[(int64_t)m * F + i] = wv[i];
         if (A.mode == PS_MODE_FIT_ONLY) {
             if (A.stats && tid == 0) A.stats[(int64_t)m * 8 + 7] = reg_used;
             return;
         }
-        // ---- predict b_n = phi_n . w (baselines/linear_baseline.py:17-33)
-        for (int n = tid; n < N; n += PS_THREADS) {
-            const float* o = obs + (int64_t)n * Do;
+        // ---- predict b_n = phi_n . w (baselines/linear_baseline.py:17-33): the time part of the dot product comes from a
+        //      per-step table (reusing the reduction scratch), the observation part is 2*Do FMAs per sample
+        double* tw = red;                                   // [tt_cap <= 1024] t*w_t + t^2*w_t2 + t^3*w_t3 + w_1
+        __syncthreads();                                    // every thread is done with A / L before they become the ring
+        for (int t = tid; t < A.tt_cap; t += PS_THREADS) {
+            const double tt = tt_s[t];
+            tw[t] = fma(tt, wv[2 * Do], fma(tt * tt, wv[2 * Do + 1], fma(tt * tt * tt, wv[2 * Do + 2], wv[2 * Do + 3])));
+        }
+        __syncthreads();
+        constexpr int MAXDO = (PS_MAXCOL - 5) / 2;
+        auto time_part = [&](int n) {
             const int step = tpos ? tpos[n] : n % H;
-            double b = 0.0;
-            for (int i = 0; i < Do; ++i) {
-                const double cl = fmin(fmax((double)__ldg(o + i), -10.0), 10.0);
-                b = fma(cl, wv[i], b);
-                b = fma(cl * cl, wv[Do + i], b);
-            }
+            if (step < A.tt_cap) return tw[step];
             const double tt = (double)step / 100.0;
-            b = fma(tt, wv[2 * Do], b);
-            b = fma(tt * tt, wv[2 * Do + 1], b);
-            b = fma(tt * tt * tt, wv[2 * Do + 2], b);
-            bval[n] = b + wv[2 * Do + 3];
+            return fma(tt, wv[2 * Do], fma(tt * tt, wv[2 * Do + 1], fma(tt * tt * tt, wv[2 * Do + 2], wv[2 * Do + 3])));
+        };
+        // Observations of the whole task stream through a 2-stage TMA ring of A.pred_tile samples (re-using the tile / A / L
+        // area, which is dead by now): thread = one sample of the tile, row stride Do floats.
+        int n_done = 0;
+        const int PT = A.pred_tile;
+        if (STAGE_L && PT > 0 && N >= PT && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0)) {
+            float* pring = reinterpret_cast<float*>(tile);
+            const int ptiles = N / PT, pfloats = PT * Do;
+            if (tid == 0) {
+                tma_load_1d(pring, obs, (uint32_t)pfloats * 4u, &s_bar_p[0]);
+                if (ptiles > 1) tma_load_1d(pring + pfloats, obs + pfloats, (uint32_t)pfloats * 4u, &s_bar_p[1]);
+            }
+            for (int t = 0; t < ptiles; ++t) {
+                tma_mbar_wait(&s_bar_p[t & 1], (uint32_t)((t >> 1) & 1));
+                if (tid < PT) {
+                    const float* src = pring + (t & 1) * pfloats + tid * Do;
+                    const int n = t * PT + tid;
+                    double b = time_part(n);
+                    for (int i = 0; i < Do; ++i) {
+                        const double cl = fmin(fmax((double)src[i], -10.0), 10.0);
+                        b = fma(cl, wv[i], b);
+                        b = fma(cl * cl, wv[Do + i], b);
+                    }
+                    bval[n] = b;
+                }
+                __syncthreads();                  // stage (t & 1) consumed
+                if (tid == 0 && t + 2 < ptiles)
+                    tma_load_1d(pring + (t & 1) * pfloats, obs + (int64_t)(t + 2) * pfloats, (uint32_t)pfloats * 4u, &s_bar_p[t & 1]);
+            }
+            n_done = ptiles * PT;
+        }
+        for (int n = n_done + tid; n < N; n += 2 * PS_THREADS) {      // rest: two samples per thread and step, loads first
+            const int n2 = n + PS_THREADS;
+            const bool two = n2 < N;
+            float oa[MAXDO], ob[MAXDO];
+#pragma unroll
+            for (int i = 0; i < MAXDO; ++i) {
+                oa[i] = i < Do ? __ldg(obs + (int64_t)n * Do + i) : 0.f;
+                ob[i] = (two && i < Do) ? __ldg(obs + (int64_t)n2 * Do + i) : 0.f;
+            }
+            double ba = time_part(n), bb = two ? time_part(n2) : 0.0;
+#pragma unroll
+            for (int i = 0; i < MAXDO; ++i) {
+                if (i < Do) {
+                    const double ca = fmin(fmax((double)oa[i], -10.0), 10.0), cb = fmin(fmax((double)ob[i], -10.0), 10.0);
+                    ba = fma(ca, wv[i], ba);
+                    ba = fma(ca * ca, wv[Do + i], ba);
+                    bb = fma(cb, wv[i], bb);
+                    bb = fma(cb * cb, wv[Do + i], bb);
+                }
+            }
+            bval[n] = ba;
+            if (two) bval[n2] = bb;
         }
     } else {
         if (A.mode == PS_MODE_FIT_ONLY) return;
         for (int n = tid; n < N; n += PS_THREADS) bval[n] = 0.0;   // ZeroBaseline.predict
     }
     __syncthreads();
+    PCLK(10);
 
-    // ---- GAE: delta_t = r_t + g b_{t+1} - b_t (b_H = 0); A_t = delta_t + g*lam A_{t+1}  (samplers/base.py:151-162)
-    const double gl = A.discount * A.gae_lambda;
+    // ---- GAE: delta_t = r_t + g b_{t+1} - b_t (b_H = 0); A_t = delta_t + g*lam A_{t+1}  (samplers/base.py:151-162);
+    //      blocks of 4 steps: loads and deltas first, then the dependent chain of 4 DFMAs
+    const double gl = A.discount * A.gae_lambda, gd = A.discount;
     double mom[2] = {0.0, 0.0};
     for (int e = tid; e < E; e += PS_THREADS) {
         double b_next = 0.0, a_next = 0.0;
         const int o = path_begin(A, m, e), L = path_begin(A, m, e + 1) - o;
-        for (int t = L - 1; t >= 0; --t) {
+        int t = L - 1;
+        for (; t >= 3; t -= 4) {
+            double b[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) b[k] = bval[o + t - k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double r = (double)(STAGE_L ? rall[o + t - k] : __ldg(rew + o + t - k));
+                d[k] = (r + gd * (k == 0 ? b_next : b[k - 1])) - b[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a_next = d[k] + gl * a_next; d[k] = a_next; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { bval[o + t - k] = d[k]; mom[0] += d[k]; }
+            b_next = b[3];
+        }
+        for (; t >= 0; --t) {
             const double b = bval[o + t];
             const double r = (double)(STAGE_L ? rall[o + t] : __ldg(rew + o + t));
-            const double a = (r + A.discount * b_next - b) + gl * a_next;
+            const double a = (r + gd * b_next - b) + gl * a_next;
             bval[o + t] = a;
             mom[0] += a;
             a_next = a;
@@ -385,6 +633,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
         }
     }
     __syncthreads();
+    PCLK(11);
 
     // ---- per-task normalisation / positive shift (utils/utils.py:59-71; population std)
     double mean = 0.0, inv = 1.0;
@@ -419,6 +668,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
     }
     for (int n = N + tid; n < NS; n += PS_THREADS) A.adv[(int64_t)m * NS + n] = 0.f;      // padding rows (variable-length paths)
     if (A.stats && tid == 0) A.stats[(int64_t)m * 8 + 7] = reg_used;
+    PCLK(12);
 }
 
 __global__ void adj_avg_rewards_kernel(int64_t n, const float* rew, double mean, double inv, float* out) {
@@ -456,70 +706,100 @@ __global__ void baseline_predict_kernel(int n_paths, const int32_t* __restrict__
 
 using namespace promp;
 
-// Chunking: enough CTAs for ~4 per SM (each CTA's front stage is latency-bound), never more than one per trajectory.
-static void proc_chunks(int M, int E, int* C, int* EPC) {
+// ---- launch geometry ------------------------------------------------------------------------------------------------
+static int proc_tt_cap(int H, int NS, bool ragged) {
+    const int n = ragged ? NS : H;
+    return ((n < 1024 ? n : 1024) + 1) & ~1;      // even: keeps the areas behind the table 16-byte aligned
+}
+static size_t proc_smem_fixed(int Do, int tt_cap) {
+    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
+    return (size_t)(2 * PS_TS * NCP + PS_THREADS * 8 + tt_cap) * 8;
+}
+static size_t proc_smem_finish_fixed(int Do) {
+    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
+    return (size_t)(NCP * NCP + PS_MAXCOL * (PS_MAXCOL + 1) + PS_MAXCOL + 4) * 8;
+}
+struct ProcGeom {
+    int C, EPC, chunk_cap, finish_cap, tt_cap, pred_tile;
+    bool stage_f, stage_l;
+    size_t smem;
+};
+// Shared memory of one CTA when a chunk holds `EPC` paths (front stage: the chunk's rewards + returns; finish stage: the
+// task's rewards + baseline; whichever is larger, because any CTA may turn out to be the finisher).
+static ProcGeom proc_geom_for(int EPC, int E, int H, int Do, int NS, bool ragged) {
+    ProcGeom g;
+    g.EPC = EPC;
+    g.C = (E + EPC - 1) / EPC;
+    g.tt_cap = proc_tt_cap(H, NS, ragged);
+    const int chunk_samples = ragged ? NS : EPC * H;
+    const size_t fixed = proc_smem_fixed(Do, g.tt_cap);
+    const size_t ring = (size_t)PS_RING * PS_TS * Do * 4;                    // TMA stages of the Gram loop
+    size_t front = fixed + ((size_t)chunk_samples * PS_SMEM_SAMPLES_BYTES + 15) / 16 * 16 + ring;
+    size_t fin = fixed + proc_smem_finish_fixed(Do) + (size_t)NS * PS_SMEM_SAMPLES_BYTES;
+    // predict ring: 2 stages of pred_tile samples inside the (dead) tile / A / L area
+    {
+        const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
+        const size_t avail = (size_t)(2 * PS_TS * NCP + NCP * NCP + PS_MAXCOL * (PS_MAXCOL + 1)) * 8;
+        g.pred_tile = 0;
+        for (int pt = 256; pt >= 32; pt >>= 1)
+            if ((size_t)2 * pt * Do * 4 <= avail) { g.pred_tile = pt; break; }
+    }
+    g.stage_f = front <= (size_t)PS_SMEM_BUDGET;
+    g.stage_l = fin <= (size_t)PS_SMEM_BUDGET;
+    if (!g.stage_f) front = fixed;
+    if (!g.stage_l) fin = fixed + proc_smem_finish_fixed(Do);
+    g.chunk_cap = g.stage_f ? chunk_samples : 0;
+    g.finish_cap = g.stage_l ? NS : 0;
+    g.smem = (front > fin ? front : fin) + 16;
+    return g;
+}
+// Chunking: ~4 CTAs per SM worth of chunks (the front stage is issue / latency-bound at 8-16 resident warps per SM, so
+// short chunks on many CTAs beat one exact wave of longer ones: measured 33 vs 38 us at 40x20x100), never more than one
+// CTA per path.
+static ProcGeom proc_geom(int M, int E, int H, int Do, int NS, bool ragged) {
     int target = (4 * 148 + M - 1) / M;
     if (target > E) target = E;
     if (target < 1) target = 1;
-    *EPC = (E + target - 1) / target;
-    *C = (E + *EPC - 1) / *EPC;
+    const int EPC = (E + target - 1) / target;
+    return proc_geom_for(EPC, E, H, Do, NS, ragged);
 }
 
 struct ProcLayout {
-    int C, EPC;
+    ProcGeom g;
     int64_t off_gram, off_stat, off_ws64, off_tpos, total;
 };
-static ProcLayout proc_layout(int M, int E, int NS, bool ragged) {
+static ProcLayout proc_layout(int M, int E, int H, int Do, int NS, bool ragged) {
     ProcLayout L;
-    proc_chunks(M, E, &L.C, &L.EPC);
+    L.g = proc_geom(M, E, H, Do, NS, ragged);
     // arrival tickets: a FIXED-size header (grid.y <= 65535 tasks), so a workspace shared by launches of different
     // shapes never finds stale partials where a later layout expects zeroed tickets
     int64_t o = 65536 * 4;
-    L.off_gram = o;  o += (int64_t)M * L.C * PS_GP * 8;
-    L.off_stat = o;  o += (int64_t)M * L.C * 8 * 8;
+    L.off_gram = o;  o += (int64_t)M * L.g.C * PS_GP * 8;
+    L.off_stat = o;  o += (int64_t)M * L.g.C * 8 * 8;
     L.off_ws64 = o;  o += (int64_t)M * 2 * NS * 8;
     L.off_tpos = o;  if (ragged) o += ((int64_t)M * NS * 4 + 7) / 8 * 8;
     L.total = o;
     return L;
 }
 
-static size_t proc_smem_fixed(int Do) {
-    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
-    return (size_t)(PS_TS * NCP + PS_THREADS * 8) * 8;
-}
-static size_t proc_smem_finish_fixed(int Do) {
-    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
-    return (size_t)(NCP * NCP + PS_MAXCOL * (PS_MAXCOL + 1) + PS_MAXCOL + 4) * 8;
-}
-
-static int launch_process(ProcArgs& A, bool ragged, cudaStream_t stream) {
-    // shared-memory staging: front stage holds a chunk's rewards + returns, the finish stage a task's rewards + baseline
-    const int chunk_samples = ragged ? A.NS : A.EPC * A.H;
-    const size_t fixed = proc_smem_fixed(A.Do);
-    size_t front = fixed + (size_t)chunk_samples * PS_SMEM_SAMPLES_BYTES;
-    size_t fin = fixed + proc_smem_finish_fixed(A.Do) + (size_t)A.NS * PS_SMEM_SAMPLES_BYTES;
-    const bool stage_f = front <= (size_t)PS_SMEM_BUDGET, stage_l = fin <= (size_t)PS_SMEM_BUDGET;
-    if (!stage_f) front = fixed;
-    if (!stage_l) fin = fixed + proc_smem_finish_fixed(A.Do);
-    A.chunk_cap = stage_f ? chunk_samples : 0;
-    A.finish_cap = stage_l ? A.NS : 0;
-    const size_t smem = (front > fin ? front : fin) + 16;
-    auto kern = stage_f ? (stage_l ? process_fused_kernel<true, true> : process_fused_kernel<true, false>)
-                        : (stage_l ? process_fused_kernel<false, true> : process_fused_kernel<false, false>);
+static int launch_process(ProcArgs& A, const ProcGeom& g, cudaStream_t stream) {
+    A.C = g.C; A.EPC = g.EPC; A.chunk_cap = g.chunk_cap; A.finish_cap = g.finish_cap; A.tt_cap = g.tt_cap;
+    A.pred_tile = g.pred_tile;
+    auto kern = g.stage_f ? (g.stage_l ? process_fused_kernel<true, true> : process_fused_kernel<true, false>)
+                          : (g.stage_l ? process_fused_kernel<false, true> : process_fused_kernel<false, false>);
     static size_t configured[4] = {0, 0, 0, 0};
-    const int which = (stage_f ? 2 : 0) + (stage_l ? 1 : 0);
-    if (smem > configured[which]) {
-        PROMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[which] = smem;
+    const int which = (g.stage_f ? 2 : 0) + (g.stage_l ? 1 : 0);
+    if (g.smem > configured[which]) {
+        PROMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        configured[which] = g.smem;
     }
-    kern<<<dim3(A.C, A.M), PS_THREADS, smem, stream>>>(A);
+    kern<<<dim3(A.C, A.M), PS_THREADS, g.smem, stream>>>(A);
     PROMP_LAUNCH_CHECK("process_fused_kernel");
     return PROMP_OK;
 }
 
 extern "C" int64_t promp_process_workspace_bytes(int M, int E, int H, int obs_dim) {
-    (void)obs_dim;
-    return proc_layout(M, E, E * H, false).total;
+    return proc_layout(M, E, H, obs_dim, E * H, false).total;
 }
 
 extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const float* obs, const float* rew,
@@ -535,7 +815,7 @@ extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const flo
                   "promp_process_samples: unknown baseline kind %d", baseline_kind);
     PROMP_REQUIRE(discount >= 0.0 && discount <= 1.0 && gae_lambda >= 0.0 && gae_lambda <= 1.0,
                   "promp_process_samples: discount and gae_lambda must be in [0,1]");   // samplers/base.py:56-57
-    const ProcLayout L = proc_layout(M, E, E * H, false);
+    const ProcLayout L = proc_layout(M, E, H, obs_dim, E * H, false);
     if (workspace_bytes < L.total) {
         set_error("promp_process_samples: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)L.total);
         return PROMP_ERR_WORKSPACE;
@@ -548,9 +828,9 @@ extern "C" int promp_process_samples(int M, int E, int H, int obs_dim, const flo
     A.returns = returns; A.adv = adv; A.coeffs = coeffs; A.stats = stats;
     A.counters = (unsigned int*)w; A.gram_p = (double*)(w + L.off_gram); A.stat_p = (double*)(w + L.off_stat);
     A.ws64 = (double*)(w + L.off_ws64);
-    A.C = L.C; A.EPC = L.EPC; A.path_off = nullptr; A.n_paths = nullptr; A.NS = E * H; A.tpos = nullptr;
+    A.path_off = nullptr; A.n_paths = nullptr; A.NS = E * H; A.tpos = nullptr;
     A.target = nullptr; A.mode = PS_MODE_PROCESS;
-    return launch_process(A, false, (cudaStream_t)stream);
+    return launch_process(A, L.g, (cudaStream_t)stream);
 }
 
 extern "C" int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, double std, float* out, void* stream) {
@@ -564,8 +844,7 @@ extern "C" int promp_adj_avg_rewards(int64_t n, const float* rew, double mean, d
 
 // ---- variable-length paths: same kernel driven by a per-task path table ------------------------------------------
 extern "C" int64_t promp_process_workspace_bytes_ragged(int M, int max_paths, int max_samples, int obs_dim) {
-    (void)obs_dim;
-    return proc_layout(M, max_paths, max_samples, true).total;
+    return proc_layout(M, max_paths, 0, obs_dim, max_samples, true).total;
 }
 
 extern "C" int promp_process_samples_ragged(int M, int max_paths, int max_samples, int obs_dim, const float* obs,
@@ -582,7 +861,7 @@ extern "C" int promp_process_samples_ragged(int M, int max_paths, int max_sample
                   "promp_process_samples_ragged: unknown baseline kind %d", baseline_kind);
     PROMP_REQUIRE(discount >= 0.0 && discount <= 1.0 && gae_lambda >= 0.0 && gae_lambda <= 1.0,
                   "promp_process_samples_ragged: discount and gae_lambda must be in [0,1]");
-    const ProcLayout L = proc_layout(M, max_paths, max_samples, true);
+    const ProcLayout L = proc_layout(M, max_paths, 0, obs_dim, max_samples, true);
     if (workspace_bytes < L.total) {
         set_error("promp_process_samples_ragged: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)L.total);
         return PROMP_ERR_WORKSPACE;
@@ -595,16 +874,15 @@ extern "C" int promp_process_samples_ragged(int M, int max_paths, int max_sample
     A.returns = returns; A.adv = adv; A.coeffs = coeffs; A.stats = stats;
     A.counters = (unsigned int*)w; A.gram_p = (double*)(w + L.off_gram); A.stat_p = (double*)(w + L.off_stat);
     A.ws64 = (double*)(w + L.off_ws64);
-    A.C = L.C; A.EPC = L.EPC; A.path_off = path_off; A.n_paths = n_paths; A.NS = max_samples;
+    A.path_off = path_off; A.n_paths = n_paths; A.NS = max_samples;
     A.tpos = (int32_t*)(w + L.off_tpos);
     A.target = nullptr; A.mode = PS_MODE_PROCESS;
-    return launch_process(A, true, (cudaStream_t)stream);
+    return launch_process(A, L.g, (cudaStream_t)stream);
 }
 
 // ---- standalone LinearFeatureBaseline.fit / predict (baselines/linear_baseline.py:55-77, 17-33) --------------------
 extern "C" int64_t promp_baseline_fit_workspace_bytes(int n_paths, int n_samples, int obs_dim) {
-    (void)obs_dim;
-    return proc_layout(1, n_paths, n_samples, true).total;
+    return proc_layout(1, n_paths, 0, obs_dim, n_samples, true).total;
 }
 
 extern "C" int promp_baseline_fit(int n_paths, int n_samples, int obs_dim, const float* obs, const double* target,
@@ -613,7 +891,7 @@ extern "C" int promp_baseline_fit(int n_paths, int n_samples, int obs_dim, const
     PROMP_REQUIRE(n_paths > 0 && n_samples > 0 && obs_dim > 0, "promp_baseline_fit: dimensions must be positive");
     PROMP_REQUIRE(2 * obs_dim + 5 <= PS_MAXCOL, "promp_baseline_fit: obs_dim %d too large (max %d)", obs_dim, (PS_MAXCOL - 5) / 2);
     PROMP_REQUIRE(obs && target && path_off && coeffs && workspace, "promp_baseline_fit: null pointer argument");
-    const ProcLayout L = proc_layout(1, n_paths, n_samples, true);
+    const ProcLayout L = proc_layout(1, n_paths, 0, obs_dim, n_samples, true);
     if (workspace_bytes < L.total) {
         set_error("promp_baseline_fit: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)L.total);
         return PROMP_ERR_WORKSPACE;
@@ -627,12 +905,12 @@ extern "C" int promp_baseline_fit(int n_paths, int n_samples, int obs_dim, const
     A.returns = nullptr; A.adv = nullptr; A.coeffs = coeffs; A.stats = nullptr;
     A.counters = (unsigned int*)w; A.gram_p = (double*)(w + L.off_gram); A.stat_p = (double*)(w + L.off_stat);
     A.ws64 = (double*)(w + L.off_ws64);
-    A.C = L.C; A.EPC = L.EPC; A.path_off = path_off; A.n_paths = nullptr; A.NS = n_samples;
+    A.path_off = path_off; A.n_paths = nullptr; A.NS = n_samples;
     A.tpos = (int32_t*)(w + L.off_tpos);
     A.target = target; A.mode = PS_MODE_FIT_ONLY;
     // reg_used is reported through an 8-double stats row when requested
     A.stats = reg_used ? reg_used - 7 : nullptr;
-    return launch_process(A, true, (cudaStream_t)stream);
+    return launch_process(A, L.g, (cudaStream_t)stream);
 }
 
 extern "C" int promp_baseline_predict(int n_paths, int n_samples, int obs_dim, const float* obs, const int32_t* path_off,
@@ -646,3 +924,15 @@ extern "C" int promp_baseline_predict(int n_paths, int n_samples, int obs_dim, c
     PROMP_LAUNCH_CHECK("baseline_predict_kernel");
     return PROMP_OK;
 }
+
+#ifdef PROMP_EXP_CLOCKS
+extern "C" int promp_debug_proc_clocks(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, promp::g_proc_clk, 16 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(promp::g_proc_clk, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

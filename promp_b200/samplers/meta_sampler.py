@@ -200,8 +200,9 @@ class MetaSampler(object):
             inner.host_reset_states(M * E)
         self._injected_noise = self._injected_init = None
         paths = PathsMetaBatch()
+        cache = {}
         for m in range(M):
-            paths[m] = LazyPathList(phase, (m,))
+            paths[m] = LazyPathList(phase, (m,), cache)
         paths.phase = phase
         return paths
 

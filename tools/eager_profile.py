@@ -36,5 +36,38 @@ def main():
         st.sort_stats('tottime').print_stats(22)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+
+
+def after_graph():
+    """bench.py order: a graph-mode Trainer.train() first, then an eager Trainer with logging."""
+    import torch
+    import bench
+    from promp_b200.utils import logger
+    logger.set_quiet(True)
+    np.random.seed(1)
+    tr = bench.build_stack(bench.WORKLOADS['point'], 'numpy')
+    tr.start_itr, tr.n_itr = 0, 10
+    tr.train()
+    torch.cuda.synchronize()
+    tr2 = bench.build_stack(bench.WORKLOADS['point'], 'numpy', use_cuda_graph=False)
+    for i in range(3):
+        tr2.train_iteration(i, log=True)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for i in range(10):
+        tr2.train_iteration(i, log=True)
+    torch.cuda.synchronize()
+    print('eager log=True after a graph-mode train(): %.3f ms / iteration' % ((time.perf_counter() - t) / 10 * 1e3))
+    pr = cProfile.Profile()
+    pr.enable()
+    for i in range(10):
+        tr2.train_iteration(i, log=True)
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats('tottime').print_stats(14)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'after_graph':
+    after_graph()
