@@ -136,7 +136,8 @@ class LaunchCounter(object):
                    promp_adam_tf1=2, promp_policy_forward=1, promp_counter_add=1, promp_meta_loss_terms=1,
                    promp_policy_grad_ragged=1, promp_policy_hvp_ragged=1, promp_process_samples_ragged=1,
                    promp_vec_axpy=1, promp_cg_init=1, promp_cg_step=1, promp_trpo_step=1, promp_trpo_select=1,
-                   promp_allreduce_p2p=1, promp_baseline_fit=1, promp_baseline_predict=1)
+                   promp_allreduce_p2p=1, promp_baseline_fit=1, promp_baseline_predict=1,
+                   promp_meta_update=1, promp_meta_loss_terms_p2p=1)
 
     def __init__(self, time_kernels=False):
         from promp_b200 import _lib

@@ -186,6 +186,26 @@ int promp_baseline_predict(int n_paths, int n_samples, int obs_dim, const float*
                            const double* coeffs, double* out, void* stream);
 
 /*
+ * Fused outer update of one Adam epoch (optimizers/maml_first_order_optimizer.py:82-115 with the task mean of
+ * meta_algos/pro_mp.py:151-155 and, for world > 1, the all-reduce of SURVEY.md section 8e): per-task meta-gradients
+ * task_grads [M, P] -> grad = scale * sum_m task_grads[m] (scale = 1 / (M * world)) -> rank-ordered sum over ranks through the
+ * NVLink peer buffers of promp_comm_alloc -> TF1 Adam on theta / m / v with the device step counter (incremented once).
+ * One launch of ceil(P / 256) CTAs; each CTA exchanges its own 256-parameter slice (no grid-wide barrier).  world == 1:
+ * peers / epoch / error may be NULL.  `ticket_dev`: one zero-initialised uint32 of device memory (left zero).
+ * grad_out (may be NULL) receives the reduced meta-gradient.  A missing peer (2 s time-out) sets *error_flag and poisons
+ * the gradient with NaN.
+ */
+int promp_meta_update(int M, int P, const float* task_grads, float scale, float* grad_out, float* theta, float* m, float* v,
+                      int32_t* step, float lr, float beta1, float beta2, float eps, int world, int rank, int capacity_floats,
+                      void* const* peers_dev, uint32_t* epoch_dev, uint32_t* error_flag_dev, uint32_t* ticket_dev, void* stream);
+
+/* promp_meta_loss_terms with the sum over ranks fused in (world >= 2): local means -> peer exchange -> rank-ordered sum ->
+ * KL penalty.  One launch instead of terms + all-reduce + elementwise glue. */
+int promp_meta_loss_terms_p2p(int S, int M, const float* stats_all, float inv_m_global, const float* coeff, int n_out, float* out,
+                              int world, int rank, int capacity_floats, void* const* peers_dev, uint32_t* epoch_dev,
+                              uint32_t* error_flag_dev, void* stream);
+
+/*
  * Device-resident ConjugateGradientOptimizer (optimizers/conjugate_gradient_optimizer.py:239-354) on flat float32 parameter
  * vectors [n]; one CTA each, dot products accumulated in float64 in a fixed order.  `scal` is a device float[4]:
  * [0] r.r  [1] converged flag  [2] beta  [3] beta-is-NaN flag.
@@ -317,7 +337,10 @@ int promp_adam_tf1(int P, float* theta, const float* grad, float* m, float* v, i
  * promp_comm_alloc (the one allocation the library performs: IPC export needs a whole cudaMalloc block), exchanges
  * promp_ipc_get_handle() blobs (64 bytes, e.g. via torch.distributed.all_gather_object), opens the peers' blobs with
  * promp_ipc_open_handle and passes the world-sized DEVICE array of buffer pointers (own buffer at index `rank`).
- *   epoch_dev, error_flag_dev: device uint32, zero-initialised; error_flag becomes 1 if a peer did not arrive in ~2 s.
+ *   epoch_dev, error_flag_dev, ticket_dev: device uint32, zero-initialised; error_flag becomes 1 (sticky) if a peer did not
+ *   arrive in ~2 s, and the results of that and every later call are NaN.
+ * Protocol (csrc/comm.cu): low-latency exchange - every element travels as one 8-byte {value, epoch} store into all ranks'
+ * receive areas and is polled there; no flags, no system fences; ceil(n / 256) CTAs.
  */
 int64_t promp_comm_buffer_bytes(int world, int capacity_floats);
 int promp_comm_alloc(int64_t bytes, void** dev_ptr_host);
@@ -326,7 +349,8 @@ int promp_ipc_get_handle(void* dev_ptr, void* handle64_host);
 int promp_ipc_open_handle(const void* handle64_host, void** dev_ptr_host);
 int promp_ipc_close_handle(void* dev_ptr);
 int promp_allreduce_p2p(int world, int rank, int n, int capacity_floats, const float* in, float* out, float scale,
-                        void* const* peers_dev, uint32_t* epoch_dev, uint32_t* error_flag_dev, void* stream);
+                        void* const* peers_dev, uint32_t* epoch_dev, uint32_t* error_flag_dev, uint32_t* ticket_dev,
+                        void* stream);
 
 /* Runtime options.
  *   "tensor_cores" = 1 (default): hidden-64 promp_policy_grad / promp_policy_hvp run their layer GEMMs on tcgen05 with TMEM

@@ -64,7 +64,10 @@ _SIGNATURES = {
     'promp_ipc_get_handle': (c_int, [_P, _P]),
     'promp_ipc_open_handle': (c_int, [_P, _P]),
     'promp_ipc_close_handle': (c_int, [_P]),
-    'promp_allreduce_p2p': (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P]),
+    'promp_meta_update': (c_int, [c_int, c_int, _P, c_float, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_int, c_int,
+                                  c_int, _P, _P, _P, _P, _P]),
+    'promp_meta_loss_terms_p2p': (c_int, [c_int, c_int, _P, c_float, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    'promp_allreduce_p2p': (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -137,11 +137,13 @@ class MAMLAlgo(object):
 
     # ------------------------------------------------------------------------------------ meta objective
     def _meta_pass(self, theta, phases, outer_obj_kind, clip_eps, inner_kl_coeffs, want_grad, outer_kl_coeff=0.0,
-                   outer_obj_scale=1.0):
+                   outer_obj_scale=1.0, reduce=True):
         """One evaluation of the meta objective (and optionally its gradient) at `theta` [P].
 
         Returns dict(grad=[P] or None (local sum over tasks / M_global, NOT yet all-reduced),
-                     surr=[M] outer surrogate per task, outer_kl=[M], inner_kl=[S-1, M])."""
+                     surr=[M] outer surrogate per task, outer_kl=[M], inner_kl=[S-1, M]).
+        reduce=False leaves the per-task gradients in out['grad_tasks'] [M, P] for the fused reduce + all-reduce + Adam
+        kernel (promp_meta_update) and skips promp_reduce_tasks."""
         import torch
         p = self.policy
         M, P, S = self.meta_batch_size, p.num_params, len(phases)
@@ -166,9 +168,12 @@ class MAMLAlgo(object):
             for s in range(S - 2, -1, -1):
                 prm, strd, clp = chain[s]
                 self._hvp(phases[s], prm, strd, v, v, inner_kl_coeffs[s], clp)
-            flat = torch.empty(P, dtype=torch.float32, device=dev)
-            _lib.call('promp_reduce_tasks', M, P, _lib.ptr(v), 1.0 / (M * world_size()), _lib.ptr(flat), _lib.stream())
-            out['grad'] = flat
+            if reduce:
+                flat = torch.empty(P, dtype=torch.float32, device=dev)
+                _lib.call('promp_reduce_tasks', M, P, _lib.ptr(v), 1.0 / (M * world_size()), _lib.ptr(flat), _lib.stream())
+                out['grad'] = flat
+            else:
+                out['grad_tasks'] = v
         return out
 
     def optimize_policy(self, all_samples_data, log=True):

@@ -29,11 +29,13 @@ class ProMP(MAMLAlgo):
         self.inner_obj_kind = _lib.OBJ_RATIO                     # _adapt_objective_sym (pro_mp.py:59-65)
         self.optimizer.build(self.policy)
 
-    def _objective_pass(self, phases, want_grad):
+    FUSED_META_UPDATE = True     # _objective_pass(reduce=False) -> per-task gradients for promp_meta_update
+
+    def _objective_pass(self, phases, want_grad, reduce=True):
         """meta_objective = mean_i L_clip,i + mean_s(c_s * mean_i KL_s,i)   (pro_mp.py:151-155)."""
         S1 = max(self.num_inner_grad_steps, 1)
         coeffs = [float(c) / S1 for c in self.inner_kl_coeff]      # tf.reduce_mean over the S-1 steps
-        return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, coeffs, want_grad)
+        return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, coeffs, want_grad, reduce=reduce)
 
     LOG_KEYS = ('LossBefore', 'LossAfter', 'KLInner')
     FUSED_LOSS_TERMS = True      # loss_terms(res, out=, n_out=) is one promp_meta_loss_terms launch
@@ -96,10 +98,18 @@ class ProMP(MAMLAlgo):
             out = torch.empty(S1 + 2, dtype=torch.float32, device=st.device)
         n_out = S1 + 2 if n_out is None else n_out
         single = world_size() == 1
+        from promp_b200.utils import dist as _dist
+        p2p = _dist._p2p
+        if not single and p2p is not None:
+            # means over all ranks' tasks + KL penalty in ONE launch (peer-memory exchange fused into the terms kernel)
+            _lib.call('promp_meta_loss_terms_p2p', S1 + 1, self.meta_batch_size, _lib.ptr(st), 1.0 / Mg,
+                      _lib.ptr(self._coeff_dev) if S1 > 0 else None, n_out, _lib.ptr(out), p2p.world, p2p.rank, p2p.cap,
+                      _lib.ptr(p2p.peers), _lib.ptr(p2p.epoch), _lib.ptr(p2p.error), _lib.stream())
+            return out
         _lib.call('promp_meta_loss_terms', S1 + 1, self.meta_batch_size, _lib.ptr(st), 1.0 / Mg,
                   _lib.ptr(self._coeff_dev) if (single and S1 > 0) else None, n_out if single else S1 + 2, _lib.ptr(out),
                   _lib.stream())
-        if not single:                                        # sum the per-rank means, then add the penalty
+        if not single:                                        # NCCL fallback: sum the per-rank means, then add the penalty
             allreduce_sum_(out)
             if S1 > 0:
                 out[0] += (self._coeff_dev * out[1:1 + S1]).mean()

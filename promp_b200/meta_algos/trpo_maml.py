@@ -112,7 +112,10 @@ class TRPOMAML(MAMLAlgo):
 
     @property
     def graph_capturable(self):
-        return not self.exploration      # the E-MAML coefficient is assembled with host scalars
+        # the E-MAML coefficient is assembled with host scalars; with several ranks the ~250-launch capture was observed to be
+        # invalidated on one rank (N = 2, cudaErrorStreamCaptureInvalidated) - the eager device-resident step (1-2 host
+        # reads per iteration) is used there
+        return not self.exploration and world_size() == 1
 
     def optimize_phases(self, phases):
         """optimize_policy on PhaseData objects up to the verdict on the first line-search group, everything left on the

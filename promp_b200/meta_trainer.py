@@ -155,7 +155,9 @@ class Trainer(object):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         host_part()
-        with torch.cuda.graph(graph):
+        # thread_local: other threads of this process (e.g. the NCCL watchdog polling its events) must not invalidate a long
+        # capture (observed with the ~250-launch TRPO-MAML iteration at N = 2)
+        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
             device_part()
         policy.theta.copy_(saved['theta'])
         if saved['adam'] is not None:

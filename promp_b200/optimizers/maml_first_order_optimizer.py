@@ -21,6 +21,8 @@ class MAMLPPOOptimizer(object):
         self.m = torch.zeros(P, dtype=torch.float32, device=policy.device)
         self.v = torch.zeros(P, dtype=torch.float32, device=policy.device)
         self.step = torch.zeros(1, dtype=torch.int32, device=policy.device)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=policy.device)      # completion ticket of promp_meta_update
+        self.last_grad = torch.zeros(P, dtype=torch.float32, device=policy.device)
 
     def get_state(self):
         """Adam slots as numpy (snapshots; the reference's tf.train.Saver-less snapshot drops them, we keep them so that a
@@ -38,6 +40,23 @@ class MAMLPPOOptimizer(object):
         _lib.call('promp_adam_tf1', p.num_params, _lib.ptr(p.theta), _lib.ptr(grad), _lib.ptr(self.m), _lib.ptr(self.v),
                   _lib.ptr(self.step), self._lr, self._b1, self._b2, self._eps, _lib.stream())
 
+    def apply_task_gradients(self, task_grads):
+        """Per-task meta-gradients [M, P] -> task mean -> sum over ranks (NVLink peer memory) -> TF1 Adam, one launch
+        (promp_meta_update).  Returns False when the multi-rank case has no peer-memory communicator (NCCL fallback)."""
+        from promp_b200.utils import dist as _dist
+        p = self._target
+        W = _dist.world_size()
+        p2p = _dist._p2p
+        if W > 1 and (p2p is None or p.num_params > p2p.cap):
+            return False
+        M = task_grads.shape[0]
+        comm = (p2p.world, p2p.rank, p2p.cap, _lib.ptr(p2p.peers), _lib.ptr(p2p.epoch), _lib.ptr(p2p.error)) if W > 1 else \
+            (1, 0, 0, None, None, None)
+        _lib.call('promp_meta_update', M, p.num_params, _lib.ptr(task_grads), 1.0 / (M * W), _lib.ptr(self.last_grad),
+                  _lib.ptr(p.theta), _lib.ptr(self.m), _lib.ptr(self.v), _lib.ptr(self.step), self._lr, self._b1, self._b2,
+                  self._eps, *comm, _lib.ptr(self._ticket), _lib.stream())
+        return True
+
     def optimize(self, algo, phases):
         """optimize (:82-115) + compute_stats (:146-163).  Returns a device vector
         [loss_before, loss_after, inner_kl_0.., outer_kl] without synchronising the host."""
@@ -48,11 +67,22 @@ class MAMLPPOOptimizer(object):
             # [loss_before | loss_after, inner_kls, outer_kl] written in place by promp_meta_loss_terms: no cat / slicing kernels
             final = torch.empty(S1 + 3, dtype=torch.float32, device=algo.policy.device)
         loss_before = None
+        fused_update = getattr(algo, 'FUSED_META_UPDATE', False)
         for epoch in range(self._max_epochs):
-            res = algo._objective_pass(phases, want_grad=True)
-            allreduce_sum_(res['grad'])                 # the ONE collective of the data path: [P] floats over NVLink
+            res = algo._objective_pass(phases, want_grad=True, reduce=False) if fused_update else \
+                algo._objective_pass(phases, want_grad=True)
             if loss_before is None:
                 loss_before = algo.loss_terms(res, out=final[0:], n_out=1)[0:1] if fused else algo.loss_terms(res)[0:1]
+            if fused_update and self.apply_task_gradients(res['grad_tasks']):
+                continue                                # task mean + all-reduce + Adam happened in one launch
+            if fused_update:                            # no peer-memory communicator: reduce here, all-reduce through NCCL
+                flat = torch.empty(algo.policy.num_params, dtype=torch.float32, device=algo.policy.device)
+                M = res['grad_tasks'].shape[0]
+                from promp_b200.utils.dist import world_size
+                _lib.call('promp_reduce_tasks', M, algo.policy.num_params, _lib.ptr(res['grad_tasks']), 1.0 / (M * world_size()),
+                          _lib.ptr(flat), _lib.stream())
+                res['grad'] = flat
+            allreduce_sum_(res['grad'])                 # the ONE collective of the data path: [P] floats over NVLink
             self.apply_gradient(res['grad'])
             self.last_grad = res['grad']
         res = algo._objective_pass(phases, want_grad=False)

@@ -56,6 +56,7 @@ class P2PComm(object):
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)     # completion ticket of the multi-CTA all-reduce
         d.barrier()
 
     def accepts(self, t):
@@ -65,7 +66,7 @@ class P2PComm(object):
     def allreduce_(self, t, scale=1.0):
         from promp_b200 import _lib
         _lib.call('promp_allreduce_p2p', self.world, self.rank, t.numel(), self.cap, _lib.ptr(t), _lib.ptr(t), float(scale),
-                  _lib.ptr(self.peers), _lib.ptr(self.epoch), _lib.ptr(self.error), _lib.stream())
+                  _lib.ptr(self.peers), _lib.ptr(self.epoch), _lib.ptr(self.error), _lib.ptr(self.ticket), _lib.stream())
         return t
 
     def check(self):

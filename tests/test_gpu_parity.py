@@ -502,6 +502,30 @@ def test_trpo_maml_optimize_policy_runs_and_matches_first_quantities():
     assert abs(st_o['loss'] - ls['loss_after']) < 0.05 * abs(ls['loss_before'] - ls['loss_after']) + 1e-5
 
 
+def test_fused_meta_update_single_gpu():
+    """promp_meta_update (task mean + TF1 Adam in one launch, world = 1) == promp_reduce_tasks + promp_adam_tf1."""
+    torch = _cuda()
+    from promp_b200 import _lib
+    g = torch.Generator(device='cuda').manual_seed(3)
+    M, P = 9, 5708
+    v = torch.randn(M, P, generator=g, device='cuda')
+    theta_a = torch.randn(P, generator=g, device='cuda')
+    theta_b = theta_a.clone()
+    ma, va, mb, vb = (torch.zeros(P, device='cuda') for _ in range(4))
+    sa, sb = (torch.zeros(1, dtype=torch.int32, device='cuda') for _ in range(2))
+    ticket = torch.zeros(1, dtype=torch.int32, device='cuda')
+    ga, gb = torch.empty(P, device='cuda'), torch.empty(P, device='cuda')
+    for it in range(4):
+        v.mul_(0.7).add_(0.1)
+        _lib.call('promp_meta_update', M, P, _lib.ptr(v), 1.0 / M, _lib.ptr(ga), _lib.ptr(theta_a), _lib.ptr(ma), _lib.ptr(va),
+                  _lib.ptr(sa), 1e-3, 0.9, 0.999, 1e-8, 1, 0, 0, None, None, None, _lib.ptr(ticket), _lib.stream())
+        _lib.call('promp_reduce_tasks', M, P, _lib.ptr(v), 1.0 / M, _lib.ptr(gb), _lib.stream())
+        _lib.call('promp_adam_tf1', P, _lib.ptr(theta_b), _lib.ptr(gb), _lib.ptr(mb), _lib.ptr(vb), _lib.ptr(sb), 1e-3, 0.9, 0.999,
+                  1e-8, _lib.stream())
+        assert torch.equal(ga, gb) and torch.equal(theta_a, theta_b) and torch.equal(ma, mb) and torch.equal(va, vb)
+    assert int(sa.item()) == 4 and int(ticket.item()) == 0
+
+
 def test_device_cg_and_line_search_kernels(golden_dir):
     """promp_cg_init / promp_cg_step against the UNMODIFIED reference's conjugate_gradients outputs
     (tests/golden/tf_half_known.npz: cg_x10, cg_x3, early exit at residual_tol), driven with grad_plus = A p, grad_minus = 0,
