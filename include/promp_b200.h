@@ -322,6 +322,18 @@ int promp_meta_loss_terms(int S, int M, const float* stats_all, float inv_m_glob
 int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, void* stream);
 
 /*
+ * Logged scalars without a host round trip per value (the Trainer reads ONE float64 vector back per iteration):
+ *   promp_phase_log_terms : out7 = AverageDiscountedReturn, AverageReturn, NumTrajs, StdReturn, MaxReturn, MinReturn
+ *                           (samplers/base.py:135-149, from the stats [M,8] of promp_process_samples; n_paths = total
+ *                           number of paths of the phase) and AveragePolicyStd = mean exp(log_std [M,Da])
+ *                           (policies/gaussian_mlp_policy.py:118-123).
+ *   promp_promp_log_terms : out3 = LossBefore, LossAfter, KLInner (pro_mp.py:193-198) from the optimizer's device vector
+ *                           [loss_before, loss_after, inner KLs (num_inner_steps), outer KL].
+ */
+int promp_phase_log_terms(int M, int act_dim, double n_paths, const double* stats, const float* log_std, double* out7, void* stream);
+int promp_promp_log_terms(int num_inner_steps, const float* final_terms, double* out3, void* stream);
+
+/*
  * tf.train.AdamOptimizer step as used by MAMLFirstOrderOptimizer.optimize
  * (optimizers/maml_first_order_optimizer.py:48-64, 102-107):
  *   t += 1; lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g^2;

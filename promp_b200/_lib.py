@@ -49,6 +49,8 @@ _SIGNATURES = {
     'promp_policy_hvp_ragged': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                         c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
     'promp_meta_loss_terms': (c_int, [c_int, c_int, _P, c_float, _P, c_int, _P, _P]),
+    'promp_phase_log_terms': (c_int, [c_int, c_int, c_double, _P, _P, _P, _P]),
+    'promp_promp_log_terms': (c_int, [c_int, _P, _P, _P]),
     'promp_reduce_tasks': (c_int, [c_int, c_int, _P, c_float, _P, _P]),
     'promp_adam_tf1': (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
     'promp_vec_axpy': (c_int, [c_int, c_float, _P, _P, _P, _P]),

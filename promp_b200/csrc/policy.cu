@@ -950,6 +950,56 @@ __global__ void __launch_bounds__(256) meta_loss_terms_kernel(int S, int M, cons
     }
 }
 
+// Logged scalars of one sampling phase as float64, straight into the vector the Trainer reads back once per iteration:
+//   out[0..5] = AverageDiscountedReturn, AverageReturn, NumTrajs, StdReturn, MaxReturn, MinReturn (samplers/base.py:135-149)
+//               from the per-task sums promp_process_samples left in stats [M, 8],
+//   out[6]    = AveragePolicyStd = mean exp(log_std) (policies/gaussian_mlp_policy.py:118-123).
+// One launch instead of ~15 reduce / elementwise / cat kernels per phase.
+__global__ void __launch_bounds__(256) phase_log_terms_kernel(int M, int Da, double n_paths, const double* __restrict__ stats,
+                                                               const float* __restrict__ log_std, double* __restrict__ out) {
+    __shared__ double red[8][6];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double v[6] = {0.0, 0.0, 0.0, -1e300, 1e300, 0.0};      // sum R0, sum G, sum G^2, max G, min G, sum exp(log_std)
+    for (int m = tid; m < M; m += 256) {
+        const double* st = stats + (int64_t)m * 8;
+        v[0] += st[0]; v[1] += st[1]; v[2] += st[2];
+        v[3] = fmax(v[3], st[3]);
+        v[4] = fmin(v[4], st[4]);
+    }
+    for (int i = tid; i < M * Da; i += 256) v[5] += (double)expf(log_std[i]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = k == 3 ? warp_max(v[k]) : k == 4 ? warp_min(v[k]) : warp_sum(v[k]);
+    if (lane == 0)
+        for (int k = 0; k < 6; ++k) red[w][k] = v[k];
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; ++i) {
+            v[0] += red[i][0]; v[1] += red[i][1]; v[2] += red[i][2]; v[5] += red[i][5];
+            v[3] = fmax(v[3], red[i][3]);
+            v[4] = fmin(v[4], red[i][4]);
+        }
+        const double mean_g = v[1] / n_paths;
+        out[0] = v[0] / n_paths;
+        out[1] = mean_g;
+        out[2] = n_paths;
+        out[3] = sqrt(fmax(v[2] / n_paths - mean_g * mean_g, 0.0));
+        out[4] = v[3];
+        out[5] = v[4];
+        out[6] = v[5] / (double)(M * Da);
+    }
+}
+
+// ProMP's logged scalars (pro_mp.py:193-198) from the optimizer's device vector [loss_before, loss_after, inner KLs.., outer KL]
+__global__ void promp_log_terms_kernel(int S1, const float* __restrict__ final_terms, double* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        out[0] = (double)final_terms[0];
+        out[1] = (double)final_terms[1];
+        float s = 0.f;
+        for (int i = 0; i < S1; ++i) s += final_terms[2 + i];
+        out[2] = S1 > 0 ? (double)(s / (float)S1) : 0.0;
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 static int g_use_tc = 1;     // promp_set_option("tensor_cores", 0|1): HID = 64 policy kernels on tcgen05 (default) or CUDA cores
 
@@ -1200,6 +1250,21 @@ extern "C" int promp_meta_loss_terms(int S, int M, const float* stats_all, float
                   "promp_meta_loss_terms: bad arguments (1 <= S <= 7 sampling phases, 1 <= n_out <= S+1)");
     meta_loss_terms_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(S, M, stats_all, inv_m_global, coeff, n_out, out);
     PROMP_LAUNCH_CHECK("meta_loss_terms_kernel");
+    return PROMP_OK;
+}
+
+extern "C" int promp_phase_log_terms(int M, int act_dim, double n_paths, const double* stats, const float* log_std, double* out7,
+                                     void* stream) {
+    PROMP_REQUIRE(M > 0 && act_dim > 0 && n_paths > 0 && stats && log_std && out7, "promp_phase_log_terms: bad arguments");
+    phase_log_terms_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(M, act_dim, n_paths, stats, log_std, out7);
+    PROMP_LAUNCH_CHECK("phase_log_terms_kernel");
+    return PROMP_OK;
+}
+
+extern "C" int promp_promp_log_terms(int num_inner_steps, const float* final_terms, double* out3, void* stream) {
+    PROMP_REQUIRE(num_inner_steps >= 0 && final_terms && out3, "promp_promp_log_terms: bad arguments");
+    promp_log_terms_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num_inner_steps, final_terms, out3);
+    PROMP_LAUNCH_CHECK("promp_log_terms_kernel");
     return PROMP_OK;
 }
 

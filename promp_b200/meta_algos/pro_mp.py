@@ -40,16 +40,22 @@ class ProMP(MAMLAlgo):
     LOG_KEYS = ('LossBefore', 'LossAfter', 'KLInner')
     FUSED_LOSS_TERMS = True      # loss_terms(res, out=, n_out=) is one promp_meta_loss_terms launch
 
-    def optimize_phases(self, phases):
-        """optimize_policy on PhaseData objects, everything left on the device.  Returns the float64 device vector
-        [LossBefore, LossAfter, KLInner] for the CUDA-graph Trainer."""
+    def optimize_phases(self, phases, out=None, want_terms=True):
+        """optimize_policy on PhaseData objects, everything left on the device.  The float64 vector [LossBefore, LossAfter,
+        KLInner] for the CUDA-graph Trainer is written into `out` (one tiny launch) when given, else returned."""
         import torch
         assert not self.adaptive_inner_kl_penalty, "adaptive KL coefficient is a host decision: not graph-capturable"
         stats = self.optimizer.optimize(self, phases)
         self.last_stats_device = stats
         self._last_stats = None
         S1 = self.num_inner_grad_steps
-        return torch.stack([stats[0], stats[1], stats[2:2 + S1].mean()]).double()
+        ret = None
+        if not want_terms:
+            return None
+        if out is None:
+            out = ret = torch.empty(3, dtype=torch.float64, device=stats.device)
+        _lib.call('promp_promp_log_terms', S1, _lib.ptr(stats), _lib.ptr(out), _lib.stream())
+        return ret
 
     def optimize_policy(self, all_samples_data, log=True):
         """ProMP.optimize_policy (pro_mp.py:165-199): K Adam epochs on the same data, then a stats pass."""

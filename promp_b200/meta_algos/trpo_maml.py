@@ -117,7 +117,7 @@ class TRPOMAML(MAMLAlgo):
         # reads per iteration) is used there
         return not self.exploration and world_size() == 1
 
-    def optimize_phases(self, phases):
+    def optimize_phases(self, phases, out=None, want_terms=True):
         """optimize_policy on PhaseData objects up to the verdict on the first line-search group, everything left on the
         device: the CUDA-graph Trainer captures this and reads the float64 result vector back with its logged scalars; if
         the verdict is `need_more` (rare) post_replay() finishes the backtracking eagerly."""

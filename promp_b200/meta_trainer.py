@@ -10,6 +10,7 @@ import time
 
 import numpy as np
 
+from promp_b200 import _lib
 from promp_b200.utils import logger
 
 
@@ -107,8 +108,10 @@ class Trainer(object):
 
         def device_part():
             policy.switch_to_pre_update()
-            phases, terms = [], []
+            phases = []
             del keys[:]
+            logvec = state.get('logvec')          # one float64 device vector holds every logged scalar of the iteration
+            off = 0
             for step in range(S):
                 phase = PhaseData(M, E, H, sampler.spec['obs_dim'], sampler.spec['act_dim'], sampler.device)
                 sampler.rollout_into(phase, sampler._static_init[step] if numpy_resets else None, None)
@@ -116,24 +119,27 @@ class Trainer(object):
                 phases.append(phase)
                 if log:
                     prefix = 'Step_%d-' % step
-                    terms.append(proc.device_log_terms(phase))
+                    # six path statistics + AveragePolicyStd in one launch, written in place
+                    _lib.call('promp_phase_log_terms', M, phase.act_dim, float(M * E), _lib.ptr(phase.stats), _lib.ptr(phase.log_std),
+                              _lib.ptr(logvec[off:off + 7]), _lib.stream())
                     keys.extend(prefix + k for k in proc.PATH_STAT_KEYS)
+                    keys.append(prefix + 'AveragePolicyStd')
+                    off += 7
                     env_terms = inner_env.device_log_terms(phase)
                     if env_terms is not None:
-                        terms.append(env_terms)
+                        logvec[off:off + env_terms.numel()].copy_(env_terms)
                         keys.extend(prefix + k for k in inner_env.DEVICE_LOG_KEYS)
-                    terms.append(policy.device_log_terms(phase))
-                    keys.append(prefix + 'AveragePolicyStd')
+                        off += env_terms.numel()
                 if step < self.num_inner_grad_steps:
                     algo.adapt_phase(phase)
-            algo_terms = algo.optimize_phases(phases)
+            n_algo = len(algo.LOG_KEYS)
+            algo_terms = algo.optimize_phases(phases, out=logvec[off:off + n_algo] if log else None, want_terms=log)
             if log:
-                terms.append(algo_terms)
+                if algo_terms is not None:        # algorithms without an in-place writer return their float64 terms
+                    logvec[off:off + n_algo].copy_(algo_terms)
                 keys.extend(algo.LOG_KEYS)
-                vec = torch.cat(terms)
-                if 'pinned' not in state:
-                    state['pinned'] = torch.empty(vec.numel(), dtype=torch.float64).pin_memory()
-                state['pinned'].copy_(vec, non_blocking=True)        # the ONE device->host copy of the iteration
+                off += n_algo
+                state['pinned'][:off].copy_(logvec[:off], non_blocking=True)   # the ONE device->host copy of the iteration
             state['phases'] = phases
 
         # The warm-up passes below are REAL meta-iterations (they size the allocator pools and JIT nothing, but they do train
@@ -145,6 +151,11 @@ class Trainer(object):
         saved = dict(theta=policy.theta.clone(), np_state=np.random.get_state(),
                      phase_counter_dev=sampler._phase_counter_dev.clone(),
                      adam=[t.clone() for t in (opt.m, opt.v, opt.step)] if hasattr(opt, 'm') else None)
+        if log:
+            n_env_keys = len(getattr(inner_env, 'DEVICE_LOG_KEYS', ()))
+            n_log = S * (7 + n_env_keys) + len(algo.LOG_KEYS)
+            state['logvec'] = torch.zeros(n_log, dtype=torch.float64, device=sampler.device)
+            state['pinned'] = torch.zeros(n_log, dtype=torch.float64).pin_memory()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
