@@ -251,7 +251,7 @@ class Trainer(object):
             else:
                 self.train_iteration(itr)
             logger.logkv('Time', time.time() - start)
-            logger.save_itr_params(itr, self.get_itr_snapshot(itr))
+            logger.save_itr_params(itr, lambda itr=itr: self.get_itr_snapshot(itr))     # built only when a file is due
             logger.dumpkvs()
         logger.log("Training finished")
 

@@ -132,9 +132,16 @@ class MetaSampler(object):
         inner = getattr(self.env, '_wrapped_env', self.env)
         sd, td = self.spec['state_dim'], self.spec['task_dim']
         if getattr(self, '_pinned_init', None) is None or len(self._pinned_init[0]) != n_phases:
-            self._static_init = [torch.empty(M, E, sd, dtype=torch.float32, device=self.device) for _ in range(n_phases)]
-            self._pinned_init = [[torch.empty(M, E, sd, dtype=torch.float32).pin_memory() for _ in range(n_phases)] for _ in range(2)]
-            self._pinned_tasks = [torch.empty(M, td, dtype=torch.float32).pin_memory() for _ in range(2)]
+            # ONE device buffer / ONE pinned buffer per slot hold [tasks | reset states of every phase]: a single H2D copy per
+            # iteration; the rollout kernels read views of the device buffer (stable addresses: CUDA-graph safe)
+            n_task, n_init = (M * td + 3) // 4 * 4, (M * E * sd + 3) // 4 * 4       # 16-byte aligned sections
+            self._static_all = torch.empty(n_task + n_phases * n_init, dtype=torch.float32, device=self.device)
+            self._pinned_all = [torch.empty(n_task + n_phases * n_init, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._static_init = [self._static_all[n_task + s * n_init:n_task + s * n_init + M * E * sd].view(M, E, sd) for s in range(n_phases)]
+            self._pinned_init = [[pa[n_task + s * n_init:n_task + s * n_init + M * E * sd].view(M, E, sd) for s in range(n_phases)]
+                                 for pa in self._pinned_all]
+            self._pinned_tasks = [pa[:M * td].view(M, td) for pa in self._pinned_all]
+            self.vec_env.task_params_per_task = self._static_all[:M * td].view(M, td)
             self._staged_tasks = [None, None]
             self._upload_done = [None, None]
         if self._upload_done[slot] is not None:
@@ -155,16 +162,14 @@ class MetaSampler(object):
         ve.tasks = self._staged_tasks[slot]
         if len(ve.tasks):
             self.env.set_task(ve.tasks[-1])
-        ve.task_params_per_task.copy_(self._pinned_tasks[slot], non_blocking=True)
+        self._static_all.copy_(self._pinned_all[slot], non_blocking=True)      # tasks + all reset states: one H2D copy
         ve._per_env_tasks_stale = True      # the per-env expansion (stepwise path only) is rebuilt on demand
-        n_phases = len(self._static_init)
-        for s in range(n_phases):
-            self._static_init[s].copy_(self._pinned_init[slot][s], non_blocking=True)
         import torch
         if self._upload_done[slot] is None:
             self._upload_done[slot] = torch.cuda.Event()
         self._upload_done[slot].record()       # draw_host_inputs(slot) waits on this before reusing the pinned buffers
         M, E = self.meta_batch_size, self.envs_per_task
+        n_phases = len(self._static_init)
         return 4 * (M * self.spec['task_dim'] + n_phases * M * E * self.spec['state_dim'])
 
     def stage_host_inputs(self, n_phases):

@@ -211,8 +211,22 @@ def load_snapshot(path):
             return pickle.load(f)
 
 
+def snapshot_due(itr):
+    """True when save_itr_params(itr, ...) would write a file (lets the Trainer skip building the snapshot - device->host
+    copies of the parameters and optimizer slots - on the iterations that are not saved)."""
+    if not _S.dir:
+        return False
+    mode, gap = _S.snapshot_mode, _S.snapshot_gap
+    if mode in ('all', 'last'):
+        return True
+    if mode in ('gap', 'last_gap'):
+        return itr % gap == 0
+    return False
+
+
 def save_itr_params(itr, params):
-    """ref logger.py:376-396: snapshot_mode all / last / gap / last_gap / none."""
+    """ref logger.py:376-396: snapshot_mode all / last / gap / last_gap / none.  `params` may be a zero-argument callable
+    that builds the snapshot; it is only called when a file is written."""
     if not _S.dir:
         return None
     mode, gap = _S.snapshot_mode, _S.snapshot_gap
@@ -232,5 +246,5 @@ def save_itr_params(itr, params):
     if name is None:
         return None
     path = osp.join(_S.dir, name)
-    _dump(params, path)
+    _dump(params() if callable(params) else params, path)
     return path
