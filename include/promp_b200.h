@@ -127,6 +127,36 @@ int promp_env_step(int env_kind, int reward_type, float sparse_radius, int norma
 int promp_env_observe(int env_kind, int n_env, const float* state, float* obs, void* stream);
 
 /*
+ * Early-terminating envs in the fused rollout (MetaPointEnv, envs/point_envs/point_env_2d.py:9-59: done when the point is
+ * within 0.01 of the origin; tests/test_integration.py) - replaces the reference's collect-until-enough loop
+ * (samplers/meta_sampler.py:87-137 with vectorized_env_executor.py:25-52) without one host round trip per env step:
+ *
+ * promp_rollout_early_term: like promp_rollout, but every env slot records a TIMELINE of `timeline_len` steps
+ *   (obs/act/mean [M,E,T,.], rew [M,E,T], done [M,E,T] u8); a path ends when the env reports done or after `horizon` steps;
+ *   the slot is reset at once (U(-2,2)^2 from Philox keyed by (env, step) - the host numpy stream cannot be followed when the
+ *   number of resets is data-dependent) and the next recorded observation is the reset state.  timeline_len >= 2*horizon - 1
+ *   guarantees that promp_paths_finalize finds enough completed samples.
+ * promp_paths_finalize: applies the reference's rule to the timelines: t* = first step at which the paths completed so far
+ *   hold >= target_samples (= M*E*H) samples; task m keeps the paths completing at steps <= t*, in (step, env index) order
+ *   (meta_sampler.py:116-125); unfinished paths are dropped.  Outputs the per-task path table of
+ *   promp_process_samples_ragged (path_off [M, max_paths+1], n_paths [M], n_valid [M]; max_paths >= E*timeline_len is always
+ *   enough) and the compacted ragged tensors obs/act/mean [M, max_samples, .], rew, done [M, max_samples]
+ *   (max_samples >= E*timeline_len).  src_slot / src_start [M, max_paths]: where every path came from.  cut_out int32[2] =
+ *   {t*, target reached}.  workspace: promp_paths_workspace_bytes, zero-filled before first use (left zero).
+ */
+int promp_rollout_early_term(int env_kind, int normalize_actions, int M, int E, int timeline_len, int horizon, int hidden,
+                             const float* params, int64_t param_stride, const float* task_params, const float* init_state,
+                             const float* noise, uint64_t seed, uint64_t stream_id, const uint64_t* stream_id_dev,
+                             int clip_reported_log_std, float min_log_std, float* obs, float* act, float* mean, float* rew,
+                             uint8_t* done, float* log_std_out, void* stream);
+int64_t promp_paths_workspace_bytes(int M, int E, int timeline_len);
+int promp_paths_finalize(int M, int E, int timeline_len, int max_paths, int max_samples, int obs_dim, int act_dim,
+                         int64_t target_samples, const uint8_t* t_done, const float* t_obs, const float* t_act, const float* t_mean,
+                         const float* t_rew, int32_t* path_off, int32_t* n_paths, int32_t* n_valid, int32_t* src_slot,
+                         int32_t* src_start, float* obs, float* act, float* mean, float* rew, uint8_t* done, int32_t* cut_out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * MetaSampleProcessor.process_samples (samplers/meta_sample_processor.py:8-49 ->
  * samplers/base.py:99-133): per task discounted returns (utils/utils.py:74-81), LinearFeatureBaseline
  * fit (baselines/linear_baseline.py:55-77, features :101-106) + predict (:17-33), GAE

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 OBJ = os.path.join(ROOT, 'build', 'obj')
 LIB = os.path.join(PKG, 'libpromp_b200.so')
-SOURCES = ('common.cu', 'rollout.cu', 'process.cu', 'policy.cu', 'comm.cu', 'trpo.cu')
+SOURCES = ('common.cu', 'rollout.cu', 'process.cu', 'policy.cu', 'comm.cu', 'trpo.cu', 'paths.cu')
 NVCC_FLAGS = ['-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -35,6 +35,10 @@ struct RolloutArgs {
     float* info;
     float* log_std_out;
     float* final_state;
+    // early-terminating envs (MetaPointEnv): the kernel records a TIMELINE of H steps per env slot; a path ends when the env
+    // reports done or after `horizon` steps, the slot is reset in-kernel (Philox) and keeps stepping.  0: fixed-horizon mode.
+    int early_term;
+    int horizon;
 };
 
 template <int KIND, int HID>
@@ -49,6 +53,7 @@ struct RolloutSmem {
     float st_mean[T_CH * T::DA];
     float st_rew[T_CH];
     float st_info[3 * T_CH];
+    unsigned char st_done[T_CH];
 };
 
 #ifdef PROMP_EXP_CLOCKS
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
     __syncwarp();
 
     const PointCornerCfg pcfg{A.reward_type, A.radius, A.normalized != 0};
+    int path_ts = 0;       // steps taken in the current path (early-termination mode)
 
     RCLK(0);
     for (int t0 = 0; t0 < A.H; t0 += T_CH) {
@@ -287,7 +293,23 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
                 r = point_corner_step(sx, sy, a[0], a[1], task[0], task[1], pcfg);
             } else if (KIND == PROMP_ENV_POINT) {
                 bool dn;
-                r = point_step(sx, sy, a[0], a[1], dn, A.normalized != 0);   // early `done` is ignored by the fused kernel
+                r = point_step(sx, sy, a[0], a[1], dn, A.normalized != 0);
+                if (A.early_term) {
+                    // executor semantics (vectorized_env_executor.py:44-52): ts += 1; done |= ts >= max_path_length; a done
+                    // env is reset at once and the NEXT observation is the reset state (point_env_2d.py:28-36: U(-2,2)^2,
+                    // drawn here from Philox keyed by (env, step) instead of the host numpy stream)
+                    ++path_ts;
+                    const bool fin = dn || path_ts >= A.horizon;
+                    if (lane == 0) S.st_done[tt] = fin ? 1 : 0;
+                    if (fin) {
+                        uint32_t rr[4];
+                        Philox::gen((uint32_t)env_id, (uint32_t)(t0 + tt), (uint32_t)A.stream_id,
+                                    0x53000000u | (uint32_t)((A.stream_id >> 32) & 0xffffffu), A.seed, rr);
+                        sx = -2.0f + 4.0f * u01(rr[0]);
+                        sy = -2.0f + 4.0f * u01(rr[1]);
+                        path_ts = 0;
+                    }
+                }
             } else if (KIND == PROMP_ENV_POINT_WALLS) {
                 r = point_walls_step(sx, sy, a[0], a[1], task, A.reward_type, A.normalized != 0);
             } else if (KIND == PROMP_ENV_POINT_MOMENTUM) {
@@ -327,7 +349,8 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(RolloutArgs A) {
             for (int i = lane; i < nt * DA; i += 32) g[i] = S.st_mean[i];
             if (lane < nt) {
                 A.rew[base + t0 + lane] = S.st_rew[lane];
-                A.done[base + t0 + lane] = (t0 + lane == A.H - 1) ? 1 : 0;   // horizon reset (vectorized_env_executor.py:46-50)
+                // horizon reset (vectorized_env_executor.py:46-50); early-termination mode: the recorded path ends
+                A.done[base + t0 + lane] = A.early_term ? S.st_done[lane] : ((t0 + lane == A.H - 1) ? 1 : 0);
                 if (T::NINFO > 0 && A.info) {
                     const int64_t tot = (int64_t)A.M * A.E * A.H;
                     A.info[base + t0 + lane] = S.st_info[lane];
@@ -485,7 +508,7 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
     PROMP_REQUIRE(reward_type >= 0 && reward_type <= 2, "promp_rollout: bad reward_type %d", reward_type);
     RolloutArgs A{reward_type, sparse_radius, normalize_actions, M, E, H, params, param_stride, task_params, init_state, noise, seed,
                   stream_id, stream_id_dev, clip_reported_log_std, min_log_std, obs, act, mean, rew, done, info, log_std_out,
-                  final_state};
+                  final_state, 0, H};
     cudaStream_t st = (cudaStream_t)stream;
     switch (env_kind) {
         case PROMP_ENV_POINT_CORNER:
@@ -510,6 +533,27 @@ extern "C" int promp_rollout(int env_kind, int reward_type, float sparse_radius,
     }
     set_error("promp_rollout: unknown env_kind %d", env_kind);
     return PROMP_ERR_INVALID_ARG;
+}
+
+// MetaPointEnv (early `done`, point_env_2d.py:9-59) in the fused kernel: every env slot records a timeline of `timeline_len`
+// steps; paths end on done / after `horizon` steps and the slot is reset in-kernel.  promp_paths_finalize then applies the
+// reference's collect-until-enough rule (meta_sampler.py:87-137) to the timelines.
+extern "C" int promp_rollout_early_term(int env_kind, int normalize_actions, int M, int E, int timeline_len, int horizon, int hidden,
+                                        const float* params, int64_t param_stride, const float* task_params,
+                                        const float* init_state, const float* noise, uint64_t seed, uint64_t stream_id,
+                                        const uint64_t* stream_id_dev, int clip_reported_log_std, float min_log_std, float* obs,
+                                        float* act, float* mean, float* rew, uint8_t* done, float* log_std_out, void* stream) {
+    PROMP_REQUIRE(env_kind == PROMP_ENV_POINT, "promp_rollout_early_term: implemented for MetaPointEnv (env_kind %d given)", env_kind);
+    PROMP_REQUIRE(M > 0 && E > 0 && timeline_len > 0 && horizon > 0, "promp_rollout_early_term: sizes must be positive");
+    PROMP_REQUIRE(M <= 65535, "promp_rollout_early_term: M=%d exceeds the grid.y limit 65535", M);
+    PROMP_REQUIRE(params && task_params && obs && act && mean && rew && done && log_std_out,
+                  "promp_rollout_early_term: null pointer argument");
+    PROMP_REQUIRE(hidden == 64 || hidden == 32, "promp_rollout_early_term: hidden size %d unsupported (32 or 64)", hidden);
+    RolloutArgs A{0, 0.f, normalize_actions, M, E, timeline_len, params, param_stride, task_params, init_state, noise, seed,
+                  stream_id, stream_id_dev, clip_reported_log_std, min_log_std, obs, act, mean, rew, done, nullptr, log_std_out,
+                  nullptr, 1, horizon};
+    cudaStream_t st = (cudaStream_t)stream;
+    return hidden == 64 ? launch_rollout<PROMP_ENV_POINT, 64>(A, st) : launch_rollout<PROMP_ENV_POINT, 32>(A, st);
 }
 
 __global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }

@@ -84,6 +84,81 @@ class RaggedPhaseData(PhaseData):
         return int(self.n_paths_host.sum())
 
 
+class DeviceRaggedPhaseData(RaggedPhaseData):
+    """RaggedPhaseData whose path table was built ON THE DEVICE (promp_paths_finalize after a fused early-termination
+    rollout): path_off / n_paths / n_valid are device tensors with worst-case shapes (max_paths = max_samples = E * T per
+    task); their host copies are fetched lazily, only when a caller asks for individual paths or logs path statistics."""
+
+    def __init__(self, M, max_paths, max_samples, obs_dim, act_dim, device):
+        import torch
+        PhaseData.__init__(self, M, 1, max_samples, obs_dim, act_dim, device)
+        self.E, self.H = max_paths, None
+        i32 = dict(dtype=torch.int32, device=device)
+        self.path_off = torch.zeros(M, max_paths + 1, **i32)
+        self.n_paths = torch.zeros(M, **i32)
+        self.n_valid = torch.zeros(M, **i32)
+        self.src_slot = torch.zeros(M, max_paths, **i32)
+        self.src_start = torch.zeros(M, max_paths, **i32)
+        self.cut = torch.zeros(2, **i32)
+        self._host_tables = None
+
+    def _tables(self):
+        if self._host_tables is None:
+            n_paths = self.n_paths.cpu().numpy()
+            self._host_tables = dict(n_paths=n_paths, n_valid=self.n_valid.cpu().numpy(),
+                                     path_off=self.path_off[:, :int(n_paths.max()) + 1].cpu().numpy())
+        return self._host_tables
+
+    def invalidate_host(self):
+        PhaseData.invalidate_host(self)
+
+    n_paths_host = property(lambda self: self._tables()['n_paths'])
+    n_valid_host = property(lambda self: self._tables()['n_valid'])
+    path_off_host = property(lambda self: self._tables()['path_off'])
+
+    @property
+    def path_lens(self):
+        t = self._tables()
+        return [list(np.diff(t['path_off'][m, :t['n_paths'][m] + 1])) for m in range(self.M)]
+
+
+class RaggedLazyPathList(object):
+    """Paths of one task of a DeviceRaggedPhaseData as the list of dicts the reference builds (meta_sampler.py:116-123);
+    the host copy of the path table is fetched on first use."""
+
+    def __init__(self, phase, m):
+        self.phase, self.m = phase, m
+        self._paths = None
+
+    def _get(self):
+        if self._paths is None:
+            p, m = self.phase, self.m
+            off = p.path_off_host[m]
+            out = []
+            for k in range(int(p.n_paths_host[m])):
+                s = slice(int(off[k]), int(off[k + 1]))
+                out.append(dict(observations=p.host('obs')[m, s], actions=p.host('act')[m, s], rewards=p.host('rew')[m, s],
+                                env_infos={}, agent_infos=dict(mean=p.host('mean')[m, s],
+                                                               log_std=np.broadcast_to(p.host('log_std')[m], (s.stop - s.start, p.act_dim)))))
+            self._paths = out
+        return self._paths
+
+    def __len__(self):
+        return len(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __add__(self, other):
+        return list(self._get()) + list(other)
+
+    def __radd__(self, other):
+        return list(other) + list(self._get())
+
+
 class RaggedSamplesData(dict):
     """SamplesData for a RaggedPhaseData: the 8 keys trimmed to the task's n_valid samples."""
 

@@ -11,7 +11,8 @@ from collections import OrderedDict
 import numpy as np
 
 from promp_b200 import _lib
-from promp_b200.samplers.device_data import PhaseData, LazyPath, LazyPathList, PathsMetaBatch
+from promp_b200.samplers.device_data import (PhaseData, LazyPath, LazyPathList, PathsMetaBatch, DeviceRaggedPhaseData,
+                                              RaggedLazyPathList)
 from promp_b200.samplers.vectorized_env_executor import MetaDeviceEnvExecutor
 from promp_b200.utils import logger
 from promp_b200.utils.dist import shard_tasks
@@ -77,12 +78,22 @@ class MetaSampler(object):
         return (self.spec is not None and hasattr(self.policy, 'sampling_params')
                 and self.spec['env_kind'] != _lib.ENV_POINT and self.envs_per_task == self.batch_size)
 
+    def _fused_early_ok(self):
+        """Early-terminating MetaPointEnv through the fused kernel + device-side path table.  Opt-in via reset_mode='device':
+        in-kernel resets cannot follow the host numpy stream (their number is data-dependent), so reset_mode='numpy' keeps the
+        reference's step loop with host draws."""
+        return (self.spec is not None and hasattr(self.policy, 'sampling_params') and self.spec['env_kind'] == _lib.ENV_POINT
+                and self.reset_mode == 'device' and self.envs_per_task == self.batch_size and self.envs_per_task <= 1024)
+
     def obtain_samples(self, log=False, log_prefix=''):
         """meta_sampler.py:59-137."""
         t0 = time.time()
         if self._fused_ok():
             paths = self._obtain_samples_fused()
             policy_time, env_time = 0.0, time.time() - t0      # one fused kernel: not separable
+        elif self._fused_early_ok():
+            paths = self._obtain_samples_fused_early()
+            policy_time, env_time = 0.0, time.time() - t0
         else:
             paths, policy_time, env_time = self._obtain_samples_stepwise()
         self.total_timesteps_sampled += self.total_samples
@@ -208,6 +219,52 @@ class MetaSampler(object):
         cache = {}
         for m in range(M):
             paths[m] = LazyPathList(phase, (m,), cache)
+        paths.phase = phase
+        return paths
+
+    def _obtain_samples_fused_early(self):
+        """Early-terminating env, no host round trip per step: promp_rollout_early_term records a timeline of 2H-1 steps per
+        env slot (paths end on done / horizon, slots reset in-kernel), promp_paths_finalize applies the reference's
+        collect-until-M*E*H-samples rule and path ordering on the device and compacts the kept paths into the ragged layout
+        the processing / policy kernels take."""
+        import torch
+        s = self.spec
+        M, E, H = self.meta_batch_size, self.envs_per_task, self.max_path_length
+        T = 2 * H - 1
+        Do, Da, dev = s['obs_dim'], s['act_dim'], self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        tl = getattr(self, '_timeline', None)
+        if tl is None:
+            tl = self._timeline = dict(obs=torch.empty(M, E, T, Do, **f32), act=torch.empty(M, E, T, Da, **f32),
+                                       mean=torch.empty(M, E, T, Da, **f32), rew=torch.empty(M, E, T, **f32),
+                                       done=torch.empty(M, E, T, dtype=torch.uint8, device=dev),
+                                       ws=torch.zeros(_lib.load().promp_paths_workspace_bytes(M, E, T) // 4 + 2, dtype=torch.int32, device=dev))
+        n_alloc = (E * T + 3) // 4 * 4        # row stride of the ragged tensors (the policy kernels want a multiple of 4)
+        phase = DeviceRaggedPhaseData(M, E * T, n_alloc, Do, Da, dev)
+        params, stride, clip = self.policy.sampling_params()
+        noise = self._injected_noise
+        if noise is not None and not isinstance(noise, torch.Tensor):
+            noise = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float32)).to(dev)
+        init = self._injected_init
+        if init is not None and not isinstance(init, torch.Tensor):
+            init = torch.from_numpy(np.ascontiguousarray(init, dtype=np.float32).reshape(M, E, -1)).to(dev)
+        self._injected_noise = self._injected_init = None
+        self._phase_counter += 1
+        _lib.call('promp_rollout_early_term', s['env_kind'], int(s.get('normalized', False)), M, E, T, H, self.policy.hidden,
+                  _lib.ptr(params), stride, _lib.ptr(self.vec_env.task_params_per_task), _lib.ptr(init), _lib.ptr(noise), self.seed,
+                  self._phase_counter, _lib.ptr(self._phase_counter_dev), clip, float(self.policy.min_log_std), _lib.ptr(tl['obs']),
+                  _lib.ptr(tl['act']), _lib.ptr(tl['mean']), _lib.ptr(tl['rew']), _lib.ptr(tl['done']), _lib.ptr(phase.log_std),
+                  _lib.stream())
+        _lib.call('promp_paths_finalize', M, E, T, E * T, n_alloc, Do, Da, M * E * H, _lib.ptr(tl['done']), _lib.ptr(tl['obs']),
+                  _lib.ptr(tl['act']), _lib.ptr(tl['mean']), _lib.ptr(tl['rew']), _lib.ptr(phase.path_off), _lib.ptr(phase.n_paths),
+                  _lib.ptr(phase.n_valid), _lib.ptr(phase.src_slot), _lib.ptr(phase.src_start), _lib.ptr(phase.obs), _lib.ptr(phase.act),
+                  _lib.ptr(phase.mean), _lib.ptr(phase.rew), _lib.ptr(phase.done), _lib.ptr(phase.cut), _lib.ptr(tl['ws']),
+                  tl['ws'].numel() * 4, _lib.stream())
+        phase.timeline = tl                 # kept for diagnostics / tests (overwritten by the next phase)
+        phase.invalidate_host()
+        paths = PathsMetaBatch()
+        for m in range(M):
+            paths[m] = RaggedLazyPathList(phase, m)
         paths.phase = phase
         return paths
 

@@ -897,6 +897,121 @@ def test_early_terminating_env_end_to_end():
 
 
 @pytest.mark.parametrize('exploration', [False, True])
+def _origin_seeking_policy(torch, M):
+    """theta with mean ~= -10 * obs through the (near-linear) tanh layers and sigma = e^-10: on normalize(MetaPointEnv) the
+    point walks 0.1 per step towards the origin and lands within 0.01 of it -> early `done` after <= 21 steps."""
+    from promp_b200.policies import MetaGaussianMLPPolicy
+    from oracle import tf_cases
+    np.random.seed(0)
+    policy = MetaGaussianMLPPolicy(name="p", obs_dim=2, action_dim=2, meta_batch_size=M, hidden_sizes=(64, 64))
+    par = tf_cases.unflatten(np.zeros(policy.num_params_logical, np.float32), 2, 2, 64)
+    c = 0.01
+    par['mean_network/hidden_0/kernel'][0, 0] = par['mean_network/hidden_0/kernel'][1, 1] = c
+    par['mean_network/hidden_1/kernel'][0, 0] = par['mean_network/hidden_1/kernel'][1, 1] = 1.0
+    par['mean_network/output/kernel'][0, 0] = par['mean_network/output/kernel'][1, 1] = -10.0 / c
+    par['log_std_network/log_std_var'][:] = -10.0
+    policy.set_params(par)
+    return policy
+
+
+def test_fused_early_termination_matches_reference_rule():
+    """MetaPointEnv through promp_rollout_early_term + promp_paths_finalize (reset_mode='device'): the device-built path
+    table and compacted tensors equal a host re-statement of the reference loop (meta_sampler.py:87-137: step all envs, append a
+    path at the step it completes in env order, stop when the completed paths hold >= M*E*H samples, drop unfinished ones)
+    applied to the recorded timelines; env dynamics, in-kernel resets, horizon logic checked on the timelines themselves; the
+    processing kernel and a ProMP step run on the result."""
+    torch = _cuda()
+    from promp_b200.envs import normalize, MetaPointEnv
+    from promp_b200.samplers import MetaSampler, MetaSampleProcessor
+    from promp_b200.baselines import LinearFeatureBaseline
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.samplers.device_data import DeviceRaggedPhaseData
+    M, E, H = 3, 6, 25
+    policy = _origin_seeking_policy(torch, M)
+    env = normalize(MetaPointEnv())
+    sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=E, meta_batch_size=M, max_path_length=H,
+                          reset_mode='device', seed=5)
+    assert sampler._fused_early_ok() and not sampler._fused_ok()
+    sampler.update_tasks()
+    policy.switch_to_pre_update()
+    paths = sampler.obtain_samples()
+    ph = paths.phase
+    assert isinstance(ph, DeviceRaggedPhaseData)
+    tl = ph.timeline
+    T = 2 * H - 1
+    done = tl['done'].cpu().numpy().astype(bool)
+    t_obs, t_act, t_rew = tl['obs'].cpu().numpy(), tl['act'].cpu().numpy(), tl['rew'].cpu().numpy()
+    # ---- timelines: dynamics, done rule, resets
+    for m in range(M):
+        for e in range(E):
+            ts = 0
+            for t in range(T):
+                s = t_obs[m, e, t].astype(np.float64)
+                a_env = np.clip(0.1 * t_act[m, e, t].astype(np.float64), -0.1, 0.1)     # NormalizedEnv map of [-0.1, 0.1]
+                s2 = s + a_env
+                assert abs(t_rew[m, e, t] + np.linalg.norm(s2)) < 1e-5
+                ts += 1
+                want_done = (abs(s2[0]) < 0.01 and abs(s2[1]) < 0.01) or ts >= H
+                assert bool(done[m, e, t]) == want_done, (m, e, t)
+                if t + 1 < T:
+                    nxt = t_obs[m, e, t + 1]
+                    if want_done:
+                        assert np.all(np.abs(nxt) <= 2.0) and np.abs(nxt - s2).max() > 1e-3      # fresh U(-2,2)^2 reset state
+                        ts = 0
+                    else:
+                        np.testing.assert_allclose(nxt, s2, atol=2e-6)
+    assert done.any() and (done.sum(-1) > 1).any()            # early terminations happened (several paths per slot)
+    # ---- host re-statement of the collect-until-enough rule on the same timelines
+    total, n_samples = M * E * H, 0
+    want_paths = [[] for _ in range(M)]
+    start = np.zeros((M, E), dtype=int)
+    t_star = None
+    for t in range(T):
+        for idx in range(M * E):
+            m, e = divmod(idx, E)
+            if done[m, e, t]:
+                want_paths[m].append((e, start[m, e], t + 1 - start[m, e]))
+                n_samples += t + 1 - start[m, e]
+                start[m, e] = t + 1
+        if n_samples >= total:
+            t_star = t
+            break
+    assert t_star is not None
+    cut = ph.cut.cpu().numpy()
+    assert cut[0] == t_star and cut[1] == 1
+    n_paths, n_valid, off = ph.n_paths_host, ph.n_valid_host, ph.path_off_host
+    obs_r, act_r, rew_r, done_r = ph.obs.cpu().numpy(), ph.act.cpu().numpy(), ph.rew.cpu().numpy(), ph.done.cpu().numpy()
+    for m in range(M):
+        assert n_paths[m] == len(want_paths[m]) and n_valid[m] == sum(p[2] for p in want_paths[m])
+        pos = 0
+        for k, (e, s0, L) in enumerate(want_paths[m]):
+            assert off[m, k] == pos and off[m, k + 1] == pos + L
+            np.testing.assert_array_equal(obs_r[m, pos:pos + L], t_obs[m, e, s0:s0 + L])
+            np.testing.assert_array_equal(act_r[m, pos:pos + L], t_act[m, e, s0:s0 + L])
+            np.testing.assert_array_equal(rew_r[m, pos:pos + L], t_rew[m, e, s0:s0 + L])
+            assert done_r[m, pos + L - 1] == 1 and done_r[m, pos:pos + L - 1].sum() == 0
+            pos += L
+        # the lazy per-task path list the reference-shaped callers see
+        assert len(paths[m]) == len(want_paths[m])
+        np.testing.assert_array_equal(paths[m][0]['observations'], t_obs[m, want_paths[m][0][0], :want_paths[m][0][2]])
+    assert int(n_valid.sum()) >= total and int(n_valid.sum()) - total < M * E * H      # enough, not everything
+    # ---- downstream kernels take the device-built ragged phase
+    proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
+    samples = proc.process_samples(paths, log='all', log_prefix='x-')
+    adv = ph.adv.cpu().numpy()
+    for m in range(M):
+        a = adv[m, :n_valid[m]]
+        assert np.isfinite(a).all() and abs(a.mean()) < 1e-4 and abs(a.std() - 1) < 1e-3
+    algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3, num_ppo_steps=2,
+                 clip_eps=0.3, init_inner_kl_penalty=5e-4, adaptive_inner_kl_penalty=False)
+    algo._adapt(samples)
+    paths2 = sampler.obtain_samples()
+    samples2 = proc.process_samples(paths2)
+    algo.optimize_policy([samples, samples2], log=False)
+    assert torch.isfinite(policy.theta).all() and np.isfinite(algo.last_stats['loss_after'])
+
+
+@pytest.mark.parametrize('exploration', [False, True])
 def test_vpg_maml_matches_oracle(exploration):
     """VPGMAML (ref meta_algos/vpg_maml.py): meta objective / gradient and the single TF1-Adam step."""
     torch = _cuda()
