@@ -898,8 +898,9 @@ def test_early_terminating_env_end_to_end():
 
 @pytest.mark.parametrize('exploration', [False, True])
 def _origin_seeking_policy(torch, M):
-    """theta with mean ~= -10 * obs through the (near-linear) tanh layers and sigma = e^-10: on normalize(MetaPointEnv) the
-    point walks 0.1 per step towards the origin and lands within 0.01 of it -> early `done` after <= 21 steps."""
+    """theta with mean ~= -100 * obs through the (near-linear) tanh layers and sigma = e^-10: on normalize(MetaPointEnv)
+    (a_env = clip(0.01 a, +-0.1), envs/normalized_env.py:109-114) the point walks 0.1 per step towards the origin and lands
+    within 0.01 of it -> early `done` after <= 21 steps."""
     from promp_b200.policies import MetaGaussianMLPPolicy
     from oracle import tf_cases
     np.random.seed(0)
@@ -908,7 +909,7 @@ def _origin_seeking_policy(torch, M):
     c = 0.01
     par['mean_network/hidden_0/kernel'][0, 0] = par['mean_network/hidden_0/kernel'][1, 1] = c
     par['mean_network/hidden_1/kernel'][0, 0] = par['mean_network/hidden_1/kernel'][1, 1] = 1.0
-    par['mean_network/output/kernel'][0, 0] = par['mean_network/output/kernel'][1, 1] = -10.0 / c
+    par['mean_network/output/kernel'][0, 0] = par['mean_network/output/kernel'][1, 1] = -100.0 / c
     par['log_std_network/log_std_var'][:] = -10.0
     policy.set_params(par)
     return policy
@@ -947,7 +948,7 @@ def test_fused_early_termination_matches_reference_rule():
             ts = 0
             for t in range(T):
                 s = t_obs[m, e, t].astype(np.float64)
-                a_env = np.clip(0.1 * t_act[m, e, t].astype(np.float64), -0.1, 0.1)     # NormalizedEnv map of [-0.1, 0.1]
+                a_env = np.clip(0.01 * t_act[m, e, t].astype(np.float64), -0.1, 0.1)    # NormalizedEnv map onto [-0.1, 0.1]
                 s2 = s + a_env
                 assert abs(t_rew[m, e, t] + np.linalg.norm(s2)) < 1e-5
                 ts += 1

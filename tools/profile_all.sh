@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 for wl in point cheetah; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$wl.csv python tools/run_iters.py $wl 4 > gpurun_out/ncu_l_$wl.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:"rollout_kernel|process_gram|process_finish|policy_grad|policy_hvp" -s 25 -c 12 -o /tmp/prof_$wl python tools/run_iters.py $wl 3 > gpurun_out/ncu_f_$wl.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"rollout_kernel|process_fused|policy_grad|policy_hvp|meta_update" -s 25 -c 12 -o /tmp/prof_$wl python tools/run_iters.py $wl 3 > gpurun_out/ncu_f_$wl.log 2>&1
   ncu -i /tmp/prof_$wl.ncu-rep --page raw --csv > gpurun_out/raw_$wl.csv 2>/dev/null
   ncu -i /tmp/prof_$wl.ncu-rep --page details --csv > gpurun_out/details_$wl.csv 2>/dev/null
 done
