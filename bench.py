@@ -9,18 +9,26 @@ A "step" is ONE FULL META-ITERATION of the hot path over one batch of synthetic 
   -> ProMP outer step (5 Adam epochs of the second-order meta-gradient + stats pass).
 metric = env-steps/s = (M*E*H*2 env steps per meta-iteration) / (time per meta-iteration), whole job.
 
-  value : device-resident loop (reset states drawn in-kernel, nothing logged to the host), CUDA events.
-  e2e   : the same iteration through the reference-facing API (Trainer.train_iteration with logging):
-          every sampling phase copies host-drawn tasks + reset states H2D and reads the logged
-          statistics D2H, as the unchanged reference Trainer would.
-  roofline     : dominant kernel (policy_hvp_kernel), algorithmic bytes / CUDA-event time vs the measured
-                 HBM peak (MEASURED_PEAKS.json).  NOTE: that kernel is fp32-FMA bound (AI ~ 500 FLOP/B), so
-                 the HBM fraction is small by construction; `fp32_tflops` gives the compute-side view.
+  value : device-resident loop (reset states drawn in-kernel, nothing logged to the host), CUDA events, one CUDA-graph replay
+          of the ~29 launches of a meta-iteration per step.
+  e2e   : the same iteration through the DEFAULT entry point of a run script, promp_b200.meta_trainer.Trainer(...).train():
+          per iteration numpy-drawn tasks + reset states (reference RNG order) -> pinned -> ONE H2D copy, graph replay (captured
+          automatically), ONE D2H of the logged scalars, every reference logger key emitted, logger.dumpkvs().
+          e2e.eager = Trainer(use_cuda_graph=False).train_iteration(itr, log=True): what configurations with a host decision
+          inside the iteration get.
+  other_configs : short measurements, in the same run and through Trainer.train(), of the other BASELINE.json configurations:
+          HalfCheetah surrogate (configs[2] per GPU = configs[4] at N = 8, weak scaling) and MAML-TRPO on PointEnv (configs[3]:
+          40 tasks in total, STRONG scaling over the N GPUs).
+  roofline     : dominant kernel (policy_grad / policy_hvp).  These kernels are issue / latency-bound (AI ~ 1 kFLOP/B, inputs
+                 L2-resident): bound = "issue", achieved / peak / frac = algorithmic fp32 TFLOP/s over the fp32-SIMT peak; the HBM
+                 view (SURVEY.md 8d bytes per sample / launch time over the MEASURED_PEAKS.json copy bandwidth) is in roofline.hbm,
+                 and the HBM-side stage (process_fused_kernel) in roofline.process_kernel.
   cpu_baseline : the CPU oracle port of the reference (oracle/) on the host cores: numpy half in min(tasks, cores) worker
                  processes (like the reference's parallel=True executor), TF1 half on PyTorch-CPU threads.
 
 --impl reference times the reference's CPU implementation (oracle port: /root/reference is absent on the
-GPU box and TF1 is not installable) on the same metric.
+GPU box and TF1 is not installable) on the same metric; launched for N GPUs it processes 40*N tasks on min(40*N, cores)
+workers, so the N > 1 ratios are like for like.
 """
 import argparse
 import json
@@ -331,9 +339,11 @@ def run_gpu(args):
                 gemm_flops=M * N * 8 * 2 * 64 * 64, ncu='policy_hvp'),
         }
         try:    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (tools/profile_all.sh)
-            km = json.load(open(os.path.join(ROOT, 'profiles', 'r01_kernel_metrics.json')))[args.workload]
+            km_file = [f for f in ('r02_kernel_metrics.json', 'r01_kernel_metrics.json')
+                       if os.path.exists(os.path.join(ROOT, 'profiles', f))][0]
+            km = json.load(open(os.path.join(ROOT, 'profiles', km_file)))[args.workload]
         except Exception:
-            km = {}
+            km_file, km = None, {}
         iter_ms = max(sum(k['total_ms_per_iter'] for k in per_kernel.values()), 1e-9)
         fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
 
@@ -350,7 +360,7 @@ def run_gpu(args):
             return dict(kernel=(kk[0] if kk else a_['ncu'] + '_kernel'), bound='issue', achieved=tfl, peak=fp32_peak, unit='TFLOP/s',
                         frac=tfl / fp32_peak, peak_source='derived: 148 SM x 128 fp32 lanes x 2 x sm_max_mhz (no measured fp32 peak in MEASURED_PEAKS.json)',
                         traffic=traffic,
-                        traffic_source='profiles/r01_kernel_metrics.json (cold-cache ncu replay; in the live loop the inputs are L2 hits)' if kk else None,
+                        traffic_source=('profiles/%s (cold-cache ncu replay; in the live loop the inputs are L2 hits)' % km_file) if kk else None,
                         hbm={'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'peak_source': peak_src,
                              'algorithmic_bytes_per_launch': a_['bytes'],
                              'bytes_rule': 'SURVEY.md 8(d): 4*(Do+2*Da+1) B per sample per launch x M*N samples'},

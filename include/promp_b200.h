@@ -329,6 +329,23 @@ int promp_policy_grad_ragged(int obs_dim, int act_dim, int hidden, int M, int N,
                              int clip_log_std, float min_log_std,
                              float* grad, float* out_params, float sgd_lr, float* stats,
                              void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * promp_policy_grad_ragged plus launch re-use (n_valid may be NULL): the inner pass of the first Adam epoch of
+ * optimize_policy repeats MAMLAlgo._adapt exactly - same theta, same phase-0 data - unless the reported-log_std clip of the
+ * step-0 graph (policies/gaussian_mlp_policy.py:71) is active.
+ *   producer (the _adapt launch): unclipped_out (device int32) = 1 iff every log_std component >= min_log_std;
+ *                                 theta_copy_out [P] = the parameters the launch used.
+ *   consumer (epoch-1 inner pass, SAME output buffers as the producer): if *skip_flag != 0 and params == skip_theta bit for bit
+ *                                 the whole grid returns at once (its outputs are already correct); else it runs normally.
+ * Both pairs may be NULL; only defined for param_stride == 0.
+ */
+int promp_policy_grad_ex(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid, const float* params,
+                         int64_t param_stride, const float* obs, const float* act, const float* adv, const float* old_mean,
+                         const float* old_log_std, int ls_per_sample, int obj_kind, float obj_scale, float clip_eps,
+                         float kl_coeff, int clip_log_std, float min_log_std, float* grad, float* out_params, float sgd_lr,
+                         float* stats, const int32_t* skip_flag, const float* skip_theta, int32_t* unclipped_out,
+                         float* theta_copy_out, void* workspace, int64_t workspace_bytes, void* stream);
 int promp_policy_hvp_ragged(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid,
                             const float* params, int64_t param_stride,
                             const float* obs, const float* act, const float* adv,

@@ -51,6 +51,8 @@ _SIGNATURES = {
                                  c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
     'promp_policy_grad_ragged': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                          c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, c_int64, _P]),
+    'promp_policy_grad_ex': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
+                                     c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     'promp_policy_hvp_ragged': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                         c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
     'promp_meta_loss_terms': (c_int, [c_int, c_int, _P, c_float, _P, c_int, _P, _P]),

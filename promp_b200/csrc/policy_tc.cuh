@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
     const int qd = warp & 3, cq = warp >> 2;               // TMEM lane quadrant, column group
     const int r = qd * 32 + lane, c0 = CW * cq;          // row / column-group role: sample row r, hidden units [c0, c0+32)
     const int cj = tid & (HID - 1), cp = tid / HID;        // column role
+    if (grad_reuse_prologue<L::P, L::LS, DA>(A)) return;    // before any TMEM allocation / barrier initialisation
     const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)

@@ -130,7 +130,7 @@ __device__ __forceinline__ double ordered_sum_ldcg(const double* p, int cnt, int
 // issued before the dependent DFMA chain, (iii) the Cholesky uses one rsqrt per column and multiplies by stored inverse
 // pivots, (iv) partials written by other CTAs are fetched with batched independent loads.
 template <bool STAGE_F, bool STAGE_L>
-__global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
+__global__ void __launch_bounds__(PS_THREADS, 3) process_fused_kernel(ProcArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int E = n_paths_of(A, m), H = A.H, Do = A.Do, NS = A.NS;
@@ -147,12 +147,14 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
     __shared__ unsigned char s_def[PS_MAXCOL];
     __shared__ double s_inv[PS_MAXCOL];
 
-    // dynamic shared memory: [red | tt_s | tile x2 | rest]; front rest = [val | rewf | obs ring], finish rest = [A | L | w |
-    // bval | rall] (the predict stage re-uses tile..L as its observation ring)
-    double* red = reinterpret_cast<double*>(smem_raw);      // 256 x 8: Gram group reduction / block_reduce scratch / tw table
-    double* tt_s = red + PS_THREADS * 8;                     // A.tt_cap (even) time features t/100
+    // dynamic shared memory: [tt_s | U | rest].  U is a union of the two feature-tile buffers (Gram loop) and the 256 x 8
+    // reduction scratch (used before / after the loop, and by the moments at the very end); front rest = [val | rewf | obs
+    // ring], finish rest = [A | L | w | bval | rall]; the predict stage re-uses U..L as its observation ring and turns the
+    // time-feature table into the time part of the prediction in place.
+    double* tt_s = reinterpret_cast<double*>(smem_raw);     // A.tt_cap (even) time features t/100
     double* tile = tt_s + A.tt_cap;                          // 2 x (PS_TS x NCP) feature rows, double-buffered
-    double* rest = tile + 2 * PS_TS * NCP;
+    double* red = tile;                                      // 256 x 8: Gram group reduction / block_reduce scratch
+    double* rest = tile + max(2 * PS_TS * NCP, PS_THREADS * 8);
     __shared__ __align__(8) uint64_t s_bar_g[PS_RING], s_bar_p[2];
 
 #ifdef PROMP_EXP_CLOCKS
@@ -250,41 +252,24 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         const int s_row = tid >> 3, part = tid & 7;          // feature rows: thread (sample s_row, column part)
-        constexpr int RAWMAX = (PS_MAXCOL + 7) / 8;          // columns per thread
-        float raw[RAWMAX];
-        int raw_step = 0;
-        // raw inputs of one tile row -> registers (global loads in flight while the previous tile is being multiplied)
-        auto fetch = [&](int n0) {
-            const int tn = min(PS_TS, ns - n0);
-            if (s_row < tn) {
-                const int n = n_lo + n0 + s_row;
-                raw_step = tpos ? tpos[n] : n % H;
-                const float* o = obs + (int64_t)n * Do;
-#pragma unroll
-                for (int k = 0; k < RAWMAX; ++k) {
-                    const int col = part + 8 * k;
-                    raw[k] = col < 2 * Do ? __ldg(o + (col < Do ? col : col - Do)) : 0.f;
-                }
-            }
-        };
+        // generic tile builder (no TMA: unaligned sources, partial last tile): feature rows straight from global memory
         auto build = [&](int n0, double* dst) {
             const int tn = min(PS_TS, ns - n0);
             if (s_row < tn) {
-                const double tt = raw_step < A.tt_cap ? tt_s[raw_step] : (double)raw_step / 100.0;
-#pragma unroll
-                for (int k = 0; k < RAWMAX; ++k) {
-                    const int col = part + 8 * k;
-                    if (col < NCP) {
-                        double v;
-                        if (col < 2 * Do) {
-                            const double cl = fmin(fmax((double)raw[k], -10.0), 10.0);
-                            v = col < Do ? cl : cl * cl;
-                        } else {
-                            const int kk = col - 2 * Do;      // t, t^2, t^3, 1, target, zero padding
-                            v = kk == 0 ? tt : kk == 1 ? tt * tt : kk == 2 ? tt * tt * tt : kk == 3 ? 1.0 : kk == 4 ? val[n0 + s_row] : 0.0;
-                        }
-                        dst[s_row * NCP + col] = v;
+                const int n = n_lo + n0 + s_row;
+                const int step = tpos ? tpos[n] : n % H;
+                const double tt = step < A.tt_cap ? tt_s[step] : (double)step / 100.0;
+                const float* o = obs + (int64_t)n * Do;
+                for (int col = part; col < NCP; col += 8) {
+                    double v;
+                    if (col < 2 * Do) {
+                        const double cl = fmin(fmax((double)__ldg(o + (col < Do ? col : col - Do)), -10.0), 10.0);
+                        v = col < Do ? cl : cl * cl;
+                    } else {
+                        const int kk = col - 2 * Do;      // t, t^2, t^3, 1, target, zero padding
+                        v = kk == 0 ? tt : kk == 1 ? tt * tt : kk == 2 ? tt * tt * tt : kk == 3 ? 1.0 : kk == 4 ? val[n0 + s_row] : 0.0;
                     }
+                    dst[s_row * NCP + col] = v;
                 }
             }
         };
@@ -349,24 +334,12 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
             }
             done_tiles = full_tiles;
         }
-        // remaining samples (everything when TMA is not usable): plain loads, one tile ahead in registers
-        {
-            const int n_start = done_tiles * PS_TS;
-            if (n_start < ns) {
-                __syncthreads();
-                fetch(n_start);
-                build(n_start, cur ? tile2 : tile);
-                __syncthreads();
-                for (int n0 = n_start; n0 < ns; n0 += PS_TS) {
-                    const int tn = min(PS_TS, ns - n0);
-                    const bool more = n0 + PS_TS < ns;
-                    if (more) fetch(n0 + PS_TS);
-                    multiply(cur ? tile2 : tile, tn);
-                    if (more) build(n0 + PS_TS, cur ? tile : tile2);
-                    __syncthreads();
-                    cur ^= 1;
-                }
-            }
+        // remaining samples (everything when TMA is not usable): plain loads
+        for (int n0 = done_tiles * PS_TS; n0 < ns; n0 += PS_TS) {
+            __syncthreads();
+            build(n0, tile);
+            __syncthreads();
+            multiply(tile, min(PS_TS, ns - n0));
         }
         PCLK(3);
         // deterministic group reduction (groups added in order g = 0..G-1), two halves of 8 accumulators
@@ -407,7 +380,7 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
     double* Afull = rest;                              // [NCP][NCP]
     const int LD = F | 1;
     double* Lm = Afull + NCP * NCP;                    // [F][LD] lower triangle
-    double* wv = Lm + PS_MAXCOL * (PS_MAXCOL + 1);     // [PS_MAXCOL]
+    double* wv = Lm + F * LD + (F * LD & 1);           // [PS_MAXCOL], 16-byte aligned
     double* bval = STAGE_L ? wv + PS_MAXCOL + 4 : A.ws64 + (int64_t)m * 2 * NS + NS;   // baseline -> advantages, float64
     float* rall = STAGE_L ? reinterpret_cast<float*>(bval + A.finish_cap) : nullptr;
 
@@ -445,46 +418,35 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
         //      solves).  A pivot that vanishes relative to its diagonal entry (only possible with reg_coeff = 0 and collinear
         //      features) marks the column rank-deficient: w_j = 0, which gives the same fitted values as the reference's
         //      minimum-norm lstsq solution (least-squares fits are unique in Phi w).
-        const int row = tid >> 2, q4 = tid & 3;
-        const int chol_threads = ((F + 7) >> 3) * 32;        // 4 lanes per row: only the warps that own rows take part
-        auto chol_sync = [&]() {
-            if (chol_threads == 32) __syncwarp();
-            else asm volatile("bar.sync 1, %0;" ::"r"(chol_threads) : "memory");
-        };
+        const int ti = tid >> 4, tk = tid & 15;             // trailing-update role: rows ti, ti+16, .. x columns tk, tk+16, ..
         for (int attempt = 0; attempt < 5; ++attempt) {
             const double reg = s_reg;
             for (int idx = tid; idx < F * F; idx += PS_THREADS) {
                 const int i = idx / F, j = idx - i * F;
                 if (j <= i) Lm[i * LD + j] = Afull[i * NCP + j] + (i == j ? reg : 0.0);
             }
-            if (tid < PS_MAXCOL) s_def[tid] = 0;
             __syncthreads();
+            // Right-looking Cholesky over the whole CTA: after column j is scaled, all 256 threads apply its outer product
+            // to the trailing triangle, so the critical path per column is one rsqrt + two barriers (every thread derives
+            // the pivot itself from shared memory: no broadcast round; the diagonal keeps d, the solves multiply by 1/sqrt(d)).
             bool bad = false;
-            if (tid < chol_threads) {
-                for (int j = 0; j < F; ++j) {
-                    double s = 0.0;
-                    if (row >= j && row < F)
-                        for (int k = q4; k < j; k += 4) s = fma(Lm[row * LD + k], Lm[j * LD + k], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    if (row == j && q4 == 0) {
-                        const double ajj = Lm[j * LD + j], d = ajj - s;
-                        if (d <= 1e-14 * fabs(ajj) && d == d && ajj == ajj && isfinite(ajj)) {
-                            s_def[j] = 1;
-                            s_piv = 1.0;
-                            s_inv[j] = 0.0;
-                        } else {
-                            const double inv = rsqrt(d);     // d < 0 or NaN input -> NaN -> retry with a larger ridge
-                            s_piv = inv;
-                            s_inv[j] = inv;
-                        }
-                    }
-                    chol_sync();
-                    const double inv = s_piv;
-                    if (!(inv > 0.0) || !isfinite(inv)) bad = true;
-                    if (row > j && row < F && q4 == 0) Lm[row * LD + j] = s_def[j] ? 0.0 : (Lm[row * LD + j] - s) * inv;
-                    chol_sync();
+            for (int j = 0; j < F; ++j) {
+                const double d = Lm[j * LD + j], a_orig = Afull[j * NCP + j] + reg;      // d stays in place: the solves use s_inv
+                const bool deficient = d <= 1e-14 * fabs(a_orig) && d == d && isfinite(a_orig);
+                const double inv = deficient ? 0.0 : rsqrt(d);      // d < 0 or NaN input -> NaN -> retry with a larger ridge
+                if (!deficient && (!(inv > 0.0) || !isfinite(inv))) bad = true;
+                if (tid == j) {
+                    s_inv[j] = inv;
+                    s_def[j] = deficient ? 1 : 0;
+                } else if (tid > j && tid < F) {
+                    Lm[tid * LD + j] *= inv;                          // rank-deficient column -> 0
                 }
+                __syncthreads();                                     // column j scaled
+                for (int i = j + 1 + ti; i < F; i += 16) {
+                    const double lij = Lm[i * LD + j];
+                    for (int k = j + 1 + tk; k <= i; k += 16) Lm[i * LD + k] = fma(-lij, Lm[k * LD + j], Lm[i * LD + k]);
+                }
+                __syncthreads();                                     // trailing triangle updated: next pivot is final
             }
             // forward L z = b, backward L^T w = z on one warp: lane l owns rows l and l+32   (b = Gram column F)
             if (tid < 32) {
@@ -524,19 +486,18 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
             return;
         }
         // ---- predict b_n = phi_n . w (baselines/linear_baseline.py:17-33): the time part of the dot product comes from a
-        //      per-step table (reusing the reduction scratch), the observation part is 2*Do FMAs per sample
-        double* tw = red;                                   // [tt_cap <= 1024] t*w_t + t^2*w_t2 + t^3*w_t3 + w_1
+        //      per-step table (overwriting the t/100 table in place), the observation part is 2*Do FMAs per sample
+        double* tw = tt_s;                                  // [tt_cap] t*w_t + t^2*w_t2 + t^3*w_t3 + w_1, in place over t/100
         __syncthreads();                                    // every thread is done with A / L before they become the ring
         for (int t = tid; t < A.tt_cap; t += PS_THREADS) {
             const double tt = tt_s[t];
             tw[t] = fma(tt, wv[2 * Do], fma(tt * tt, wv[2 * Do + 1], fma(tt * tt * tt, wv[2 * Do + 2], wv[2 * Do + 3])));
         }
         __syncthreads();
-        constexpr int MAXDO = (PS_MAXCOL - 5) / 2;
         auto time_part = [&](int n) {
             const int step = tpos ? tpos[n] : n % H;
             if (step < A.tt_cap) return tw[step];
-            const double tt = (double)step / 100.0;
+            const double tt = (double)step / 100.0;          // beyond the table (very long variable-length paths)
             return fma(tt, wv[2 * Do], fma(tt * tt, wv[2 * Do + 1], fma(tt * tt * tt, wv[2 * Do + 2], wv[2 * Do + 3])));
         };
         // Observations of the whole task stream through a 2-stage TMA ring of A.pred_tile samples (re-using the tile / A / L
@@ -555,13 +516,21 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
                 if (tid < PT) {
                     const float* src = pring + (t & 1) * pfloats + tid * Do;
                     const int n = t * PT + tid;
-                    double b = time_part(n);
-                    for (int i = 0; i < Do; ++i) {
-                        const double cl = fmin(fmax((double)src[i], -10.0), 10.0);
-                        b = fma(cl, wv[i], b);
-                        b = fma(cl * cl, wv[Do + i], b);
+                    double b = time_part(n), b2 = 0.0, b3 = 0.0, b4 = 0.0;      // four chains: the fp64 FMA latency, not its
+                    int i = 0;                                                    // throughput, limits this loop
+                    for (; i + 1 < Do; i += 2) {
+                        const double c0 = fmin(fmax((double)src[i], -10.0), 10.0), c1 = fmin(fmax((double)src[i + 1], -10.0), 10.0);
+                        b = fma(c0, wv[i], b);
+                        b2 = fma(c0 * c0, wv[Do + i], b2);
+                        b3 = fma(c1, wv[i + 1], b3);
+                        b4 = fma(c1 * c1, wv[Do + i + 1], b4);
                     }
-                    bval[n] = b;
+                    if (i < Do) {
+                        const double c0 = fmin(fmax((double)src[i], -10.0), 10.0);
+                        b = fma(c0, wv[i], b);
+                        b2 = fma(c0 * c0, wv[Do + i], b2);
+                    }
+                    bval[n] = (b + b2) + (b3 + b4);
                 }
                 __syncthreads();                  // stage (t & 1) consumed
                 if (tid == 0 && t + 2 < ptiles)
@@ -569,28 +538,15 @@ __global__ void __launch_bounds__(PS_THREADS) process_fused_kernel(ProcArgs A) {
             }
             n_done = ptiles * PT;
         }
-        for (int n = n_done + tid; n < N; n += 2 * PS_THREADS) {      // rest: two samples per thread and step, loads first
-            const int n2 = n + PS_THREADS;
-            const bool two = n2 < N;
-            float oa[MAXDO], ob[MAXDO];
-#pragma unroll
-            for (int i = 0; i < MAXDO; ++i) {
-                oa[i] = i < Do ? __ldg(obs + (int64_t)n * Do + i) : 0.f;
-                ob[i] = (two && i < Do) ? __ldg(obs + (int64_t)n2 * Do + i) : 0.f;
+        for (int n = n_done + tid; n < N; n += PS_THREADS) {      // rest (tail / no TMA): straight from global memory
+            const float* o = obs + (int64_t)n * Do;
+            double b = time_part(n);
+            for (int i = 0; i < Do; ++i) {
+                const double cl = fmin(fmax((double)__ldg(o + i), -10.0), 10.0);
+                b = fma(cl, wv[i], b);
+                b = fma(cl * cl, wv[Do + i], b);
             }
-            double ba = time_part(n), bb = two ? time_part(n2) : 0.0;
-#pragma unroll
-            for (int i = 0; i < MAXDO; ++i) {
-                if (i < Do) {
-                    const double ca = fmin(fmax((double)oa[i], -10.0), 10.0), cb = fmin(fmax((double)ob[i], -10.0), 10.0);
-                    ba = fma(ca, wv[i], ba);
-                    ba = fma(ca * ca, wv[Do + i], ba);
-                    bb = fma(cb, wv[i], bb);
-                    bb = fma(cb * cb, wv[Do + i], bb);
-                }
-            }
-            bval[n] = ba;
-            if (two) bval[n2] = bb;
+            bval[n] = b;
         }
     } else {
         if (A.mode == PS_MODE_FIT_ONLY) return;
@@ -713,11 +669,12 @@ static int proc_tt_cap(int H, int NS, bool ragged) {
 }
 static size_t proc_smem_fixed(int Do, int tt_cap) {
     const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
-    return (size_t)(2 * PS_TS * NCP + PS_THREADS * 8 + tt_cap) * 8;
+    const int u = 2 * PS_TS * NCP > PS_THREADS * 8 ? 2 * PS_TS * NCP : PS_THREADS * 8;      // tiles and scratch share one area
+    return (size_t)(u + tt_cap) * 8;
 }
 static size_t proc_smem_finish_fixed(int Do) {
-    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
-    return (size_t)(NCP * NCP + PS_MAXCOL * (PS_MAXCOL + 1) + PS_MAXCOL + 4) * 8;
+    const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4, F = 2 * Do + 4, LD = F | 1;
+    return (size_t)(NCP * NCP + F * LD + (F * LD & 1) + PS_MAXCOL + 4) * 8;
 }
 struct ProcGeom {
     int C, EPC, chunk_cap, finish_cap, tt_cap, pred_tile;
@@ -739,7 +696,8 @@ static ProcGeom proc_geom_for(int EPC, int E, int H, int Do, int NS, bool ragged
     // predict ring: 2 stages of pred_tile samples inside the (dead) tile / A / L area
     {
         const int NC = 2 * Do + 5, NCP = (NC + 3) / 4 * 4;
-        const size_t avail = (size_t)(2 * PS_TS * NCP + NCP * NCP + PS_MAXCOL * (PS_MAXCOL + 1)) * 8;
+        const int F = 2 * Do + 4, LD = F | 1;
+        const size_t avail = (size_t)(2 * PS_TS * NCP + NCP * NCP + F * LD) * 8;
         g.pred_tile = 0;
         for (int pt = 256; pt >= 32; pt >>= 1)
             if ((size_t)2 * pt * Do * 4 <= avail) { g.pred_tile = pt; break; }

@@ -80,18 +80,21 @@ class MAMLAlgo(object):
         return phase
 
     def _grad(self, phase, params, stride, obj_kind, obj_scale=1.0, clip_eps=0.0, kl_coeff=0.0, clip_log_std=0,
-              grad=None, out_params=None, sgd_lr=0.0, stats=None):
+              grad=None, out_params=None, sgd_lr=0.0, stats=None, produce=None, reuse=None):
+        """One promp_policy_grad launch.  produce / reuse = (flag int32[1], theta copy [P]): the launch re-use protocol of
+        promp_policy_grad_ex (the _adapt launch produces, the identical inner pass of the first Adam epoch re-uses)."""
         p = self.policy
         ws = self._workspace(phase.N)
         full = getattr(phase, 'log_std_full', None)
         old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
         n_valid = getattr(phase, 'n_valid', None)           # variable-length paths: per-task sample counts
-        entry, extra = ('promp_policy_grad', ()) if n_valid is None else ('promp_policy_grad_ragged', (_lib.ptr(n_valid),))
-        _lib.call(entry, p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N, *extra,
+        skip = (_lib.ptr(reuse[0]), _lib.ptr(reuse[1])) if reuse is not None else (None, None)
+        prod = (_lib.ptr(produce[0]), _lib.ptr(produce[1])) if produce is not None else (None, None)
+        _lib.call('promp_policy_grad_ex', p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, phase.N, _lib.ptr(n_valid),
                   _lib.ptr(params), stride, _lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.adv),
                   _lib.ptr(phase.mean), _lib.ptr(old_ls), per_sample, obj_kind, float(obj_scale), float(clip_eps),
                   float(kl_coeff), int(clip_log_std), float(p.min_log_std), _lib.ptr(grad), _lib.ptr(out_params),
-                  float(sgd_lr), _lib.ptr(stats), _lib.ptr(ws), ws.numel() * 4, _lib.stream())
+                  float(sgd_lr), _lib.ptr(stats), skip[0], skip[1], prod[0], prod[1], _lib.ptr(ws), ws.numel() * 4, _lib.stream())
 
     def _hvp(self, phase, params, stride, vec, out, kl_coeff, clip_log_std, stats=None):
         p = self.policy
@@ -107,33 +110,42 @@ class MAMLAlgo(object):
                   _lib.ptr(stats), _lib.ptr(ws), ws.numel() * 4, _lib.stream())
 
     # ------------------------------------------------------------------------------------ inner step
-    def adapt_phase(self, phase):
-        """_adapt on a PhaseData directly (no per-task dict views): used by the CUDA-graph Trainer."""
+    def _adapt_launch(self, phase):
+        """theta_i' = theta_i - alpha * grad surr_i(theta_i) for all tasks in one launch (MAMLAlgo._adapt, base.py:217-242).  From
+        the shared pre-update parameters the launch also leaves what the first Adam epoch's identical inner pass needs to
+        skip itself (promp_policy_grad_ex): its outputs (gradient, theta', stats row 0 of a [S, M, 4] buffer), a copy of the
+        parameters it used and the no-clip flag."""
         import torch
         p = self.policy
         params, stride, _ = p.sampling_params()
         M, P = self.meta_batch_size, p.num_params
         grad = torch.empty(M, P, dtype=torch.float32, device=p.device)
         new = torch.empty(M, P, dtype=torch.float32, device=p.device)
-        self._grad(phase, params, stride, self.inner_obj_kind, grad=grad, out_params=new, sgd_lr=self.inner_lr)
+        produce, stats = None, None
+        self._adapt_cache = None
+        if stride == 0 and params is p.theta and getattr(phase, 'n_valid', None) is None:
+            if getattr(self, '_reuse_bufs', None) is None:
+                self._reuse_bufs = (torch.zeros(1, dtype=torch.int32, device=p.device),
+                                    torch.empty(P, dtype=torch.float32, device=p.device))
+            stats_all = torch.empty(self.num_inner_grad_steps + 1, M, 4, dtype=torch.float32, device=p.device)
+            produce, stats = self._reuse_bufs, stats_all[0]
+            self._adapt_cache = dict(phase=phase, adv=phase.adv, gen=getattr(phase, 'generation', 0), grad=grad, new=new,
+                                     stats_all=stats_all)
+        # the adapt graph is fed parameter placeholders: no log_std clip (gaussian_mlp_policy.py:164-182)
+        self._grad(phase, params, stride, self.inner_obj_kind, grad=grad, out_params=new, sgd_lr=self.inner_lr, stats=stats,
+                   produce=produce)
         self.last_inner_grad = grad
         p.update_task_parameters(new)
+
+    def adapt_phase(self, phase):
+        """_adapt on a PhaseData directly (no per-task dict views): used by the CUDA-graph Trainer."""
+        self._adapt_launch(phase)
 
     def _adapt(self, samples):
         """MAMLAlgo._adapt (base.py:217-242): theta_i' = theta_i - alpha * grad surr_i(theta_i), all tasks
         in one launch, result stays on the device and becomes the sampling policy."""
-        import torch
         assert len(samples) == self.meta_batch_size
-        phase = self._phase_of(samples)
-        p = self.policy
-        params, stride, _ = p.sampling_params()
-        M, P = self.meta_batch_size, p.num_params
-        grad = torch.empty(M, P, dtype=torch.float32, device=p.device)
-        new = torch.empty(M, P, dtype=torch.float32, device=p.device)
-        # the adapt graph is fed parameter placeholders: no log_std clip (gaussian_mlp_policy.py:164-182)
-        self._grad(phase, params, stride, self.inner_obj_kind, grad=grad, out_params=new, sgd_lr=self.inner_lr)
-        self.last_inner_grad = grad
-        p.update_task_parameters(new)
+        self._adapt_launch(self._phase_of(samples))
 
     # ------------------------------------------------------------------------------------ meta objective
     def _meta_pass(self, theta, phases, outer_obj_kind, clip_eps, inner_kl_coeffs, want_grad, outer_kl_coeff=0.0,
@@ -152,7 +164,26 @@ class MAMLAlgo(object):
         chain = []
         # one stats buffer per evaluation, fully written by the kernels (no fills, no copies): row s = launch s
         stats_all = torch.empty(S, M, 4, dtype=torch.float32, device=dev)
+        # The inner pass at step 0 repeats the _adapt launch as long as theta has not been updated since (first Adam epoch,
+        # "loss before" passes): aim it at the SAME output buffers and let the kernel skip itself after verifying on the
+        # device that the parameters are bit-identical and the step-0 log_std clip is inactive.  Host-side conditions: same
+        # phase object / advantage tensor / data generation, shared parameters, same number of inner steps; only the FIRST pass
+        # after _adapt takes this route.
+        cache = getattr(self, '_adapt_cache', None)
+        reuse0 = (cache is not None and S >= 2 and theta is p.theta and cache['phase'] is phases[0]
+                  and cache['adv'] is phases[0].adv and cache['gen'] == getattr(phases[0], 'generation', 0)
+                  and cache['stats_all'].shape[0] == S)
+        if reuse0:
+            stats_all = cache['stats_all']
+            self._adapt_cache = None          # one consumer: later passes (updated theta) use their own buffers
         for s in range(S - 1):
+            if s == 0 and reuse0:
+                g, nxt = cache['grad'], cache['new']
+                self._grad(phases[0], cur, stride, self.inner_obj_kind, clip_log_std=clip, grad=g, out_params=nxt,
+                           sgd_lr=self.inner_lr, stats=stats_all[0], reuse=self._reuse_bufs)
+                chain.append((cur, stride, clip))
+                cur, stride, clip = nxt, P, 0
+                continue
             g = torch.empty(M, P, dtype=torch.float32, device=dev)
             nxt = torch.empty(M, P, dtype=torch.float32, device=dev)
             self._grad(phases[s], cur, stride, self.inner_obj_kind, clip_log_std=clip, grad=g, out_params=nxt,

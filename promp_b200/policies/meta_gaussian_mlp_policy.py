@@ -27,7 +27,8 @@ def _is_tanh(fn):
 
 class MetaGaussianMLPPolicy(object):
     def __init__(self, meta_batch_size, obs_dim, action_dim, name='policy', hidden_sizes=(32, 32), learn_std=True,
-                 hidden_nonlinearity='tanh', output_nonlinearity=None, init_std=1., min_std=1e-6, device=None):
+                 hidden_nonlinearity='tanh', output_nonlinearity=None, init_std=1., min_std=1e-6, device=None,
+                 _skip_param_init=False):
         import torch
         _lib.require_cuda()
         hidden_sizes = tuple(int(h) for h in hidden_sizes)
@@ -75,7 +76,9 @@ class MetaGaussianMLPPolicy(object):
         for key, shape in self.param_shapes.items():
             if key.endswith('kernel'):
                 lim = math.sqrt(6.0 / (shape[0] + shape[1]))
-                flat.append(np.random.uniform(-lim, lim, size=shape).reshape(-1))
+                # unpickling overwrites the parameters right away: do not perturb the seeded global RNG stream for it
+                flat.append(np.zeros(int(np.prod(shape))) if _skip_param_init
+                            else np.random.uniform(-lim, lim, size=shape).reshape(-1))
             elif key.endswith('bias'):
                 flat.append(np.zeros(int(np.prod(shape))))
             else:
@@ -223,5 +226,5 @@ class MetaGaussianMLPPolicy(object):
         return {'init_args': dict(self._init_args), 'network_params': self.get_param_values()}
 
     def __setstate__(self, state):
-        self.__init__(**state['init_args'])
+        self.__init__(_skip_param_init=True, **state['init_args'])      # no Xavier draw: loading must not consume np.random
         self.set_params(state['network_params'])

@@ -34,6 +34,7 @@ class PhaseData(object):
         self.coeffs = None
         self.stats = None
         self.adj_avg_rewards = None
+        self.generation = 0          # bumped whenever a kernel rewrites this phase's tensors in place
         self._host = {}
 
     def host(self, name):
@@ -44,7 +45,9 @@ class PhaseData(object):
         return self._host[name]
 
     def invalidate_host(self):
+        """Called after every kernel that rewrote device tensors of this phase (rollout, processing)."""
         self._host = {}
+        self.generation += 1
 
     def bytes_per_step(self):
         return 4 * (self.obs_dim + 2 * self.act_dim + 1) + 1 + 8 * len(self.info_keys)

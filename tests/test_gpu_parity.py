@@ -76,8 +76,17 @@ def test_rollout_matches_reference_golden(golden_dir):
         np.testing.assert_allclose(obs, g['it%d_obs' % it], rtol=0, atol=2e-5)
         np.testing.assert_allclose(act, g['it%d_act' % it], rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(mean, g['it%d_mean' % it], rtol=1e-4, atol=2e-5)
-        bad = np.abs(rew - g['it%d_rew' % it]) > 1e-4      # sparse reward is discontinuous: allow rare boundary flips
-        assert bad.mean() < 0.005, bad.mean()
+        # the sparse reward is discontinuous (point_env_2d_corner.py:68-76): a float32 state may fall on the other side of a
+        # branch boundary.  Every mismatch must sit ON such a boundary of the reference state s' (L1 radius 0.5, or a
+        # nearest-corner tie x = 0 / y = 0), and there may be at most 3 of them in 2 000 samples.
+        bad = np.abs(rew - g['it%d_rew' % it]) > 1e-4
+        assert bad.sum() <= 3, int(bad.sum())
+        ref_obs = g['it%d_obs' % it]
+        for m_, e_, t_ in zip(*np.nonzero(bad)):
+            if t_ + 1 < H:
+                x, y = ref_obs[m_, e_, t_ + 1]
+                margin = min(abs(abs(x) + abs(y) - 0.5), abs(x), abs(y))
+                assert margin < 1e-3, (m_, e_, t_, x, y)
     # the numpy stream was consumed exactly like the reference consumed it
     assert np.array_equal(np.random.uniform(size=4), g['rng_probe_after'])
 
@@ -500,6 +509,55 @@ def test_trpo_maml_optimize_policy_runs_and_matches_first_quantities():
     th_o, st_o = orc.optimize(theta0, cpus)
     assert st_o['rejected'] is False
     assert abs(st_o['loss'] - ls['loss_after']) < 0.05 * abs(ls['loss_before'] - ls['loss_after']) + 1e-5
+
+
+def test_first_epoch_inner_pass_reuses_adapt_launch_exactly():
+    """The inner pass of the first Adam epoch repeats MAMLAlgo._adapt; it skips itself on the device (promp_policy_grad_ex) iff
+    the parameters are bit-identical to the ones _adapt used and the step-0 log_std clip is inactive.  Checked: identical
+    results with and without the shortcut; a parameter change after _adapt, or an active clip, makes the kernel run (results
+    equal the uncached evaluation, not the stale cache)."""
+    torch = _cuda()
+    from promp_b200.meta_algos import ProMP
+    M, E, H = 4, 5, 40
+
+    def evaluate(mutate=None, use_cache=True, ls=None):
+        env, policy, sampler, proc = _make_stack('point', M, E, H, seed=11)
+        if ls is not None:
+            th = policy.theta.clone()
+            th[-2:] = ls
+            policy.theta.copy_(th)
+        algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3, num_ppo_steps=5,
+                     clip_eps=0.3, init_inner_kl_penalty=5e-4, adaptive_inner_kl_penalty=False)
+        np.random.seed(4)
+        sampler.update_tasks()
+        policy.switch_to_pre_update()
+        phases = []
+        for step in range(2):
+            paths = sampler.obtain_samples()
+            samples = proc.process_samples(paths)
+            phases.append(samples[0].phase)
+            if step == 0:
+                algo._adapt(samples)
+        assert algo._adapt_cache is not None
+        if mutate is not None:
+            mutate(policy)
+        if not use_cache:
+            algo._adapt_cache = None
+        res = algo._objective_pass(phases, want_grad=True)
+        terms = algo.loss_terms(res).cpu().numpy()
+        return res['grad'].cpu().numpy(), terms, algo
+
+    g_c, t_c, algo = evaluate()
+    assert algo._adapt_cache is None                      # consumed by the first pass
+    g_n, t_n, _ = evaluate(use_cache=False)
+    assert np.array_equal(g_c, g_n) and np.array_equal(t_c, t_n)
+    bump = lambda pol: pol.theta.add_(1e-3)
+    g_c, t_c, _ = evaluate(mutate=bump)
+    g_n, t_n, _ = evaluate(mutate=bump, use_cache=False)
+    assert np.array_equal(g_c, g_n) and np.array_equal(t_c, t_n)
+    g_c, t_c, _ = evaluate(ls=-15.0)                      # below log(1e-6): the step-0 graph clips, _adapt does not
+    g_n, t_n, _ = evaluate(ls=-15.0, use_cache=False)
+    assert np.array_equal(g_c, g_n) and np.array_equal(t_c, t_n)
 
 
 def test_fused_meta_update_single_gpu():
