@@ -346,6 +346,44 @@ int promp_policy_grad_ex(int obs_dim, int act_dim, int hidden, int M, int N, con
                          float kl_coeff, int clip_log_std, float min_log_std, float* grad, float* out_params, float sgd_lr,
                          float* stats, const int32_t* skip_flag, const float* skip_theta, int32_t* unclipped_out,
                          float* theta_copy_out, void* workspace, int64_t workspace_bytes, void* stream);
+/*
+ * The gradient chain of one meta-objective evaluation in ONE launch (tf.gradients through the M per-task sub-graphs of
+ * meta_algos/base.py:158-215 + the outer objective of pro_mp.py:88-163 / trpo_maml.py:69-159):
+ *   stage 0..S-2  kind 0, inner objective, grad + out_params (theta_{s+1,m} = theta_{s,m} - sgd_lr * grad)     = promp_policy_grad
+ *   stage S-1     kind 0, outer objective at the adapted parameters, grad = v (or NULL: values only)          = promp_policy_grad
+ *   stage S..     kind 1, v <- v - inner_lr * H_s v + kl_coeff * grad KL_s   for s = S-2 .. 0                 = promp_policy_hvp
+ * Stage k of task m depends on stage k-1 of the same task only (its params / vec may be the out_params / grad / out of the
+ * previous stage); a persistent dataflow kernel pulls (stage, task, tiles) work items from a device-side queue and lets the
+ * stages of different tasks overlap.  Each stage has the semantics and argument meaning of the stand-alone entry point named
+ * above (per-task sums are taken in a different, still deterministic, order).  skip_flag / skip_theta: launch re-use for
+ * stage 0, as in promp_policy_grad_ex.  Shapes without tensor-core kernels (hidden != 64) and promp_set_option("chain", 0)
+ * run the stages as separate launches.  The workspace (>= promp_policy_chain_workspace_bytes) starts with control words
+ * that must be zero before the first call and are left zero: allocate it zero-filled once and do not share it with other
+ * entry points.  `stages` is a HOST array (read during the call).
+ */
+typedef struct {
+    int32_t kind;                  /* 0 = gradient stage, 1 = Hessian-vector stage */
+    int32_t N;                     /* samples per task of this stage's phase */
+    const int32_t* n_valid;        /* [M] or NULL (variable-length paths) */
+    const float* params;
+    int64_t param_stride;
+    const float *obs, *act, *adv, *old_mean, *old_log_std;
+    int32_t ls_per_sample, obj_kind;
+    float obj_scale, clip_eps, kl_coeff;
+    int32_t clip_log_std;
+    float* grad;                   /* gradient stage */
+    float* out_params;
+    float sgd_lr;
+    float inner_lr;                /* HVP stage */
+    const float* vec;
+    float* out;
+    float* stats;                  /* [M,4] or NULL */
+} promp_policy_stage;
+int64_t promp_policy_chain_workspace_bytes(int obs_dim, int act_dim, int hidden, int M, int n_stages,
+                                           const promp_policy_stage* stages);
+int promp_policy_chain(int obs_dim, int act_dim, int hidden, int M, float min_log_std, int n_stages,
+                       const promp_policy_stage* stages, const int32_t* skip_flag, const float* skip_theta,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 int promp_policy_hvp_ragged(int obs_dim, int act_dim, int hidden, int M, int N, const int32_t* n_valid,
                             const float* params, int64_t param_stride,
                             const float* obs, const float* act, const float* adv,

@@ -6,7 +6,7 @@ device is present, the product path raises.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('PROMP_B200_LIB', os.path.join(_HERE, 'libpromp_b200.so'))   # override: kernel experiments
@@ -18,6 +18,17 @@ OBJ_RATIO, OBJ_LOGLIK, OBJ_CLIP, OBJ_NONE = 0, 1, 2, 3
 BASELINE_ZERO, BASELINE_LINEAR_FEATURE = 0, 1
 
 _P = c_void_p
+
+
+class PolicyStage(ctypes.Structure):
+    """promp_policy_stage of include/promp_b200.h (one stage of promp_policy_chain)."""
+    _fields_ = [('kind', c_int32), ('N', c_int32), ('n_valid', _P), ('params', _P), ('param_stride', c_int64),
+                ('obs', _P), ('act', _P), ('adv', _P), ('old_mean', _P), ('old_log_std', _P),
+                ('ls_per_sample', c_int32), ('obj_kind', c_int32), ('obj_scale', c_float), ('clip_eps', c_float),
+                ('kl_coeff', c_float), ('clip_log_std', c_int32), ('grad', _P), ('out_params', _P), ('sgd_lr', c_float),
+                ('inner_lr', c_float), ('vec', _P), ('out', _P), ('stats', _P)]
+
+
 _SIGNATURES = {
     'promp_last_error': (c_char_p, []),
     'promp_version': (c_int, []),
@@ -55,6 +66,8 @@ _SIGNATURES = {
                                      c_float, c_float, c_float, c_int, c_float, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     'promp_policy_hvp_ragged': (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, c_int,
                                         c_float, c_float, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
+    'promp_policy_chain_workspace_bytes': (c_int64, [c_int, c_int, c_int, c_int, c_int, _P]),
+    'promp_policy_chain': (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_int64, _P]),
     'promp_meta_loss_terms': (c_int, [c_int, c_int, _P, c_float, _P, c_int, _P, _P]),
     'promp_phase_log_terms': (c_int, [c_int, c_int, c_double, _P, _P, _P, _P]),
     'promp_promp_log_terms': (c_int, [c_int, _P, _P, _P]),

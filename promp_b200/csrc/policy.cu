@@ -1134,6 +1134,143 @@ static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st
                          PLayout<DO, DA, HID>::P, ws, ws_bytes, st, "policy_hvp_kernel");
 }
 
+// ---- dataflow chain (policy_chain_tc_kernel): work-item plan + launch ---------------------------------------------
+static int g_chain = 1;          // promp_set_option("chain", 0|1): 0 = promp_policy_chain launches its stages one by one
+static int g_chain_q = 0;        // promp_set_option("chain_q", q): tiles per work item (0 = automatic)
+static int g_chain_taper = 1;    // promp_set_option("chain_taper", 0|1): last stage's items shrink to one tile towards the end
+
+struct ChainPlan {
+    ChainStageInfo info[CHAIN_MAX_STAGES];
+    int n_items;
+    int64_t ctrl_bytes, bytes;     // control words (zero on entry, left zero); whole workspace
+};
+static int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+// Items are (stage, task, q consecutive tiles).  q = the largest of 4, 2, 1 that still gives every stage at least one item
+// per SM; the last stage (nothing left to fill its tail with) uses q, q/2 and 1 on the first half, third quarter and last
+// quarter of its tasks, so the final imbalance over the SMs is one tile.
+static ChainPlan plan_chain(int n_stages, const int* kinds, const int* Ns, int M, int P) {
+    ChainPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    const int sms = sm_count();
+    int base = 0;
+    for (int s = 0; s < n_stages; ++s) {
+        ChainStageInfo& I = pl.info[s];
+        I.kind = kinds[s];
+        I.ntiles = (Ns[s] + TBT - 1) / TBT;
+        int q = 4;
+        if (g_chain_q > 0) q = g_chain_q;
+        else while (q > 1 && (int64_t)M * ((I.ntiles + q - 1) / q) < sms) q >>= 1;
+        if (q > I.ntiles) q = I.ntiles;
+        I.item_base = base;
+        const bool taper = g_chain_taper && s == n_stages - 1 && q > 1 && M >= 4;
+        if (!taper) {
+            I.n_regions = 1;
+            I.reg_m0[0] = 0, I.reg_m0[1] = M;
+            I.reg_q[0] = q;
+            I.reg_item0[0] = 0;
+            I.n_items = M * ((I.ntiles + q - 1) / q);
+        } else {
+            const int q2 = q > 2 ? q / 2 : q;              // q = 2: three quarters at 2, the last quarter at 1
+            const int mB = M - M / 4, mA = q2 < q ? M / 2 : mB;
+            I.n_regions = 0;
+            int items = 0;
+            const int m0[4] = {0, mA, mB, M}, qs[3] = {q, q2, 1};
+            for (int r = 0; r < 3; ++r) {
+                if (m0[r + 1] <= m0[r]) continue;
+                I.reg_m0[I.n_regions] = m0[r];
+                I.reg_q[I.n_regions] = qs[r];
+                I.reg_item0[I.n_regions] = items;
+                items += (m0[r + 1] - m0[r]) * ((I.ntiles + qs[r] - 1) / qs[r]);
+                ++I.n_regions;
+            }
+            I.reg_m0[I.n_regions] = M;
+            I.n_items = items;
+        }
+        base += I.n_items;
+    }
+    pl.n_items = base;
+    // fixed layout whatever n_stages is: chains of different length share one workspace, and the words must stay zero between them
+    pl.ctrl_bytes = align_up(16 + (int64_t)2 * CHAIN_MAX_STAGES * M * sizeof(int), 128);
+    pl.bytes = pl.ctrl_bytes + (int64_t)pl.n_items * (P + PSTAT) * sizeof(float);
+    return pl;
+}
+
+template <int DO, int DA, int HID>
+static constexpr bool chain_tc_ok() {
+    if constexpr (HID == TC_HID) return ChainSmem<DO, DA, 2>::SIZE <= 227 * 1024 && ChainSmem<DO, DA, 4>::SIZE <= 227 * 1024;
+    return false;
+}
+
+template <int DO, int DA, int NQ>
+static int launch_chain_nq(ChainArgs& C, cudaStream_t st) {
+    static int configured = 0;
+    constexpr int smem = ChainSmem<DO, DA, NQ>::SIZE;
+    auto kernel = policy_chain_tc_kernel<DO, DA, NQ>;
+    if (!configured) {
+        PROMP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = 1;
+    }
+    int grid = sm_count();
+    if (grid > C.n_items) grid = C.n_items;
+    kernel<<<grid, 128 * NQ, smem, st>>>(C);
+    PROMP_LAUNCH_CHECK("policy_chain_tc_kernel");
+    return PROMP_OK;
+}
+
+// kinds / Ns / A: the stages in order.  Falls back to one launch per stage (same results up to summation order) for the
+// shapes the tcgen05 kernels do not cover or when the "chain" option is off.
+template <int DO, int DA, int HID>
+static int launch_chain(int n_stages, const int* kinds, PolicyArgs* A, const int* skip_flag, const float* skip_theta, void* ws,
+                        int64_t ws_bytes, cudaStream_t st) {
+    constexpr int P = PLayout<DO, DA, HID>::P;
+    int Ns[CHAIN_MAX_STAGES];
+    for (int s = 0; s < n_stages; ++s) Ns[s] = A[s].N;
+    const int M = A[0].M;
+    const ChainPlan pl = plan_chain(n_stages, kinds, Ns, M, P);
+    if constexpr (chain_tc_ok<DO, DA, HID>()) {
+        if (g_use_tc && g_chain) {
+            if (ws_bytes < pl.bytes) {
+                set_error("policy chain workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.bytes);
+                return PROMP_ERR_WORKSPACE;
+            }
+            ChainArgs C;
+            memset(&C, 0, sizeof(C));
+            C.n_stages = n_stages, C.n_items = pl.n_items, C.M = M;
+            C.ctrl = (int*)ws;
+            C.ready = (int*)ws + 4;
+            C.skip_flag = skip_flag, C.skip_theta = skip_theta;
+            float* partial = (float*)((char*)ws + pl.ctrl_bytes);
+            for (int s = 0; s < n_stages; ++s) {
+                C.info[s] = pl.info[s];
+                C.st[s] = A[s];
+                C.st[s].counters = (int*)ws + 4 + (CHAIN_MAX_STAGES + s) * M;
+                C.st[s].partial = partial;            // slots are numbered by global item id
+            }
+            if (tc_column_groups(DO) == 4) return launch_chain_nq<DO, DA, 4>(C, st);
+            return launch_chain_nq<DO, DA, 2>(C, st);
+        }
+    }
+    // one launch per stage; their (counters + partial) workspace starts after the chain's control words
+    void* ws1 = (char*)ws + pl.ctrl_bytes;
+    const int64_t ws1_bytes = ws_bytes - pl.ctrl_bytes;
+    for (int s = 0; s < n_stages; ++s) {
+        PolicyArgs a = A[s];
+        if (s == 0) a.skip_flag = skip_flag, a.skip_theta = skip_theta;
+        const int rc = kinds[s] == 0 ? launch_grad_any<DO, DA, HID>(a, ws1, ws1_bytes, st) : launch_hvp<DO, DA, HID>(a, ws1, ws1_bytes, st);
+        if (rc != PROMP_OK) return rc;
+    }
+    return PROMP_OK;
+}
+
+template <int DO, int DA, int HID>
+static int64_t chain_ws_bytes(int n_stages, const int* kinds, const int* Ns, int M) {
+    const ChainPlan pl = plan_chain(n_stages, kinds, Ns, M, PLayout<DO, DA, HID>::P);
+    int nmax = 1;
+    for (int s = 0; s < n_stages; ++s) nmax = Ns[s] > nmax ? Ns[s] : nmax;
+    const int64_t single = pl.ctrl_bytes + promp_policy_workspace_bytes(M, nmax, DO, DA, HID);
+    return pl.bytes > single ? pl.bytes : single;
+}
+
 template <int DO, int DA, int HID>
 static int launch_forward(int M, int N, const float* params, int64_t stride, const float* obs, float* mean,
                           cudaStream_t st) {
@@ -1262,10 +1399,76 @@ extern "C" int promp_policy_hvp(int obs_dim, int act_dim, int hidden, int M, int
                                    stats, workspace, workspace_bytes, stream);
 }
 
+static int chain_stage_args(const promp_policy_stage* stages, int n_stages, int M, float min_log_std, PolicyArgs* A, int* kinds, int* Ns) {
+    PROMP_REQUIRE(stages != nullptr && n_stages >= 1 && n_stages <= CHAIN_MAX_STAGES,
+                  "promp_policy_chain: 1..%d stages (got %d)", CHAIN_MAX_STAGES, n_stages);
+    for (int s = 0; s < n_stages; ++s) {
+        const promp_policy_stage& g = stages[s];
+        PROMP_REQUIRE(g.kind == 0 || g.kind == 1, "promp_policy_chain: stage %d has kind %d (0 = gradient, 1 = HVP)", s, g.kind);
+        PROMP_REQUIRE(g.N > 0 && g.params && g.obs && g.act && g.adv && g.old_mean && g.old_log_std,
+                      "promp_policy_chain: stage %d: null pointer / non-positive N", s);
+        PolicyArgs& a = A[s];
+        memset(&a, 0, sizeof(a));
+        a.M = M; a.N = g.N; a.params = g.params; a.param_stride = g.param_stride;
+        a.obs = g.obs; a.act = g.act; a.adv = g.adv; a.old_mean = g.old_mean; a.old_ls = g.old_log_std;
+        a.ls_per_sample = g.ls_per_sample; a.obj_kind = g.obj_kind; a.kl_coeff = g.kl_coeff;
+        a.clip_log_std = g.clip_log_std; a.min_log_std = min_log_std; a.stats = g.stats; a.n_valid = g.n_valid;
+        if (g.kind == 0) {
+            PROMP_REQUIRE(g.obj_kind >= 0 && g.obj_kind <= 3, "promp_policy_chain: stage %d: bad obj_kind %d", s, g.obj_kind);
+            PROMP_REQUIRE(!(g.out_params && !g.grad), "promp_policy_chain: stage %d: out_params needs grad", s);
+            a.obj_scale = g.obj_scale; a.clip_eps = g.clip_eps; a.grad = g.grad; a.out_params = g.out_params; a.sgd_lr = g.sgd_lr;
+        } else {
+            PROMP_REQUIRE(g.obj_kind == PROMP_OBJ_RATIO || g.obj_kind == PROMP_OBJ_LOGLIK,
+                          "promp_policy_chain: stage %d: HVP inner objective must be RATIO or LOGLIK (got %d)", s, g.obj_kind);
+            PROMP_REQUIRE(g.vec && g.out, "promp_policy_chain: stage %d: vec / out must not be null", s);
+            a.obj_scale = 1.f; a.vec = g.vec; a.out = g.out; a.inner_lr = g.inner_lr;
+        }
+        kinds[s] = g.kind;
+        Ns[s] = g.N;
+    }
+    return PROMP_OK;
+}
+
+extern "C" int64_t promp_policy_chain_workspace_bytes(int obs_dim, int act_dim, int hidden, int M, int n_stages,
+                                                      const promp_policy_stage* stages) {
+    if (stages == nullptr || n_stages < 1 || n_stages > CHAIN_MAX_STAGES || M < 1) return -1;
+    int kinds[CHAIN_MAX_STAGES], Ns[CHAIN_MAX_STAGES];
+    for (int s = 0; s < n_stages; ++s) kinds[s] = stages[s].kind, Ns[s] = stages[s].N > 0 ? stages[s].N : 1;
+    PROMP_DISPATCH_DIMS(chain_ws_bytes, n_stages, kinds, Ns, M)
+}
+
+extern "C" int promp_policy_chain(int obs_dim, int act_dim, int hidden, int M, float min_log_std, int n_stages,
+                                  const promp_policy_stage* stages, const int32_t* skip_flag, const float* skip_theta,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+    PROMP_REQUIRE(M > 0 && workspace != nullptr, "promp_policy_chain: M must be positive and workspace non-null");
+    PROMP_REQUIRE((skip_flag == nullptr) == (skip_theta == nullptr), "promp_policy_chain: skip_flag / skip_theta come as a pair");
+    PolicyArgs A[CHAIN_MAX_STAGES];
+    int kinds[CHAIN_MAX_STAGES], Ns[CHAIN_MAX_STAGES];
+    const int rc = chain_stage_args(stages, n_stages, M, min_log_std, A, kinds, Ns);
+    if (rc != PROMP_OK) return rc;
+    PROMP_REQUIRE(!skip_flag || (kinds[0] == 0 && A[0].param_stride == 0),
+                  "promp_policy_chain: launch re-use is defined for a gradient stage 0 on shared parameters (param_stride 0)");
+    cudaStream_t s = (cudaStream_t)stream;
+    PROMP_DISPATCH_DIMS(launch_chain, n_stages, kinds, A, skip_flag, skip_theta, workspace, workspace_bytes, s)
+}
+
 extern "C" int promp_set_option(const char* name, int value) {
     PROMP_REQUIRE(name != nullptr, "promp_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) {
         g_use_tc = value ? 1 : 0;
+        return PROMP_OK;
+    }
+    if (strcmp(name, "chain") == 0) {          // promp_policy_chain: dataflow kernel (1, default) or one launch per stage (0)
+        g_chain = value ? 1 : 0;
+        return PROMP_OK;
+    }
+    if (strcmp(name, "chain_q") == 0) {        // tiles per work item of the dataflow kernel (0 = automatic)
+        PROMP_REQUIRE(value >= 0 && value <= 64, "promp_set_option: chain_q must be in [0, 64]");
+        g_chain_q = value;
+        return PROMP_OK;
+    }
+    if (strcmp(name, "chain_taper") == 0) {    // shrinking items at the end of the last stage (1, default) or uniform (0)
+        g_chain_taper = value ? 1 : 0;
         return PROMP_OK;
     }
     if (strcmp(name, "tc_threads") == 0) {

@@ -231,6 +231,91 @@ __device__ __forceinline__ int wgrad_mma_index(int warp, int lane, int nt, int i
     return (16 * (warp & 3) + g + 8 * (i >> 1)) * TC_HID + 8 * NT * (warp >> 2) + 8 * nt + 2 * t + (i & 1);
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Work decomposition seen by the tile loops below.  Both tcgen05 kernels are written against this interface:
+//   [g_lo, g_hi)            the caller's range in the task-major tile list (ntiles tiles per task)
+//   my_slot(m)              partial slot this range writes for task m
+//   n_contrib / contrib_slot the slots of task m, in the fixed order in which its last arriver sums them
+//   wait_task / publish_task dependency on / completion of task m (dataflow kernel only)
+//   ldp                     parameter loads: read-only path (.nc) when nothing in this launch writes them, L2 (.cg) otherwise
+// UniformSched = the stand-alone launches (CTA c owns tiles [c q, (c+1) q), kmax slots per CTA); ItemSched = one work
+// item of policy_chain_tc_kernel (tiles [tile_lo, tile_hi) of ONE task; slots are numbered by item id).
+struct UniformSched {
+    int ntiles, g_lo, g_hi, q, kmax;
+    __device__ __forceinline__ UniformSched(int M, int N, int q_, int kmax_, int tb) {
+        ntiles = (N + tb - 1) / tb;
+        q = q_;
+        kmax = kmax_;
+        g_lo = blockIdx.x * q;
+        g_hi = min(g_lo + q, M * ntiles);
+    }
+    __device__ __forceinline__ int first_task(int c) const { return (c * q) / ntiles; }
+    __device__ __forceinline__ int cta_lo(int m) const { return (m * ntiles) / q; }
+    __device__ __forceinline__ int cta_hi(int m) const { return ((m + 1) * ntiles - 1) / q; }
+    __device__ __forceinline__ int my_slot(int m) const { return blockIdx.x * kmax + (m - first_task(blockIdx.x)); }
+    __device__ __forceinline__ int n_contrib(int m) const { return cta_hi(m) - cta_lo(m) + 1; }
+    __device__ __forceinline__ int contrib_slot(int m, int i) const {
+        const int c = cta_lo(m) + i;
+        return c * kmax + (m - first_task(c));
+    }
+    __device__ __forceinline__ void wait_task(int) const {}
+    __device__ __forceinline__ void publish_task(int) const {}
+    static __device__ __forceinline__ float ldp(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float4 ldp4(const float4* p) { return __ldg(p); }
+};
+struct ItemSched {
+    int ntiles, g_lo, g_hi;
+    int item, first_item, n_items;        // this item's id; the ids of its task's items in this stage
+    const int* ready_prev;                // [M] flags of the previous stage (nullptr: no dependency)
+    int* ready_mine;                      // [M] flags of this stage
+    __device__ __forceinline__ int my_slot(int) const { return item; }
+    __device__ __forceinline__ int n_contrib(int) const { return n_items; }
+    __device__ __forceinline__ int contrib_slot(int, int i) const { return first_item + i; }
+    __device__ __forceinline__ void wait_task(int m) const {       // called by every thread of the CTA
+        if (ready_prev == nullptr) return;
+        if (threadIdx.x == 0) {
+            int v;
+            unsigned spins = 0;
+            long long t0 = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(ready_prev + m) : "memory");
+                if (v == 0 && (++spins & 0xfffu) == 0) {          // safety net: a producer that never arrives is a bug, not a wait
+                    const long long t = clock64();
+                    if (t0 == 0) t0 = t;
+                    else if (t - t0 > 8000000000ll) {              // ~4 s
+                        printf("promp_b200: policy chain item %d waited > 4 s for task %d of the previous stage\n", item, m);
+                        __trap();
+                    }
+                }
+            } while (v == 0);
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void publish_task(int m) const {    // called by every thread of the task's last arriver
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(ready_mine + m), "r"(1) : "memory");
+    }
+    static __device__ __forceinline__ float ldp(const float* p) { return __ldcg(p); }
+    static __device__ __forceinline__ float4 ldp4(const float4* p) { return __ldcg(p); }
+};
+
+// Sum one float4 column of a task's partial slots in contributor order, eight independent L2 loads in flight.
+template <class Sched>
+__device__ __forceinline__ float4 reduce_slots4(const float* partial, const Sched& sc, int pstride, int m, int n, int p) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = (i0 + u < n) ? __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)sc.contrib_slot(m, i0 + u) * pstride + p))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s.x += v[u].x, s.y += v[u].y, s.z += v[u].z, s.w += v[u].w;
+    }
+    return s;
+}
+
 #ifdef PROMP_EXP_CLOCKS
 // experiment build only: per-phase clock64 totals of CTA 0 (tools/kernel_time.py --clocks)
 __device__ unsigned long long g_phase_clk[16];
@@ -245,8 +330,12 @@ __device__ unsigned long long g_phase_clk[16];
 #else
 #define PCLK(i)
 #endif
-template <int DO, int DA, int NQ>
-__global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs A) {
+// The tile loop of the gradient kernel over the range `sc` describes.  TMEM (>= 128 columns at `tmem`) and the mbarrier
+// are set up by the caller; `phase` is the barrier's running parity; `cached_th` = the parameter vector whose weights
+// the shared-memory tiles currently hold (nullptr: none) - kept across calls by the dataflow kernel.
+template <int DO, int DA, int NQ, class Sched>
+__device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO, DA, NQ>& S, const Sched& sc, uint32_t tmem,
+                                              uint64_t* bar, uint32_t& phase, const float*& cached_th) {
     constexpr int HID = TC_HID;
     using L = PLayout<DO, DA, HID>;
     using SL = SmallLayout<DO, DA>;
@@ -256,8 +345,6 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
     constexpr int PSTRIDE = L::P + PSTAT;
     constexpr int NPART = TCT / HID, BPP = TBT / NPART;     // column role: 4 slices of 32 rows
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SM& S = *reinterpret_cast<SM*>(smem_raw);
 #ifdef PROMP_EXP_CLOCKS
     __shared__ unsigned long long s_clk[16];
     __shared__ long long s_last;
@@ -272,27 +359,12 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
     const int qd = warp & 3, cq = warp >> 2;               // TMEM lane quadrant, column group
     const int r = qd * 32 + lane, c0 = CW * cq;          // row / column-group role: sample row r, hidden units [c0, c0+32)
     const int cj = tid & (HID - 1), cp = tid / HID;        // column role
-    if (grad_reuse_prologue<L::P, L::LS, DA>(A)) return;    // before any TMEM allocation / barrier initialisation
-    const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
     int Nm = N;
     const bool want_grad = A.grad != nullptr;
     const float* th = nullptr;
     HeadIn<DA> hin;
-    uint32_t phase = 0;
-
-    // ---- TMEM + mbarrier setup
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&S.tmem_base)), "n"(128));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-    }
-    if (tid == 0) mbar_init(&S.bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
 
     float gW1[NT][4], gB1f[NT], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
@@ -309,23 +381,38 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
-    auto load_task = [&](int m, bool first) {
+    auto load_task = [&](int m) {
+        sc.wait_task(m);
         if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
         th = A.params + (int64_t)m * A.param_stride;
-        if (!first && A.param_stride == 0) return;
-        __syncthreads();
-        for (int i = tid; i < DO * HID + HID; i += TCT) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);          // W0, b0
-        for (int i = tid; i < HID; i += TCT) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
-        for (int i = tid; i < HID * DA + 2 * DA; i += TCT) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);       // W2, b2, ls
-        for (int i = tid; i < HID * HID; i += TCT) {
-            const int k = i / HID, j = i % HID;
-            const float w = __ldg(th + L::W1 + i), wl = w - tf32_trunc(w);
-            *reinterpret_cast<float*>(S.W1_hi + core_off(k, j, SCW)) = w;
-            *reinterpret_cast<float*>(S.W1_lo + core_off(k, j, SCW)) = wl;
-            *reinterpret_cast<float*>(S.W1T_hi + core_off(j, k, SCW)) = w;
-            *reinterpret_cast<float*>(S.W1T_lo + core_off(j, k, SCW)) = wl;
+        const bool reload = th != cached_th;      // CTA-uniform: do the shared-memory tiles already hold these weights?
+        cached_th = th;
+        if (reload) __syncthreads();
+        for (int i = tid; reload && i < DO * HID + HID; i += TCT) S.Ps[SL::W0 + i] = Sched::ldp(th + L::W0 + i);          // W0, b0
+        for (int i = tid; reload && i < HID; i += TCT) S.Ps[SL::B1 + i] = Sched::ldp(th + L::B1 + i);
+        for (int i = tid; reload && i < HID * DA + 2 * DA; i += TCT) S.Ps[SL::W2 + i] = Sched::ldp(th + L::W2 + i);       // W2, b2, ls
+        // W1 in both operand layouts, 4 elements (one 16-byte shared-memory store, conflict-free) per thread and buffer
+        for (int u = tid; reload && u < HID * HID / 4; u += TCT) {
+            float4 w, wl;
+            {       // backward operand: tile row = k, K = j; one 16-byte load of W1[k][4 jg ..]
+                const int jg = u % (HID / 4), k = u / (HID / 4);
+                w = Sched::ldp4(reinterpret_cast<const float4*>(th + L::W1 + k * HID + 4 * jg));
+                wl = make_float4(w.x - tf32_trunc(w.x), w.y - tf32_trunc(w.y), w.z - tf32_trunc(w.z), w.w - tf32_trunc(w.w));
+                const int off = jg * SCW + (k >> 3) * 128 + (k & 7) * 16;
+                *reinterpret_cast<float4*>(S.W1_hi + off) = w;
+                *reinterpret_cast<float4*>(S.W1_lo + off) = wl;
+            }
+            {       // forward operand: tile row = j, K = k; W1[4 kg .. 4 kg + 3][j], lanes run over j
+                const int j = u % HID, kg = u / HID;
+                const float* src = th + L::W1 + 4 * kg * HID + j;
+                w = make_float4(Sched::ldp(src), Sched::ldp(src + HID), Sched::ldp(src + 2 * HID), Sched::ldp(src + 3 * HID));
+                wl = make_float4(w.x - tf32_trunc(w.x), w.y - tf32_trunc(w.y), w.z - tf32_trunc(w.z), w.w - tf32_trunc(w.w));
+                const int off = kg * SCW + (j >> 3) * 128 + (j & 7) * 16;
+                *reinterpret_cast<float4*>(S.W1T_hi + off) = w;
+                *reinterpret_cast<float4*>(S.W1T_lo + off) = wl;
+            }
         }
-        __syncthreads();
+        if (reload) __syncthreads();
 #pragma unroll
         for (int d = 0; d < DA; ++d) {
             const float raw = S.Ps[SL::LS + d];
@@ -336,7 +423,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         }
     };
     auto flush = [&](int m) {
-        float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+        float* part = A.partial + (int64_t)sc.my_slot(m) * PSTRIDE;
         float* scr = reinterpret_cast<float*>(S.A1);      // A1 + LO (contiguous, 2 tiles): free between tiles (all MMAs have completed)
         static_assert(NPART * DO * HID * 4 <= 2 * TILE_A_BYTES && NPART * HID * DA * 4 <= 2 * TILE_A_BYTES, "flush scratch");
         __syncthreads();
@@ -397,8 +484,8 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         __threadfence();
         __syncthreads();
         PCLK(14);
-        const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
-        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
+        const int n_c = sc.n_contrib(m);
+        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == n_c - 1);
         __syncthreads();
         PCLK(15);
         if (S.last) {
@@ -406,12 +493,12 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
             // the trailing float4 of every partial slot holds the objective / KL / ratio sums: reduced by the same loop
             static_assert(L::P % 4 == 0 && PSTAT == 4, "stats ride on the float4 reduction");
             if (!want_grad && tid == 0 && A.stats) {
-                const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, L::P);
+                const float4 s = reduce_slots4(A.partial, sc, PSTRIDE, m, n_c, L::P);
                 A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN, A.stats[(int64_t)m * 4 + 2] = s.z * invN;
             }
             if (want_grad) {
                 for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
-                    const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                    const float4 s = reduce_slots4(A.partial, sc, PSTRIDE, m, n_c, p);
                     if (p == L::P) {
                         if (A.stats)
                             A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN,
@@ -420,25 +507,26 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
                     }
                     *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
                     if (A.out_params) {
-                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(th + p));
+                        const float4 t4 = Sched::ldp4(reinterpret_cast<const float4*>(th + p));
                         *reinterpret_cast<float4*>(A.out_params + (int64_t)m * L::P + p) =
                             make_float4(t4.x - A.sgd_lr * s.x, t4.y - A.sgd_lr * s.y, t4.z - A.sgd_lr * s.z, t4.w - A.sgd_lr * s.w);
                     }
                 }
             }
             if (tid == 0) A.counters[m] = 0;
+            sc.publish_task(m);
         }
         __syncthreads();
     };
 
     int cur_m = -1;
-    for (int g = ts.g_lo; g < ts.g_hi; ++g) {
-        const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+    for (int g = sc.g_lo; g < sc.g_hi; ++g) {
+        const int m = g / sc.ntiles, tile = g - m * sc.ntiles;
         PCLK(10);
         if (m != cur_m) {
             if (cur_m >= 0) flush(cur_m);
             PCLK(11);
-            load_task(m, cur_m < 0);
+            load_task(m);
             zero_acc();
             cur_m = m;
             PCLK(12);
@@ -482,10 +570,10 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         if (warp_u == 0 && elect_one()) {      // warp-uniform branch + elect: descriptors go straight to uniform registers
             tc_fence_after();
             issue_gemm_3xtf32(tmem, S.A0, S.LO, S.W1T_hi, S.W1T_lo);
-            umma_commit(&S.bar);
+            umma_commit(bar);
             PCLK(13);
         }
-        mbar_wait(&S.bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
         PCLK(2);
@@ -597,7 +685,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
         if (warp_u == 0 && elect_one()) {      // warp-uniform branch + elect: descriptors go straight to uniform registers
             tc_fence_after();
             issue_gemm_3xtf32(tmem + 64, S.A1, S.LO, S.W1_hi, S.W1_lo);
-            umma_commit(&S.bar);
+            umma_commit(bar);
         }
         PCLK(6);
         // ---- ... while the warps do the weight gradient gW1 += H1^T D2 (mma.sync 3xTF32) and the bias column sums
@@ -605,7 +693,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
             wgrad_mma_tile<true, NT>(S.A0, S.A1, 1.f, warp, lane, gW1, gB1f);
         }
         PCLK(7);
-        mbar_wait(&S.bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
         float dh1[CW];
@@ -639,13 +727,46 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs 
     PCLK(10);
     if (cur_m >= 0) flush(cur_m);
     PCLK(11);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(128));
 #ifdef PROMP_EXP_CLOCKS
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int i = 0; i < 16; ++i) g_phase_clk[i] += s_clk[i];
 #endif
+}
+
+// TMEM allocation + mbarrier set-up / tear-down shared by the three tcgen05 kernels (warp 0 allocates; one barrier).
+template <int COLS>
+__device__ __forceinline__ uint32_t tc_setup(uint32_t* tmem_slot, uint64_t* bar) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *tmem_slot;
+}
+template <int COLS>
+__device__ __forceinline__ void tc_teardown(uint32_t tmem) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(COLS));
+}
+
+template <int DO, int DA, int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) policy_grad_tc_kernel(PolicyArgs A) {
+    using SM = GradTcSmem<DO, DA, NQ>;
+    using L = PLayout<DO, DA, TC_HID>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+    if (grad_reuse_prologue<L::P, L::LS, DA>(A)) return;    // before any TMEM allocation / barrier initialisation
+    const UniformSched sc(A.M, A.N, A.q, A.kmax, TBT);
+    const uint32_t tmem = tc_setup<128>(&S.tmem_base, &S.bar);
+    uint32_t phase = 0;
+    const float* cached_th = nullptr;
+    grad_tc_tiles<DO, DA, NQ>(A, S, sc, tmem, &S.bar, phase, cached_th);
+    tc_teardown<128>(tmem);
 }
 
 
@@ -706,8 +827,10 @@ __device__ __forceinline__ void issue_gemm_3xtf32_ts(uint32_t d_tmem, const unsi
         umma_tf32(d_tmem, umma_desc(a0 + 2 * s * SCA, SCA, 128), umma_desc(bh + 2 * s * SCW, SCW, 128), idesc, 1);
 }
 
-template <int DO, int DA, int NQ>
-__global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A) {
+// Tile loop of the HVP kernel; same calling convention as grad_tc_tiles (TMEM: 512 columns... 384 used).
+template <int DO, int DA, int NQ, class Sched>
+__device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, DA, NQ>& S, const Sched& sc, uint32_t tmem,
+                                             uint64_t* bar, uint32_t& phase, const float*& cached_th) {
     constexpr int HID = TC_HID;
     using L = PLayout<DO, DA, HID>;
     using SL = SmallLayout<DO, DA>;
@@ -717,8 +840,6 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
     constexpr int PSTRIDE = L::P + PSTAT;
     constexpr int NPART = TCT / HID, BPP = TBT / NPART;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SM& S = *reinterpret_cast<SM*>(smem_raw);
     float* const sX = reinterpret_cast<float*>(S.T2a);
     float* const sMUP = reinterpret_cast<float*>(S.WB[0]);
     static_assert(TBT * DOP * 4 <= TILE_A_BYTES && NQ * TBT * 2 * DA * 4 <= 2 * TILE_W_BYTES, "aliased buffers must fit");
@@ -728,7 +849,6 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
     const int qd = warp & 3, cq = warp >> 2;               // TMEM lane quadrant, column group
     const int r = qd * 32 + lane, c0 = CW * cq;
     const int cj = tid & (HID - 1), cp = tid / HID;
-    const TileSched ts(A.M, A.N, A.q, TBT);
     const int N = A.N;
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
     int Nm = N;
@@ -737,18 +857,6 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
     const float* vg = nullptr;
     HeadIn<DA> hin;
     float rls[DA];
-    uint32_t phase = 0;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&S.tmem_base)), "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-    }
-    if (tid == 0) mbar_init(&S.bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     constexpr uint32_t C_Z2 = 0, C_RZ2 = 64, C_DH1 = 128, C_CH1 = 192, C_LOA = 256, C_LOB = 320;
 
@@ -766,22 +874,24 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
         gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
-    auto load_task = [&](int m, bool first) {
+    auto load_task = [&](int m) {
+        sc.wait_task(m);
         if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
         th = A.params + (int64_t)m * A.param_stride;
         vg = A.vec + (int64_t)m * L::P;
         __syncthreads();
-        const bool reload_p = first || A.param_stride != 0;
+        const bool reload_p = th != cached_th;      // CTA-uniform: S.Ps already holds these parameters
+        cached_th = th;
         for (int i = tid; i < DO * HID + HID; i += TCT) {
-            if (reload_p) S.Ps[SL::W0 + i] = __ldg(th + L::W0 + i);
+            if (reload_p) S.Ps[SL::W0 + i] = Sched::ldp(th + L::W0 + i);
             S.Vs[SL::W0 + i] = __ldcg(vg + L::W0 + i);
         }
         for (int i = tid; i < HID; i += TCT) {
-            if (reload_p) S.Ps[SL::B1 + i] = __ldg(th + L::B1 + i);
+            if (reload_p) S.Ps[SL::B1 + i] = Sched::ldp(th + L::B1 + i);
             S.Vs[SL::B1 + i] = __ldcg(vg + L::B1 + i);
         }
         for (int i = tid; i < HID * DA + 2 * DA; i += TCT) {
-            if (reload_p) S.Ps[SL::W2 + i] = __ldg(th + L::W2 + i);
+            if (reload_p) S.Ps[SL::W2 + i] = Sched::ldp(th + L::W2 + i);
             S.Vs[SL::W2 + i] = __ldcg(vg + L::W2 + i);
         }
         __syncthreads();
@@ -796,20 +906,36 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
         }
     };
     // (re)fill the weight buffer from L2: forward = [W1^T, V1^T], backward = [W1, ac*V1], each as hi (fp32) + lo
+    // 4 elements per thread and buffer: one conflict-free 16-byte shared-memory store each (the element-wise version paid a
+    // 4-way bank conflict on every forward-layout store: 1.0 M of the kernel's 1.2 M conflicts in the round-1 profile)
     auto load_weights = [&](bool fwd) {
-        for (int i = tid; i < HID * HID; i += TCT) {
-            const int k = i / HID, j = i % HID;
-            const float w = __ldg(th + L::W1 + i);
-            const float v = (fwd ? 1.f : ac) * __ldcg(vg + L::W1 + i);
-            const int off = fwd ? core_off(j, k, SCW) : core_off(k, j, SCW);
-            *reinterpret_cast<float*>(S.WB[0] + off) = w;
-            *reinterpret_cast<float*>(S.WB[1] + off) = w - tf32_trunc(w);
-            *reinterpret_cast<float*>(S.WB[2] + off) = v;
-            *reinterpret_cast<float*>(S.WB[3] + off) = v - tf32_trunc(v);
+        for (int u = tid; u < HID * HID / 4; u += TCT) {
+            float4 w, v;
+            int off;
+            if (fwd) {      // tile row = j, K = k: W1[4 kg .. 4 kg + 3][j], lanes run over j (coalesced 4-byte loads)
+                const int j = u % HID, kg = u / HID;
+                const float* sw = th + L::W1 + 4 * kg * HID + j;
+                const float* sv = vg + L::W1 + 4 * kg * HID + j;
+                w = make_float4(Sched::ldp(sw), Sched::ldp(sw + HID), Sched::ldp(sw + 2 * HID), Sched::ldp(sw + 3 * HID));
+                v = make_float4(__ldcg(sv), __ldcg(sv + HID), __ldcg(sv + 2 * HID), __ldcg(sv + 3 * HID));
+                off = kg * SCW + (j >> 3) * 128 + (j & 7) * 16;
+            } else {        // tile row = k, K = j: one 16-byte load of W1[k][4 jg ..]
+                const int jg = u % (HID / 4), k = u / (HID / 4);
+                w = Sched::ldp4(reinterpret_cast<const float4*>(th + L::W1 + k * HID + 4 * jg));
+                v = __ldcg(reinterpret_cast<const float4*>(vg + L::W1 + k * HID + 4 * jg));
+                v = make_float4(ac * v.x, ac * v.y, ac * v.z, ac * v.w);
+                off = jg * SCW + (k >> 3) * 128 + (k & 7) * 16;
+            }
+            *reinterpret_cast<float4*>(S.WB[0] + off) = w;
+            *reinterpret_cast<float4*>(S.WB[1] + off) =
+                make_float4(w.x - tf32_trunc(w.x), w.y - tf32_trunc(w.y), w.z - tf32_trunc(w.z), w.w - tf32_trunc(w.w));
+            *reinterpret_cast<float4*>(S.WB[2] + off) = v;
+            *reinterpret_cast<float4*>(S.WB[3] + off) =
+                make_float4(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y), v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w));
         }
     };
     auto flush = [&](int m) {
-        float* part = A.partial + ((int64_t)blockIdx.x * A.kmax + (m - ts.first_task(blockIdx.x))) * PSTRIDE;
+        float* part = A.partial + (int64_t)sc.my_slot(m) * PSTRIDE;
         float* scr = reinterpret_cast<float*>(S.T2a);     // T2a + T2b (contiguous, 2 tiles)
         static_assert(NPART * DO * HID * 4 <= 2 * TILE_A_BYTES && NPART * HID * DA * 4 <= 2 * TILE_A_BYTES, "flush scratch");
         __syncthreads();
@@ -867,13 +993,13 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
         }
         __threadfence();
         __syncthreads();
-        const int c_lo = ts.cta_lo(m), c_hi = ts.cta_hi(m);
-        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == c_hi - c_lo);
+        const int n_c = sc.n_contrib(m);
+        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == n_c - 1);
         __syncthreads();
         if (S.last) {
             __threadfence();
             for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
-                const float4 s = reduce_segments4(A.partial, ts, A.kmax, PSTRIDE, m, c_lo, c_hi, p);
+                const float4 s = reduce_slots4(A.partial, sc, PSTRIDE, m, n_c, p);
                 if (p == L::P) {                  // trailing float4 of the slot: objective / KL / ratio sums
                     if (A.stats)
                         A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN,
@@ -884,16 +1010,17 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
                 *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) = make_float4(v4.x + s.x, v4.y + s.y, v4.z + s.z, v4.w + s.w);
             }
             if (tid == 0) A.counters[m] = 0;
+            sc.publish_task(m);
         }
         __syncthreads();
     };
 
     int cur_m = -1;
-    for (int g = ts.g_lo; g < ts.g_hi; ++g) {
-        const int m = g / ts.ntiles, tile = g - m * ts.ntiles;
+    for (int g = sc.g_lo; g < sc.g_hi; ++g) {
+        const int m = g / sc.ntiles, tile = g - m * sc.ntiles;
         if (m != cur_m) {
             if (cur_m >= 0) flush(cur_m);
-            load_task(m, cur_m < 0);
+            load_task(m);
             zero_acc();
             cur_m = m;
         }
@@ -947,9 +1074,9 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A
             issue_gemm_3xtf32_ts(tmem + C_Z2, S.H1, tmem + C_LOA, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_RZ2, S.R1, tmem + C_LOB, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_RZ2, S.H1, tmem + C_LOA, S.WB[2], S.WB[3], 1);
-            umma_commit(&S.bar);
+            umma_commit(bar);
         }
-        mbar_wait(&S.bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
         float h2[CW], r2[CW];
@@ -1092,7 +1219,7 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
             issue_gemm_3xtf32_ts(tmem + C_DH1, S.T2a, tmem + C_LOA, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_CH1, S.T2b, tmem + C_LOB, S.WB[0], S.WB[1], 0);
             issue_gemm_3xtf32_ts(tmem + C_CH1, S.T2a, tmem + C_LOA, S.WB[2], S.WB[3], 1);
-            umma_commit(&S.bar);
+            umma_commit(bar);
         }
         // ---- ... overlapped with the weight gradients out_W1 += H1^T C2 + R1^T (ac D2) (mma.sync 3xTF32) and colsum(C2)
         {
@@ -1100,7 +1227,7 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
             wgrad_mma_tile<true, NT>(S.H1, S.T2b, 1.f, warp, lane, gW1, gB1f);
             wgrad_mma_tile<false, NT>(S.R1, S.T2a, ac, warp, lane, gW1, unused);
         }
-        mbar_wait(&S.bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
         float dh1[CW], ch1[CW];
@@ -1138,9 +1265,134 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
         }
     }
     if (cur_m >= 0) flush(cur_m);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+}
+
+template <int DO, int DA, int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) policy_hvp_tc_kernel(PolicyArgs A) {
+    using SM = HvpTcSmem<DO, DA, NQ>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+    const UniformSched sc(A.M, A.N, A.q, A.kmax, TBT);
+    const uint32_t tmem = tc_setup<512>(&S.tmem_base, &S.bar);
+    uint32_t phase = 0;
+    const float* cached_th = nullptr;
+    hvp_tc_tiles<DO, DA, NQ>(A, S, sc, tmem, &S.bar, phase, cached_th);
+    tc_teardown<512>(tmem);
+}
+
+// =================================================================================================================
+// Dataflow kernel: the whole gradient chain of one meta-objective evaluation in ONE persistent launch
+//   stage 0..S-2   inner gradients + SGD step (theta_{s+1,m} = theta_{s,m} - alpha grad)        grad_tc_tiles
+//   stage S-1      outer gradient v_m at the adapted parameters                                  grad_tc_tiles
+//   stage S..      backward chain v_m <- v_m - alpha H v_m + c grad KL                           hvp_tc_tiles
+// Stage k of task m only depends on stage k-1 of the SAME task, so the stages of different tasks overlap: CTAs pull work
+// items (a few consecutive tiles of one task in one stage; ids ordered by stage, then task) from a device-side queue,
+// the last arriver of a (stage, task) reduces its partial slots in item order (deterministic) and raises that task's
+// ready flag, and an item of stage k+1 spins on the flag of its task before it reads the parameters / direction vector
+// the previous stage produced.  Every id below the one a CTA holds has been taken by a CTA that is already running, so
+// the spin always terminates whatever the residency.  Versus three launches this removes the tile-quantisation loss of
+// each launch (640 tiles on 148 SMs = 5 rounds for 4.3), two launch tails and the idle time between them; the items of
+// the last stage get smaller towards the end so the final imbalance is one tile.
+// Control words (queue, finished-CTA count, ready flags, arrival counters) are zero on entry and left zero by the last
+// CTA to finish.
+constexpr int CHAIN_MAX_STAGES = 6;
+constexpr int CHAIN_MAX_REGIONS = 3;
+struct ChainStageInfo {
+    int kind;                              // 0 = gradient stage, 1 = HVP stage
+    int ntiles;                            // 128-sample tiles per task
+    int item_base, n_items;                // global ids of the stage's items: [item_base, item_base + n_items)
+    int n_regions;
+    int reg_m0[CHAIN_MAX_REGIONS + 1];     // region r = tasks [reg_m0[r], reg_m0[r+1])
+    int reg_q[CHAIN_MAX_REGIONS];          // tiles per item in region r
+    int reg_item0[CHAIN_MAX_REGIONS];      // stage-relative id of the region's first item
+};
+struct ChainArgs {
+    int n_stages, n_items, M;
+    int* ctrl;                             // [0] work queue, [1] finished CTAs
+    int* ready;                            // [n_stages][M]
+    const int* skip_flag;                  // launch re-use of stage 0 (see PolicyArgs): both null or both set
+    const float* skip_theta;
+    ChainStageInfo info[CHAIN_MAX_STAGES];
+    PolicyArgs st[CHAIN_MAX_STAGES];
+};
+
+template <int DO, int DA, int NQ>
+struct ChainSmem {
+    static constexpr int BODY = (int)((sizeof(GradTcSmem<DO, DA, NQ>) > sizeof(HvpTcSmem<DO, DA, NQ>) ? sizeof(GradTcSmem<DO, DA, NQ>)
+                                                                                                    : sizeof(HvpTcSmem<DO, DA, NQ>)) + 15) / 16 * 16;
+    static constexpr int SIZE = BODY + 32;     // + {mbarrier, TMEM base, current item}
+};
+
+template <int DO, int DA, int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __grid_constant__ ChainArgs C) {
+    using GS = GradTcSmem<DO, DA, NQ>;
+    using HS = HvpTcSmem<DO, DA, NQ>;
+    using L = PLayout<DO, DA, TC_HID>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GS& G = *reinterpret_cast<GS*>(smem_raw);              // the two layouts time-share the same bytes
+    HS& H = *reinterpret_cast<HS*>(smem_raw);
+    unsigned char* ctl = smem_raw + ChainSmem<DO, DA, NQ>::BODY;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ctl);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8);
+    int* cur_item = reinterpret_cast<int*>(ctl + 12);
+    const int tid = threadIdx.x;
+
+    // launch re-use: stage 0 repeats an earlier stand-alone launch whose outputs are still in place (see promp_policy_grad_ex)
+    bool skip0 = false;
+    if (C.skip_flag) {
+        bool same = *reinterpret_cast<const volatile int*>(C.skip_flag) != 0;
+        for (int i = tid; i < L::P && same; i += blockDim.x)
+            same = __float_as_uint(__ldcg(C.st[0].params + i)) == __float_as_uint(__ldcg(C.skip_theta + i));
+        skip0 = __syncthreads_and(same ? 1 : 0) != 0;
+    }
+    const uint32_t tmem = tc_setup<512>(tmem_slot, bar);
+    uint32_t phase = 0;
+    const float* cached_g = nullptr;
+    const float* cached_h = nullptr;
+    for (;;) {
+        __syncthreads();                                   // everybody is done with the previous item (and its *cur_item)
+        if (tid == 0) *cur_item = atomicAdd(C.ctrl, 1);
+        __syncthreads();
+        const int it = *cur_item;
+        if (it >= C.n_items) break;
+        int s = 0;
+        while (s + 1 < C.n_stages && it >= C.info[s + 1].item_base) ++s;
+        if (s == 0 && skip0) continue;
+        const ChainStageInfo& I = C.info[s];
+        const int j = it - I.item_base;
+        int r = 0;
+        while (r + 1 < I.n_regions && j >= I.reg_item0[r + 1]) ++r;
+        const int q = I.reg_q[r], per_task = (I.ntiles + q - 1) / q;
+        const int jr = j - I.reg_item0[r];
+        const int mr = jr / per_task, k = jr - mr * per_task;
+        const int m = I.reg_m0[r] + mr;
+        ItemSched sc;
+        sc.ntiles = I.ntiles;
+        sc.g_lo = m * I.ntiles + k * q;
+        sc.g_hi = m * I.ntiles + min(k * q + q, I.ntiles);
+        sc.item = it;
+        sc.first_item = I.item_base + I.reg_item0[r] + mr * per_task;
+        sc.n_items = per_task;
+        sc.ready_prev = (s > 0 && !(s == 1 && skip0)) ? C.ready + (s - 1) * C.M : nullptr;
+        sc.ready_mine = C.ready + s * C.M;
+        if (I.kind == 0) {
+            cached_h = nullptr;
+            grad_tc_tiles<DO, DA, NQ>(C.st[s], G, sc, tmem, bar, phase, cached_g);
+        } else {
+            cached_g = nullptr;
+            hvp_tc_tiles<DO, DA, NQ>(C.st[s], H, sc, tmem, bar, phase, cached_h);
+        }
+    }
+    tc_teardown<512>(tmem);
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(C.ctrl + 1, 1) == (int)gridDim.x - 1) {       // every CTA has left the loop: nobody reads the flags any more
+            for (int i = 0; i < C.n_stages * C.M; ++i) C.ready[i] = 0;
+            C.ctrl[0] = 0;
+            C.ctrl[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace promp

@@ -11,6 +11,9 @@ differentiate through the inner SGD step.  Here the same quantities are produced
 which is exactly d/dtheta of the meta objective for any number of inner steps (the backward chain
 is the transpose of d theta_{s+1} / d theta_s = I - alpha H_s).
 """
+import ctypes
+import os
+
 import numpy as np
 
 from promp_b200 import _lib
@@ -41,6 +44,9 @@ class MAMLAlgo(object):
         self.trainable_inner_step_size = trainable_inner_step_size
         self._optimization_keys = None
         self._ws = None
+        self._ws_chain = None
+        # the gradient chain of a meta-objective evaluation as ONE dataflow launch (promp_policy_chain) or as one launch per stage
+        self.use_chain = os.environ.get('PROMP_B200_CHAIN', '1') != '0'
 
     # ------------------------------------------------------------------------------------ helpers
     def _workspace(self, N):
@@ -95,6 +101,38 @@ class MAMLAlgo(object):
                   _lib.ptr(phase.mean), _lib.ptr(old_ls), per_sample, obj_kind, float(obj_scale), float(clip_eps),
                   float(kl_coeff), int(clip_log_std), float(p.min_log_std), _lib.ptr(grad), _lib.ptr(out_params),
                   float(sgd_lr), _lib.ptr(stats), skip[0], skip[1], prod[0], prod[1], _lib.ptr(ws), ws.numel() * 4, _lib.stream())
+
+    def _stage(self, kind, phase, params, stride, obj_kind, obj_scale=1.0, clip_eps=0.0, kl_coeff=0.0, clip_log_std=0, grad=None,
+               out_params=None, sgd_lr=0.0, vec=None, out=None, stats=None):
+        """One promp_policy_stage (kind 0: the arguments of _grad, kind 1: those of _hvp)."""
+        full = getattr(phase, 'log_std_full', None)
+        old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
+        st = _lib.PolicyStage()
+        st.kind, st.N, st.n_valid = kind, phase.N, _lib.ptr(getattr(phase, 'n_valid', None))
+        st.params, st.param_stride = _lib.ptr(params), stride
+        st.obs, st.act, st.adv, st.old_mean, st.old_log_std = (_lib.ptr(phase.obs), _lib.ptr(phase.act), _lib.ptr(phase.adv),
+                                                               _lib.ptr(phase.mean), _lib.ptr(old_ls))
+        st.ls_per_sample, st.obj_kind, st.obj_scale, st.clip_eps = per_sample, obj_kind, float(obj_scale), float(clip_eps)
+        st.kl_coeff, st.clip_log_std = float(kl_coeff), int(clip_log_std)
+        st.grad, st.out_params, st.sgd_lr = _lib.ptr(grad), _lib.ptr(out_params), float(sgd_lr)
+        st.inner_lr, st.vec, st.out, st.stats = float(self.inner_lr), _lib.ptr(vec), _lib.ptr(out), _lib.ptr(stats)
+        return st
+
+    def _run_chain(self, stages, reuse=None):
+        """promp_policy_chain over a list of PolicyStage (all buffers must stay alive until the launch has run)."""
+        import torch
+        p = self.policy
+        arr = (_lib.PolicyStage * len(stages))(*stages)
+        need = _lib.load().promp_policy_chain_workspace_bytes(p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, len(stages),
+                                                              ctypes.cast(arr, ctypes.c_void_p))
+        if need < 0:
+            raise _lib.PrompLibraryError("promp_policy_chain_workspace_bytes: " + _lib.last_error())
+        if self._ws_chain is None or self._ws_chain.numel() * 4 < need:
+            self._ws_chain = torch.zeros((need + 3) // 4, dtype=torch.int32, device=p.device)   # control words start at zero
+        ws = self._ws_chain
+        skip = (_lib.ptr(reuse[0]), _lib.ptr(reuse[1])) if reuse is not None else (None, None)
+        _lib.call('promp_policy_chain', p.obs_dim, p.action_dim, p.hidden, self.meta_batch_size, float(p.min_log_std), len(stages),
+                  ctypes.cast(arr, ctypes.c_void_p), skip[0], skip[1], _lib.ptr(ws), ws.numel() * 4, _lib.stream())
 
     def _hvp(self, phase, params, stride, vec, out, kl_coeff, clip_log_std, stats=None):
         p = self.policy
@@ -176,6 +214,38 @@ class MAMLAlgo(object):
         if reuse0:
             stats_all = cache['stats_all']
             self._adapt_cache = None          # one consumer: later passes (updated theta) use their own buffers
+        if self.use_chain and (S >= 2 or want_grad):
+            # the whole chain - inner gradients + SGD steps, outer gradient, backward Hessian-vector chain - as ONE launch
+            stages = []
+            for s in range(S - 1):
+                if s == 0 and reuse0:
+                    g, nxt = cache['grad'], cache['new']
+                else:
+                    g = torch.empty(M, P, dtype=torch.float32, device=dev)
+                    nxt = torch.empty(M, P, dtype=torch.float32, device=dev)
+                stages.append(self._stage(0, phases[s], cur, stride, self.inner_obj_kind, clip_log_std=clip, grad=g, out_params=nxt,
+                                          sgd_lr=self.inner_lr, stats=stats_all[s]))
+                chain.append((cur, stride, clip, g))
+                cur, stride, clip = nxt, P, 0
+            v = torch.empty(M, P, dtype=torch.float32, device=dev) if want_grad else None
+            stages.append(self._stage(0, phases[-1], cur, stride, outer_obj_kind, obj_scale=outer_obj_scale, clip_eps=clip_eps,
+                                      kl_coeff=outer_kl_coeff, clip_log_std=clip, grad=v, stats=stats_all[S - 1]))
+            if want_grad:
+                for s in range(S - 2, -1, -1):
+                    prm, strd, clp, _ = chain[s]
+                    stages.append(self._stage(1, phases[s], prm, strd, self.inner_obj_kind, kl_coeff=inner_kl_coeffs[s],
+                                              clip_log_std=clp, vec=v, out=v))
+            self._run_chain(stages, reuse=self._reuse_bufs if reuse0 else None)
+            out = dict(surr=stats_all[S - 1, :, 0], outer_kl=stats_all[S - 1, :, 1], inner_kl=stats_all[:S - 1, :, 1],
+                       stats_all=stats_all, grad=None)
+            if want_grad:
+                if reduce:
+                    flat = torch.empty(P, dtype=torch.float32, device=dev)
+                    _lib.call('promp_reduce_tasks', M, P, _lib.ptr(v), 1.0 / (M * world_size()), _lib.ptr(flat), _lib.stream())
+                    out['grad'] = flat
+                else:
+                    out['grad_tasks'] = v
+            return out
         for s in range(S - 1):
             if s == 0 and reuse0:
                 g, nxt = cache['grad'], cache['new']

@@ -1510,3 +1510,37 @@ def test_point_walls_and_momentum_envs(golden_dir):
     Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=1, num_inner_grad_steps=1).train()
     kv = logger.last_dump()
     assert np.isfinite(kv['LossAfter']) and np.isfinite(kv['Step_1-AverageReturn']) and not torch.equal(policy.theta, th0)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('Do,Da,M,N,S1', [(2, 2, 40, 2000, 1), (17, 6, 40, 4000, 1), (2, 2, 10, 2000, 1), (2, 2, 3, 130, 1),
+                                          (2, 2, 7, 700, 2), (4, 2, 5, 391, 1)])
+def test_dataflow_chain_matches_separate_launches(Do, Da, M, N, S1):
+    """promp_policy_chain (inner gradients -> outer gradient -> HVP chain as ONE persistent dataflow launch with per-task ready
+    flags) against the same stages as stand-alone launches, at the BASELINE.json sizes (configs[1] 40x2000, configs[2] 40x4000,
+    configs[3] 10 tasks per GPU) and at ragged-edge sizes.  Same kernels' tile code, different partition of the per-task sums:
+    equal to float32 summation noise; the chain itself is bitwise run-to-run deterministic and leaves its control words zero."""
+    torch = _cuda()
+    policy, algo = _algo(torch, 'promp', M, Do, Da, 64, S1=S1)
+    theta = policy.theta.cpu().numpy()
+    phases = [_random_phase(torch, M, N, Do, Da, theta, 20 + s, 64)[1] for s in range(S1 + 1)]
+
+    def run(chain, want_grad=True):
+        algo.use_chain = chain
+        res = algo._objective_pass(phases, want_grad=want_grad, reduce=False)
+        torch.cuda.synchronize()
+        return (res['grad_tasks'].clone() if want_grad else None), res['stats_all'].clone()
+    g_ref, st_ref = run(False)
+    g1, st1 = run(True)
+    g2, st2 = run(True)
+    assert torch.equal(g1, g2) and torch.equal(st1, st2), "dataflow chain is not run-to-run deterministic"
+    assert torch.isfinite(g1).all()
+    for m in range(M):
+        e = rel_err(g1[m].cpu().numpy(), g_ref[m].cpu().numpy())
+        assert e < 2e-5, (m, e)
+    np.testing.assert_allclose(st1[:, :, :3].cpu().numpy(), st_ref[:, :, :3].cpu().numpy(), rtol=2e-5, atol=1e-6)
+    # values-only chain (the statistics pass after the last Adam epoch)
+    _, st3 = run(True, want_grad=False)
+    np.testing.assert_allclose(st3[:, :, :3].cpu().numpy(), st_ref[:, :, :3].cpu().numpy(), rtol=2e-5, atol=1e-6)
+    ctrl = algo._ws_chain[:4 + 2 * 6 * M].cpu().numpy()
+    assert (ctrl == 0).all(), "control words (queue, finished-CTA count, ready flags, arrival counters) must be left zero"
