@@ -1135,7 +1135,9 @@ static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st
 }
 
 // ---- dataflow chain (policy_chain_tc_kernel): work-item plan + launch ---------------------------------------------
-static int g_chain = 1;          // promp_set_option("chain", 0|1): 0 = promp_policy_chain launches its stages one by one
+static int g_chain = -1;         // promp_set_option("chain", -1|0|1): dataflow kernel always (1), never (0: one launch per stage), or
+                                 // where it wins (-1, default): chains whose stages are short - at most two tiles per SM - so that
+                                 // launch tails and the tile-quantisation of every single launch dominate (measured)
 static int g_chain_q = 0;        // promp_set_option("chain_q", q): tiles per work item (0 = automatic)
 static int g_chain_taper = 1;    // promp_set_option("chain_taper", 0|1): last stage's items shrink to one tile towards the end
 
@@ -1228,7 +1230,9 @@ static int launch_chain(int n_stages, const int* kinds, PolicyArgs* A, const int
     const int M = A[0].M;
     const ChainPlan pl = plan_chain(n_stages, kinds, Ns, M, P);
     if constexpr (chain_tc_ok<DO, DA, HID>()) {
-        if (g_use_tc && g_chain) {
+        bool small = true;
+        for (int s = 0; s < n_stages; ++s) small = small && (int64_t)M * pl.info[s].ntiles <= 2 * sm_count();
+        if (g_use_tc && (g_chain == 1 || (g_chain < 0 && small))) {
             if (ws_bytes < pl.bytes) {
                 set_error("policy chain workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.bytes);
                 return PROMP_ERR_WORKSPACE;
@@ -1458,8 +1462,8 @@ extern "C" int promp_set_option(const char* name, int value) {
         g_use_tc = value ? 1 : 0;
         return PROMP_OK;
     }
-    if (strcmp(name, "chain") == 0) {          // promp_policy_chain: dataflow kernel (1, default) or one launch per stage (0)
-        g_chain = value ? 1 : 0;
+    if (strcmp(name, "chain") == 0) {          // promp_policy_chain: dataflow kernel (1), one launch per stage (0), automatic (-1)
+        g_chain = value < 0 ? -1 : (value ? 1 : 0);
         return PROMP_OK;
     }
     if (strcmp(name, "chain_q") == 0) {        // tiles per work item of the dataflow kernel (0 = automatic)
@@ -1530,6 +1534,15 @@ extern "C" int promp_adam_tf1(int P, float* theta, const float* grad, float* m, 
 }
 
 #ifdef PROMP_EXP_CLOCKS
+extern "C" int promp_debug_chain_clocks(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, promp::g_chain_clk, 16 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(promp::g_chain_clk, z, sizeof(z));
+    }
+    return 0;
+}
 extern "C" int promp_debug_phase_clocks(unsigned long long* out16, int reset) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out16, promp::g_phase_clk, 16 * sizeof(unsigned long long));

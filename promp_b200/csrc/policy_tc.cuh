@@ -240,6 +240,28 @@ __device__ __forceinline__ int wgrad_mma_index(int warp, int lane, int nt, int i
 //   ldp                     parameter loads: read-only path (.nc) when nothing in this launch writes them, L2 (.cg) otherwise
 // UniformSched = the stand-alone launches (CTA c owns tiles [c q, (c+1) q), kmax slots per CTA); ItemSched = one work
 // item of policy_chain_tc_kernel (tiles [tile_lo, tile_hi) of ONE task; slots are numbered by item id).
+#ifdef PROMP_EXP_CLOCKS
+// experiment build only: clock64 totals over ALL CTAs of policy_chain_tc_kernel (thread 0 of each CTA):
+// 0 queue pop + decode, 1 dependency wait, 2 parameter / weight load, 3 tiles, 4 flush up to the ticket, 5 last-arriver
+// reduction + publish, 6 items, 7 last arrivals, 8 whole kernel (sum over CTAs), 9 CTAs
+__device__ unsigned long long g_chain_clk[16];
+__device__ long long g_chain_last[1024];
+#define CCLK(i)                                                                                  \
+    do {                                                                                         \
+        if (threadIdx.x == 0) {                                                                  \
+            const long long t_ = clock64();                                                      \
+            atomicAdd(&g_chain_clk[i], (unsigned long long)(t_ - g_chain_last[blockIdx.x]));     \
+            g_chain_last[blockIdx.x] = t_;                                                       \
+        }                                                                                        \
+    } while (0)
+#define CCNT(i)                                            \
+    do {                                                   \
+        if (threadIdx.x == 0) atomicAdd(&g_chain_clk[i], 1ull); \
+    } while (0)
+#else
+#define CCLK(i)
+#define CCNT(i)
+#endif
 struct UniformSched {
     int ntiles, g_lo, g_hi, q, kmax;
     __device__ __forceinline__ UniformSched(int M, int N, int q_, int kmax_, int tb) {
@@ -260,6 +282,7 @@ struct UniformSched {
     }
     __device__ __forceinline__ void wait_task(int) const {}
     __device__ __forceinline__ void publish_task(int) const {}
+    __device__ __forceinline__ void clk(int) const {}
     static __device__ __forceinline__ float ldp(const float* p) { return __ldg(p); }
     static __device__ __forceinline__ float4 ldp4(const float4* p) { return __ldg(p); }
 };
@@ -271,6 +294,7 @@ struct ItemSched {
     __device__ __forceinline__ int my_slot(int) const { return item; }
     __device__ __forceinline__ int n_contrib(int) const { return n_items; }
     __device__ __forceinline__ int contrib_slot(int, int i) const { return first_item + i; }
+    __device__ __forceinline__ void clk(int i) const { CCLK(i); }
     __device__ __forceinline__ void wait_task(int m) const {       // called by every thread of the CTA
         if (ready_prev == nullptr) return;
         if (threadIdx.x == 0) {
@@ -283,18 +307,22 @@ struct ItemSched {
                     const long long t = clock64();
                     if (t0 == 0) t0 = t;
                     else if (t - t0 > 8000000000ll) {              // ~4 s
+#ifndef PROMP_CHAIN_NO_PRINTF
                         printf("promp_b200: policy chain item %d waited > 4 s for task %d of the previous stage\n", item, m);
+#endif
                         __trap();
                     }
                 }
             } while (v == 0);
         }
         __syncthreads();
+        CCLK(1);
     }
     __device__ __forceinline__ void publish_task(int m) const {    // called by every thread of the task's last arriver
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(ready_mine + m), "r"(1) : "memory");
+        CCNT(7);
     }
     static __device__ __forceinline__ float ldp(const float* p) { return __ldcg(p); }
     static __device__ __forceinline__ float4 ldp4(const float4* p) { return __ldcg(p); }
@@ -423,6 +451,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
         }
     };
     auto flush = [&](int m) {
+        sc.clk(3);
         float* part = A.partial + (int64_t)sc.my_slot(m) * PSTRIDE;
         float* scr = reinterpret_cast<float*>(S.A1);      // A1 + LO (contiguous, 2 tiles): free between tiles (all MMAs have completed)
         static_assert(NPART * DO * HID * 4 <= 2 * TILE_A_BYTES && NPART * HID * DA * 4 <= 2 * TILE_A_BYTES, "flush scratch");
@@ -481,13 +510,16 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
             for (int w = 0; w < NW; ++w) s += S.red[tid * NW + w];
             part[L::P + tid] = s;
         }
-        __threadfence();
         __syncthreads();
         PCLK(14);
         const int n_c = sc.n_contrib(m);
-        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == n_c - 1);
+        if (tid == 0) {          // release by ONE thread: the barrier above orders the CTA's partial-slot writes before this fence
+            __threadfence();
+            S.last = (atomicAdd(A.counters + m, 1) == n_c - 1);
+        }
         __syncthreads();
         PCLK(15);
+        sc.clk(4);
         if (S.last) {
             __threadfence();
             // the trailing float4 of every partial slot holds the objective / KL / ratio sums: reduced by the same loop
@@ -515,10 +547,24 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
             }
             if (tid == 0) A.counters[m] = 0;
             sc.publish_task(m);
+            sc.clk(5);
         }
         __syncthreads();
     };
 
+    // observation prefetch (small observation / action spaces: one or two elements per thread, registers to spare)
+    constexpr int XR = (TBT * DOP) / TCT;
+    constexpr bool XPRE = (TBT * DOP) % TCT == 0 && XR >= 1 && XR <= 2 && DA <= 2;
+    float xq[XPRE ? XR : 1], ha[DA], hmo[DA], hlso[DA], hadv = 0.f;
+    auto fetch_x = [&](int g_, float (&dst)[XPRE ? XR : 1]) {
+        const int m_ = g_ / sc.ntiles, n0_ = (g_ - m_ * sc.ntiles) * TBT;
+        const int nb_ = max(0, min(TBT, (A.n_valid ? __ldg(A.n_valid + m_) : N) - n0_));
+#pragma unroll
+        for (int e = 0; e < (XPRE ? XR : 1); ++e) {
+            const int i = tid + e * TCT, b = i / DOP, c = i % DOP;
+            dst[e] = (b < nb_ && c < DO) ? __ldg(A.obs + ((int64_t)m_ * N + n0_ + b) * DO + c) : 0.f;
+        }
+    };
     int cur_m = -1;
     for (int g = sc.g_lo; g < sc.g_hi; ++g) {
         const int m = g / sc.ntiles, tile = g - m * sc.ntiles;
@@ -527,6 +573,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
             if (cur_m >= 0) flush(cur_m);
             PCLK(11);
             load_task(m);
+            sc.clk(2);
             zero_acc();
             cur_m = m;
             PCLK(12);
@@ -534,9 +581,28 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
         const int n0 = tile * TBT, nb = max(0, min(TBT, Nm - n0));
         const int64_t g0 = (int64_t)m * N + n0;
         __syncthreads();
-        for (int i = tid; i < TBT * DOP; i += TCT) {
-            const int b = i / DOP, c = i % DOP;
-            S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+        if constexpr (XPRE) {
+            // software pipeline: this tile's observations were fetched while the previous tile was processed; the next
+            // tile's are fetched now, and the Gaussian head's per-sample inputs are requested ~10 k cycles before their use
+            if (g == sc.g_lo) fetch_x(g, xq);
+#pragma unroll
+            for (int e = 0; e < XR; ++e) S.X[tid + e * TCT] = xq[e];
+            if (g + 1 < sc.g_hi) fetch_x(g + 1, xq);
+            if (cq == 0 && r < nb) {
+                const int64_t n = g0 + r;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    ha[d] = __ldg(A.act + n * DA + d);
+                    hmo[d] = __ldg(A.old_mean + n * DA + d);
+                    hlso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                }
+                hadv = __ldg(A.adv + n);
+            }
+        } else {
+            for (int i = tid; i < TBT * DOP; i += TCT) {
+                const int b = i / DOP, c = i % DOP;
+                S.X[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
+            }
         }
         __syncthreads();
         PCLK(0);
@@ -611,11 +677,15 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) sm += S.MUP[(q * TBT + r) * DA + d];
                     mu[d] = sm;
-                    a[d] = __ldg(A.act + n * DA + d);
-                    mo[d] = __ldg(A.old_mean + n * DA + d);
-                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    if constexpr (XPRE) {
+                        a[d] = ha[d], mo[d] = hmo[d], lso[d] = hlso[d];
+                    } else {
+                        a[d] = __ldg(A.act + n * DA + d);
+                        mo[d] = __ldg(A.old_mean + n * DA + d);
+                        lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    }
                 }
-                const float adv = __ldg(A.adv + n);
+                const float adv = XPRE ? hadv : __ldg(A.adv + n);
                 HeadOut<DA> o;
                 gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
                 const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
@@ -935,6 +1005,7 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
         }
     };
     auto flush = [&](int m) {
+        sc.clk(3);
         float* part = A.partial + (int64_t)sc.my_slot(m) * PSTRIDE;
         float* scr = reinterpret_cast<float*>(S.T2a);     // T2a + T2b (contiguous, 2 tiles)
         static_assert(NPART * DO * HID * 4 <= 2 * TILE_A_BYTES && NPART * HID * DA * 4 <= 2 * TILE_A_BYTES, "flush scratch");
@@ -991,11 +1062,14 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
             for (int w = 0; w < NW; ++w) s += S.red[tid * NW + w];
             part[L::P + tid] = s;
         }
-        __threadfence();
         __syncthreads();
         const int n_c = sc.n_contrib(m);
-        if (tid == 0) S.last = (atomicAdd(A.counters + m, 1) == n_c - 1);
+        if (tid == 0) {          // release by ONE thread: the barrier above orders the CTA's partial-slot writes before this fence
+            __threadfence();
+            S.last = (atomicAdd(A.counters + m, 1) == n_c - 1);
+        }
         __syncthreads();
+        sc.clk(4);
         if (S.last) {
             __threadfence();
             for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
@@ -1011,16 +1085,30 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
             }
             if (tid == 0) A.counters[m] = 0;
             sc.publish_task(m);
+            sc.clk(5);
         }
         __syncthreads();
     };
 
+    constexpr int XR = (TBT * DOP) / TCT;
+    constexpr bool XPRE = (TBT * DOP) % TCT == 0 && XR >= 1 && XR <= 2 && DA <= 2;
+    float xq[XPRE ? XR : 1], xc[XPRE ? XR : 1], ha[DA], hmo[DA], hlso[DA], hadv = 0.f;
+    auto fetch_x = [&](int g_, float (&dst)[XPRE ? XR : 1]) {
+        const int m_ = g_ / sc.ntiles, n0_ = (g_ - m_ * sc.ntiles) * TBT;
+        const int nb_ = max(0, min(TBT, (A.n_valid ? __ldg(A.n_valid + m_) : N) - n0_));
+#pragma unroll
+        for (int e = 0; e < (XPRE ? XR : 1); ++e) {
+            const int i = tid + e * TCT, b = i / DOP, c = i % DOP;
+            dst[e] = (b < nb_ && c < DO) ? __ldg(A.obs + ((int64_t)m_ * N + n0_ + b) * DO + c) : 0.f;
+        }
+    };
     int cur_m = -1;
     for (int g = sc.g_lo; g < sc.g_hi; ++g) {
         const int m = g / sc.ntiles, tile = g - m * sc.ntiles;
         if (m != cur_m) {
             if (cur_m >= 0) flush(cur_m);
             load_task(m);
+            sc.clk(2);
             zero_acc();
             cur_m = m;
         }
@@ -1033,7 +1121,24 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
                 sX[i] = (b < nb && c < DO) ? __ldg(A.obs + (g0 + b) * DO + c) : 0.f;
             }
         };
-        load_x();
+        if constexpr (XPRE) {      // software pipeline, as in grad_tc_tiles; xc keeps this tile's elements for the second use below
+            if (g == sc.g_lo) fetch_x(g, xq);
+#pragma unroll
+            for (int e = 0; e < XR; ++e) xc[e] = xq[e], sX[tid + e * TCT] = xc[e];
+            if (g + 1 < sc.g_hi) fetch_x(g + 1, xq);
+            if (cq == 0 && r < nb) {
+                const int64_t n = g0 + r;
+#pragma unroll
+                for (int d = 0; d < DA; ++d) {
+                    ha[d] = __ldg(A.act + n * DA + d);
+                    hmo[d] = __ldg(A.old_mean + n * DA + d);
+                    hlso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                }
+                hadv = __ldg(A.adv + n);
+            }
+        } else {
+            load_x();
+        }
         load_weights(true);
         __syncthreads();
         // ---- layer 0 and its tangent (CUDA cores, row / column-group role); lo parts of H1 / R1 -> TMEM
@@ -1125,11 +1230,15 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
                     for (int q = 0; q < NQ; ++q) sm += sMUP[((q * TBT + r) * 2 + 0) * DA + d], sr += sMUP[((q * TBT + r) * 2 + 1) * DA + d];
                     mu[d] = sm;
                     rmu[d] = sr;
-                    a[d] = __ldg(A.act + n * DA + d);
-                    mo[d] = __ldg(A.old_mean + n * DA + d);
-                    lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    if constexpr (XPRE) {
+                        a[d] = ha[d], mo[d] = hmo[d], lso[d] = hlso[d];
+                    } else {
+                        a[d] = __ldg(A.act + n * DA + d);
+                        mo[d] = __ldg(A.old_mean + n * DA + d);
+                        lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    }
                 }
-                const float adv = __ldg(A.adv + n);
+                const float adv = XPRE ? hadv : __ldg(A.adv + n);
                 HeadOut<DA> o;
                 gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
                 const float wt = o.w * invN, kc = A.kl_coeff * invN;
@@ -1249,7 +1358,12 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
                 c1[e] = ch1[4 * c4 + e] * (1.f - hv[e] * hv[e]) + ac * dh1[4 * c4 + e] * (-2.f * hv[e] * rv[e]);
             *p = make_float4(c1[0], c1[1], c1[2], c1[3]);
         }
-        load_x();              // D2 (T2a) is dead: bring the observations back for the input-layer gradient
+        if constexpr (XPRE) {  // D2 (T2a) is dead: bring the observations back for the input-layer gradient
+#pragma unroll
+            for (int e = 0; e < XR; ++e) sX[tid + e * TCT] = xc[e];
+        } else {
+            load_x();
+        }
         __syncthreads();
         // ---- out_W0 += X^T C1 ; out_b0 += colsum C1 (column role)
         {
@@ -1345,6 +1459,10 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __gr
             same = __float_as_uint(__ldcg(C.st[0].params + i)) == __float_as_uint(__ldcg(C.skip_theta + i));
         skip0 = __syncthreads_and(same ? 1 : 0) != 0;
     }
+#ifdef PROMP_EXP_CLOCKS
+    if (tid == 0) g_chain_last[blockIdx.x] = clock64();
+    const long long t_begin = clock64();
+#endif
     const uint32_t tmem = tc_setup<512>(tmem_slot, bar);
     uint32_t phase = 0;
     const float* cached_g = nullptr;
@@ -1355,6 +1473,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __gr
         __syncthreads();
         const int it = *cur_item;
         if (it >= C.n_items) break;
+        CCNT(6);
         int s = 0;
         while (s + 1 < C.n_stages && it >= C.info[s + 1].item_base) ++s;
         if (s == 0 && skip0) continue;
@@ -1375,6 +1494,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __gr
         sc.n_items = per_task;
         sc.ready_prev = (s > 0 && !(s == 1 && skip0)) ? C.ready + (s - 1) * C.M : nullptr;
         sc.ready_mine = C.ready + s * C.M;
+        CCLK(0);
         if (I.kind == 0) {
             cached_h = nullptr;
             grad_tc_tiles<DO, DA, NQ>(C.st[s], G, sc, tmem, bar, phase, cached_g);
@@ -1384,6 +1504,12 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __gr
         }
     }
     tc_teardown<512>(tmem);
+#ifdef PROMP_EXP_CLOCKS
+    if (tid == 0) {
+        atomicAdd(&g_chain_clk[8], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&g_chain_clk[9], 1ull);
+    }
+#endif
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(C.ctrl + 1, 1) == (int)gridDim.x - 1) {       // every CTA has left the loop: nobody reads the flags any more

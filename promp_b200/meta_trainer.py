@@ -168,8 +168,20 @@ class Trainer(object):
         host_part()
         # thread_local: other threads of this process (e.g. the NCCL watchdog polling its events) must not invalidate a long
         # capture (observed with the ~250-launch TRPO-MAML iteration at N = 2)
-        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
-            device_part()
+        # No cyclic garbage collection while the stream is capturing: a collected object that owns CUDA resources (e.g. the
+        # CUDAGraph of an earlier Trainer, kept alive by the reference cycle of its step closure) destroys them from this
+        # thread, which is a prohibited call during capture and invalidates it (observed: cudaErrorStreamCaptureInvalidated
+        # at a random launch of the second Trainer of a process).
+        import gc
+        gc.collect()
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                device_part()
+        finally:
+            if gc_was_enabled:
+                gc.enable()
         policy.theta.copy_(saved['theta'])
         if saved['adam'] is not None:
             for dst, src in zip((opt.m, opt.v, opt.step), saved['adam']):

@@ -1525,10 +1525,16 @@ def test_dataflow_chain_matches_separate_launches(Do, Da, M, N, S1):
     theta = policy.theta.cpu().numpy()
     phases = [_random_phase(torch, M, N, Do, Da, theta, 20 + s, 64)[1] for s in range(S1 + 1)]
 
+    from promp_b200 import _lib
+
     def run(chain, want_grad=True):
         algo.use_chain = chain
-        res = algo._objective_pass(phases, want_grad=want_grad, reduce=False)
-        torch.cuda.synchronize()
+        _lib.set_option('chain', 1)          # force the dataflow kernel (the default picks it for short stages only)
+        try:
+            res = algo._objective_pass(phases, want_grad=want_grad, reduce=False)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_option('chain', -1)
         return (res['grad_tasks'].clone() if want_grad else None), res['stats_all'].clone()
     g_ref, st_ref = run(False)
     g1, st1 = run(True)
