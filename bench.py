@@ -167,6 +167,8 @@ class LaunchCounter(object):
 
         def call(name, *args):
             k = me.KERNELS.get(name, 0)
+            if name == 'promp_policy_chain':     # one dataflow kernel or one kernel per stage: ask the library which
+                k = me._lib.load().promp_policy_chain_num_launches(args[0], args[1], args[2], args[3], args[5], args[6])
             me.count += k
             me.calls[name] = me.calls.get(name, 0) + 1
             if me.time_kernels and k:
@@ -318,6 +320,9 @@ def run_gpu(args):
     out = None
     # ---- per-kernel timing pass (instrumented, not part of the timed loops; every rank runs it because the
     #      iteration contains the all-reduce) --------------------------------------------------------------
+    # stand-alone launches of the policy kernels here (promp_policy_chain would time a whole gradient chain as one unit; at this
+    # size it launches the same kernels one after the other anyway - see promp_policy_chain_num_launches)
+    tr_dev.algo.use_chain = False
     with LaunchCounter(time_kernels=True) as lk:
         for i in range(3):
             tr_dev.train_iteration(i, log=False)

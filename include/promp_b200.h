@@ -381,6 +381,8 @@ typedef struct {
 } promp_policy_stage;
 int64_t promp_policy_chain_workspace_bytes(int obs_dim, int act_dim, int hidden, int M, int n_stages,
                                            const promp_policy_stage* stages);
+/* kernels promp_policy_chain launches for these stages with the current options: 1 (dataflow kernel) or n_stages */
+int promp_policy_chain_num_launches(int obs_dim, int act_dim, int hidden, int M, int n_stages, const promp_policy_stage* stages);
 int promp_policy_chain(int obs_dim, int act_dim, int hidden, int M, float min_log_std, int n_stages,
                        const promp_policy_stage* stages, const int32_t* skip_flag, const float* skip_theta,
                        void* workspace, int64_t workspace_bytes, void* stream);

@@ -1197,6 +1197,13 @@ static ChainPlan plan_chain(int n_stages, const int* kinds, const int* Ns, int M
     return pl;
 }
 
+// the automatic choice: dataflow kernel for chains of short stages (at most two tiles per SM), one launch per stage otherwise
+static bool chain_uses_dataflow(const ChainPlan& pl, int n_stages, int M) {
+    bool small = true;
+    for (int s = 0; s < n_stages; ++s) small = small && (int64_t)M * pl.info[s].ntiles <= 2 * sm_count();
+    return g_use_tc && (g_chain == 1 || (g_chain < 0 && small));
+}
+
 template <int DO, int DA, int HID>
 static constexpr bool chain_tc_ok() {
     if constexpr (HID == TC_HID) return ChainSmem<DO, DA, 2>::SIZE <= 227 * 1024 && ChainSmem<DO, DA, 4>::SIZE <= 227 * 1024;
@@ -1230,9 +1237,7 @@ static int launch_chain(int n_stages, const int* kinds, PolicyArgs* A, const int
     const int M = A[0].M;
     const ChainPlan pl = plan_chain(n_stages, kinds, Ns, M, P);
     if constexpr (chain_tc_ok<DO, DA, HID>()) {
-        bool small = true;
-        for (int s = 0; s < n_stages; ++s) small = small && (int64_t)M * pl.info[s].ntiles <= 2 * sm_count();
-        if (g_use_tc && (g_chain == 1 || (g_chain < 0 && small))) {
+        if (chain_uses_dataflow(pl, n_stages, M)) {
             if (ws_bytes < pl.bytes) {
                 set_error("policy chain workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.bytes);
                 return PROMP_ERR_WORKSPACE;
@@ -1264,6 +1269,15 @@ static int launch_chain(int n_stages, const int* kinds, PolicyArgs* A, const int
         if (rc != PROMP_OK) return rc;
     }
     return PROMP_OK;
+}
+
+template <int DO, int DA, int HID>
+static int chain_num_launches(int n_stages, const int* kinds, const int* Ns, int M) {
+    if constexpr (chain_tc_ok<DO, DA, HID>()) {
+        const ChainPlan pl = plan_chain(n_stages, kinds, Ns, M, PLayout<DO, DA, HID>::P);
+        if (chain_uses_dataflow(pl, n_stages, M)) return 1;
+    }
+    return n_stages;
 }
 
 template <int DO, int DA, int HID>
@@ -1439,6 +1453,14 @@ extern "C" int64_t promp_policy_chain_workspace_bytes(int obs_dim, int act_dim, 
     int kinds[CHAIN_MAX_STAGES], Ns[CHAIN_MAX_STAGES];
     for (int s = 0; s < n_stages; ++s) kinds[s] = stages[s].kind, Ns[s] = stages[s].N > 0 ? stages[s].N : 1;
     PROMP_DISPATCH_DIMS(chain_ws_bytes, n_stages, kinds, Ns, M)
+}
+
+extern "C" int promp_policy_chain_num_launches(int obs_dim, int act_dim, int hidden, int M, int n_stages,
+                                               const promp_policy_stage* stages) {
+    if (stages == nullptr || n_stages < 1 || n_stages > CHAIN_MAX_STAGES || M < 1) return -1;
+    int kinds[CHAIN_MAX_STAGES], Ns[CHAIN_MAX_STAGES];
+    for (int s = 0; s < n_stages; ++s) kinds[s] = stages[s].kind, Ns[s] = stages[s].N > 0 ? stages[s].N : 1;
+    PROMP_DISPATCH_DIMS(chain_num_launches, n_stages, kinds, Ns, M)
 }
 
 extern "C" int promp_policy_chain(int obs_dim, int act_dim, int hidden, int M, float min_log_std, int n_stages,

@@ -112,10 +112,10 @@ class TRPOMAML(MAMLAlgo):
 
     @property
     def graph_capturable(self):
-        # the E-MAML coefficient is assembled with host scalars; with several ranks the ~250-launch capture was observed to be
-        # invalidated on one rank (N = 2, cudaErrorStreamCaptureInvalidated) - the eager device-resident step (1-2 host
-        # reads per iteration) is used there
-        return not self.exploration and world_size() == 1
+        # the E-MAML coefficient is assembled with host scalars.  (Round 2 ran several ranks eagerly because the ~250-launch
+        # capture was invalidated now and then: that was Python's cyclic GC destroying an older CUDAGraph during the capture,
+        # fixed in Trainer.capture_graph.)
+        return not self.exploration
 
     def optimize_phases(self, phases, out=None, want_terms=True):
         """optimize_policy on PhaseData objects up to the verdict on the first line-search group, everything left on the
