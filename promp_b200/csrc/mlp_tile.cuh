@@ -96,12 +96,55 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ A, const fl
 // ------------------------------------------------------------------------------------------------
 // Diagonal-Gaussian head for one sample (ref: policies/distributions/diagonal_gaussian.py:16-109).
 // Everything the objective kinds need, evaluated in float32 like the TF graph.
+// Everything that depends only on the policy's log_std (a per-task constant) is computed ONCE per task
+// (head_in_finish): the per-sample path multiplies by reciprocals instead of dividing - the head is a serial dependent
+// chain executed by one thread per sample row, and its ~5 IEEE divisions + 1 expf per action dimension were most of it.
 template <int DA>
 struct HeadIn {
     float ls[DA];      // new log_std (after the optional clip)
     float sig[DA];     // exp(ls)
     float ls_mask[DA]; // 0 where the clip is active (gradient does not reach the variable), else 1
+    float inv_sig[DA]; // 1 / sig
+    float s2[DA];      // sig^2
+    float inv_den[DA]; // 1 / (2 sig^2 + 1e-8)            (kl_sym denominator)
+    float c1[DA];      // 1 - 2 sig^2 / den                d KL / d log_std = c1 - c2 * num
+    float c2[DA];      // 4 sig^2 / den^2
+    float sum_ls;      // sum_d ls
 };
+template <int DA>
+__device__ __forceinline__ void head_in_finish(HeadIn<DA>& h) {
+    h.sum_ls = 0.f;
+#pragma unroll
+    for (int d = 0; d < DA; ++d) {
+        h.inv_sig[d] = 1.f / h.sig[d];
+        h.s2[d] = h.sig[d] * h.sig[d];
+        const float den = 2.f * h.s2[d] + 1e-8f;
+        h.inv_den[d] = 1.f / den;
+        h.c1[d] = 1.f - 2.f * h.s2[d] / den;
+        h.c2[d] = 4.f * h.s2[d] / (den * den);
+        h.sum_ls += h.ls[d];
+    }
+}
+// The old (sampling) distribution's log_std: per task when the phase stores one row per task, else per sample.
+template <int DA>
+struct HeadOld {
+    float ls[DA];
+    float so2[DA];     // exp(ls)^2
+    float inv_so[DA];  // 1 / exp(ls)
+    float sum_ls;
+};
+template <int DA>
+__device__ __forceinline__ void head_old_from(const float* ls_old, HeadOld<DA>& ho) {
+    ho.sum_ls = 0.f;
+#pragma unroll
+    for (int d = 0; d < DA; ++d) {
+        const float so = expf(ls_old[d]);
+        ho.ls[d] = ls_old[d];
+        ho.so2[d] = so * so;
+        ho.inv_so[d] = 1.f / so;
+        ho.sum_ls += ls_old[d];
+    }
+}
 
 template <int DA>
 struct HeadOut {
@@ -117,31 +160,25 @@ struct HeadOut {
 constexpr float LOG_2PI = 1.8378770664093453f;
 
 template <int DA>
-__device__ __forceinline__ void gaussian_head(const HeadIn<DA>& hin, const float* mu, const float* a, const float* mu_old,
-                                              const float* ls_old, float adv, int obj_kind, float clip_eps,
-                                              HeadOut<DA>& o) {
-    float sum_ls = 0.f, sum_z2 = 0.f, sum_lso = 0.f, sum_zo2 = 0.f, kl = 0.f;
+__device__ __forceinline__ void gaussian_head(const HeadIn<DA>& hin, const HeadOld<DA>& ho, const float* mu, const float* a,
+                                              const float* mu_old, float adv, int obj_kind, float clip_eps, HeadOut<DA>& o) {
+    float sum_z2 = 0.f, sum_zo2 = 0.f, kl = 0.f;
 #pragma unroll
     for (int d = 0; d < DA; ++d) {
-        const float z = (a[d] - mu[d]) / hin.sig[d];
+        const float z = (a[d] - mu[d]) * hin.inv_sig[d];
         o.zeta[d] = z;
-        sum_ls += hin.ls[d];
         sum_z2 += z * z;
-        const float so = expf(ls_old[d]);
-        const float zo = (a[d] - mu_old[d]) / so;
-        sum_lso += ls_old[d];
+        const float zo = (a[d] - mu_old[d]) * ho.inv_so[d];
         sum_zo2 += zo * zo;
         // kl_sym (:16-44): (dmu^2 + so^2 - sn^2) / (2 sn^2 + 1e-8) + ls_new - ls_old
         const float dm = mu_old[d] - mu[d];
-        const float s2 = hin.sig[d] * hin.sig[d];
-        const float num = dm * dm + so * so - s2;
-        const float den = 2.f * s2 + 1e-8f;
-        kl += num / den + hin.ls[d] - ls_old[d];
-        o.dkl_dmu[d] = -2.f * dm / den;
-        o.dkl_dls[d] = 1.f - 2.f * s2 / den - 4.f * s2 * num / (den * den);
+        const float num = dm * dm + ho.so2[d] - hin.s2[d];
+        kl += num * hin.inv_den[d] + hin.ls[d] - ho.ls[d];
+        o.dkl_dmu[d] = -2.f * dm * hin.inv_den[d];
+        o.dkl_dls[d] = hin.c1[d] - hin.c2[d] * num;
     }
-    const float logp_new = -sum_ls - 0.5f * sum_z2 - 0.5f * DA * LOG_2PI;   // log_likelihood_sym (:89-109)
-    const float logp_old = -sum_lso - 0.5f * sum_zo2 - 0.5f * DA * LOG_2PI;
+    const float logp_new = -hin.sum_ls - 0.5f * sum_z2 - 0.5f * DA * LOG_2PI;   // log_likelihood_sym (:89-109)
+    const float logp_old = -ho.sum_ls - 0.5f * sum_zo2 - 0.5f * DA * LOG_2PI;
     const float ratio = expf(logp_new - logp_old);                           // likelihood_ratio_sym (:71-87)
     o.ratio = ratio;
     o.kl = kl;

@@ -124,6 +124,7 @@ __device__ __forceinline__ void load_head_consts(const float* P, int clip, float
         hin.ls_mask[d] = clipped ? 0.f : 1.f;
         hin.sig[d] = expf(hin.ls[d]);
     }
+    head_in_finish<DA>(hin);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -387,11 +388,13 @@ __global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A
                     }
                     const float adv = __ldg(A.adv + n);
                     HeadOut<DA> o;
-                    gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                    HeadOld<DA> ho;
+                    head_old_from<DA>(lso, ho);
+                    gaussian_head<DA>(hin, ho, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
                     const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
 #pragma unroll
                     for (int d = 0; d < DA; ++d) {
-                        dmu[d] = wt * o.zeta[d] / hin.sig[d] + kc * o.dkl_dmu[d];
+                        dmu[d] = wt * o.zeta[d] * hin.inv_sig[d] + kc * o.dkl_dmu[d];
                         dls[d] = (wt * (o.zeta[d] * o.zeta[d] - 1.f) + kc * o.dkl_dls[d]) * hin.ls_mask[d];
                     }
                     s_obj += o.obj;
@@ -754,18 +757,20 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
                     }
                     const float adv = __ldg(A.adv + n);
                     HeadOut<DA> o;
-                    gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                    HeadOld<DA> ho;
+                    head_old_from<DA>(lso, ho);
+                    gaussian_head<DA>(hin, ho, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
                     const float wt = o.w * invN, kc = A.kl_coeff * invN;
                     // tangent of log p:  R l = sum_d (zeta/sig) R mu + (zeta^2 - 1) R ls
                     float rl = 0.f;
 #pragma unroll
                     for (int d = 0; d < DA; ++d)
-                        rl += (o.zeta[d] / hin.sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
+                        rl += (o.zeta[d] * hin.inv_sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
                     // d w / d logp: RATIO w = -A r -> R w = w R l ; LOGLIK w = -A -> 0
                     const float rwt = (A.obj_kind == PROMP_OBJ_RATIO) ? wt * rl : 0.f;
 #pragma unroll
                     for (int d = 0; d < DA; ++d) {
-                        const float is = 1.f / hin.sig[d], z = o.zeta[d];
+                        const float is = hin.inv_sig[d], z = o.zeta[d];
                         const float rz = -rmu[d] * is - z * rls[d];
                         dmu[d] = wt * z * is;
                         const float rdmu = rwt * z * is + wt * (rz * is - z * rls[d] * is);

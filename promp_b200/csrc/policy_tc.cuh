@@ -165,6 +165,8 @@ struct GradTcSmem {
     float MUP[NQ * TBT * DA];
     float DMU[TBT * DA];
     float red[3 * 4 * NQ];
+    HeadIn<DA> hin;           // per-task constants of the Gaussian head (written by thread 0 in load_task)
+    HeadOld<DA> hold;         // ... of the old distribution when the phase stores one log_std row per task
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
     int last;
@@ -392,7 +394,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
     int Nm = N;
     const bool want_grad = A.grad != nullptr;
     const float* th = nullptr;
-    HeadIn<DA> hin;
+    HeadIn<DA>& hin = S.hin;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
 
     float gW1[NT][4], gB1f[NT], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
@@ -440,15 +442,25 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
                 *reinterpret_cast<float4*>(S.W1T_lo + off) = wl;
             }
         }
-        if (reload) __syncthreads();
+        __syncthreads();          // Ps is in place; every reader of the previous task's hin / hold is done
+        if (tid == 0) {
 #pragma unroll
-        for (int d = 0; d < DA; ++d) {
-            const float raw = S.Ps[SL::LS + d];
-            const bool clipped = A.clip_log_std && (raw < A.min_log_std);
-            hin.ls[d] = clipped ? A.min_log_std : raw;
-            hin.ls_mask[d] = clipped ? 0.f : 1.f;
-            hin.sig[d] = expf(hin.ls[d]);
+            for (int d = 0; d < DA; ++d) {
+                const float raw = S.Ps[SL::LS + d];
+                const bool clipped = A.clip_log_std && (raw < A.min_log_std);
+                hin.ls[d] = clipped ? A.min_log_std : raw;
+                hin.ls_mask[d] = clipped ? 0.f : 1.f;
+                hin.sig[d] = expf(hin.ls[d]);
+            }
+            head_in_finish<DA>(hin);
+            if (!A.ls_per_sample) {
+                float lso[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) lso[d] = __ldg(A.old_ls + (int64_t)m * DA + d);
+                head_old_from<DA>(lso, S.hold);
+            }
         }
+        __syncthreads();
     };
     auto flush = [&](int m) {
         sc.clk(3);
@@ -594,7 +606,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
                 for (int d = 0; d < DA; ++d) {
                     ha[d] = __ldg(A.act + n * DA + d);
                     hmo[d] = __ldg(A.old_mean + n * DA + d);
-                    hlso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    if (A.ls_per_sample) hlso[d] = __ldg(A.old_ls + n * DA + d);
                 }
                 hadv = __ldg(A.adv + n);
             }
@@ -670,7 +682,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
             float dmu[DA], dls[DA];
             if (r < nb) {
                 const int64_t n = g0 + r;
-                float mu[DA], a[DA], mo[DA], lso[DA];
+                float mu[DA], a[DA], mo[DA];
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
                     float sm = S.Ps[SL::B2 + d];
@@ -678,20 +690,28 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
                     for (int q = 0; q < NQ; ++q) sm += S.MUP[(q * TBT + r) * DA + d];
                     mu[d] = sm;
                     if constexpr (XPRE) {
-                        a[d] = ha[d], mo[d] = hmo[d], lso[d] = hlso[d];
+                        a[d] = ha[d], mo[d] = hmo[d];
                     } else {
                         a[d] = __ldg(A.act + n * DA + d);
                         mo[d] = __ldg(A.old_mean + n * DA + d);
-                        lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
                     }
                 }
                 const float adv = XPRE ? hadv : __ldg(A.adv + n);
                 HeadOut<DA> o;
-                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                if (A.ls_per_sample) {
+                    float lso[DA];
+                    HeadOld<DA> ho;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) lso[d] = XPRE ? hlso[d] : __ldg(A.old_ls + n * DA + d);
+                    head_old_from<DA>(lso, ho);
+                    gaussian_head<DA>(hin, ho, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
+                } else {
+                    gaussian_head<DA>(hin, S.hold, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
+                }
                 const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
-                    dmu[d] = wt * o.zeta[d] / hin.sig[d] + kc * o.dkl_dmu[d];
+                    dmu[d] = wt * o.zeta[d] * hin.inv_sig[d] + kc * o.dkl_dmu[d];
                     dls[d] = (wt * (o.zeta[d] * o.zeta[d] - 1.f) + kc * o.dkl_dls[d]) * hin.ls_mask[d];
                 }
                 s_obj += o.obj;
@@ -867,6 +887,8 @@ struct HvpTcSmem {
     float DMU[TBT * DA];
     float CMU[TBT * DA];
     float red[3 * 4 * NQ];
+    HeadIn<DA> hin;           // per-task constants of the Gaussian head (written by thread 0 in load_task)
+    HeadOld<DA> hold;         // ... of the old distribution when the phase stores one log_std row per task
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
     int last;
@@ -925,7 +947,7 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
     const float ac = -A.inner_lr;
     const float* th = nullptr;
     const float* vg = nullptr;
-    HeadIn<DA> hin;
+    HeadIn<DA>& hin = S.hin;
     float rls[DA];
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
     constexpr uint32_t C_Z2 = 0, C_RZ2 = 64, C_DH1 = 128, C_CH1 = 192, C_LOA = 256, C_LOB = 320;
@@ -965,15 +987,26 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
             S.Vs[SL::W2 + i] = __ldcg(vg + L::W2 + i);
         }
         __syncthreads();
+        if (tid == 0) {
 #pragma unroll
-        for (int d = 0; d < DA; ++d) {
-            const float raw = S.Ps[SL::LS + d];
-            const bool clipped = A.clip_log_std && (raw < A.min_log_std);
-            hin.ls[d] = clipped ? A.min_log_std : raw;
-            hin.ls_mask[d] = clipped ? 0.f : 1.f;
-            hin.sig[d] = expf(hin.ls[d]);
-            rls[d] = S.Vs[SL::LS + d] * hin.ls_mask[d];
+            for (int d = 0; d < DA; ++d) {
+                const float raw = S.Ps[SL::LS + d];
+                const bool clipped = A.clip_log_std && (raw < A.min_log_std);
+                hin.ls[d] = clipped ? A.min_log_std : raw;
+                hin.ls_mask[d] = clipped ? 0.f : 1.f;
+                hin.sig[d] = expf(hin.ls[d]);
+            }
+            head_in_finish<DA>(hin);
+            if (!A.ls_per_sample) {
+                float lso[DA];
+#pragma unroll
+                for (int d = 0; d < DA; ++d) lso[d] = __ldg(A.old_ls + (int64_t)m * DA + d);
+                head_old_from<DA>(lso, S.hold);
+            }
         }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < DA; ++d) rls[d] = S.Vs[SL::LS + d] * hin.ls_mask[d];
     };
     // (re)fill the weight buffer from L2: forward = [W1^T, V1^T], backward = [W1, ac*V1], each as hi (fp32) + lo
     // 4 elements per thread and buffer: one conflict-free 16-byte shared-memory store each (the element-wise version paid a
@@ -1132,7 +1165,7 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
                 for (int d = 0; d < DA; ++d) {
                     ha[d] = __ldg(A.act + n * DA + d);
                     hmo[d] = __ldg(A.old_mean + n * DA + d);
-                    hlso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
+                    if (A.ls_per_sample) hlso[d] = __ldg(A.old_ls + n * DA + d);
                 }
                 hadv = __ldg(A.adv + n);
             }
@@ -1222,7 +1255,7 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
             float dmu[DA], cmu[DA], cls[DA];
             if (r < nb) {
                 const int64_t n = g0 + r;
-                float mu[DA], rmu[DA], a[DA], mo[DA], lso[DA];
+                float mu[DA], rmu[DA], a[DA], mo[DA];
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
 float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
@@ -1231,25 +1264,33 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
                     mu[d] = sm;
                     rmu[d] = sr;
                     if constexpr (XPRE) {
-                        a[d] = ha[d], mo[d] = hmo[d], lso[d] = hlso[d];
+                        a[d] = ha[d], mo[d] = hmo[d];
                     } else {
                         a[d] = __ldg(A.act + n * DA + d);
                         mo[d] = __ldg(A.old_mean + n * DA + d);
-                        lso[d] = A.ls_per_sample ? __ldg(A.old_ls + n * DA + d) : __ldg(A.old_ls + (int64_t)m * DA + d);
                     }
                 }
                 const float adv = XPRE ? hadv : __ldg(A.adv + n);
                 HeadOut<DA> o;
-                gaussian_head<DA>(hin, mu, a, mo, lso, adv, A.obj_kind, A.clip_eps, o);
+                if (A.ls_per_sample) {
+                    float lso[DA];
+                    HeadOld<DA> ho;
+#pragma unroll
+                    for (int d = 0; d < DA; ++d) lso[d] = XPRE ? hlso[d] : __ldg(A.old_ls + n * DA + d);
+                    head_old_from<DA>(lso, ho);
+                    gaussian_head<DA>(hin, ho, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
+                } else {
+                    gaussian_head<DA>(hin, S.hold, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
+                }
                 const float wt = o.w * invN, kc = A.kl_coeff * invN;
                 float rl_ = 0.f;
 #pragma unroll
                 for (int d = 0; d < DA; ++d)
-                    rl_ += (o.zeta[d] / hin.sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
+                    rl_ += (o.zeta[d] * hin.inv_sig[d]) * rmu[d] + (o.zeta[d] * o.zeta[d] - 1.f) * rls[d];
                 const float rwt = (A.obj_kind == PROMP_OBJ_RATIO) ? wt * rl_ : 0.f;
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
-                    const float is = 1.f / hin.sig[d], z = o.zeta[d];
+                    const float is = hin.inv_sig[d], z = o.zeta[d];
                     const float rz = -rmu[d] * is - z * rls[d];
                     dmu[d] = wt * z * is;
                     const float rdmu = rwt * z * is + wt * (rz * is - z * rls[d] * is);
