@@ -397,7 +397,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
     HeadIn<DA>& hin = S.hin;
     const uint32_t tmem_row = tmem + ((uint32_t)(qd * 32) << 16);
 
-    float gW1[NT][4], gB1f[NT], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-warp partials in lane 0
+    float gW1[NT][4], gB1f[NT], gW0p[DO], gW2p[DA], gB0c, gB2w[DA], gLSw[DA];   // gB2w/gLSw: per-thread partials (cq == 0 rows)
     float s_obj, s_kl, s_ratio;
     auto zero_acc = [&]() {
 #pragma unroll
@@ -506,9 +506,10 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
                 part[L::W2 + idx] = s;
             }
             __syncthreads();
-            if (cq == 0 && lane == 0) {
 #pragma unroll
-                for (int d = 0; d < DA; ++d) scr[qd * 2 * DA + d] = gB2w[d], scr[qd * 2 * DA + DA + d] = gLSw[d];
+            for (int d = 0; d < DA; ++d) {                 // (uniform over the CTA: every warp takes part in the shuffles)
+                const float s1 = warp_sum(gB2w[d]), s2 = warp_sum(gLSw[d]);
+                if (cq == 0 && lane == 0) scr[qd * 2 * DA + d] = s1, scr[qd * 2 * DA + DA + d] = s2;
             }
             __syncthreads();
             if (tid < 2 * DA) part[L::B2 + tid] = scr[tid] + scr[2 * DA + tid] + scr[4 * DA + tid] + scr[6 * DA + tid];   // b2 then log_std
@@ -724,10 +725,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
 #pragma unroll
             for (int d = 0; d < DA; ++d) {
                 S.DMU[r * DA + d] = dmu[d];
-                if (want_grad) {                                               // gB2 / g_log_std column sums
-                    const float s1 = warp_sum(dmu[d]), s2 = warp_sum(dls[d]);
-                    if (lane == 0) gB2w[d] += s1, gLSw[d] += s2;
-                }
+                gB2w[d] += dmu[d], gLSw[d] += dls[d];      // gB2 / g_log_std: per-thread partials, reduced over the warp at flush
             }
         }
         if (!want_grad) continue;
@@ -1080,9 +1078,10 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
             part[L::W2 + idx] = s;
         }
         __syncthreads();
-        if (cq == 0 && lane == 0) {
 #pragma unroll
-            for (int d = 0; d < DA; ++d) scr[qd * 2 * DA + d] = gB2w[d], scr[qd * 2 * DA + DA + d] = gLSw[d];
+        for (int d = 0; d < DA; ++d) {                     // (uniform over the CTA: every warp takes part in the shuffles)
+            const float s1 = warp_sum(gB2w[d]), s2 = warp_sum(gLSw[d]);
+            if (cq == 0 && lane == 0) scr[qd * 2 * DA + d] = s1, scr[qd * 2 * DA + DA + d] = s2;
         }
         __syncthreads();
         if (tid < 2 * DA) part[L::B2 + tid] = scr[tid] + scr[2 * DA + tid] + scr[4 * DA + tid] + scr[6 * DA + tid];
@@ -1308,8 +1307,7 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
 #pragma unroll
             for (int d = 0; d < DA; ++d) {
                 S.DMU[r * DA + d] = dmu[d], S.CMU[r * DA + d] = cmu[d];
-                const float s1 = warp_sum(cmu[d]), s2 = warp_sum(cls[d]);
-                if (lane == 0) gB2w[d] += s1, gLSw[d] += s2;
+                gB2w[d] += cmu[d], gLSw[d] += cls[d];      // per-thread partials, reduced over the warp at flush
             }
         }
         __syncthreads();
