@@ -346,6 +346,32 @@ __device__ __forceinline__ float4 reduce_slots4(const float* partial, const Sche
     return s;
 }
 
+// The same sums for ALL of a thread's columns p = 4 tid + i * 4 * threads (i < NP) at once: NP x 4 independent 16-byte L2 loads
+// in flight instead of one column at a time - the last arriver's reduction sits on the tail of the kernel and is pure L2
+// latency.  Slots are added in contributor order, so the result is bit-identical to reduce_slots4.
+template <int NP, class Sched>
+__device__ __forceinline__ void reduce_slots4_wide(const float* partial, const Sched& sc, int pstride, int m, int n, int p0, int pstep,
+                                                   int pend, float4 (&acc)[NP]) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < n; c0 += 4) {
+        float4 v[NP][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t base = (c0 + u < n) ? (int64_t)sc.contrib_slot(m, c0 + u) * pstride : -1;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const int p = p0 + i * pstep;
+                v[i][u] = (base >= 0 && p < pend) ? __ldcg(reinterpret_cast<const float4*>(partial + base + p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < NP; ++i) acc[i].x += v[i][u].x, acc[i].y += v[i][u].y, acc[i].z += v[i][u].z, acc[i].w += v[i][u].w;
+    }
+}
+
 #ifdef PROMP_EXP_CLOCKS
 // experiment build only: per-phase clock64 totals of CTA 0 (tools/kernel_time.py --clocks)
 __device__ unsigned long long g_phase_clk[16];
@@ -542,19 +568,28 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
                 A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN, A.stats[(int64_t)m * 4 + 2] = s.z * invN;
             }
             if (want_grad) {
-                for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
-                    const float4 s = reduce_slots4(A.partial, sc, PSTRIDE, m, n_c, p);
+                constexpr int NPASS = (L::P + 4 + 4 * TCT - 1) / (4 * TCT);
+                float4 sum[NPASS], t4[NPASS];
+#pragma unroll
+                for (int i = 0; i < NPASS; ++i) {          // requested together with the slot loads below
+                    const int p = 4 * tid + i * 4 * TCT;
+                    t4[i] = (A.out_params && p < L::P) ? Sched::ldp4(reinterpret_cast<const float4*>(th + p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                reduce_slots4_wide<NPASS>(A.partial, sc, PSTRIDE, m, n_c, 4 * tid, 4 * TCT, L::P + 4, sum);
+#pragma unroll
+                for (int i = 0; i < NPASS; ++i) {
+                    const int p = 4 * tid + i * 4 * TCT;
+                    const float4 s = sum[i];
                     if (p == L::P) {
                         if (A.stats)
                             A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN,
                                                     A.stats[(int64_t)m * 4 + 2] = s.z * invN;
-                        continue;
-                    }
-                    *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
-                    if (A.out_params) {
-                        const float4 t4 = Sched::ldp4(reinterpret_cast<const float4*>(th + p));
-                        *reinterpret_cast<float4*>(A.out_params + (int64_t)m * L::P + p) =
-                            make_float4(t4.x - A.sgd_lr * s.x, t4.y - A.sgd_lr * s.y, t4.z - A.sgd_lr * s.z, t4.w - A.sgd_lr * s.w);
+                    } else if (p < L::P) {
+                        *reinterpret_cast<float4*>(A.grad + (int64_t)m * L::P + p) = s;
+                        if (A.out_params)
+                            *reinterpret_cast<float4*>(A.out_params + (int64_t)m * L::P + p) =
+                                make_float4(t4[i].x - A.sgd_lr * s.x, t4[i].y - A.sgd_lr * s.y, t4[i].z - A.sgd_lr * s.z,
+                                            t4[i].w - A.sgd_lr * s.w);
                     }
                 }
             }
@@ -1104,16 +1139,26 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
         sc.clk(4);
         if (S.last) {
             __threadfence();
-            for (int p = 4 * tid; p < L::P + 4; p += 4 * TCT) {
-                const float4 s = reduce_slots4(A.partial, sc, PSTRIDE, m, n_c, p);
+            constexpr int NPASS = (L::P + 4 + 4 * TCT - 1) / (4 * TCT);
+            float4 sum[NPASS], v4[NPASS];
+#pragma unroll
+            for (int i = 0; i < NPASS; ++i) {              // requested together with the slot loads below
+                const int p = 4 * tid + i * 4 * TCT;
+                v4[i] = (p < L::P) ? __ldcg(reinterpret_cast<const float4*>(vg + p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            reduce_slots4_wide<NPASS>(A.partial, sc, PSTRIDE, m, n_c, 4 * tid, 4 * TCT, L::P + 4, sum);
+#pragma unroll
+            for (int i = 0; i < NPASS; ++i) {
+                const int p = 4 * tid + i * 4 * TCT;
+                const float4 s = sum[i];
                 if (p == L::P) {                  // trailing float4 of the slot: objective / KL / ratio sums
                     if (A.stats)
                         A.stats[(int64_t)m * 4 + 0] = s.x * invN, A.stats[(int64_t)m * 4 + 1] = s.y * invN,
                                                 A.stats[(int64_t)m * 4 + 2] = s.z * invN;
-                    continue;
+                } else if (p < L::P) {
+                    *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) =
+                        make_float4(v4[i].x + s.x, v4[i].y + s.y, v4[i].z + s.z, v4[i].w + s.w);
                 }
-                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(vg + p));
-                *reinterpret_cast<float4*>(A.out + (int64_t)m * L::P + p) = make_float4(v4.x + s.x, v4.y + s.y, v4.z + s.z, v4.w + s.w);
             }
             if (tid == 0) A.counters[m] = 0;
             sc.publish_task(m);
