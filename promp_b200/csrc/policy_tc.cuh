@@ -769,12 +769,14 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
         // ---- output-layer gradients (column role) from the fp32 H2 tile
         {
             const int b0 = cp * BPP;
-#pragma unroll 4
-            for (int bb = 0; bb < BPP; ++bb) {
-                const int b = b0 + bb;
-                const float h = *reinterpret_cast<const float*>(S.A1 + core_off(b, cj, SCA));
+            // b0 is a multiple of 8: row b0 + bb of column cj sits at a compile-time offset from row b0 (fully unrolled)
+            const unsigned char* colp = S.A1 + core_off(b0, cj, SCA);
+            const float* dmu0 = S.DMU + b0 * DA;
 #pragma unroll
-                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.DMU[b * DA + d], gW2p[d]);
+            for (int bb = 0; bb < BPP; ++bb) {
+                const float h = *reinterpret_cast<const float*>(colp + (bb >> 3) * 128 + (bb & 7) * 16);
+#pragma unroll
+                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, dmu0[bb * DA + d], gW2p[d]);
             }
         }
         __syncthreads();
@@ -837,13 +839,14 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
         // ---- gW0 += X^T D1, gB0 += colsum(D1) (column role)
         {
             const int b0 = cp * BPP;
-#pragma unroll 4
+            const unsigned char* colp = S.A0 + core_off(b0, cj, SCA);
+            const float* x0 = S.X + b0 * DOP;
+#pragma unroll
             for (int bb = 0; bb < BPP; ++bb) {
-                const int b = b0 + bb;
-                const float d1 = *reinterpret_cast<const float*>(S.A0 + core_off(b, cj, SCA));
+                const float d1 = *reinterpret_cast<const float*>(colp + (bb >> 3) * 128 + (bb & 7) * 16);
                 gB0c += d1;
 #pragma unroll
-                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(S.X[b * DOP + i], d1, gW0p[i]);
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(x0[bb * DOP + i], d1, gW0p[i]);
             }
         }
     }
@@ -1361,14 +1364,16 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
         // ---- output layer (column role): out_W2 += H2^T CMU + ac R2^T DMU ; out_b2 += colsum CMU ; out_ls += colsum CLS
         {
             const int b0 = cp * BPP;
-#pragma unroll 4
+            const int off0 = core_off(b0, cj, SCA);      // rows b0 + bb at compile-time offsets (b0 is a multiple of 8)
+            const float* cmu0 = S.CMU + b0 * DA;
+            const float* dmu0 = S.DMU + b0 * DA;
+#pragma unroll
             for (int bb = 0; bb < BPP; ++bb) {
-                const int b = b0 + bb;
-                const int off = core_off(b, cj, SCA);
+                const int off = off0 + (bb >> 3) * 128 + (bb & 7) * 16;
                 const float h = *reinterpret_cast<const float*>(S.T2a + off);
                 const float rr = ac * *reinterpret_cast<const float*>(S.T2b + off);
 #pragma unroll
-                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, S.CMU[b * DA + d], fmaf(rr, S.DMU[b * DA + d], gW2p[d]));
+                for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, cmu0[bb * DA + d], fmaf(rr, dmu0[bb * DA + d], gW2p[d]));
             }
         }
         __syncthreads();
@@ -1452,13 +1457,14 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
         // ---- out_W0 += X^T C1 ; out_b0 += colsum C1 (column role)
         {
             const int b0 = cp * BPP;
-#pragma unroll 4
+            const unsigned char* colp = S.H1 + core_off(b0, cj, SCA);
+            const float* x0 = sX + b0 * DOP;
+#pragma unroll
             for (int bb = 0; bb < BPP; ++bb) {
-                const int b = b0 + bb;
-                const float c1 = *reinterpret_cast<const float*>(S.H1 + core_off(b, cj, SCA));
+                const float c1 = *reinterpret_cast<const float*>(colp + (bb >> 3) * 128 + (bb & 7) * 16);
                 gB0c += c1;
 #pragma unroll
-                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(sX[b * DOP + i], c1, gW0p[i]);
+                for (int i = 0; i < DO; ++i) gW0p[i] = fmaf(x0[bb * DOP + i], c1, gW0p[i]);
             }
         }
     }

@@ -10,4 +10,5 @@ for wl in point cheetah; do
   ncu -i /tmp/prof_$wl.ncu-rep --page details --csv > gpurun_out/details_$wl.csv 2>/dev/null
 done
 ncu -i /tmp/prof_point.ncu-rep --page source --csv --print-source cuda,sass --kernel-name regex:policy_hvp --launch-count 1 2>/dev/null | gzip > gpurun_out/src_hvp_point.csv.gz
+ncu -i /tmp/prof_point.ncu-rep --page source --csv --print-source cuda,sass --kernel-name regex:policy_grad --launch-count 1 2>/dev/null | gzip > gpurun_out/src_grad_point.csv.gz
 ls -la gpurun_out
