@@ -195,7 +195,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 // COLSUM: also accumulate the column sums of D (unscaled) from the B fragments: csum[nt] holds, per lane, the partial
 // over this lane's sample rows for column 32 (warp>>2) + 8 nt + (lane>>2); reduce over lane&3 at flush time.
-template <bool COLSUM, int NT>
+template <bool COLSUM, int NT, bool UNIT = false>
 __device__ __forceinline__ void wgrad_mma_tile(const unsigned char* __restrict__ At, const unsigned char* __restrict__ Dt,
                                                float scale, int warp, int lane, float (&acc)[NT][4], float (&csum)[NT]) {
     const int g = lane >> 2, t = lane & 3;
@@ -214,8 +214,8 @@ __device__ __forceinline__ void wgrad_mma_tile(const unsigned char* __restrict__
             const float d0 = *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128);
             const float d1 = *reinterpret_cast<const float*>(dp + nt * 2 * SCA + s * 128 + 16);
             if (COLSUM) csum[nt] += d0 + d1;
-            split_tf32(scale * d0, bh[nt][0], bl[nt][0]);
-            split_tf32(scale * d1, bh[nt][1], bl[nt][1]);
+            split_tf32(UNIT ? d0 : scale * d0, bh[nt][0], bl[nt][0]);      // UNIT: scale == 1 (no multiply)
+            split_tf32(UNIT ? d1 : scale * d1, bh[nt][1], bl[nt][1]);
         }
         // term-major order: consecutive MMAs hit different accumulators (no back-to-back dependent issue)
 #pragma unroll
@@ -772,8 +772,11 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
             // b0 is a multiple of 8: row b0 + bb of column cj sits at a compile-time offset from row b0 (fully unrolled)
             const unsigned char* colp = S.A1 + core_off(b0, cj, SCA);
             const float* dmu0 = S.DMU + b0 * DA;
+#pragma unroll(BPP <= 16 ? 2 : 1)
+            for (int b8 = 0; b8 < BPP; b8 += 8)
 #pragma unroll
-            for (int bb = 0; bb < BPP; ++bb) {
+            for (int b1 = 0; b1 < 8; ++b1) {
+                const int bb = b8 + b1;
                 const float h = *reinterpret_cast<const float*>(colp + (bb >> 3) * 128 + (bb & 7) * 16);
 #pragma unroll
                 for (int d = 0; d < DA; ++d) gW2p[d] = fmaf(h, dmu0[bb * DA + d], gW2p[d]);
@@ -815,7 +818,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
         PCLK(6);
         // ---- ... while the warps do the weight gradient gW1 += H1^T D2 (mma.sync 3xTF32) and the bias column sums
         {
-            wgrad_mma_tile<true, NT>(S.A0, S.A1, 1.f, warp, lane, gW1, gB1f);
+            wgrad_mma_tile<true, NT, true>(S.A0, S.A1, 1.f, warp, lane, gW1, gB1f);
         }
         PCLK(7);
         mbar_wait(bar, phase);
@@ -841,8 +844,11 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
             const int b0 = cp * BPP;
             const unsigned char* colp = S.A0 + core_off(b0, cj, SCA);
             const float* x0 = S.X + b0 * DOP;
+#pragma unroll(BPP <= 16 ? 2 : 1)
+            for (int b8 = 0; b8 < BPP; b8 += 8)
 #pragma unroll
-            for (int bb = 0; bb < BPP; ++bb) {
+            for (int b1 = 0; b1 < 8; ++b1) {
+                const int bb = b8 + b1;
                 const float d1 = *reinterpret_cast<const float*>(colp + (bb >> 3) * 128 + (bb & 7) * 16);
                 gB0c += d1;
 #pragma unroll
@@ -1367,8 +1373,11 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
             const int off0 = core_off(b0, cj, SCA);      // rows b0 + bb at compile-time offsets (b0 is a multiple of 8)
             const float* cmu0 = S.CMU + b0 * DA;
             const float* dmu0 = S.DMU + b0 * DA;
+#pragma unroll(BPP <= 16 ? 2 : 1)
+            for (int b8 = 0; b8 < BPP; b8 += 8)
 #pragma unroll
-            for (int bb = 0; bb < BPP; ++bb) {
+            for (int b1 = 0; b1 < 8; ++b1) {
+                const int bb = b8 + b1;
                 const int off = off0 + (bb >> 3) * 128 + (bb & 7) * 16;
                 const float h = *reinterpret_cast<const float*>(S.T2a + off);
                 const float rr = ac * *reinterpret_cast<const float*>(S.T2b + off);
@@ -1422,7 +1431,7 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
         // ---- ... overlapped with the weight gradients out_W1 += H1^T C2 + R1^T (ac D2) (mma.sync 3xTF32) and colsum(C2)
         {
             float unused[NT] = {};
-            wgrad_mma_tile<true, NT>(S.H1, S.T2b, 1.f, warp, lane, gW1, gB1f);
+            wgrad_mma_tile<true, NT, true>(S.H1, S.T2b, 1.f, warp, lane, gW1, gB1f);
             wgrad_mma_tile<false, NT>(S.R1, S.T2a, ac, warp, lane, gW1, unused);
         }
         mbar_wait(bar, phase);
@@ -1459,8 +1468,11 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
             const int b0 = cp * BPP;
             const unsigned char* colp = S.H1 + core_off(b0, cj, SCA);
             const float* x0 = sX + b0 * DOP;
+#pragma unroll(BPP <= 16 ? 2 : 1)
+            for (int b8 = 0; b8 < BPP; b8 += 8)
 #pragma unroll
-            for (int bb = 0; bb < BPP; ++bb) {
+            for (int b1 = 0; b1 < 8; ++b1) {
+                const int bb = b8 + b1;
                 const float c1 = *reinterpret_cast<const float*>(colp + (bb >> 3) * 128 + (bb & 7) * 16);
                 gB0c += c1;
 #pragma unroll
