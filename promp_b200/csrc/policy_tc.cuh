@@ -1008,6 +1008,11 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
         gB0c = 0.f;
         s_obj = s_kl = s_ratio = 0.f;
     };
+    // The direction vector may be read through the read-only path only if nothing in this launch writes it: out != vec (the
+    // in-place form v <- v - alpha H v rewrites task m's slice at its flush) and no producer stage in the same launch.
+    const bool vec_ro = A.out != A.vec;
+    auto ldv = [&](const float* p) { return vec_ro ? Sched::ldp(p) : __ldcg(p); };
+    auto ldv4 = [&](const float4* p) { return vec_ro ? Sched::ldp4(p) : __ldcg(p); };
     auto load_task = [&](int m) {
         sc.wait_task(m);
         if (A.n_valid) { Nm = __ldg(A.n_valid + m); invN = 1.0f / (float)max(Nm, 1); }
@@ -1018,15 +1023,15 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
         cached_th = th;
         for (int i = tid; i < DO * HID + HID; i += TCT) {
             if (reload_p) S.Ps[SL::W0 + i] = Sched::ldp(th + L::W0 + i);
-            S.Vs[SL::W0 + i] = __ldcg(vg + L::W0 + i);
+            S.Vs[SL::W0 + i] = ldv(vg + L::W0 + i);
         }
         for (int i = tid; i < HID; i += TCT) {
             if (reload_p) S.Ps[SL::B1 + i] = Sched::ldp(th + L::B1 + i);
-            S.Vs[SL::B1 + i] = __ldcg(vg + L::B1 + i);
+            S.Vs[SL::B1 + i] = ldv(vg + L::B1 + i);
         }
         for (int i = tid; i < HID * DA + 2 * DA; i += TCT) {
             if (reload_p) S.Ps[SL::W2 + i] = Sched::ldp(th + L::W2 + i);
-            S.Vs[SL::W2 + i] = __ldcg(vg + L::W2 + i);
+            S.Vs[SL::W2 + i] = ldv(vg + L::W2 + i);
         }
         __syncthreads();
         if (tid == 0) {
@@ -1062,12 +1067,12 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
                 const float* sw = th + L::W1 + 4 * kg * HID + j;
                 const float* sv = vg + L::W1 + 4 * kg * HID + j;
                 w = make_float4(Sched::ldp(sw), Sched::ldp(sw + HID), Sched::ldp(sw + 2 * HID), Sched::ldp(sw + 3 * HID));
-                v = make_float4(__ldcg(sv), __ldcg(sv + HID), __ldcg(sv + 2 * HID), __ldcg(sv + 3 * HID));
+                v = make_float4(ldv(sv), ldv(sv + HID), ldv(sv + 2 * HID), ldv(sv + 3 * HID));
                 off = kg * SCW + (j >> 3) * 128 + (j & 7) * 16;
             } else {        // tile row = k, K = j: one 16-byte load of W1[k][4 jg ..]
                 const int jg = u % (HID / 4), k = u / (HID / 4);
                 w = Sched::ldp4(reinterpret_cast<const float4*>(th + L::W1 + k * HID + 4 * jg));
-                v = __ldcg(reinterpret_cast<const float4*>(vg + L::W1 + k * HID + 4 * jg));
+                v = ldv4(reinterpret_cast<const float4*>(vg + L::W1 + k * HID + 4 * jg));
                 v = make_float4(ac * v.x, ac * v.y, ac * v.z, ac * v.w);
                 off = jg * SCW + (k >> 3) * 128 + (k & 7) * 16;
             }

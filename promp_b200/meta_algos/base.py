@@ -233,8 +233,12 @@ class MAMLAlgo(object):
             if want_grad:
                 for s in range(S - 2, -1, -1):
                     prm, strd, clp, _ = chain[s]
+                    # out-of-place: a direction vector nothing in the launch writes may be read through the read-only path
+                    v_out = torch.empty(M, P, dtype=torch.float32, device=dev)
                     stages.append(self._stage(1, phases[s], prm, strd, self.inner_obj_kind, kl_coeff=inner_kl_coeffs[s],
-                                              clip_log_std=clp, vec=v, out=v))
+                                              clip_log_std=clp, vec=v, out=v_out))
+                    chain.append(v)       # the stage list holds raw pointers: keep every buffer alive until the launch is enqueued
+                    v = v_out
             self._run_chain(stages, reuse=self._reuse_bufs if reuse0 else None)
             out = dict(surr=stats_all[S - 1, :, 0], outer_kl=stats_all[S - 1, :, 1], inner_kl=stats_all[:S - 1, :, 1],
                        stats_all=stats_all, grad=None)
@@ -268,7 +272,9 @@ class MAMLAlgo(object):
         if want_grad:
             for s in range(S - 2, -1, -1):
                 prm, strd, clp = chain[s]
-                self._hvp(phases[s], prm, strd, v, v, inner_kl_coeffs[s], clp)
+                v_out = torch.empty(M, P, dtype=torch.float32, device=dev)
+                self._hvp(phases[s], prm, strd, v, v_out, inner_kl_coeffs[s], clp)
+                v = v_out
             if reduce:
                 flat = torch.empty(P, dtype=torch.float32, device=dev)
                 _lib.call('promp_reduce_tasks', M, P, _lib.ptr(v), 1.0 / (M * world_size()), _lib.ptr(flat), _lib.stream())
