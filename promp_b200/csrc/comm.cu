@@ -119,7 +119,24 @@ __global__ void __launch_bounds__(256) meta_update_kernel(MetaUpdateArgs A) {
     const int t = *A.step + 1;
     float g = 0.f;
     if (p < A.P) {
-        for (int m = 0; m < A.M; ++m) g += A.v[(int64_t)m * A.P + p];
+        // task sum in task order (bit-identical to promp_reduce_tasks), 16 independent L2 loads in flight per round trip
+        const float* col = A.v + p;
+        int m = 0;
+        for (; m + 16 <= A.M; m += 16) {
+            float x[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) x[u] = __ldcg(col + (int64_t)(m + u) * A.P);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) g += x[u];
+        }
+        {
+            float x[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) x[u] = (m + u < A.M) ? __ldcg(col + (int64_t)(m + u) * A.P) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (m + u < A.M) g += x[u];
+        }
         g *= A.scale;
     }
     uint32_t epoch = 0;

@@ -1141,8 +1141,7 @@ static int launch_hvp(PolicyArgs& A, void* ws, int64_t ws_bytes, cudaStream_t st
 
 // ---- dataflow chain (policy_chain_tc_kernel): work-item plan + launch ---------------------------------------------
 static int g_chain = -1;         // promp_set_option("chain", -1|0|1): dataflow kernel always (1), never (0: one launch per stage), or
-                                 // where it wins (-1, default): chains whose stages are short - at most two tiles per SM - so that
-                                 // launch tails and the tile-quantisation of every single launch dominate (measured)
+                                 // where it wins (-1, default; see chain_uses_dataflow)
 static int g_chain_q = 0;        // promp_set_option("chain_q", q): tiles per work item (0 = automatic)
 static int g_chain_taper = 1;    // promp_set_option("chain_taper", 0|1): last stage's items shrink to one tile towards the end
 
@@ -1202,11 +1201,16 @@ static ChainPlan plan_chain(int n_stages, const int* kinds, const int* Ns, int M
     return pl;
 }
 
-// the automatic choice: dataflow kernel for chains of short stages (at most two tiles per SM), one launch per stage otherwise
+// the automatic choice: dataflow kernel for chains whose stages have one to three tiles per SM (where launch tails and the
+// tile quantisation of every single launch dominate: measured wins of 2-10 %, profiles/r02_chain_time.txt), one launch per stage
+// below (a stage is not even one wave: nothing to balance) and above (per-item flushes outweigh the gain)
 static bool chain_uses_dataflow(const ChainPlan& pl, int n_stages, int M) {
-    bool small = true;
-    for (int s = 0; s < n_stages; ++s) small = small && (int64_t)M * pl.info[s].ntiles <= 2 * sm_count();
-    return g_use_tc && (g_chain == 1 || (g_chain < 0 && small));
+    bool fits = true;
+    for (int s = 0; s < n_stages; ++s) {
+        const int64_t T = (int64_t)M * pl.info[s].ntiles;
+        fits = fits && T >= sm_count() && T <= 3 * sm_count();
+    }
+    return g_use_tc && (g_chain == 1 || (g_chain < 0 && fits));
 }
 
 template <int DO, int DA, int HID>
