@@ -282,3 +282,40 @@ def test_path_stacking_matches_reference_utils():
     for k in ('a', 'b'):
         np.testing.assert_array_equal(got['nested'][k], want['nested'][k])
     assert _stack([]) == {} and _stack([{}, {}]) == {}
+
+
+def test_policy_chain_plan_host_side():
+    """promp_policy_chain's host-side planning (no GPU work): which shapes the automatic choice sends to the dataflow kernel
+    (one to three 128-sample tiles per SM and stage; the SM count falls back to 148 without a device), the workspace bound, and
+    argument validation through the C ABI."""
+    import ctypes
+    from promp_b200 import _lib
+    lib = _lib.load()
+
+    def stages(kinds, N):
+        arr = (_lib.PolicyStage * len(kinds))()
+        for i, k in enumerate(kinds):
+            arr[i].kind, arr[i].N = k, N
+        return arr, ctypes.cast(arr, ctypes.c_void_p)
+    full = [0, 0, 1]
+    for (Do, Da, hid, M, N, want) in [(2, 2, 64, 10, 2000, 1), (2, 2, 64, 20, 2000, 1), (2, 2, 64, 40, 2000, 3),
+                                      (2, 2, 64, 5, 2000, 3), (17, 6, 64, 10, 4000, 1), (17, 6, 64, 40, 4000, 3),
+                                      (2, 2, 32, 10, 2000, 3)]:          # hidden 32: no tensor-core kernels, always per stage
+        arr, ptr = stages(full, N)
+        assert lib.promp_policy_chain_num_launches(Do, Da, hid, M, 3, ptr) == want, (Do, Da, hid, M, N)
+        ws = lib.promp_policy_chain_workspace_bytes(Do, Da, hid, M, 3, ptr)
+        assert ws >= lib.promp_policy_workspace_bytes(M, N, Do, Da, hid) > 0
+    try:
+        _lib.set_option('chain', 1)
+        arr, ptr = stages(full, 2000)
+        assert lib.promp_policy_chain_num_launches(2, 2, 64, 40, 3, ptr) == 1
+        _lib.set_option('chain', 0)
+        assert lib.promp_policy_chain_num_launches(2, 2, 64, 10, 3, ptr) == 3
+    finally:
+        _lib.set_option('chain', -1)
+    arr, ptr = stages(full, 2000)
+    assert lib.promp_policy_chain_num_launches(2, 2, 64, 10, 7, ptr) < 0          # more than 6 stages
+    assert lib.promp_policy_chain_workspace_bytes(3, 3, 64, 10, 3, ptr) < 0       # unsupported dimensions
+    # the launch entry validates before touching the device
+    rc = lib.promp_policy_chain(2, 2, 64, 10, ctypes.c_float(-13.8), 3, ptr, None, None, ctypes.c_void_p(16), 1 << 20, None)
+    assert rc == -1 and 'null pointer' in _lib.last_error()
