@@ -147,7 +147,7 @@ class LaunchCounter(object):
                    promp_allreduce_p2p=1, promp_baseline_fit=1, promp_baseline_predict=1,
                    promp_meta_update=1, promp_meta_loss_terms_p2p=1, promp_policy_grad_ex=1, promp_rollout_early_term=1,
                    promp_paths_finalize=4, promp_phase_log_terms=1, promp_promp_log_terms=1,
-                   promp_policy_chain=1)
+                   promp_policy_chain=1, promp_adapt_kl_coeff=1)
     # entry points that launch the same kernel are timed under one name
     ALIAS = dict(promp_policy_grad_ex='promp_policy_grad', promp_policy_grad_ragged='promp_policy_grad',
                  promp_policy_hvp_ragged='promp_policy_hvp', promp_process_samples_ragged='promp_process_samples')

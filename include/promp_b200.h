@@ -378,6 +378,8 @@ typedef struct {
     const float* vec;
     float* out;
     float* stats;                  /* [M,4] or NULL */
+    const float* kl_coeff_dev;     /* NULL, or a device float: the stage uses kl_coeff * (*kl_coeff_dev) (device-resident
+                                      adaptive coefficient, see promp_adapt_kl_coeff) */
 } promp_policy_stage;
 int64_t promp_policy_chain_workspace_bytes(int obs_dim, int act_dim, int hidden, int M, int n_stages,
                                            const promp_policy_stage* stages);
@@ -419,6 +421,13 @@ int promp_reduce_tasks(int M, int P, const float* in, float scale, float* out, v
  */
 int promp_phase_log_terms(int M, int act_dim, double n_paths, const double* stats, const float* log_std, double* out7, void* stream);
 int promp_promp_log_terms(int num_inner_steps, const float* final_terms, double* out3, void* stream);
+/* ProMP's adaptive inner-KL coefficient rule (meta_algos/pro_mp.py:201-214) applied on the device, so that an iteration with
+ * adaptive_inner_kl_penalty=True (the reference class default) has no host decision and can be replayed as a CUDA graph:
+ *   coeff_dev[s] /= 2 if KL_s < kl_target / 1.5;  *= 2 if KL_s > kl_target * 1.5     (KL_s = final_terms[2 + s]; adapt != 0)
+ * out4 (device double[4], optional) = the four scalars ProMP logs (pro_mp.py:193-198): LossBefore, LossAfter, KLInner (as
+ * promp_promp_log_terms) and KLCoeffInner = mean_s coeff_dev[s] after the update. */
+int promp_adapt_kl_coeff(int num_inner_steps, const float* final_terms, double kl_target, int adapt, float* coeff_dev,
+                         double* out4, void* stream);
 
 /*
  * tf.train.AdamOptimizer step as used by MAMLFirstOrderOptimizer.optimize

@@ -26,7 +26,7 @@ class PolicyStage(ctypes.Structure):
                 ('obs', _P), ('act', _P), ('adv', _P), ('old_mean', _P), ('old_log_std', _P),
                 ('ls_per_sample', c_int32), ('obj_kind', c_int32), ('obj_scale', c_float), ('clip_eps', c_float),
                 ('kl_coeff', c_float), ('clip_log_std', c_int32), ('grad', _P), ('out_params', _P), ('sgd_lr', c_float),
-                ('inner_lr', c_float), ('vec', _P), ('out', _P), ('stats', _P)]
+                ('inner_lr', c_float), ('vec', _P), ('out', _P), ('stats', _P), ('kl_coeff_dev', _P)]
 
 
 _SIGNATURES = {
@@ -72,6 +72,7 @@ _SIGNATURES = {
     'promp_meta_loss_terms': (c_int, [c_int, c_int, _P, c_float, _P, c_int, _P, _P]),
     'promp_phase_log_terms': (c_int, [c_int, c_int, c_double, _P, _P, _P, _P]),
     'promp_promp_log_terms': (c_int, [c_int, _P, _P, _P]),
+    'promp_adapt_kl_coeff': (c_int, [c_int, _P, c_double, c_int, _P, _P, _P]),
     'promp_reduce_tasks': (c_int, [c_int, c_int, _P, c_float, _P, _P]),
     'promp_adam_tf1': (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
     'promp_vec_axpy': (c_int, [c_int, c_float, _P, _P, _P, _P]),

@@ -54,7 +54,13 @@ struct PolicyArgs {
     const float* skip_theta;
     int* unclipped_out;
     float* theta_copy_out;
+    // optional device-resident multiplier of kl_coeff (ProMP's adaptive inner-KL coefficient lives on the device so that an
+    // iteration has no host decision: promp_adapt_kl_coeff updates it between launches)
+    const float* kl_coeff_ptr;
 };
+__device__ __forceinline__ float kl_coeff_eff(const PolicyArgs& A) {
+    return A.kl_coeff_ptr ? A.kl_coeff * __ldcg(A.kl_coeff_ptr) : A.kl_coeff;
+}
 
 // consumer / producer halves of the launch re-use protocol above; returns true if the calling CTA must exit
 template <int P, int LS, int DA>
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A
     if (grad_reuse_prologue<L::P, L::LS, DA>(A)) return;
     const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
+    const float kl_eff = kl_coeff_eff(A);
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
     int Nm = N;
     const bool want_grad = A.grad != nullptr;
@@ -391,7 +398,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) policy_grad_kernel(PolicyArgs A
                     HeadOld<DA> ho;
                     head_old_from<DA>(lso, ho);
                     gaussian_head<DA>(hin, ho, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
-                    const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
+                    const float wt = A.obj_scale * o.w * invN, kc = kl_eff * invN;
 #pragma unroll
                     for (int d = 0; d < DA; ++d) {
                         dmu[d] = wt * o.zeta[d] * hin.inv_sig[d] + kc * o.dkl_dmu[d];
@@ -525,6 +532,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
     const int cj = tid % HID, cp = tid / HID;
     const TileSched ts(A.M, A.N, A.q);
     const int N = A.N;
+    const float kl_eff = kl_coeff_eff(A);
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
     int Nm = N;
     const float ac = -A.inner_lr;                 // coefficient of H vec in `out`
@@ -760,7 +768,7 @@ __global__ void __launch_bounds__(PT_THREADS) policy_hvp_kernel(PolicyArgs A) {
                     HeadOld<DA> ho;
                     head_old_from<DA>(lso, ho);
                     gaussian_head<DA>(hin, ho, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
-                    const float wt = o.w * invN, kc = A.kl_coeff * invN;
+                    const float wt = o.w * invN, kc = kl_eff * invN;
                     // tangent of log p:  R l = sum_d (zeta/sig) R mu + (zeta^2 - 1) R ls
                     float rl = 0.f;
 #pragma unroll
@@ -1033,6 +1041,35 @@ __global__ void promp_log_terms_kernel(int S1, const float* __restrict__ final_t
         float s = 0.f;
         for (int i = 0; i < S1; ++i) s += final_terms[2 + i];
         out[2] = S1 > 0 ? (double)(s / (float)S1) : 0.0;
+    }
+}
+
+// ProMP._adapt_kl_coeff (pro_mp.py:201-214) on the device: coeff_s /= 2 if KL_s < target / 1.5, *= 2 if KL_s > target * 1.5
+// (comparisons in double like the reference's Python floats; halving / doubling is exact in float32).  out4 (optional):
+// ProMP's four logged scalars [LossBefore, LossAfter, KLInner, KLCoeffInner (after the update)] (pro_mp.py:193-198).
+__global__ void adapt_kl_coeff_kernel(int S1, const float* __restrict__ final_terms, double target, int adapt, float* __restrict__ coeff,
+                                      double* __restrict__ out4) {
+    if (threadIdx.x == 0) {
+        if (out4) {
+            out4[0] = (double)final_terms[0];
+            out4[1] = (double)final_terms[1];
+            float s = 0.f;
+            for (int i = 0; i < S1; ++i) s += final_terms[2 + i];
+            out4[2] = S1 > 0 ? (double)(s / (float)S1) : 0.0;
+        }
+        double* out_mean = out4 ? out4 + 3 : nullptr;
+        double sum = 0.0;
+        for (int i = 0; i < S1; ++i) {
+            float c = coeff[i];
+            if (adapt) {
+                const double kl = (double)final_terms[2 + i];
+                if (kl < target / 1.5) c *= 0.5f;
+                else if (kl > target * 1.5) c *= 2.0f;
+                coeff[i] = c;
+            }
+            sum += (double)c;
+        }
+        if (out_mean) *out_mean = S1 > 0 ? sum / (double)S1 : 0.0;
     }
 }
 
@@ -1440,6 +1477,7 @@ static int chain_stage_args(const promp_policy_stage* stages, int n_stages, int 
         a.obs = g.obs; a.act = g.act; a.adv = g.adv; a.old_mean = g.old_mean; a.old_ls = g.old_log_std;
         a.ls_per_sample = g.ls_per_sample; a.obj_kind = g.obj_kind; a.kl_coeff = g.kl_coeff;
         a.clip_log_std = g.clip_log_std; a.min_log_std = min_log_std; a.stats = g.stats; a.n_valid = g.n_valid;
+        a.kl_coeff_ptr = g.kl_coeff_dev;
         if (g.kind == 0) {
             PROMP_REQUIRE(g.obj_kind >= 0 && g.obj_kind <= 3, "promp_policy_chain: stage %d: bad obj_kind %d", s, g.obj_kind);
             PROMP_REQUIRE(!(g.out_params && !g.grad), "promp_policy_chain: stage %d: out_params needs grad", s);
@@ -1551,6 +1589,15 @@ extern "C" int promp_promp_log_terms(int num_inner_steps, const float* final_ter
     PROMP_REQUIRE(num_inner_steps >= 0 && final_terms && out3, "promp_promp_log_terms: bad arguments");
     promp_log_terms_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num_inner_steps, final_terms, out3);
     PROMP_LAUNCH_CHECK("promp_log_terms_kernel");
+    return PROMP_OK;
+}
+
+extern "C" int promp_adapt_kl_coeff(int num_inner_steps, const float* final_terms, double kl_target, int adapt, float* coeff_dev,
+                                    double* out4, void* stream) {
+    PROMP_REQUIRE(num_inner_steps >= 0 && num_inner_steps <= 7 && final_terms && (coeff_dev || num_inner_steps == 0),
+                  "promp_adapt_kl_coeff: bad arguments");
+    adapt_kl_coeff_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num_inner_steps, final_terms, kl_target, adapt, coeff_dev, out4);
+    PROMP_LAUNCH_CHECK("adapt_kl_coeff_kernel");
     return PROMP_OK;
 }
 

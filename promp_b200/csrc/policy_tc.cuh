@@ -416,6 +416,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
     const int r = qd * 32 + lane, c0 = CW * cq;          // row / column-group role: sample row r, hidden units [c0, c0+32)
     const int cj = tid & (HID - 1), cp = tid / HID;        // column role
     const int N = A.N;
+    const float kl_eff = kl_coeff_eff(A);      // kl_coeff, times the device-resident multiplier when there is one
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
     int Nm = N;
     const bool want_grad = A.grad != nullptr;
@@ -744,7 +745,7 @@ __device__ __forceinline__ void grad_tc_tiles(const PolicyArgs& A, GradTcSmem<DO
                 } else {
                     gaussian_head<DA>(hin, S.hold, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
                 }
-                const float wt = A.obj_scale * o.w * invN, kc = A.kl_coeff * invN;
+                const float wt = A.obj_scale * o.w * invN, kc = kl_eff * invN;
 #pragma unroll
                 for (int d = 0; d < DA; ++d) {
                     dmu[d] = wt * o.zeta[d] * hin.inv_sig[d] + kc * o.dkl_dmu[d];
@@ -984,6 +985,7 @@ __device__ __forceinline__ void hvp_tc_tiles(const PolicyArgs& A, HvpTcSmem<DO, 
     const int r = qd * 32 + lane, c0 = CW * cq;
     const int cj = tid & (HID - 1), cp = tid / HID;
     const int N = A.N;
+    const float kl_eff = kl_coeff_eff(A);      // kl_coeff, times the device-resident multiplier when there is one
     float invN = 1.0f / (float)N;       // both re-set per task when A.n_valid is given (variable-length paths)
     int Nm = N;
     const float ac = -A.inner_lr;
@@ -1340,7 +1342,7 @@ float sm = S.Ps[SL::B2 + d], sr = S.Vs[SL::B2 + d];
                 } else {
                     gaussian_head<DA>(hin, S.hold, mu, a, mo, adv, A.obj_kind, A.clip_eps, o);
                 }
-                const float wt = o.w * invN, kc = A.kl_coeff * invN;
+                const float wt = o.w * invN, kc = kl_eff * invN;
                 float rl_ = 0.f;
 #pragma unroll
                 for (int d = 0; d < DA; ++d)

@@ -103,7 +103,7 @@ class MAMLAlgo(object):
                   float(sgd_lr), _lib.ptr(stats), skip[0], skip[1], prod[0], prod[1], _lib.ptr(ws), ws.numel() * 4, _lib.stream())
 
     def _stage(self, kind, phase, params, stride, obj_kind, obj_scale=1.0, clip_eps=0.0, kl_coeff=0.0, clip_log_std=0, grad=None,
-               out_params=None, sgd_lr=0.0, vec=None, out=None, stats=None):
+               out_params=None, sgd_lr=0.0, vec=None, out=None, stats=None, kl_coeff_dev=None):
         """One promp_policy_stage (kind 0: the arguments of _grad, kind 1: those of _hvp)."""
         full = getattr(phase, 'log_std_full', None)
         old_ls, per_sample = (full, 1) if full is not None else (phase.log_std, 0)
@@ -116,6 +116,7 @@ class MAMLAlgo(object):
         st.kl_coeff, st.clip_log_std = float(kl_coeff), int(clip_log_std)
         st.grad, st.out_params, st.sgd_lr = _lib.ptr(grad), _lib.ptr(out_params), float(sgd_lr)
         st.inner_lr, st.vec, st.out, st.stats = float(self.inner_lr), _lib.ptr(vec), _lib.ptr(out), _lib.ptr(stats)
+        st.kl_coeff_dev = _lib.ptr(kl_coeff_dev)      # optional device-resident multiplier of kl_coeff
         return st
 
     def _run_chain(self, stages, reuse=None):
@@ -187,7 +188,7 @@ class MAMLAlgo(object):
 
     # ------------------------------------------------------------------------------------ meta objective
     def _meta_pass(self, theta, phases, outer_obj_kind, clip_eps, inner_kl_coeffs, want_grad, outer_kl_coeff=0.0,
-                   outer_obj_scale=1.0, reduce=True):
+                   outer_obj_scale=1.0, reduce=True, inner_kl_coeffs_dev=None):
         """One evaluation of the meta objective (and optionally its gradient) at `theta` [P].
 
         Returns dict(grad=[P] or None (local sum over tasks / M_global, NOT yet all-reduced),
@@ -214,6 +215,11 @@ class MAMLAlgo(object):
         if reuse0:
             stats_all = cache['stats_all']
             self._adapt_cache = None          # one consumer: later passes (updated theta) use their own buffers
+        if inner_kl_coeffs_dev is not None and not self.use_chain:
+            # the stand-alone entry points take the coefficient by value: read the device vector back (eager diagnostics only)
+            host = inner_kl_coeffs_dev.cpu().numpy()
+            inner_kl_coeffs = [float(np.float32(sc) * np.float32(c)) for sc, c in zip(inner_kl_coeffs, host)]
+            inner_kl_coeffs_dev = None
         if self.use_chain and (S >= 2 or want_grad):
             # the whole chain - inner gradients + SGD steps, outer gradient, backward Hessian-vector chain - as ONE launch
             stages = []
@@ -236,7 +242,8 @@ class MAMLAlgo(object):
                     # out-of-place: a direction vector nothing in the launch writes may be read through the read-only path
                     v_out = torch.empty(M, P, dtype=torch.float32, device=dev)
                     stages.append(self._stage(1, phases[s], prm, strd, self.inner_obj_kind, kl_coeff=inner_kl_coeffs[s],
-                                              clip_log_std=clp, vec=v, out=v_out))
+                                              clip_log_std=clp, vec=v, out=v_out,
+                                              kl_coeff_dev=None if inner_kl_coeffs_dev is None else inner_kl_coeffs_dev[s:s + 1]))
                     chain.append(v)       # the stage list holds raw pointers: keep every buffer alive until the launch is enqueued
                     v = v_out
             self._run_chain(stages, reuse=self._reuse_bufs if reuse0 else None)

@@ -20,7 +20,8 @@ class ProMP(MAMLAlgo):
         self.clip_eps = clip_eps
         self.target_inner_step = target_inner_step
         self.adaptive_inner_kl_penalty = adaptive_inner_kl_penalty
-        self.inner_kl_coeff = init_inner_kl_penalty * np.ones(self.num_inner_grad_steps)
+        self._coeff_live = None
+        self._inner_kl_coeff = init_inner_kl_penalty * np.ones(self.num_inner_grad_steps)
         self.anneal_coeff = 1
         self.anneal_factor = anneal_factor
         self._optimization_keys = ['observations', 'actions', 'advantages', 'agent_infos']
@@ -31,30 +32,62 @@ class ProMP(MAMLAlgo):
 
     FUSED_META_UPDATE = True     # _objective_pass(reduce=False) -> per-task gradients for promp_meta_update
 
+    # ---- inner-KL coefficients: a host array (the reference's attribute) or, while a CUDA-graph Trainer drives the algorithm, a
+    # device vector that promp_adapt_kl_coeff updates in place - then an adaptive-KL iteration has no host decision.
+    @property
+    def inner_kl_coeff(self):
+        if self._coeff_live is not None:          # the device copy is the authority: read it back (synchronises)
+            self._inner_kl_coeff = self._coeff_live.cpu().numpy().astype(np.float64)
+        return self._inner_kl_coeff
+
+    @inner_kl_coeff.setter
+    def inner_kl_coeff(self, value):
+        self._inner_kl_coeff = np.asarray(value, dtype=np.float64)
+        if getattr(self, '_coeff_live', None) is not None:
+            import torch
+            self._coeff_live.copy_(torch.as_tensor(self._inner_kl_coeff, dtype=torch.float32))
+
+    def _device_coeffs(self):
+        """Switch to the device-resident coefficient vector (first call: upload the host values; not inside a capture)."""
+        import torch
+        if self._coeff_live is None:
+            host = np.asarray(self._inner_kl_coeff, dtype=np.float32)
+            self._coeff_live = torch.from_numpy(host.copy()).to(self.policy.device)
+        return self._coeff_live
+
     def _objective_pass(self, phases, want_grad, reduce=True):
         """meta_objective = mean_i L_clip,i + mean_s(c_s * mean_i KL_s,i)   (pro_mp.py:151-155)."""
         S1 = max(self.num_inner_grad_steps, 1)
-        coeffs = [float(c) / S1 for c in self.inner_kl_coeff]      # tf.reduce_mean over the S-1 steps
+        if self._coeff_live is not None:          # c_s read from the device: the stage gets the 1 / S1 of tf.reduce_mean as its scale
+            return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, [1.0 / S1] * self.num_inner_grad_steps,
+                                   want_grad, reduce=reduce, inner_kl_coeffs_dev=self._coeff_live)
+        coeffs = [float(c) / S1 for c in self._inner_kl_coeff]      # tf.reduce_mean over the S-1 steps
         return self._meta_pass(self.policy.theta, phases, _lib.OBJ_CLIP, self.clip_eps, coeffs, want_grad, reduce=reduce)
 
-    LOG_KEYS = ('LossBefore', 'LossAfter', 'KLInner')
+    LOG_KEYS = ('LossBefore', 'LossAfter', 'KLInner', 'KLCoeffInner')
     FUSED_LOSS_TERMS = True      # loss_terms(res, out=, n_out=) is one promp_meta_loss_terms launch
 
     def optimize_phases(self, phases, out=None, want_terms=True):
-        """optimize_policy on PhaseData objects, everything left on the device.  The float64 vector [LossBefore, LossAfter,
-        KLInner] for the CUDA-graph Trainer is written into `out` (one tiny launch) when given, else returned."""
+        """optimize_policy on PhaseData objects, everything left on the device - including the adaptive inner-KL coefficient rule.
+        The float64 vector [LossBefore, LossAfter, KLInner, KLCoeffInner] for the CUDA-graph Trainer is written into `out` (one
+        tiny launch) when given, else returned."""
         import torch
-        assert not self.adaptive_inner_kl_penalty, "adaptive KL coefficient is a host decision: not graph-capturable"
+        if self.adaptive_inner_kl_penalty:
+            self._device_coeffs()                # KL coefficients on the device: the adaptive rule below needs no host decision
         stats = self.optimizer.optimize(self, phases)
         self.last_stats_device = stats
         self._last_stats = None
         S1 = self.num_inner_grad_steps
         ret = None
-        if not want_terms:
-            return None
-        if out is None:
-            out = ret = torch.empty(3, dtype=torch.float64, device=stats.device)
-        _lib.call('promp_promp_log_terms', S1, _lib.ptr(stats), _lib.ptr(out), _lib.stream())
+        if out is None and want_terms:
+            out = ret = torch.empty(4, dtype=torch.float64, device=stats.device)
+        # one tiny launch: the four logged scalars + _adapt_kl_coeff (pro_mp.py:201-214) on the device; out[3] = KLCoeffInner after
+        # the update, as the reference logs it
+        if want_terms or self.adaptive_inner_kl_penalty:
+            coeff = self._coeff_live if self._coeff_live is not None else self._coeff_dev    # fixed: loss_terms' cached device copy
+            _lib.call('promp_adapt_kl_coeff', S1, _lib.ptr(stats), float(self.target_inner_step),
+                      int(bool(self.adaptive_inner_kl_penalty)), _lib.ptr(coeff) if S1 > 0 else None,
+                      _lib.ptr(out) if want_terms else None, _lib.stream())
         return ret
 
     def optimize_policy(self, all_samples_data, log=True):
@@ -96,10 +129,14 @@ class ProMP(MAMLAlgo):
         Mg = self.meta_batch_size * world_size()
         S1 = self.num_inner_grad_steps
         st = res['stats_all']
-        key = tuple(float(c) for c in self.inner_kl_coeff)
-        if getattr(self, '_coeff_key', None) != key:          # cached on the device (no H2D inside a graph capture)
-            self._coeff_dev = torch.tensor(key, dtype=torch.float32, device=st.device)
-            self._coeff_key = key
+        if self._coeff_live is not None:
+            self._coeff_dev = self._coeff_live                # the live device vector (updated by promp_adapt_kl_coeff)
+            self._coeff_key = None
+        else:
+            key = tuple(float(c) for c in self._inner_kl_coeff)
+            if getattr(self, '_coeff_key', None) != key:      # cached on the device (no H2D inside a graph capture)
+                self._coeff_dev = torch.tensor(key, dtype=torch.float32, device=st.device)
+                self._coeff_key = key
         if out is None:
             out = torch.empty(S1 + 2, dtype=torch.float32, device=st.device)
         n_out = S1 + 2 if n_out is None else n_out

@@ -84,13 +84,13 @@ class Trainer(object):
         go into a second pinned staging slot while the GPU executes iteration i, so step() only starts the H2D copies and
         the replay.  The draw ORDER is unchanged (same values for the same iteration), but the global numpy RNG is
         consumed one iteration ahead - do not interleave other np.random users with step().
-        Requirements: device policy + fixed-horizon device env, fixed KL coefficient.  With world_size > 1 the
+        Requirements: device policy + fixed-horizon device env (ProMP's adaptive KL coefficient rule runs on the device:
+        promp_adapt_kl_coeff).  With world_size > 1 the
         NCCL all-reduces of the meta-gradient are captured into the graph as well."""
         import torch
         from promp_b200.samplers.device_data import PhaseData
         sampler, proc, algo, policy = self.sampler, self.sample_processor, self.algo, self.policy
         assert sampler._fused_ok(), "graph mode needs the fused rollout path"
-        assert not getattr(algo, 'adaptive_inner_kl_penalty', False), "adaptive KL coefficient is a host decision"
         assert hasattr(algo, 'optimize_phases'), "graph mode needs an algorithm with a device-only outer step (ProMP, TRPOMAML)"
         S = self.num_inner_grad_steps + 1
         M, E, H = sampler.meta_batch_size, sampler.envs_per_task, sampler.max_path_length
@@ -149,6 +149,7 @@ class Trainer(object):
         opt = getattr(algo, 'optimizer', None)
         torch.cuda.synchronize()
         saved = dict(theta=policy.theta.clone(), np_state=np.random.get_state(),
+                     kl_coeff=np.array(algo.inner_kl_coeff, dtype=np.float64) if hasattr(algo, 'inner_kl_coeff') else None,
                      phase_counter_dev=sampler._phase_counter_dev.clone(),
                      adam=[t.clone() for t in (opt.m, opt.v, opt.step)] if hasattr(opt, 'm') else None)
         if log:
@@ -187,6 +188,8 @@ class Trainer(object):
             for dst, src in zip((opt.m, opt.v, opt.step), saved['adam']):
                 dst.copy_(src)
         sampler._phase_counter_dev.copy_(saved['phase_counter_dev'])
+        if saved['kl_coeff'] is not None:
+            algo.inner_kl_coeff = saved['kl_coeff']      # the warm-up iterations adapted it (device copy included)
         np.random.set_state(saved['np_state'])
         torch.cuda.synchronize()
         self._graph = graph
@@ -224,7 +227,7 @@ class Trainer(object):
                         logger.logkv(k, int(v) if k.endswith('NumTrajs') else float(v))
                 if hasattr(algo, 'post_replay'):
                     algo.post_replay(hidden, state['phases'])
-                if hasattr(algo, 'inner_kl_coeff'):
+                if hasattr(algo, 'inner_kl_coeff') and 'KLCoeffInner' not in keys:
                     logger.logkv('KLCoeffInner', float(np.mean(algo.inner_kl_coeff)))
                 logger.logkv('Itr', itr)
                 logger.logkv('n_timesteps', sampler.total_timesteps_sampled)
@@ -245,10 +248,9 @@ class Trainer(object):
 
     def graph_capturable(self):
         """True when a meta-iteration has no data-dependent host decision: fused fixed-horizon rollouts and an algorithm
-        with a device-only outer step (ProMP with a fixed KL coefficient)."""
+        with a device-only outer step (ProMP - its adaptive inner-KL coefficient rule runs on the device - and TRPO-MAML)."""
         return bool(self.sampler._fused_ok() and hasattr(self.algo, 'optimize_phases')
-                    and getattr(self.algo, 'graph_capturable', True)
-                    and not getattr(self.algo, 'adaptive_inner_kl_penalty', False))
+                    and getattr(self.algo, 'graph_capturable', True))
 
     def train(self):
         """meta_trainer.py:59-152.  The default entry point of a run script."""

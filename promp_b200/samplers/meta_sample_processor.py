@@ -206,6 +206,11 @@ class MetaSampleProcessor(object):
         """Device-only entry: run the processing kernel on a PhaseData (no host traffic)."""
         run_process_kernel(phase, self.discount, self.gae_lambda, getattr(self.baseline, '_reg_coeff', 1e-5),
                            _baseline_kind(self.baseline), self.normalize_adv, self.positive_adv)
+        if hasattr(self.baseline, '_coeffs') and _baseline_kind(self.baseline) == 1:
+            # the reference's baseline object holds the last fit = the last task's (baselines/linear_baseline.py:55-77): a lazy
+            # view of the device buffer, fetched on demand (a replayed CUDA graph rewrites the same buffer every iteration)
+            self.baseline._lazy_coeffs = (phase, phase.M - 1)
+            self.baseline._coeffs = _LazyCoeffs(phase)
         return phase
 
     def compute_adj_avg_rewards(self, phase, allreduce=None):
@@ -235,9 +240,6 @@ class MetaSampleProcessor(object):
             _lib.require_cuda()
             phase = _phase_from_host_paths(paths_meta_batch, torch.device('cuda', torch.cuda.current_device()))
         self.process_phase(phase)
-        if hasattr(self.baseline, '_coeffs') and _baseline_kind(self.baseline) == 1:
-            self.baseline._lazy_coeffs = (phase, phase.M - 1)
-            self.baseline._coeffs = _LazyCoeffs(phase)      # last task's fit, fetched on demand
         cls = RaggedSamplesData if isinstance(phase, RaggedPhaseData) else SamplesData
         samples = [cls(phase, m, self) for m in range(phase.M)]
         self._log_path_stats(phase, log, log_prefix)

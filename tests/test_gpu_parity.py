@@ -1550,3 +1550,61 @@ def test_dataflow_chain_matches_separate_launches(Do, Da, M, N, S1):
     np.testing.assert_allclose(st3[:, :, :3].cpu().numpy(), st_ref[:, :, :3].cpu().numpy(), rtol=2e-5, atol=1e-6)
     ctrl = algo._ws_chain[:4 + 2 * 6 * M].cpu().numpy()
     assert (ctrl == 0).all(), "control words (queue, finished-CTA count, ready flags, arrival counters) must be left zero"
+
+
+@pytest.mark.parametrize('target', [1e3, 1e-12])
+def test_adaptive_kl_coefficient_on_device_matches_host_rule(target):
+    """ProMP(adaptive_inner_kl_penalty=True) - the reference class default (pro_mp.py:40, 201-214): the CUDA-graph Trainer applies
+    the halve / double rule on the device (promp_adapt_kl_coeff), the eager path on the host like the reference.  Same seeds ->
+    the same coefficient sequence, logged KLCoeffInner and parameters.  target 1e3: the inner KL is below target / 1.5 (halve
+    every iteration); 1e-12: above target * 1.5 (double every iteration) - decisions that do not depend on the action noise, which
+    the two modes draw from differently keyed Philox streams."""
+    torch = _cuda()
+    from promp_b200.meta_algos import ProMP
+    from promp_b200.meta_trainer import Trainer
+    from promp_b200.utils import logger
+    logger.set_quiet(True)
+    M, E, H, n_itr = 6, 5, 40, 4
+
+    def run(graph):
+        env, policy, sampler, proc = _make_stack('point', M, E, H, seed=5)
+        algo = ProMP(policy=policy, inner_lr=0.1, meta_batch_size=M, num_inner_grad_steps=1, learning_rate=1e-3, num_ppo_steps=5,
+                     clip_eps=0.3, target_inner_step=target, init_inner_kl_penalty=1e-2, adaptive_inner_kl_penalty=True)
+        trainer = Trainer(algo=algo, policy=policy, env=env, sampler=sampler, sample_processor=proc, n_itr=n_itr,
+                          num_inner_grad_steps=1, use_cuda_graph=graph)
+        assert trainer.graph_capturable()                 # adaptive KL no longer forces the eager path
+        step = trainer.capture_graph(warmup=2, log=True) if graph else None
+        np.random.seed(77)
+        logged = []
+        for itr in range(n_itr):
+            if graph:
+                step(itr)
+            else:
+                trainer.train_iteration(itr, log=True)
+            logged.append(float(dict(logger.getkvs())['KLCoeffInner']))
+            logger.dumpkvs()
+        return policy.theta.clone(), logged, np.array(algo.inner_kl_coeff, dtype=np.float64)
+    th_g, log_g, c_g = run(True)
+    th_e, log_e, c_e = run(False)
+    factor = 0.5 if target == 1e3 else 2.0
+    want = [1e-2 * factor ** (i + 1) for i in range(n_itr)]
+    np.testing.assert_allclose(log_e, want, rtol=1e-6)          # the host rule did what the case is built to do
+    np.testing.assert_allclose(log_g, log_e, rtol=1e-6)
+    np.testing.assert_allclose(c_g, c_e, rtol=1e-6)
+    assert torch.isfinite(th_g).all() and torch.isfinite(th_e).all()
+    # (the two modes draw their action noise from differently keyed Philox streams, so the parameters themselves differ)
+    # the kernels read the coefficient from the device: same meta-gradient, bit for bit, as with the host value
+    policy, algo = _algo(torch, 'promp', 4, 2, 2, 64, S1=1)
+    theta = policy.theta.cpu().numpy()
+    phases = [_random_phase(torch, 4, 300, 2, 2, theta, 40 + s_, 64)[1] for s_ in range(2)]
+    algo.inner_kl_coeff = np.array([3e-3])
+    g_host = algo._objective_pass(phases, want_grad=True)['grad'].clone()
+    live = algo._device_coeffs()
+    g_dev = algo._objective_pass(phases, want_grad=True)['grad'].clone()
+    assert torch.equal(g_host, g_dev)
+    live.mul_(2.0)                                             # what promp_adapt_kl_coeff does in place
+    g_dev2 = algo._objective_pass(phases, want_grad=True)['grad'].clone()
+    assert not torch.equal(g_dev2, g_dev) and float(algo.inner_kl_coeff[0]) == pytest.approx(6e-3, rel=1e-6)
+    algo._coeff_live = None
+    algo.inner_kl_coeff = np.array([6e-3])
+    assert torch.equal(algo._objective_pass(phases, want_grad=True)['grad'], g_dev2)
