@@ -123,12 +123,12 @@ def build_stack(wl, reset_mode, task_shard=None, algo='promp', tasks=None, **tra
     sampler = MetaSampler(env=env, policy=policy, rollouts_per_meta_task=wl['E'], meta_batch_size=M,
                           max_path_length=wl['H'], parallel=True, reset_mode=reset_mode, seed=1, task_shard=task_shard)
     proc = MetaSampleProcessor(baseline=LinearFeatureBaseline(), discount=0.99, gae_lambda=1, normalize_adv=True)
-    if algo == 'promp':
+    if algo in ('promp', 'promp_adaptive_kl'):
         alg = ProMP(policy=policy, inner_lr=PROMP['inner_lr'], meta_batch_size=M,
                     num_inner_grad_steps=PROMP['num_inner_grad_steps'], learning_rate=PROMP['learning_rate'],
                     num_ppo_steps=PROMP['num_ppo_steps'], clip_eps=PROMP['clip_eps'],
                     target_inner_step=PROMP['target_inner_step'], init_inner_kl_penalty=PROMP['init_inner_kl_penalty'],
-                    adaptive_inner_kl_penalty=PROMP['adaptive_inner_kl_penalty'])
+                    adaptive_inner_kl_penalty=True if algo == 'promp_adaptive_kl' else PROMP['adaptive_inner_kl_penalty'])
     else:
         alg = TRPOMAML(policy=policy, step_size=TRPO['step_size'], inner_type=TRPO['inner_type'], inner_lr=TRPO['inner_lr'],
                        meta_batch_size=M, num_inner_grad_steps=TRPO['num_inner_grad_steps'], exploration=False)
@@ -303,8 +303,12 @@ def run_gpu(args):
             tr = build_stack(wl_x, 'numpy', shard, algo=algo, tasks=tasks_per_gpu)
             ms, wall = timed_train(tr, 3, n_steps)
             n_env = tasks_per_gpu * world * wl_x['E'] * wl_x['H'] * 2
-            extras[key] = dict(workload=wl_x['name'] if algo == 'promp' else 'MAML-TRPO (maml_run_mujoco.py config: step_size 0.01, '
-                               'inner_type log_likelihood) on MetaPointEnvCorner, meta_batch=40 in total (BASELINE.json configs[3])',
+            wl_name = {'promp': wl_x['name'],
+                       'promp_adaptive_kl': wl_x['name'] + ' with adaptive_inner_kl_penalty=True (the reference CLASS default, pro_mp.py:40; '
+                                            'the run script sets False): halve / double rule applied on the device'}.get(
+                algo, 'MAML-TRPO (maml_run_mujoco.py config: step_size 0.01, inner_type log_likelihood) on MetaPointEnvCorner, '
+                      'meta_batch=40 in total (BASELINE.json configs[3])')
+            extras[key] = dict(workload=wl_name,
                                algo=algo, scaling=scaling, tasks_per_gpu=tasks_per_gpu, tasks_total=tasks_per_gpu * world,
                                n_gpus=world, steps=n_steps, ms_per_step=ms / n_steps, wall_ms_per_step=wall / n_steps,
                                value=n_env * n_steps / (ms * 1e-3), unit='env-steps/s', meta_iters_per_sec=n_steps / (ms * 1e-3),
@@ -316,6 +320,8 @@ def run_gpu(args):
         extra(other + '_promp_weak', WORKLOADS[other], 'promp', WORKLOADS[other]['M'], 'weak', max(5, args.steps // 2))
         if 40 % world == 0:
             extra('point_trpo_strong', WORKLOADS['point'], 'trpo', 40 // world, 'strong', max(3, args.steps // 4))
+        if world == 1:
+            extra('point_promp_adaptive_kl', WORKLOADS['point'], 'promp_adaptive_kl', WORKLOADS['point']['M'], 'weak', max(5, args.steps // 2))
 
     out = None
     # ---- per-kernel timing pass (instrumented, not part of the timed loops; every rank runs it because the
