@@ -1256,11 +1256,11 @@ static constexpr bool chain_tc_ok() {
     return false;
 }
 
-template <int DO, int DA, int NQ>
+template <int DO, int DA, int NQ, bool HAS_HVP>
 static int launch_chain_nq(ChainArgs& C, cudaStream_t st) {
     static int configured = 0;
     constexpr int smem = ChainSmem<DO, DA, NQ>::SIZE;
-    auto kernel = policy_chain_tc_kernel<DO, DA, NQ>;
+    auto kernel = policy_chain_tc_kernel<DO, DA, NQ, HAS_HVP>;
     if (!configured) {
         PROMP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = 1;
@@ -1301,8 +1301,11 @@ static int launch_chain(int n_stages, const int* kinds, PolicyArgs* A, const int
                 C.st[s].counters = (int*)ws + 4 + (CHAIN_MAX_STAGES + s) * M;
                 C.st[s].partial = partial;            // slots are numbered by global item id
             }
-            if (tc_column_groups(DO) == 4) return launch_chain_nq<DO, DA, 4>(C, st);
-            return launch_chain_nq<DO, DA, 2>(C, st);
+            bool has_hvp = false;
+            for (int s = 0; s < n_stages; ++s) has_hvp = has_hvp || kinds[s] == 1;
+            if (tc_column_groups(DO) == 4)
+                return has_hvp ? launch_chain_nq<DO, DA, 4, true>(C, st) : launch_chain_nq<DO, DA, 4, false>(C, st);
+            return has_hvp ? launch_chain_nq<DO, DA, 2, true>(C, st) : launch_chain_nq<DO, DA, 2, false>(C, st);
         }
     }
     // one launch per stage; their (counters + partial) workspace starts after the chain's control words

@@ -1546,7 +1546,7 @@ struct ChainSmem {
     static constexpr int SIZE = BODY + 32;     // + {mbarrier, TMEM base, current item}
 };
 
-template <int DO, int DA, int NQ>
+template <int DO, int DA, int NQ, bool HAS_HVP = true>
 __global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __grid_constant__ ChainArgs C) {
     using GS = GradTcSmem<DO, DA, NQ>;
     using HS = HvpTcSmem<DO, DA, NQ>;
@@ -1604,10 +1604,10 @@ __global__ void __launch_bounds__(128 * NQ, 1) policy_chain_tc_kernel(const __gr
         sc.ready_prev = (s > 0 && !(s == 1 && skip0)) ? C.ready + (s - 1) * C.M : nullptr;
         sc.ready_mine = C.ready + s * C.M;
         CCLK(0);
-        if (I.kind == 0) {
+        if (!HAS_HVP || I.kind == 0) {
             cached_h = nullptr;
             grad_tc_tiles<DO, DA, NQ>(C.st[s], G, sc, tmem, bar, phase, cached_g);
-        } else {
+        } else if constexpr (HAS_HVP) {
             cached_g = nullptr;
             hvp_tc_tiles<DO, DA, NQ>(C.st[s], H, sc, tmem, bar, phase, cached_h);
         }
