@@ -17,8 +17,9 @@ metric = env-steps/s = (M*E*H*2 env steps per meta-iteration) / (time per meta-i
           e2e.eager = Trainer(use_cuda_graph=False).train_iteration(itr, log=True): what configurations with a host decision
           inside the iteration get.
   other_configs : short measurements, in the same run and through Trainer.train(), of the other BASELINE.json configurations:
-          HalfCheetah surrogate (configs[2] per GPU = configs[4] at N = 8, weak scaling) and MAML-TRPO on PointEnv (configs[3]:
-          40 tasks in total, STRONG scaling over the N GPUs).
+          HalfCheetah surrogate (configs[2] per GPU = configs[4] at N = 8, weak scaling), MAML-TRPO on PointEnv (configs[3]:
+          40 tasks in total, STRONG scaling over the N GPUs) and, at N = 1, ProMP with adaptive_inner_kl_penalty=True (the
+          reference class default; the rule runs on the device, so the iteration is still one graph replay).
   roofline     : dominant kernel (policy_grad / policy_hvp).  These kernels are issue / latency-bound (AI ~ 1 kFLOP/B, inputs
                  L2-resident): bound = "issue", achieved / peak / frac = algorithmic fp32 TFLOP/s over the fp32-SIMT peak; the HBM
                  view (SURVEY.md 8d bytes per sample / launch time over the MEASURED_PEAKS.json copy bandwidth) is in roofline.hbm,
