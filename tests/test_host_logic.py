@@ -319,3 +319,27 @@ def test_policy_chain_plan_host_side():
     # the launch entry validates before touching the device
     rc = lib.promp_policy_chain(2, 2, 64, 10, ctypes.c_float(-13.8), 3, ptr, None, None, ctypes.c_void_p(16), 1 << 20, None)
     assert rc == -1 and 'null pointer' in _lib.last_error()
+
+
+def test_policy_stage_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of promp_policy_stage has the size and field offsets a C compiler gives the header's struct (the header
+    is plain C: compiled here with gcc, no CUDA needed)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from promp_b200 import _lib
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip("no gcc")
+    fields = [name for name, _ in _lib.PolicyStage._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "promp_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(promp_policy_stage));\n' +
+                   ''.join('  printf("%%zu\\n", offsetof(promp_policy_stage, %s));\n' % f for f in fields) +
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.PolicyStage)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_lib.PolicyStage, f).offset == off, f
